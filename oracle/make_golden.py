@@ -1,0 +1,322 @@
+"""
+TEST INFRASTRUCTURE ONLY -- golden-vector generator.
+
+Runs the UNMODIFIED reference (imported from /root/reference through
+oracle/_ref_import.py) on seeded synthetic inputs and writes small fixtures to
+tests/golden/.  Run in the build container only:
+
+    python -m oracle.make_golden
+
+Versions the goldens were produced with are stored in each file's `versions` field.
+Inputs/weights are regenerated from seeds by oracle.vae_oracle.make_* so they are
+not stored.  Large tensors (fc1/fc8 weight grads, x_rec at B=64) are stored as a
+digest: (sum, L2 norm, values at 4096 seeded indices).
+"""
+import copy
+import os
+import sys
+import tempfile
+
+import numpy as np
+import scipy
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import _ref_import, spec_oracle, vae_oracle  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+FULL_LIMIT = 20000
+N_DIGEST = 4096
+
+
+def versions():
+    return "torch=%s numpy=%s scipy=%s" % (torch.__version__, np.__version__,
+                                           scipy.__version__)
+
+
+def digest_indices(numel, salt=0):
+    rng = np.random.default_rng(77 + salt)
+    return rng.integers(0, numel, size=N_DIGEST)
+
+
+def digest(a, salt=0):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    idx = digest_indices(a.size, salt)
+    return np.concatenate([[a.sum(), np.sqrt((a * a).sum())], a[idx]])
+
+
+def store(out, key, arr):
+    arr = np.asarray(arr)
+    if arr.size <= FULL_LIMIT:
+        out[key] = arr
+    else:
+        out[key + "__digest"] = digest(arr)
+
+
+def load_into_reference(model, P):
+    sd = model.state_dict()
+    for k in sd:
+        sd[k] = P[k].clone()
+    model.load_state_dict(sd)
+
+
+class _InjectNoise:
+    """Feeds prepared (eps_W, eps_D) to LowRankMultivariateNormal.rsample by
+    replacing torch's `_standard_normal` helper in that module (torch internal;
+    the reference's own code stays unmodified)."""
+
+    def __init__(self, tensors):
+        import torch.distributions.lowrank_multivariate_normal as lr
+        self.lr = lr
+        self.queue = list(tensors)
+
+    def __enter__(self):
+        self.orig = self.lr._standard_normal
+
+        def fake(shape, dtype, device):
+            t = self.queue.pop(0)
+            assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+            return t.to(dtype)
+        self.lr._standard_normal = fake
+        return self
+
+    def __exit__(self, *a):
+        self.lr._standard_normal = self.orig
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.abs(b).max()
+    return np.abs(a - b).max() / den if den > 0 else np.abs(a).max()
+
+
+def vae_case(ref_vae, name, seed, batch, train, prec=10.0):
+    """Reference run twice on identical weights/inputs/noise: its stock fp32 path
+    (noise drawn by the reference itself under torch.manual_seed) and the same
+    unmodified code in float64 (`.double()`, noise injected) as the exact
+    answer.  Stored: the float64 results, and for each tensor the relative
+    error of the reference's own fp32 result against it (`err32:*`)."""
+    P = vae_oracle.make_params(seed)
+    x = vae_oracle.make_input(seed, batch)
+    out = {"versions": np.array(versions()), "seed": seed, "batch": batch,
+           "train": int(train), "model_precision": prec}
+    # The noise the reference draws (eps_W first, then eps_D).
+    torch.manual_seed(seed)
+    eps_w = torch.randn(batch, 1)
+    eps_d = torch.randn(batch, 32)
+    out["eps_w"] = eps_w.numpy()
+    out["eps_d"] = eps_d.numpy()
+
+    def run(dtype, inject):
+        model = ref_vae.VAE(save_dir='', model_precision=prec, device_name='cpu')
+        load_into_reference(model, P)
+        model.to(dtype)
+        model.train(train)
+        xx = x.to(dtype)
+        res = {}
+        m2 = copy.deepcopy(model)
+        with torch.no_grad():
+            mu, u, d = m2.encode(xx)
+        res["mu"], res["u"], res["d"] = mu.numpy(), u.numpy(), d.numpy()
+        m3 = copy.deepcopy(model)
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            if inject:
+                with _InjectNoise([eps_w, eps_d]):
+                    _, z, x_rec = m3.forward(xx, return_latent_rec=True)
+            else:
+                _, z, x_rec = m3.forward(xx, return_latent_rec=True)
+        res["z"], res["x_rec"] = z, x_rec
+        # forward + backward exactly as train_epoch does (vae.py:348-352).
+        torch.manual_seed(seed)
+        model.optimizer.zero_grad()
+        if inject:
+            with _InjectNoise([eps_w, eps_d]):
+                loss = model.forward(xx)
+        else:
+            loss = model.forward(xx)
+        res["loss"] = np.array(loss.item(), dtype=np.float64)
+        loss.backward()
+        for k, p in model.named_parameters():
+            res["grad:" + k] = p.grad.numpy().copy()
+        for k, b in model.named_buffers():
+            res["buf:" + k] = b.numpy().copy()
+        return res
+
+    r32 = run(torch.float32, inject=False)
+    r64 = run(torch.float64, inject=True)
+    for k, v in r64.items():
+        store(out, k, v)
+        if k.startswith("buf:") and k.endswith("tracked"):
+            continue
+        out["err32:" + k] = np.array(rel_err(r32[k], v))
+    out["loss32"] = r32["loss"]
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    worst = max(float(out[k]) for k in out if k.startswith("err32:grad"))
+    print(name, "loss64", float(r64["loss"]), "loss32", float(r32["loss"]),
+          "worst fp32-reference grad err vs fp64: %.2e" % worst)
+
+
+def adam_case(ref_vae, name, seed, batch, steps):
+    """`steps` reference train steps (vae.py:348-353) in float64 (truth) and in
+    the stock fp32 path; noise injected so both see identical draws."""
+    P = vae_oracle.make_params(seed)
+    out = {"versions": np.array(versions()), "seed": seed, "batch": batch,
+           "steps": steps}
+
+    def run(dtype):
+        model = ref_vae.VAE(save_dir='', device_name='cpu')
+        load_into_reference(model, P)
+        model.to(dtype)
+        model.train()
+        losses = []
+        for s in range(steps):
+            x = vae_oracle.make_input(seed + s, batch).to(dtype)
+            ew, ed = vae_oracle.make_noise(seed + s, batch)
+            model.optimizer.zero_grad()
+            with _InjectNoise([ew, ed]):
+                loss = model.forward(x)
+            losses.append(loss.item())
+            loss.backward()
+            model.optimizer.step()
+        res = {"losses": np.array(losses, dtype=np.float64)}
+        for k, p in model.named_parameters():
+            res["param:" + k] = p.detach().numpy().copy()
+        for k, b in model.named_buffers():
+            res["buf:" + k] = b.numpy().copy()
+        return res
+
+    r32, r64 = run(torch.float32), run(torch.float64)
+    for k, v in r64.items():
+        store(out, k, v)
+        if k.startswith("buf:") and k.endswith("tracked"):
+            continue
+        out["err32:" + k] = np.array(rel_err(r32[k], v))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "losses", r64["losses"], r32["losses"])
+
+
+def spec_cases(ref_pre):
+    out = {"versions": np.array(versions())}
+    # --- mouse-syllable params (time stretch, linear freqs), int16 @ 250 kHz
+    p = dict(spec_oracle.MOUSE_P)
+    fs = p['fs']
+    audio = spec_oracle.synth_audio(11, int(0.6 * fs), fs)
+    cases = [
+        ("mouse_a", 0.100, 0.180), ("mouse_b", 0.2503, 0.2871),
+        ("mouse_full", 0.30, 0.50),          # duration == max_dur
+        ("mouse_neg", -0.02, 0.05),          # s1 < 0
+        ("mouse_end", 0.55, 0.62),           # s2 > len(audio)
+        ("mouse_short", 0.4000, 0.4030),     # < nperseg samples -> zeros
+    ]
+    for name, t1, t2 in cases:
+        spec, flag = ref_pre.get_spec(t1, t2, audio, p, fs=fs)
+        assert flag
+        out[name] = spec
+        out[name + "_t"] = np.array([t1, t2])
+    # --- finch window params (mel), explicit target_times, int16 @ 32 kHz
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    audio2 = spec_oracle.synth_audio(12, int(4.0 * fs), fs)
+    for name, onset in [("finch_a", 1.2345), ("finch_b", 0.01), ("finch_c", 3.87),
+                        ("finch_d", 2.000004)]:
+        offset = onset + p['window_length']
+        tt = np.linspace(onset, offset, 128)
+        spec, _ = ref_pre.get_spec(max(0.0, onset - 0.05), offset + 0.05, audio2,
+                                   p, fs=fs, target_times=tt)
+        out[name] = spec
+        out[name + "_t"] = np.array([onset])
+    # --- float32 audio, non-mel, no DC removal, non-50% overlap
+    p3 = dict(spec_oracle.FINCH_P)
+    p3.update(mel=False, noverlap=384, max_dur=0.3, time_stretch=True)
+    audio3 = (spec_oracle.synth_audio(13, int(2.0 * fs), fs, dtype=np.float64)
+              / 3.0).astype(np.float32)
+    spec, _ = ref_pre.get_spec(0.5, 0.7, audio3, p3, fs=fs, remove_dc_offset=False)
+    out["f32_a"] = spec
+    np.savez_compressed(os.path.join(GOLDEN, "spec_cases.npz"), **out)
+    print("spec cases:", [k for k in out if not k.endswith("_t")])
+
+
+def sampler_cases(ref_win, ref_ds, ref_pre):
+    from scipy.io import wavfile
+    out = {"versions": np.array(versions())}
+    p = dict(spec_oracle.FINCH_P)
+    p['get_spec'] = ref_pre.get_spec
+    fs = p['fs']
+    with tempfile.TemporaryDirectory() as tmp:
+        adir, rdir = os.path.join(tmp, "audio"), os.path.join(tmp, "rois")
+        os.mkdir(adir)
+        os.mkdir(rdir)
+        names = ["b_song", "a_song", "d_song", "c_song", "e_song"]
+        rng = np.random.default_rng(5)
+        for i, nm in enumerate(names):
+            audio = spec_oracle.synth_audio(100 + i, int(3.0 * fs), fs)
+            wavfile.write(os.path.join(adir, nm + ".wav"), fs, audio)
+            n_roi = 1 + (i % 3)
+            starts = np.sort(rng.uniform(0.1, 2.0, size=n_roi))
+            rois = np.stack([starts, starts + rng.uniform(0.2, 0.8, size=n_roi)], 1)
+            np.savetxt(os.path.join(rdir, nm + ".txt"), rois)
+        part = ref_win.get_window_partition([adir], [rdir], split=0.8)
+        out["part_train_audio"] = np.array(
+            [os.path.basename(s) for s in part['train']['audio']])
+        out["part_train_rois"] = np.array(
+            [os.path.basename(s) for s in part['train']['rois']])
+        out["part_test_audio"] = np.array(
+            [os.path.basename(s) for s in part['test']['audio']])
+        part1 = ref_win.get_window_partition([adir], [rdir], split=1.0)
+        out["part1_audio"] = np.array(
+            [os.path.basename(s) for s in part1['train']['audio']])
+        out["part1_rois"] = np.array(
+            [os.path.basename(s) for s in part1['train']['rois']])
+        ds = ref_win.FixedWindowDataset(part1['train']['audio'],
+                                        part1['train']['rois'], p,
+                                        transform=None)
+        out["file_weights"] = ds.file_weights
+        for seed in (0, 1, 7):
+            specs, fidx, onsets, offsets = ds.__getitem__(
+                np.arange(12), seed=seed, return_seg_info=True)
+            out["seed%d_files" % seed] = np.array(fidx, dtype=np.int64)
+            out["seed%d_onsets" % seed] = np.array(onsets, dtype=np.float64)
+            out["seed%d_offsets" % seed] = np.array(offsets, dtype=np.float64)
+            if seed == 0:
+                out["seed0_specs"] = np.stack(specs[:3]).astype(np.float64)
+        # syllable partition: only file listing + seed-42 shuffle matter.
+        hdir = os.path.join(tmp, "h5")
+        os.mkdir(hdir)
+        for i in range(13):
+            open(os.path.join(hdir, "syllables_%04d.hdf5" % i), "w").close()
+        open(os.path.join(hdir, "notes.txt"), "w").close()
+        sp = ref_ds.get_syllable_partition([hdir], 0.75)
+        out["syll_train"] = np.array([os.path.basename(s) for s in sp['train']])
+        out["syll_test"] = np.array([os.path.basename(s) for s in sp['test']])
+        sp2 = ref_ds.get_syllable_partition([hdir], 1.0, shuffle=False,
+                                            max_num_files=5)
+        out["syll2_train"] = np.array([os.path.basename(s) for s in sp2['train']])
+    np.savez_compressed(os.path.join(GOLDEN, "sampler_cases.npz"), **out)
+    print("sampler cases ok")
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(8)
+    ref_vae, ref_pre, ref_win, ref_ds = _ref_import.import_reference()
+    which = sys.argv[1:] or ["vae", "adam", "spec", "sampler"]
+    if "vae" in which:
+        vae_case(ref_vae, "vae_train_b7", seed=0, batch=7, train=True)
+        vae_case(ref_vae, "vae_eval_b7", seed=1, batch=7, train=False)
+        vae_case(ref_vae, "vae_train_b64", seed=2, batch=64, train=True)
+        vae_case(ref_vae, "vae_train_b1", seed=3, batch=1, train=True, prec=4.0)
+    if "adam" in which:
+        adam_case(ref_vae, "adam_b5_s3", seed=4, batch=5, steps=3)
+    if "spec" in which:
+        spec_cases(ref_pre)
+    if "sampler" in which:
+        sampler_cases(ref_win, ref_ds, ref_pre)
+
+
+if __name__ == "__main__":
+    main()

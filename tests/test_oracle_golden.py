@@ -1,0 +1,101 @@
+"""CPU: the oracle restatements (oracle/) against the golden vectors produced by
+the reference's own code (oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec_oracle, vae_oracle
+from tests.helpers import check_against_golden, load_golden, rel_err
+
+TOL64 = 1e-9   # float64 restatement vs the reference's own code run in float64
+
+
+def grad_tol(g, key, floor=1e-4, k=3.0):
+    """Tolerance policy for fp32 results (DESIGN.md "Parity"): within rtol 1e-4
+    of the exact (float64) answer, or within 3x of the error the reference's own
+    fp32 path makes on the same tensor, whichever is larger.  The second clause
+    matters only for gradients at B>=64, which are ill-conditioned (BN backward
+    cancels the dominant gradient component; the reference's fp32 CPU result is
+    itself 1e-3 away from the float64 one)."""
+    return max(floor, k * float(g["err32:" + key]))
+
+
+def _to(P, dtype):
+    return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in P.items()}
+
+
+@pytest.mark.parametrize("name", ["vae_train_b7", "vae_eval_b7", "vae_train_b1",
+                                  "vae_train_b64"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_vae_oracle_matches_reference_golden(name, dtype):
+    g = load_golden(name)
+    seed, batch, train = int(g["seed"]), int(g["batch"]), bool(g["train"])
+    prec = float(g["model_precision"])
+    torch.set_num_threads(8)
+    P = _to(vae_oracle.make_params(seed), dtype)
+    x = vae_oracle.make_input(seed, batch).to(dtype)
+    ew = torch.from_numpy(g["eps_w"]).to(dtype)
+    ed = torch.from_numpy(g["eps_d"]).to(dtype)
+    out, grads, newbuf = vae_oracle.loss_and_grads(P, x, ew, ed, prec, train)
+    f64 = dtype == torch.float64
+    tol = TOL64 if f64 else 2e-5
+    assert abs(out["loss"].item() - float(g["loss"])) <= tol * abs(float(g["loss"]))
+    for k in ("mu", "u", "d", "z"):
+        assert rel_err(out[k].numpy(), g[k]) <= tol, k
+    check_against_golden(g, "", "x_rec", out["x_rec"].numpy(), tol)
+    for k, v in grads.items():
+        check_against_golden(g, "grad:", k, v.numpy(),
+                             TOL64 if f64 else grad_tol(g, "grad:" + k))
+    for k in g.files:
+        if not k.startswith("buf:"):
+            continue
+        kk = k[4:]
+        got = newbuf[kk] if (train and kk in newbuf) else P[kk]
+        if kk.endswith("num_batches_tracked"):
+            assert int(got) == int(g[k])
+        else:
+            assert rel_err(got.numpy(), g[k]) <= tol, kk
+
+
+def test_adam_trajectory_matches_reference_golden():
+    g = load_golden("adam_b5_s3")
+    seed, batch, steps = int(g["seed"]), int(g["batch"]), int(g["steps"])
+    P = _to(vae_oracle.make_params(seed), torch.float64)
+    keys = [k for k, _ in vae_oracle.param_order()]
+    st = {"step": 0, "m": {k: torch.zeros_like(P[k]) for k in keys},
+          "v": {k: torch.zeros_like(P[k]) for k in keys}}
+    for s in range(steps):
+        x = vae_oracle.make_input(seed + s, batch).double()
+        ew, ed = vae_oracle.make_noise(seed + s, batch)
+        loss = vae_oracle.train_step_cpu(P, st, x, ew.double(), ed.double())
+        assert abs(loss.item() - g["losses"][s]) <= 1e-7 * abs(g["losses"][s])
+    for k in keys:
+        check_against_golden(g, "param:", k, P[k].numpy(), 1e-7)
+
+
+def test_get_spec_oracle_matches_reference_golden():
+    g = load_golden("spec_cases")
+    p = dict(spec_oracle.MOUSE_P)
+    fs = p['fs']
+    audio = spec_oracle.synth_audio(11, int(0.6 * fs), fs)
+    for name in ["mouse_a", "mouse_b", "mouse_full", "mouse_neg", "mouse_end",
+                 "mouse_short"]:
+        t1, t2 = g[name + "_t"]
+        spec, flag = spec_oracle.get_spec(t1, t2, audio, p, fs=fs)
+        assert flag and spec.shape == (128, 128)
+        assert np.abs(spec - g[name]).max() <= 1e-9, name
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    audio2 = spec_oracle.synth_audio(12, int(4.0 * fs), fs)
+    for name in ["finch_a", "finch_b", "finch_c", "finch_d"]:
+        onset = float(g[name + "_t"][0])
+        spec = spec_oracle.fixed_window_item([audio2], fs, p, 0, onset)
+        assert np.abs(spec - g[name]).max() <= 1e-9, name
+    p3 = dict(spec_oracle.FINCH_P)
+    p3.update(mel=False, noverlap=384, max_dur=0.3, time_stretch=True)
+    audio3 = (spec_oracle.synth_audio(13, int(2.0 * fs), fs, dtype=np.float64)
+              / 3.0).astype(np.float32)
+    spec, _ = spec_oracle.get_spec(0.5, 0.7, audio3, p3, fs=fs,
+                                   remove_dc_offset=False)
+    # the reference computes this one in float32 (complex64 STFT)
+    assert np.abs(spec - g["f32_a"]).max() <= 1e-5
