@@ -1,0 +1,72 @@
+// Fused Adam over the flat parameter buffer (torch.optim.Adam defaults;
+// ava/models/vae.py:119,353).  One elementwise pass: reads p,g,m,v; writes p,m,v.
+#include "common.cuh"
+
+namespace ava {
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n4, long long n, const float* step_count, double lr_d, double b1_d, double b2_d,
+            double eps_d, float gscale) {
+  // Scalars exactly as torch.optim.Adam forms them (Python doubles, rounded to fp32 once):
+  // step number of THIS update (torch increments `step` before using it)
+  const double t = (double)step_count[0] + 1.0;
+  const double bc1 = 1.0 - pow(b1_d, t);
+  const double bc2 = 1.0 - pow(b2_d, t);
+  const float step_size = (float)(lr_d / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float b1 = (float)b1_d, b2 = (float)b2_d, eps = (float)eps_d;
+  const float omb1 = (float)(1.0 - b1_d), omb2 = (float)(1.0 - b2_d);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define AVA_ADAM1(c)                                         \
+  {                                                          \
+    float gg = gv.c * gscale;                                \
+    mv.c = b1 * mv.c + omb1 * gg;                            \
+    vv.c = b2 * vv.c + omb2 * gg * gg;                       \
+    float denom = sqrtf(vv.c) * inv_sqrt_bc2 + eps;          \
+    pv.c = pv.c - step_size * (mv.c / denom);                \
+  }
+    AVA_ADAM1(x) AVA_ADAM1(y) AVA_ADAM1(z) AVA_ADAM1(w)
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // scalar tail
+  if (blockIdx.x == 0) {
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      float gg = g[i] * gscale;
+      float mm = b1 * m[i] + omb1 * gg;
+      float vv = b2 * v[i] + omb2 * gg * gg;
+      m[i] = mm;
+      v[i] = vv;
+      p[i] = p[i] - step_size * (mm / (sqrtf(vv) * inv_sqrt_bc2 + eps));
+    }
+  }
+}
+
+__global__ void adam_bump_step_kernel(float* step_count) { step_count[0] += 1.f; }
+
+}  // namespace ava
+
+extern "C" int ava_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float* step_count,
+                                  double lr, double beta1, double beta2, double eps, float grad_scale,
+                                  void* stream_) {
+  using namespace ava;
+  if (n <= 0) return 0;
+  AVA_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+                  ((uintptr_t)v % 16 == 0),
+              "adam_step: buffers must be 16-byte aligned");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  long long n4 = n / 4;
+  long long want = (n4 + 255) / 256;
+  int grid = (int)(want < 1 ? 1 : (want > 16 * kNumSMs ? 16 * kNumSMs : want));
+  adam_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n4, n, step_count, lr, beta1, beta2, eps, grad_scale);
+  if (check_launch("adam")) return 1;
+  adam_bump_step_kernel<<<1, 1, 0, stream>>>(step_count);
+  return check_launch("adam_bump_step");
+}

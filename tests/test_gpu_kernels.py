@@ -1,0 +1,336 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes) and
+checked against float64 torch CPU references of the same arithmetic."""
+import ctypes
+import importlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+PKG = "autoencoded-vocal-analysis_b200"
+LAYERS = [("conv1", 1, 8, 1, 128, 0), ("conv2", 8, 8, 2, 128, 0), ("conv3", 8, 16, 1, 64, 0),
+          ("conv4", 16, 16, 2, 64, 0), ("conv5", 16, 24, 1, 32, 0), ("conv6", 24, 24, 2, 32, 0),
+          ("conv7", 24, 32, 1, 16, 0), ("convt1", 32, 24, 1, 16, 1), ("convt2", 24, 24, 2, 16, 1),
+          ("convt3", 24, 16, 1, 32, 1), ("convt4", 16, 16, 2, 32, 1), ("convt5", 16, 8, 1, 64, 1),
+          ("convt6", 8, 8, 2, 64, 1), ("convt7", 8, 1, 1, 128, 1)]
+TOL = 1e-4   # fp32 kernels vs float64 reference (north_star rtol 1e-4)
+
+
+@pytest.fixture(scope="module")
+def L():
+    lib = importlib.import_module(PKG + "._lib")
+    lib.lib()
+    return lib
+
+
+def dev(t, dtype=torch.float32):
+    return t.to(dtype).cuda().contiguous()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def layer_ref(l, x, w, b, gamma, beta, train, rm, rv):
+    name, ci, co, s, h, tr = LAYERS[l]
+    xn = F.batch_norm(x, rm.clone(), rv.clone(), gamma, beta, training=train, momentum=0.1, eps=1e-5)
+    if tr:
+        y = F.conv_transpose2d(xn, w, b, stride=s, padding=1, output_padding=s - 1)
+    else:
+        y = F.conv2d(xn, w, b, stride=s, padding=1)
+    if l != 13:
+        y = F.relu(y)
+    return xn, y
+
+
+def make_layer_inputs(l, B, seed):
+    name, ci, co, s, h, tr = LAYERS[l]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, ci, h, h, generator=g, dtype=torch.float64) * 0.7 + 0.3
+    wshape = (ci, co, 3, 3) if tr else (co, ci, 3, 3)
+    w = torch.randn(wshape, generator=g, dtype=torch.float64) / np.sqrt(9 * ci)
+    b = torch.randn(co, generator=g, dtype=torch.float64) * 0.1
+    gamma = torch.rand(ci, generator=g, dtype=torch.float64) + 0.5
+    beta = torch.randn(ci, generator=g, dtype=torch.float64) * 0.2
+    rm = torch.randn(ci, generator=g, dtype=torch.float64) * 0.1
+    rv = torch.rand(ci, generator=g, dtype=torch.float64) + 0.5
+    # round everything to fp32-representable values so both sides see identical inputs
+    return [t.float().double() for t in (x, w, b, gamma, beta, rm, rv)]
+
+
+@pytest.mark.parametrize("l", range(14))
+@pytest.mark.parametrize("train", [True, False])
+def test_bnconv_fwd(L, l, train):
+    B = 3
+    name, ci, co, s, h, tr = LAYERS[l]
+    x, w, b, gamma, beta, rm, rv = make_layer_inputs(l, B, 100 + l)
+    _, y_ref = layer_ref(l, x, w, b, gamma, beta, train, rm, rv)
+    dx, dw, db, dg, dbeta, drm, drv = [dev(t) for t in (x, w, b, gamma, beta, rm, rv)]
+    stats = torch.zeros(2 * 64, dtype=torch.float64, device="cuda")
+    L.call("ava_b200_channel_stats", dx.data_ptr(), B, ci, h * h, stats.data_ptr(), stream())
+    ho = y_ref.shape[-1]
+    y = torch.empty(B, co, ho, ho, device="cuda")
+    L.call("ava_b200_bnconv_fwd", l, B, dx.data_ptr(), y.data_ptr(), dw.data_ptr(), db.data_ptr(),
+           dg.data_ptr(), dbeta.data_ptr(), stats.data_ptr(), drm.data_ptr(), drv.data_ptr(),
+           1 if train else 0, stats.data_ptr() + 8 * 64, stream())
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu().numpy(), y_ref.numpy()) <= TOL
+    st = stats.cpu().numpy()
+    # input statistics kernel
+    assert rel_err(st[:ci], x.sum(dim=(0, 2, 3)).numpy()) <= 1e-5
+    assert rel_err(st[32:32 + ci], (x * x).sum(dim=(0, 2, 3)).numpy()) <= 1e-5
+    # epilogue statistics of the output (the next BN's batch statistics)
+    assert rel_err(st[64:64 + co], y_ref.sum(dim=(0, 2, 3)).numpy()) <= 1e-4
+    assert rel_err(st[96:96 + co], (y_ref * y_ref).sum(dim=(0, 2, 3)).numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("l", range(14))
+@pytest.mark.parametrize("next_bn", [True, False])
+def test_bnconv_bwd(L, l, next_bn):
+    B = 3
+    name, ci, co, s, h, tr = LAYERS[l]
+    x, w, b, gamma, beta, rm, rv = make_layer_inputs(l, B, 200 + l)
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    b.requires_grad_(True)
+    gen = torch.Generator().manual_seed(300 + l)
+    xn, y = layer_ref(l, x, w, b, gamma, beta, True, rm, rv)
+    xn.retain_grad()
+    y.retain_grad()
+    g2 = (torch.rand(co, generator=gen, dtype=torch.float64) + 0.5).float().double()
+    if next_bn:
+        out = F.batch_norm(y, None, None, g2, None, training=True, eps=1e-5)
+    else:
+        out = y
+    R = torch.randn(out.shape, generator=gen, dtype=torch.float64).float().double()
+    (out * R).sum().backward()
+    # what the next layer's backward-data epilogue would have accumulated
+    ho = y.shape[-1]
+    yd = y.detach()
+    mean_y = yd.mean(dim=(0, 2, 3), keepdim=True)
+    nstats = torch.zeros(64, dtype=torch.float64)
+    nstats[:co] = yd.sum(dim=(0, 2, 3))
+    nstats[32:32 + co] = (yd * yd).sum(dim=(0, 2, 3))
+    ndstats = torch.zeros(64, dtype=torch.float64)
+    ndstats[:co] = R.sum(dim=(0, 2, 3))
+    ndstats[32:32 + co] = (R * (yd - mean_y)).sum(dim=(0, 2, 3))
+    x = x.detach()
+    stats = torch.zeros(64, dtype=torch.float64)
+    stats[:ci] = x.sum(dim=(0, 2, 3))
+    stats[32:32 + ci] = (x * x).sum(dim=(0, 2, 3))
+    d = lambda t: dev(t)          # noqa: E731
+    d64 = lambda t: t.cuda()      # noqa: E731
+    dx, dw_, dg, dbeta, dR, dy, dg2 = d(x), d(w.detach()), d(gamma), d(beta), d(R), d(yd), d(g2)
+    dstats, dnstats, dndstats = d64(stats), d64(nstats), d64(ndstats)
+    ng = dg2.data_ptr() if next_bn else None
+    ns = dnstats.data_ptr() if next_bn else None
+    nd = dndstats.data_ptr() if next_bn else None
+    # --- weight gradient
+    ws_bytes = L.lib().ava_b200_bnconv_bwd_weight_ws(l, B)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    gw = torch.full(w.shape, 7.0, device="cuda")
+    gb = torch.full((co,), 7.0, device="cuda")
+    L.call("ava_b200_bnconv_bwd_weight", l, B, dR.data_ptr(), dy.data_ptr(), ng, ns, nd, dx.data_ptr(),
+           dg.data_ptr(), dbeta.data_ptr(), dstats.data_ptr(), gw.data_ptr(), gb.data_ptr(),
+           ws.data_ptr(), stream())
+    # --- data gradient
+    gin = torch.empty(B, ci, h, h, device="cuda")
+    dst = torch.zeros(64, dtype=torch.float64, device="cuda")
+    L.call("ava_b200_bnconv_bwd_data", l, B, dR.data_ptr(), dy.data_ptr(), ng, ns, nd, dw_.data_ptr(),
+           dx.data_ptr(), dstats.data_ptr(), gin.data_ptr(), dst.data_ptr(), stream())
+    torch.cuda.synchronize()
+    assert rel_err(gw.cpu().numpy(), w.grad.numpy()) <= TOL, "dw"
+    # a bias in front of a BatchNorm has (nearly) zero gradient: absolute tolerance scaled by
+    # the magnitude of the terms that cancel
+    dz_scale = np.abs(y.grad.numpy()).sum() / co
+    assert np.abs(gb.cpu().numpy() - b.grad.numpy()).max() <= 1e-5 * dz_scale, "db"
+    assert rel_err(gin.cpu().numpy(), xn.grad.numpy()) <= TOL, "g_in"
+    mean_x = x.mean(dim=(0, 2, 3), keepdim=True)
+    dbeta_ref = xn.grad.sum(dim=(0, 2, 3)).numpy()
+    dgc_ref = (xn.grad * (x - mean_x)).sum(dim=(0, 2, 3)).numpy()
+    got = dst.cpu().numpy()
+    scale = max(np.abs(xn.grad.numpy()).sum() / ci, 1e-30)   # cancellation-aware scale
+    assert np.abs(got[:ci] - dbeta_ref).max() <= 1e-5 * scale, "dbeta"
+    assert np.abs(got[32:32 + ci] - dgc_ref).max() <= 1e-5 * scale, "dgamma"
+
+
+@pytest.mark.parametrize("M,N,K,act,groups", [(64, 1024, 8192, 1, 1), (7, 256, 1024, 1, 1),
+                                             (5, 192, 256, 1, 1), (33, 32, 64, 0, 3),
+                                             (130, 8192, 1024, 1, 1), (3, 64, 32, 2, 1),
+                                             (9, 20, 64, 0, 3)])
+def test_linear_fwd_bwd(L, M, N, K, act, groups):
+    gen = torch.Generator().manual_seed(M * 7 + N)
+    G = groups
+    x = (torch.randn(M, G * K, generator=gen, dtype=torch.float64) * 0.5).float().double()
+    w = (torch.randn(G, N, K, generator=gen, dtype=torch.float64) / np.sqrt(K)).float().double()
+    b = (torch.randn(G, N, generator=gen, dtype=torch.float64) * 0.1).float().double()
+    w.requires_grad_(True)
+    b.requires_grad_(True)
+    x.requires_grad_(True)
+    ys = []
+    for g in range(G):
+        pre = F.linear(x[:, g * K:(g + 1) * K], w[g], b[g])
+        ys.append(F.relu(pre) if act == 1 else (torch.exp(pre) if act == 2 else pre))
+    y_ref = torch.cat(ys, dim=1)
+    dY = torch.randn(M, G * N, generator=gen, dtype=torch.float64).float().double()
+    dx_, dw_, db_ = dev(x.detach()), dev(w.detach()), dev(b.detach())
+    y = torch.empty(M, G * N, device="cuda")
+    ws_bytes = max(L.lib().ava_b200_linear_ws_bytes(M, N, K), 1 << 20)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    L.call("ava_b200_linear_fwd", dx_.data_ptr(), G * K, dw_.data_ptr(), db_.data_ptr(), y.data_ptr(),
+           G * N, M, N, K, act, G, K, N * K, N, N, 0, ws.data_ptr(), ws_bytes, stream())
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu().numpy(), y_ref.detach().numpy()) <= TOL
+    if act == 2:
+        return
+    # backward: upstream gradient dY w.r.t. the post-activation output
+    (y_ref * dY).sum().backward()
+    ddy = dev(dY)
+    mask = y.data_ptr() if act == 1 else None
+    gw = torch.full((G, N, K), 3.0, device="cuda")
+    gb = torch.full((G, N), 3.0, device="cuda")
+    gx = torch.full((M, G * K), 3.0, device="cuda")
+    L.call("ava_b200_linear_bwd_weight", ddy.data_ptr(), G * N, mask, dx_.data_ptr(), G * K,
+           gw.data_ptr(), gb.data_ptr(), M, N, K, G, N, K, N * K, N, 0, ws.data_ptr(), ws_bytes,
+           stream())
+    L.call("ava_b200_linear_bwd_data", ddy.data_ptr(), G * N, mask, dw_.data_ptr(), gx.data_ptr(),
+           G * K, M, N, K, G, N, N * K, K, 0, 0, ws.data_ptr(), ws_bytes, stream())
+    torch.cuda.synchronize()
+    assert rel_err(gw.cpu().numpy(), w.grad.numpy()) <= TOL
+    assert rel_err(gb.cpu().numpy(), b.grad.numpy()) <= TOL
+    assert rel_err(gx.cpu().numpy(), x.grad.numpy()) <= TOL
+
+
+@pytest.mark.parametrize("B,Z", [(1, 32), (64, 32), (13, 8), (5, 64)])
+def test_latent_and_recon(L, B, Z):
+    from oracle import vae_oracle
+    gen = torch.Generator().manual_seed(B + Z)
+    heads = (torch.randn(B, 3 * Z, generator=gen, dtype=torch.float64) * 0.5).float().double()
+    ew = torch.randn(B, 1, generator=gen, dtype=torch.float64).float().double()
+    ed = torch.randn(B, Z, generator=gen, dtype=torch.float64).float().double()
+    gz = torch.randn(B, Z, generator=gen, dtype=torch.float64).float().double()
+    heads.requires_grad_(True)
+    mu, u, logd = heads[:, :Z], heads[:, Z:2 * Z], heads[:, 2 * Z:]
+    d = torch.exp(logd)
+    z = vae_oracle.rsample(mu, u.unsqueeze(-1), d, ew, ed)
+    ent = vae_oracle.entropy(u.unsqueeze(-1), d).sum()
+    # loss part that depends on the heads: 1/2 sum z^2 - H + <gz, z> (gz = decoder gradient)
+    (0.5 * (z * z).sum() - ent + (gz * z).sum()).backward()
+    dh, dew, ded, dgz = dev(heads.detach()), dev(ew), dev(ed), dev(gz)
+    zz = torch.empty(B, Z, device="cuda")
+    dd = torch.empty(B, Z, device="cuda")
+    acc = torch.zeros(4, dtype=torch.float64, device="cuda")
+    L.call("ava_b200_latent_fwd", dh.data_ptr(), dew.data_ptr(), ded.data_ptr(), B, Z, zz.data_ptr(),
+           dd.data_ptr(), acc.data_ptr(), stream())
+    gh = torch.empty(B, 3 * Z, device="cuda")
+    L.call("ava_b200_latent_bwd", dh.data_ptr(), dew.data_ptr(), ded.data_ptr(), zz.data_ptr(),
+           dgz.data_ptr(), B, Z, gh.data_ptr(), stream())
+    # recon
+    n = B * 16384
+    x = torch.rand(n, generator=gen, dtype=torch.float64).float().double()
+    xr = (x + torch.randn(n, generator=gen, dtype=torch.float64)).float().double()
+    g = torch.empty(n, device="cuda")
+    dx_, dxr_ = dev(x), dev(xr)
+    L.call("ava_b200_recon", dx_.data_ptr(), dxr_.data_ptr(), n, 10.0, g.data_ptr(),
+           acc.data_ptr(), stream())
+    loss = torch.zeros(1, device="cuda")
+    lsum = torch.full((1,), 5.0, dtype=torch.float64, device="cuda")
+    L.call("ava_b200_elbo_finalize", acc.data_ptr(), Z, 16384, 10.0, loss.data_ptr(), lsum.data_ptr(),
+           stream())
+    torch.cuda.synchronize()
+    a = acc.cpu().numpy()
+    assert rel_err(zz.cpu().numpy(), z.detach().numpy()) <= 1e-6
+    assert rel_err(dd.cpu().numpy(), d.detach().numpy()) <= 1e-6
+    assert abs(a[0] - (z * z).sum().item()) <= 1e-5 * (z * z).sum().item()
+    assert abs(a[2] - ent.item()) <= 1e-5 * abs(ent.item())
+    sse = ((x - xr) ** 2).sum().item()
+    assert abs(a[1] - sse) <= 1e-5 * sse
+    assert rel_err(g.cpu().numpy(), (10.0 * (xr - x)).numpy()) <= 1e-6
+    assert rel_err(gh.cpu().numpy(), heads.grad.numpy()) <= 1e-5
+    want = 0.5 * ((z * z).sum().item() + Z * np.log(2 * np.pi)) \
+        + 0.5 * 16384 * np.log(2 * np.pi / 10.0) + 0.5 * 10.0 * sse - ent.item()
+    assert abs(loss.item() - want) <= 1e-6 * abs(want)
+    assert abs(lsum.item() - 5.0 - want) <= 1e-6 * abs(want)
+
+
+def test_adam_matches_torch(L):
+    from oracle import vae_oracle
+    n = 100003
+    gen = torch.Generator().manual_seed(5)
+    p = torch.randn(n, generator=gen)
+    m = torch.zeros(n)
+    v = torch.zeros(n)
+    pad = (n + 3) // 4 * 4
+    dp, dm, dv = [torch.zeros(pad, device="cuda") for _ in range(3)]
+    dp[:n] = p.cuda()
+    step = torch.zeros(1, device="cuda")
+    p64, m64, v64 = p.double(), m.double(), v.double()
+    for t in range(1, 4):
+        g = torch.randn(n, generator=gen) * (10.0 ** (t - 2))
+        dg = torch.zeros(pad, device="cuda")
+        dg[:n] = g.cuda()
+        L.call("ava_b200_adam_step", dp.data_ptr(), dg.data_ptr(), dm.data_ptr(), dv.data_ptr(), n,
+               step.data_ptr(), 1e-3, 0.9, 0.999, 1e-8, 1.0, stream())
+        vae_oracle.adam_step(p64, g.double(), m64, v64, t)
+    torch.cuda.synchronize()
+    assert step.item() == 3.0
+    assert rel_err(dp[:n].cpu().numpy(), p64.numpy()) <= 1e-6
+    assert rel_err(dm[:n].cpu().numpy(), m64.numpy()) <= 1e-6
+    assert rel_err(dv[:n].cpu().numpy(), v64.numpy()) <= 1e-6
+
+
+def test_bn_bookkeeping(L):
+    from oracle import vae_oracle
+    gen = torch.Generator().manual_seed(11)
+    chans = [vae_oracle.bn_channels()[i + 1] for i in range(14)]
+    counts = [1000 + 37 * i for i in range(14)]
+    counts[3] = 0   # skipped layer
+    stats = torch.zeros(14 * 64, dtype=torch.float64)
+    dstats = torch.zeros(14 * 64, dtype=torch.float64)
+    run = torch.zeros(14 * 64)
+    means, variances = [], []
+    for l, c in enumerate(chans):
+        n = max(counts[l], 1)
+        mean = torch.randn(c, generator=gen, dtype=torch.float64)
+        var = torch.rand(c, generator=gen, dtype=torch.float64) + 0.1
+        stats[l * 64:l * 64 + c] = mean * n
+        stats[l * 64 + 32:l * 64 + 32 + c] = (var + mean * mean) * n
+        dstats[l * 64:l * 64 + c] = torch.randn(c, generator=gen, dtype=torch.float64)
+        dstats[l * 64 + 32:l * 64 + 32 + c] = torch.randn(c, generator=gen, dtype=torch.float64)
+        run[l * 64:l * 64 + c] = torch.randn(c, generator=gen)
+        run[l * 64 + 32:l * 64 + 32 + c] = torch.rand(c, generator=gen) + 0.5
+        means.append(mean)
+        variances.append(var)
+    run0 = run.clone()
+    dstat, ddstat, drun = stats.cuda(), dstats.cuda(), run.cuda()
+    nbt = torch.full((14,), 4, dtype=torch.int64, device="cuda")
+    hc = (ctypes.c_int * 14)(*chans)
+    hn = (ctypes.c_longlong * 14)(*counts)
+    rm_off = (ctypes.c_int * 14)(*[i * 64 for i in range(14)])
+    rv_off = (ctypes.c_int * 14)(*[i * 64 + 32 for i in range(14)])
+    L.call("ava_b200_bn_update_running", dstat.data_ptr(), hc, hn, drun.data_ptr(), rm_off, rv_off,
+           nbt.data_ptr(), 0.1, stream())
+    grads = torch.zeros(14 * 64, device="cuda")
+    L.call("ava_b200_bn_param_grads", dstat.data_ptr(), ddstat.data_ptr(), hc, hn, grads.data_ptr(),
+           rm_off, rv_off, stream())
+    torch.cuda.synchronize()
+    got, gg = drun.cpu(), grads.cpu()
+    for l, c in enumerate(chans):
+        sl_m, sl_v = slice(l * 64, l * 64 + c), slice(l * 64 + 32, l * 64 + 32 + c)
+        if counts[l] == 0:
+            assert torch.equal(got[sl_m], run0[sl_m]) and int(nbt[l]) == 4
+            continue
+        n = counts[l]
+        assert int(nbt[l]) == 5
+        want_m = 0.9 * run0[sl_m].double() + 0.1 * means[l]
+        want_v = 0.9 * run0[sl_v].double() + 0.1 * variances[l] * n / (n - 1)
+        assert rel_err(got[sl_m].numpy(), want_m.numpy()) <= 1e-6
+        assert rel_err(got[sl_v].numpy(), want_v.numpy()) <= 1e-6
+        invstd = 1.0 / torch.sqrt(variances[l] + 1e-5)
+        assert rel_err(gg[sl_m].numpy(), (invstd * dstats[sl_v]).numpy()) <= 1e-6
+        assert rel_err(gg[sl_v].numpy(), dstats[sl_m].numpy()) <= 1e-6
