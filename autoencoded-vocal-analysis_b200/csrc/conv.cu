@@ -62,44 +62,87 @@ struct GconvParams {
 
 template <int KIND, int TW>
 struct TileGeom {
-  // output tile (S1,S2) or input tile (UP) handled by 64 thread slots
+  // sub-tile handled by 64 thread slots: output tile (S1,S2) or input tile (UP)
   static constexpr int TH = (KIND == K_UP) ? 128 / TW : 256 / TW;
   static constexpr int IN_ROWS = (KIND == K_S1) ? TH + 2 : (KIND == K_S2 ? 2 * TH + 1 : TH + 1);
-  static constexpr int IN_COLS = (KIND == K_S1) ? TW + 2 : (KIND == K_S2 ? 2 * TW + 1 : TW + 1);
-  // row pitch chosen so that the two row groups sharing a warp (TW=16) hit disjoint banks
-  static constexpr int PITCH = (KIND == K_S1) ? (TW == 32 ? 34 : 20)
-                               : (KIND == K_S2) ? (TW == 32 ? 65 : 34)
-                                                : (TW == 32 ? 33 : 24);
+  // aligned interior of a staged row, loaded as float4 quads; halo columns are scalars
+  static constexpr int QUADS = (KIND == K_S2) ? TW / 2 : TW / 4;
+  // shared-memory row layout (floats):
+  //   S1: [3]=left halo, [4..TW+3]=interior, [TW+4]=right halo
+  //   S2: odd input columns at [3..TW+3] (j=0 is the left halo), even columns at [EO..EO+TW-1]
+  //   UP: [0..TW-1]=interior, [TW]=right halo
+  // pitches: interior 16-byte aligned, and for TW=16 (two row groups per warp) the second
+  // group lands 16 banks away from the first
+  static constexpr int EO = TW + 4;
+  static constexpr int PITCH = (KIND == K_S1) ? (TW == 32 ? 40 : 28)
+                               : (KIND == K_S2) ? (TW == 32 ? 68 : 38)
+                                                : (TW == 32 ? 36 : 24);
   static constexpr int PLANE = IN_ROWS * PITCH;
+  // raw (untransformed) staging rows filled by cp.async: same as the final layout except
+  // that S2 rows are still interleaved: [3]=left halo, [4..2TW+3]=interior
+  static constexpr int RAW_PITCH = (KIND == K_S2) ? 2 * TW + 4 : PITCH;
+  static constexpr int RAW_PLANE = IN_ROWS * RAW_PITCH;
 };
 
-template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
-__global__ void __launch_bounds__(64 * ((CO >= 8) ? CO / 8 : 1))
-    gconv_kernel(const GconvParams P) {
+template <int KIND, int CI, int CO, int TW, int INMODE>
+struct GconvCfg {
   using G = TileGeom<KIND, TW>;
-  constexpr int COT = (CO >= 8) ? 8 : CO;
-  constexpr int NCOG = CO / COT;
-  constexpr int NT = 64 * NCOG;
-  constexpr int CIC = (CI >= 8) ? 8 : CI;
-  constexpr int NCHUNK = CI / CIC;
+  static constexpr int COT = (CO >= 8) ? 8 : CO;
+  static constexpr int NCOG = CO / COT;
+  // threads: 64 slots x NCOG channel groups x NSUB sub-tiles (256, or 192 for CO=24)
+  static constexpr int NSUB = (NCOG >= 3) ? 1 : 4 / NCOG;
+  static constexpr int NT = 64 * NCOG * NSUB;
+  // input channels per pipeline stage: largest divisor of CI keeping a raw stage <= 37 KB
+  // (24 KB in DZ mode, which stages two raw tensors): 2 (3) stage buffers per CTA, 2 CTAs/SM
+  static constexpr int LIMIT = (INMODE == IN_DZ) ? 6144 : 9472;
+  static constexpr int stage_floats(int c) { return NSUB * c * G::RAW_PLANE; }
+  static constexpr int CIC = (CI % 8 == 0 && stage_floats(8) <= LIMIT)   ? 8
+                             : (CI % 4 == 0 && stage_floats(4) <= LIMIT) ? 4
+                             : (CI % 2 == 0 && stage_floats(2) <= LIMIT) ? 2
+                                                                         : 1;
+  static constexpr int NCHUNK = CI / CIC;
+  static constexpr int STAGE = NSUB * CIC * G::PLANE;          // floats, transformed tile
+  static constexpr int RAW_STAGE = NSUB * CIC * G::RAW_PLANE;  // floats, raw staging
+};
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Software-pipelined: while the FMA loop runs on the transformed tile of stage i, the raw
+// rows of stage i+1 stream into a staging buffer with cp.async (non-blocking: the whole stage
+// is in flight at once); a short shared->shared pass then applies the BatchNorm transform /
+// BN+ReLU backward and the zero padding.  Two CTAs per SM interleave their phases.
+template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
+__global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, 2) gconv_kernel(const GconvParams P) {
+  using G = TileGeom<KIND, TW>;
+  using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
+  constexpr int COT = C::COT, NCOG = C::NCOG, NSUB = C::NSUB, NT = C::NT;
+  constexpr int CIC = C::CIC, NCHUNK = C::NCHUNK;
   constexpr int NOUT = (KIND == K_UP) ? 8 : 4;
 
   extern __shared__ __align__(16) float smem[];
-  float* s_w = smem;                      // [CI][9][CO]
-  float* s_in = s_w + CI * 9 * CO;        // [CIC][IN_ROWS][PITCH_]
-  float* s_c0 = s_in + CIC * G::PLANE;    // scale | p
-  float* s_c1 = s_c0 + 32;                // shift | q
-  float* s_red = s_c1 + 64;             // [2*CO] cross-warp reduction
-  float* s_bias = s_red + 64;             // [CO]
-  DzCoef* s_dz = reinterpret_cast<DzCoef*>(s_bias + 32);  // [32] (IN_DZ)
+  float* s_w = smem;                                // [CI][9][CO]
+  float* s_in = s_w + CI * 9 * CO;                  // [NSUB][CIC][IN_ROWS][PITCH] transformed
+  float* s_rawg = s_in + C::STAGE;                  // [RAW_STAGE] raw input (cp.async)
+  float* s_rawy = s_rawg + C::RAW_STAGE;            // [RAW_STAGE] raw saved activation (IN_DZ)
+  float* s_c0 = s_rawy + (INMODE == IN_DZ ? C::RAW_STAGE : 0);  // AFFINE scale
+  float* s_c1 = s_c0 + 32;                          // AFFINE shift
+  float* s_red = s_c1 + 32;                         // [2*CO] cross-warp reduction
+  float* s_bias = s_red + 64;                       // [CO]
+  DzCoef* s_dz = reinterpret_cast<DzCoef*>(s_bias + 32);   // [32] (IN_DZ)
   double* s_meand = reinterpret_cast<double*>(s_dz + 32);  // [32] EPI_BWD: mean of own BN
 
   const int tid = threadIdx.x;
-  const int slot = tid & 63;
-  const int cog = tid >> 6;
-  const int lx = slot % TW;
-  const int rg = slot / TW;
-
   const int H_in = P.H_in, W_in = P.W_in;
   const int H_out = (KIND == K_S1) ? H_in : (KIND == K_S2 ? H_in / 2 : H_in * 2);
   const int W_out = (KIND == K_S1) ? W_in : (KIND == K_S2 ? W_in / 2 : W_in * 2);
@@ -108,6 +151,124 @@ __global__ void __launch_bounds__(64 * ((CO >= 8) ? CO / 8 : 1))
   const int tiles_y = ((KIND == K_UP) ? H_in : H_out) / G::TH;
   const int tiles_per_img = tiles_x * tiles_y;
   const int ntiles = P.B * tiles_per_img;
+  const int ngroups = (ntiles + NSUB - 1) / NSUB;
+
+  constexpr int TPR = G::QUADS + 1;
+  constexpr int NTASK = CIC * G::IN_ROWS * TPR;
+
+  // ---- raw rows of stage (grp, ch) -> staging buffer, asynchronously
+  auto issue = [&](int grp, int ch) {
+    const int tile0 = grp * NSUB;
+#pragma unroll
+    for (int sb = 0; sb < NSUB; ++sb) {
+      const int ltile = tile0 + sb;
+      if (ltile >= ntiles) break;
+      const int ln = ltile / tiles_per_img;
+      const int lrem = ltile - ln * tiles_per_img;
+      const int lty = lrem / tiles_x, ltx = lrem - lty * tiles_x;
+      const int iy0 = (KIND == K_S1) ? lty * G::TH - 1 : (KIND == K_S2 ? 2 * lty * G::TH - 1 : lty * G::TH);
+      const int X0 = (KIND == K_S2) ? 2 * ltx * TW : ltx * TW;
+      const size_t img_base = ((size_t)ln * CI + (size_t)ch * CIC) * H_in * W_in;
+      const int sbase = sb * CIC * G::RAW_PLANE;
+#pragma unroll 2
+      for (int t = tid; t < NTASK; t += NT) {
+        const int q = t % TPR;
+        const int rr = t / TPR;
+        const int r = rr % G::IN_ROWS;
+        const int ci = rr / G::IN_ROWS;
+        const int gy = iy0 + r;
+        if (gy < 0 || gy >= H_in) continue;
+        const size_t rowoff = img_base + ((size_t)ci * H_in + gy) * W_in;
+        const int so = sbase + ci * G::RAW_PLANE + r * G::RAW_PITCH;
+        if (q < G::QUADS) {
+          const size_t off = rowoff + X0 + 4 * q;
+          const int sc = (KIND == K_UP) ? 4 * q : 4 + 4 * q;
+          cp_async16(s_rawg + so + sc, P.in + off);
+          if (INMODE == IN_DZ) cp_async16(s_rawy + so + sc, P.in_y + off);
+        } else {
+          const int gx0 = (KIND == K_UP) ? X0 + TW : X0 - 1;
+          const int sc0 = (KIND == K_UP) ? TW : 3;
+          if (gx0 >= 0 && gx0 < W_in) {
+            cp_async4(s_rawg + so + sc0, P.in + rowoff + gx0);
+            if (INMODE == IN_DZ) cp_async4(s_rawy + so + sc0, P.in_y + rowoff + gx0);
+          }
+          if (KIND == K_S1 && X0 + TW < W_in) {
+            cp_async4(s_rawg + so + TW + 4, P.in + rowoff + X0 + TW);
+            if (INMODE == IN_DZ) cp_async4(s_rawy + so + TW + 4, P.in_y + rowoff + X0 + TW);
+          }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  auto xform1 = [&](float a, float y, int cc) -> float {
+    if (INMODE == IN_AFFINE) return fmaf(a, s_c0[cc], s_c1[cc]);
+    return (P.relu_mask && !(y > 0.f)) ? 0.f : dz_apply(s_dz[cc], a, y);
+  };
+
+  // ---- staging buffer -> transformed tile (BN apply / BN+ReLU backward; zero padding AFTER)
+  auto transform = [&](int grp, int ch) {
+    const int tile0 = grp * NSUB;
+#pragma unroll
+    for (int sb = 0; sb < NSUB; ++sb) {
+      const int ltile = tile0 + sb;
+      if (ltile >= ntiles) break;
+      const int lrem = ltile % tiles_per_img;
+      const int lty = lrem / tiles_x, ltx = lrem - lty * tiles_x;
+      const int iy0 = (KIND == K_S1) ? lty * G::TH - 1 : (KIND == K_S2 ? 2 * lty * G::TH - 1 : lty * G::TH);
+      const int X0 = (KIND == K_S2) ? 2 * ltx * TW : ltx * TW;
+      const int sbase = sb * CIC * G::RAW_PLANE;
+      float* sdst = s_in + sb * CIC * G::PLANE;
+#pragma unroll 2
+      for (int t = tid; t < NTASK; t += NT) {
+        const int q = t % TPR;
+        const int rr = t / TPR;
+        const int r = rr % G::IN_ROWS;
+        const int ci = rr / G::IN_ROWS;
+        const int gy = iy0 + r;
+        const bool rowok = gy >= 0 && gy < H_in;
+        const int cc = ch * CIC + ci;
+        const int so = sbase + ci * G::RAW_PLANE + r * G::RAW_PITCH;
+        float* srow = sdst + ci * G::PLANE + r * G::PITCH;
+        if (q < G::QUADS) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rowok) {
+            const int sc = (KIND == K_UP) ? 4 * q : 4 + 4 * q;
+            const float4 a = *reinterpret_cast<const float4*>(s_rawg + so + sc);
+            float4 y = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (INMODE == IN_DZ) y = *reinterpret_cast<const float4*>(s_rawy + so + sc);
+            v = make_float4(xform1(a.x, y.x, cc), xform1(a.y, y.y, cc), xform1(a.z, y.z, cc),
+                            xform1(a.w, y.w, cc));
+          }
+          if (KIND == K_S1) {
+            *reinterpret_cast<float4*>(srow + 4 + 4 * q) = v;
+          } else if (KIND == K_S2) {
+            *reinterpret_cast<float2*>(srow + G::EO + 2 * q) = make_float2(v.x, v.z);  // even columns
+            *reinterpret_cast<float2*>(srow + 4 + 2 * q) = make_float2(v.y, v.w);      // odd j=2q+1,2q+2
+          } else {
+            *reinterpret_cast<float4*>(srow + 4 * q) = v;
+          }
+        } else {
+          const int gx0 = (KIND == K_UP) ? X0 + TW : X0 - 1;
+          const int sc0 = (KIND == K_UP) ? TW : 3;
+          float h0 = 0.f;
+          if (rowok && gx0 >= 0 && gx0 < W_in)
+            h0 = xform1(s_rawg[so + sc0], (INMODE == IN_DZ) ? s_rawy[so + sc0] : 1.f, cc);
+          srow[sc0] = h0;
+          if (KIND == K_S1) {
+            float h1 = 0.f;
+            if (rowok && X0 + TW < W_in)
+              h1 = xform1(s_rawg[so + TW + 4], (INMODE == IN_DZ) ? s_rawy[so + TW + 4] : 1.f, cc);
+            srow[TW + 4] = h1;
+          }
+        }
+      }
+    }
+  };
+
+  // first stage's loads go out before anything else
+  if ((int)blockIdx.x < ngroups) issue(blockIdx.x, 0);
 
   // ---- one-time per CTA: weights, coefficients
   for (int idx = tid; idx < CI * 9 * CO; idx += NT) {
@@ -131,28 +292,24 @@ __global__ void __launch_bounds__(64 * ((CO >= 8) ? CO / 8 : 1))
     if (EPI == EPI_BWD) s_meand[tid] = P.stats_self[tid] / P.out_count;
   }
   if (tid < 2 * CO) s_red[tid] = 0.f;
-  __syncthreads();
+
+  const int sub = tid / (64 * NCOG);
+  const int t2 = tid - sub * (64 * NCOG);
+  const int slot = t2 & 63;
+  const int cog = t2 >> 6;
+  const int lx = slot % TW;
+  const int rg = slot / TW;
 
   float st1[COT], st2[COT];
 #pragma unroll
   for (int c = 0; c < COT; ++c) st1[c] = st2[c] = 0.f;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int tile = grp * NSUB + sub;
+    const bool tvalid = tile < ntiles;
     const int n = tile / tiles_per_img;
     const int trem = tile - n * tiles_per_img;
     const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
-    // origin of the staged input tile in input coordinates
-    int iy0, ix0;
-    if (KIND == K_S1) {
-      iy0 = ty * G::TH - 1;
-      ix0 = tx * TW - 1;
-    } else if (KIND == K_S2) {
-      iy0 = 2 * ty * G::TH - 1;
-      ix0 = 2 * tx * TW - 1;
-    } else {
-      iy0 = ty * G::TH;
-      ix0 = tx * TW;
-    }
 
     float acc[NOUT][COT];
 #pragma unroll
@@ -162,128 +319,127 @@ __global__ void __launch_bounds__(64 * ((CO >= 8) ? CO / 8 : 1))
 
 #pragma unroll 1
     for (int ch = 0; ch < NCHUNK; ++ch) {
-      __syncthreads();  // previous chunk / tile fully consumed
-      // ---- stage CIC input planes, transformed
-      const size_t img_base = ((size_t)n * CI + (size_t)ch * CIC) * H_in * W_in;
-      for (int idx = tid; idx < CIC * G::IN_ROWS * G::IN_COLS; idx += NT) {
-        int c = idx % G::IN_COLS;
-        int r = (idx / G::IN_COLS) % G::IN_ROWS;
-        int ci = idx / (G::IN_COLS * G::IN_ROWS);
-        int gy = iy0 + r, gx = ix0 + c;
-        float v = 0.f;
-        if (gy >= 0 && gy < H_in && gx >= 0 && gx < W_in) {
-          size_t off = img_base + ((size_t)ci * H_in + gy) * W_in + gx;
-          int cc = ch * CIC + ci;
-          if (INMODE == IN_AFFINE) {
-            v = fmaf(__ldg(P.in + off), s_c0[cc], s_c1[cc]);
-          } else {
-            float yv = __ldg(P.in_y + off);
-            float gv = __ldg(P.in + off);
-            v = (P.relu_mask && !(yv > 0.f)) ? 0.f : dz_apply(s_dz[cc], gv, yv);
-          }
-        }
-        int sc = c;
-        if (KIND == K_S2) sc = (c & 1) ? (TW + 1 + (c >> 1)) : (c >> 1);  // odd cols first, then even
-        s_in[ci * G::PLANE + r * G::PITCH + sc] = v;
+      cp_async_wait_all();
+      __syncthreads();  // this stage's raw rows have landed; previous FMA loop is done with s_in
+      transform(grp, ch);
+      __syncthreads();  // s_in ready; staging buffer free again
+      // prefetch the next stage while computing this one
+      if (ch + 1 < NCHUNK) {
+        issue(grp, ch + 1);
+      } else if (grp + (int)gridDim.x < ngroups) {
+        issue(grp + gridDim.x, 0);
       }
-      __syncthreads();
-
-      // ---- accumulate
+      if (tvalid) {
+        const float* s_mine = s_in + sub * CIC * G::PLANE;
 #pragma unroll 2
-      for (int ci = 0; ci < CIC; ++ci) {
-        const float* tw = s_w + ((ch * CIC + ci) * 9) * CO + cog * COT;
-        if (KIND == K_S1) {
-          const float* tin = s_in + ci * G::PLANE + (4 * rg) * G::PITCH + lx;
-          float v[6][3];
+        for (int ci = 0; ci < CIC; ++ci) {
+          const float* tw = s_w + ((ch * CIC + ci) * 9) * CO + cog * COT;
+          if (KIND == K_S1) {
+            const float* tin = s_mine + ci * G::PLANE + (4 * rg) * G::PITCH + lx + 3;
+            float v[6][3];
 #pragma unroll
-          for (int r = 0; r < 6; ++r)
+            for (int r = 0; r < 6; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[r][c] = tin[r * G::PITCH + c];
+              for (int c = 0; c < 3; ++c) v[r][c] = tin[r * G::PITCH + c];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            float wv[COT];
+            for (int k = 0; k < 9; ++k) {
+              float wv[COT];
 #pragma unroll
-            for (int c = 0; c < COT; ++c) wv[c] = tw[k * CO + c];
+              for (int c = 0; c < COT; ++c) wv[c] = tw[k * CO + c];
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+              for (int r = 0; r < 4; ++r)
 #pragma unroll
-              for (int c = 0; c < COT; ++c) acc[r][c] = fmaf(v[r + k / 3][k % 3], wv[c], acc[r][c]);
-          }
-        } else if (KIND == K_S2) {
-          const float* tin = s_in + ci * G::PLANE + (8 * rg) * G::PITCH;
-          float v[9][3];
+                for (int c = 0; c < COT; ++c) acc[r][c] = fmaf(v[r + k / 3][k % 3], wv[c], acc[r][c]);
+            }
+          } else if (KIND == K_S2) {
+            const float* tin = s_mine + ci * G::PLANE + (8 * rg) * G::PITCH;
+            float v[9][3];
 #pragma unroll
-          for (int r = 0; r < 9; ++r) {
-            v[r][0] = tin[r * G::PITCH + lx];                // col 2x-1 (odd plane, index x)
-            v[r][1] = tin[r * G::PITCH + TW + 1 + lx];       // col 2x   (even plane)
-            v[r][2] = tin[r * G::PITCH + lx + 1];            // col 2x+1
-          }
+            for (int r = 0; r < 9; ++r) {
+              v[r][0] = tin[r * G::PITCH + 3 + lx];       // input col 2x-1
+              v[r][1] = tin[r * G::PITCH + G::EO + lx];   // input col 2x
+              v[r][2] = tin[r * G::PITCH + 4 + lx];       // input col 2x+1
+            }
 #pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            float wv[COT];
+            for (int k = 0; k < 9; ++k) {
+              float wv[COT];
 #pragma unroll
-            for (int c = 0; c < COT; ++c) wv[c] = tw[k * CO + c];
+              for (int c = 0; c < COT; ++c) wv[c] = tw[k * CO + c];
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+              for (int r = 0; r < 4; ++r)
 #pragma unroll
-              for (int c = 0; c < COT; ++c) acc[r][c] = fmaf(v[2 * r + k / 3][k % 3], wv[c], acc[r][c]);
-          }
-        } else {
-          const float* tin = s_in + ci * G::PLANE + (2 * rg) * G::PITCH + lx;
-          float v[3][2];
+                for (int c = 0; c < COT; ++c) acc[r][c] = fmaf(v[2 * r + k / 3][k % 3], wv[c], acc[r][c]);
+            }
+          } else {
+            const float* tin = s_mine + ci * G::PLANE + (2 * rg) * G::PITCH + lx;
+            float v[3][2];
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            v[r][0] = tin[r * G::PITCH];
-            v[r][1] = tin[r * G::PITCH + 1];
-          }
-          // out index o = a*4 + oa*2 + ob  (a: input row of the pair, oa/ob: output parity)
+            for (int r = 0; r < 3; ++r) {
+              v[r][0] = tin[r * G::PITCH];
+              v[r][1] = tin[r * G::PITCH + 1];
+            }
+            // out index o = a*4 + oa*2 + ob  (a: input row of the pair, oa/ob: output parity)
 #pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            const int ky = k / 3, kx = k % 3;
-            float wv[COT];
+            for (int k = 0; k < 9; ++k) {
+              const int ky = k / 3, kx = k % 3;
+              float wv[COT];
 #pragma unroll
-            for (int c = 0; c < COT; ++c) wv[c] = tw[k * CO + c];
-            // output parity this tap feeds, and which neighbour it reads
-            const int oa = (ky == 1) ? 0 : 1, dy = (ky == 0) ? 1 : 0;
-            const int ob = (kx == 1) ? 0 : 1, dx = (kx == 0) ? 1 : 0;
+              for (int c = 0; c < COT; ++c) wv[c] = tw[k * CO + c];
+              // output parity this tap feeds, and which neighbour it reads
+              const int oa = (ky == 1) ? 0 : 1, dy = (ky == 0) ? 1 : 0;
+              const int ob = (kx == 1) ? 0 : 1, dx = (kx == 0) ? 1 : 0;
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
+              for (int a = 0; a < 2; ++a)
 #pragma unroll
-              for (int c = 0; c < COT; ++c)
-                acc[a * 4 + oa * 2 + ob][c] = fmaf(v[a + dy][dx], wv[c], acc[a * 4 + oa * 2 + ob][c]);
+                for (int c = 0; c < COT; ++c)
+                  acc[a * 4 + oa * 2 + ob][c] = fmaf(v[a + dy][dx], wv[c], acc[a * 4 + oa * 2 + ob][c]);
+            }
           }
         }
       }
     }
+    if (!tvalid) continue;
 
-    // ---- epilogue
+    // ---- epilogue (the next tile group's loads are already in flight)
+    if (EPI == EPI_BWD) {
+      // sum g and sum g*x per channel (centred with the exact mean at the very end); all
+      // NOUT*COT loads of x are issued before the first one is used
+      float xs[NOUT][COT];
 #pragma unroll
-    for (int o = 0; o < NOUT; ++o) {
-      int oy, ox;
-      if (KIND == K_UP) {
-        oy = 2 * (ty * G::TH + 2 * rg + (o >> 2)) + ((o >> 1) & 1);
-        ox = 2 * (tx * TW + lx) + (o & 1);
-      } else {
-        oy = ty * G::TH + 4 * rg + o;
-        ox = tx * TW + lx;
+      for (int o = 0; o < NOUT; ++o) {
+        int oy, ox;
+        if (KIND == K_UP) {
+          oy = 2 * (ty * G::TH + 2 * rg + (o >> 2)) + ((o >> 1) & 1);
+          ox = 2 * (tx * TW + lx) + (o & 1);
+        } else {
+          oy = ty * G::TH + 4 * rg + o;
+          ox = tx * TW + lx;
+        }
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+          const int co = cog * COT + c;
+          const float* px = P.x_self + (((size_t)n * CO + co) * H_out + oy) * W_out + ox;
+          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(xs[o][c]) : "l"(px));
+        }
       }
 #pragma unroll
-      for (int c = 0; c < COT; ++c) {
-        const int co = cog * COT + c;
-        const size_t off = (((size_t)n * CO + co) * H_out + oy) * W_out + ox;
-        float v = acc[o][c];
-        if (EPI == EPI_FWD) {
-          v += s_bias[co];
+      for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+          st1[c] += acc[o][c];
+          st2[c] = fmaf(acc[o][c], xs[o][c], st2[c]);
+        }
+    } else {
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+          float v = acc[o][c] + s_bias[cog * COT + c];
           if (P.relu_out) v = fmaxf(v, 0.f);
           st1[c] += v;
           st2[c] = fmaf(v, v, st2[c]);
-        } else {
-          float xc = (float)((double)__ldg(P.x_self + off) - s_meand[co]);
-          st1[c] += v;
-          st2[c] = fmaf(v, xc, st2[c]);
+          acc[o][c] = v;
         }
-        acc[o][c] = v;
-      }
     }
     if (P.out) {
       if (KIND == K_UP) {
@@ -313,7 +469,7 @@ __global__ void __launch_bounds__(64 * ((CO >= 8) ? CO / 8 : 1))
     }
   }
 
-  // ---- per-channel statistics: warp shuffle -> smem -> one fp64 atomic per channel per CTA
+  // ---- per-channel statistics: warp shuffle -> smem atomics -> one fp64 atomic per channel
   double* dst = (EPI == EPI_FWD) ? P.stats_out : P.dstats;
   if (dst != nullptr) {
 #pragma unroll
@@ -327,8 +483,10 @@ __global__ void __launch_bounds__(64 * ((CO >= 8) ? CO / 8 : 1))
     }
     __syncthreads();
     if (tid < CO) {
-      atomicAdd(&dst[tid], (double)s_red[tid]);
-      atomicAdd(&dst[32 + tid], (double)s_red[CO + tid]);
+      const double a = (double)s_red[tid], b = (double)s_red[CO + tid];
+      atomicAdd(&dst[tid], a);
+      // EPI_BWD: sum g*(x - mean) = sum g*x - mean * sum g, centred in fp64
+      atomicAdd(&dst[32 + tid], (EPI == EPI_BWD) ? b - s_meand[tid] * a : b);
     }
   }
 }
@@ -336,16 +494,20 @@ __global__ void __launch_bounds__(64 * ((CO >= 8) ? CO / 8 : 1))
 template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
 static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   using G = TileGeom<KIND, TW>;
-  constexpr int COT = (CO >= 8) ? 8 : CO;
-  constexpr int NT = 64 * (CO / COT);
-  constexpr int CIC = (CI >= 8) ? 8 : CI;
-  const size_t smem = (size_t)(CI * 9 * CO + CIC * G::PLANE + 32 * 4 + 64 + 32) * sizeof(float) + 32 * sizeof(DzCoef) + 32 * sizeof(double);
+  using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
+  const size_t smem =
+      (size_t)(CI * 9 * CO + C::STAGE + (INMODE == IN_DZ ? 2 : 1) * C::RAW_STAGE + 64 + 64 + 32) * sizeof(float) +
+      32 * sizeof(DzCoef) + 32 * sizeof(double);
   auto kern = gconv_kernel<KIND, CI, CO, TW, INMODE, EPI>;
   static int max_ctas = 0;
   if (max_ctas == 0) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("gconv: cannot reserve %zu bytes of shared memory", smem);
+      return 1;
+    }
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, smem);
     if (per_sm < 1) per_sm = 1;
     max_ctas = per_sm * kNumSMs;
   }
@@ -355,8 +517,9 @@ static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   const int tiles_y = ((KIND == K_UP) ? P.H_in : H_out) / G::TH;
   const long long ntiles = (long long)P.B * tiles_x * tiles_y;
   if (ntiles == 0) return 0;
-  int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
-  kern<<<grid, NT, smem, stream>>>(P);
+  const long long ngroups = (ntiles + C::NSUB - 1) / C::NSUB;
+  int grid = (int)(ngroups < max_ctas ? ngroups : max_ctas);
+  kern<<<grid, C::NT, smem, stream>>>(P);
   return check_launch("gconv");
 }
 
@@ -405,7 +568,7 @@ struct WTile {
 
 // CONVT == 0: G uses the DZ loader, I the AFFINE loader; CONVT == 1: the other way round.
 template <int S, int CG, int CI, int TWG, int CONVT>
-__global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams P) {
+__global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgradParams P) {
   using T = WTile<S, TWG>;
   constexpr int GT = (CI == 1) ? 1 : 8;   // g-channels per thread
   constexpr int NGQ = CG / GT;
@@ -461,40 +624,135 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams P) {
     const int trem = tile - n * tiles_per_img;
     const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
     const int gy0 = ty * T::THG, gx0 = tx * TWG;
-    const int iy0 = S * gy0 - 1, ix0 = S * gx0 - 1;
+    const int iy0 = S * gy0 - 1;
     __syncthreads();
-    // ---- stage G tile (no halo, always in range)
-    for (int idx = tid; idx < CG * T::THG * TWG; idx += 256) {
-      int x = idx % TWG;
-      int y = (idx / TWG) % T::THG;
-      int c = idx / (TWG * T::THG);
-      size_t off = (((size_t)n * CG + c) * Hg + gy0 + y) * Wg + gx0 + x;
-      float v;
-      if (CONVT) {
-        v = fmaf(__ldg(P.g_a + off), s_aff[c], s_aff[32 + c]);
-      } else {
-        float yv = __ldg(P.g_y + off);
-        v = (P.relu_mask && !(yv > 0.f)) ? 0.f : dz_apply(s_dz[c], __ldg(P.g_a + off), yv);
-      }
-      s_g[c * T::G_PLANE + y * TWG + x] = v;
-    }
-    // ---- stage I tile (halo, zero padded after the transform)
-    for (int idx = tid; idx < CI * T::I_ROWS * T::I_COLS; idx += 256) {
-      int x = idx % T::I_COLS;
-      int y = (idx / T::I_COLS) % T::I_ROWS;
-      int c = idx / (T::I_COLS * T::I_ROWS);
-      int gy = iy0 + y, gx = ix0 + x;
-      float v = 0.f;
-      if (gy >= 0 && gy < Hi && gx >= 0 && gx < Wi) {
-        size_t off = (((size_t)n * CI + c) * Hi + gy) * Wi + gx;
-        if (CONVT) {
-          float yv = __ldg(P.i_y + off);
-          v = (P.relu_mask && !(yv > 0.f)) ? 0.f : dz_apply(s_dz[c], __ldg(P.i_a + off), yv);
-        } else {
-          v = fmaf(__ldg(P.i_a + off), s_aff[c], s_aff[32 + c]);
+    // ---- stage G tile (no halo, always in range): aligned float4 quads, loads batched so
+    // that U (x2 for the DZ side) 16-byte loads per thread are in flight
+    {
+      constexpr int QG = TWG / 4;
+      constexpr int NTASK = CG * T::THG * QG;
+      constexpr int U = CONVT ? 8 : 4;
+#pragma unroll 1
+      for (int t0 = tid; t0 < NTASK; t0 += 256 * U) {
+        float4 ra[U], ry[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = t0 + u * 256;
+          if (t < NTASK) {
+            const int q = t % QG;
+            const int y = (t / QG) % T::THG;
+            const int c = t / (QG * T::THG);
+            const size_t off = (((size_t)n * CG + c) * Hg + gy0 + y) * Wg + gx0 + 4 * q;
+            ra[u] = __ldg(reinterpret_cast<const float4*>(P.g_a + off));
+            if (!CONVT) ry[u] = __ldg(reinterpret_cast<const float4*>(P.g_y + off));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = t0 + u * 256;
+          if (t < NTASK) {
+            const int q = t % QG;
+            const int y = (t / QG) % T::THG;
+            const int c = t / (QG * T::THG);
+            const float4 a = ra[u];
+            float4 v;
+            if (CONVT) {
+              const float sc = s_aff[c], sh = s_aff[32 + c];
+              v = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
+            } else {
+              const float4 yv = ry[u];
+              const DzCoef k = s_dz[c];
+              const bool m = P.relu_mask != 0;
+              v.x = (m && !(yv.x > 0.f)) ? 0.f : dz_apply(k, a.x, yv.x);
+              v.y = (m && !(yv.y > 0.f)) ? 0.f : dz_apply(k, a.y, yv.y);
+              v.z = (m && !(yv.z > 0.f)) ? 0.f : dz_apply(k, a.z, yv.z);
+              v.w = (m && !(yv.w > 0.f)) ? 0.f : dz_apply(k, a.w, yv.w);
+            }
+            *reinterpret_cast<float4*>(s_g + c * T::G_PLANE + y * TWG + 4 * q) = v;
+          }
         }
       }
-      s_i[c * T::I_PLANE + y * T::I_PITCH + x] = v;
+    }
+    // ---- stage I tile: aligned interior quads (stored one column to the right of the left
+    // halo), scalar halo columns, zero rows/cols outside the image (padding AFTER the transform)
+    {
+      constexpr int QI = S * TWG / 4;
+      constexpr int TPR = QI + 1;
+      constexpr int NTASK = CI * T::I_ROWS * TPR;
+      constexpr int U = CONVT ? 4 : 8;
+      const int X0 = S * gx0;
+#pragma unroll 1
+      for (int t0 = tid; t0 < NTASK; t0 += 256 * U) {
+        float4 ra[U], ry[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = t0 + u * 256;
+          ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          ry[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (t < NTASK) {
+            const int q = t % TPR;
+            const int y = (t / TPR) % T::I_ROWS;
+            const int c = t / (TPR * T::I_ROWS);
+            const int gy = iy0 + y;
+            if (gy >= 0 && gy < Hi) {
+              const size_t rowoff = (((size_t)n * CI + c) * Hi + gy) * Wi;
+              if (q < QI) {
+                const size_t off = rowoff + X0 + 4 * q;
+                ra[u] = __ldg(reinterpret_cast<const float4*>(P.i_a + off));
+                if (CONVT) ry[u] = __ldg(reinterpret_cast<const float4*>(P.i_y + off));
+              } else {
+                if (X0 - 1 >= 0) {
+                  ra[u].x = __ldg(P.i_a + rowoff + X0 - 1);
+                  if (CONVT) ry[u].x = __ldg(P.i_y + rowoff + X0 - 1);
+                }
+                if (S == 1 && X0 + TWG < Wi) {
+                  ra[u].y = __ldg(P.i_a + rowoff + X0 + TWG);
+                  if (CONVT) ry[u].y = __ldg(P.i_y + rowoff + X0 + TWG);
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = t0 + u * 256;
+          if (t < NTASK) {
+            const int q = t % TPR;
+            const int y = (t / TPR) % T::I_ROWS;
+            const int c = t / (TPR * T::I_ROWS);
+            const int gy = iy0 + y;
+            const bool rowok = gy >= 0 && gy < Hi;
+            const float4 a = ra[u];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowok) {
+              if (CONVT) {
+                const float4 yv = ry[u];
+                const DzCoef k = s_dz[c];
+                const bool m = P.relu_mask != 0;
+                v.x = (m && !(yv.x > 0.f)) ? 0.f : dz_apply(k, a.x, yv.x);
+                v.y = (m && !(yv.y > 0.f)) ? 0.f : dz_apply(k, a.y, yv.y);
+                if (q < QI) {
+                  v.z = (m && !(yv.z > 0.f)) ? 0.f : dz_apply(k, a.z, yv.z);
+                  v.w = (m && !(yv.w > 0.f)) ? 0.f : dz_apply(k, a.w, yv.w);
+                }
+              } else {
+                const float sc = s_aff[c], sh = s_aff[32 + c];
+                v = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
+              }
+            }
+            float* srow = s_i + c * T::I_PLANE + y * T::I_PITCH;
+            if (q < QI) {
+              srow[1 + 4 * q] = v.x;
+              srow[2 + 4 * q] = v.y;
+              srow[3 + 4 * q] = v.z;
+              srow[4 + 4 * q] = v.w;
+            } else {
+              srow[0] = (X0 - 1 >= 0) ? v.x : 0.f;
+              if (S == 1) srow[TWG + 1] = (X0 + TWG < Wi) ? v.y : 0.f;
+            }
+          }
+        }
+      }
     }
     __syncthreads();
     if (!active) continue;
@@ -772,9 +1030,9 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* g_out, 
     P.Hg = P.Wg = ho;
     switch (layer) {
       case 0: rc = launch_wgrad<1, 8, 1, 32, 0>(P, dw, db, ws, stream); break;
-      case 1: rc = launch_wgrad<2, 8, 8, 16, 0>(P, dw, db, ws, stream); break;
+      case 1: rc = launch_wgrad<2, 8, 8, 32, 0>(P, dw, db, ws, stream); break;
       case 2: rc = launch_wgrad<1, 16, 8, 32, 0>(P, dw, db, ws, stream); break;
-      case 3: rc = launch_wgrad<2, 16, 16, 16, 0>(P, dw, db, ws, stream); break;
+      case 3: rc = launch_wgrad<2, 16, 16, 32, 0>(P, dw, db, ws, stream); break;
       case 4: rc = launch_wgrad<1, 24, 16, 32, 0>(P, dw, db, ws, stream); break;
       case 5: rc = launch_wgrad<2, 24, 24, 16, 0>(P, dw, db, ws, stream); break;
       case 6: rc = launch_wgrad<1, 32, 24, 16, 0>(P, dw, db, ws, stream); break;
@@ -790,9 +1048,9 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* g_out, 
       case 7: rc = launch_wgrad<1, 32, 24, 16, 1>(P, dw, db, ws, stream); break;
       case 8: rc = launch_wgrad<2, 24, 24, 16, 1>(P, dw, db, ws, stream); break;
       case 9: rc = launch_wgrad<1, 24, 16, 32, 1>(P, dw, db, ws, stream); break;
-      case 10: rc = launch_wgrad<2, 16, 16, 16, 1>(P, dw, db, ws, stream); break;
+      case 10: rc = launch_wgrad<2, 16, 16, 32, 1>(P, dw, db, ws, stream); break;
       case 11: rc = launch_wgrad<1, 16, 8, 32, 1>(P, dw, db, ws, stream); break;
-      case 12: rc = launch_wgrad<2, 8, 8, 16, 1>(P, dw, db, ws, stream); break;
+      case 12: rc = launch_wgrad<2, 8, 8, 32, 1>(P, dw, db, ws, stream); break;
       case 13: rc = launch_wgrad<1, 8, 1, 32, 1>(P, dw, db, ws, stream); break;
     }
     return rc;

@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--all-kernels", action="store_true", help="list every native call, not the top 12")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -314,7 +315,7 @@ def main():
             agg = prof.summary(B, args.steps)
             tot = sum(d["ms"] for d in agg.values())
             top = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
-            for key, d in top[:12]:
+            for key, d in (top if args.all_kernels else top[:12]):
                 gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
                 tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
                 kernels.append({"call": key.replace("ava_b200_", ""), "share": round(d["ms"] / tot, 4),
