@@ -1,0 +1,140 @@
+"""
+Methods for feeding syllable data to the VAE: drop-in for ``ava.models.vae_dataset``.
+
+``get_syllable_partition`` and ``SyllableDataset`` keep the reference behaviour
+(ava/models/vae_dataset.py:21-145): seed-42 file shuffle, ``i // sylls_per_file`` /
+``i % sylls_per_file`` indexing, float32 items.  ``get_syllable_data_loaders`` returns,
+instead of fork-based torch DataLoaders (4 worker processes re-opening an HDF5 file per
+item), ``DeviceSyllableLoader`` objects: the whole split is read once, kept resident in
+HBM as fp32, and batches are gathered on the device, so the train step never waits on the
+host.  They iterate like a DataLoader (``for batch in loader``), have ``.dataset`` and
+``len()``, and yield ``[b,128,128]`` fp32 CUDA tensors (ragged last batch kept,
+``drop_last=False`` as in the reference).
+"""
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .utils import _get_sylls_per_file, get_hdf5s_from_dir, numpy_to_tensor, read_specs
+
+EPSILON = 1e-9
+
+
+def get_syllable_partition(dirs, split, shuffle=True, max_num_files=None):
+    """Partition the filenames into a random test/train split
+    (ava/models/vae_dataset.py:21-59)."""
+    assert(split > 0.0 and split <= 1.0)
+    filenames = []
+    for dir in dirs:
+        filenames += get_hdf5s_from_dir(dir)
+    # Reproducibly shuffle.
+    filenames = sorted(filenames)
+    if shuffle:
+        np.random.seed(42)
+        np.random.shuffle(filenames)
+        np.random.seed(None)
+    if max_num_files is not None:
+        filenames = filenames[:max_num_files]
+    index = int(round(split * len(filenames)))
+    return {'train': filenames[:index], 'test': filenames[index:]}
+
+
+class SyllableDataset(Dataset):
+    """torch.utils.data.Dataset for animal vocalization syllables
+    (ava/models/vae_dataset.py:98-145)."""
+
+    def __init__(self, filenames, sylls_per_file, transform=None):
+        self.filenames = filenames
+        self.sylls_per_file = sylls_per_file
+        self.transform = transform
+
+    def __len__(self):
+        return len(self.filenames) * self.sylls_per_file
+
+    def __getitem__(self, index):
+        result = []
+        single_index = False
+        try:
+            iterator = iter(index)  # noqa: F841
+        except TypeError:
+            index = [index]
+            single_index = True
+        for i in index:
+            load_filename = self.filenames[i // self.sylls_per_file]
+            file_index = i % self.sylls_per_file
+            spec = np.asarray(read_specs(load_filename)[file_index])
+            if self.transform:
+                spec = self.transform(spec)
+            result.append(spec)
+        if single_index:
+            return result[0]
+        return result
+
+
+class DeviceSyllableLoader:
+    """All syllables of a split resident on the device; batches are device-side gathers.
+
+    Iteration order: a fresh ``torch.randperm`` per epoch when ``shuffle`` (the reference's
+    DataLoader(shuffle=True) also draws a torch permutation), else dataset order."""
+
+    def __init__(self, dataset, batch_size=64, shuffle=False, device=None, rank=0, world_size=1):
+        self.dataset = dataset
+        self.batch_size = batch_size
+        self.shuffle = shuffle
+        self.device = torch.device(device) if device is not None else \
+            torch.device("cuda", torch.cuda.current_device())
+        self.rank, self.world_size = rank, world_size
+        chunks = [np.asarray(read_specs(fn), dtype=np.float32) for fn in dataset.filenames]
+        for c in chunks:
+            assert len(c) == dataset.sylls_per_file, "files must hold sylls_per_file syllables"
+        data = np.concatenate(chunks) if chunks else np.zeros((0, 128, 128), np.float32)
+        self.data = torch.from_numpy(data).to(self.device)
+
+    def __len__(self):
+        n = len(self.dataset)
+        return (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = len(self.dataset)
+        if self.shuffle:
+            order = torch.randperm(n).to(self.device)
+        else:
+            order = None
+        # data-parallel: every rank walks the same global batches and takes its slice
+        for start in range(0, n, self.batch_size):
+            stop = min(n, start + self.batch_size)
+            if self.world_size > 1:
+                per = (stop - start + self.world_size - 1) // self.world_size
+                lo = min(stop, start + self.rank * per)
+                hi = min(stop, lo + per)
+            else:
+                lo, hi = start, stop
+            if hi <= lo:
+                continue
+            if order is None:
+                yield self.data[lo:hi]
+            else:
+                yield self.data.index_select(0, order[lo:hi])
+
+
+def get_syllable_data_loaders(partition, batch_size=64, shuffle=(True, False), num_workers=4,
+                              device=None, rank=0, world_size=1):
+    """Return a pair of loaders given a test/train split
+    (ava/models/vae_dataset.py:62-94).  `num_workers` is accepted for compatibility and
+    ignored (no worker processes are needed)."""
+    sylls_per_file = _get_sylls_per_file(partition)
+    train_dataset = SyllableDataset(filenames=partition['train'], transform=numpy_to_tensor,
+                                    sylls_per_file=sylls_per_file)
+    train_dataloader = DeviceSyllableLoader(train_dataset, batch_size=batch_size, shuffle=shuffle[0],
+                                            device=device, rank=rank, world_size=world_size)
+    if not partition['test']:
+        return {'train': train_dataloader, 'test': None}
+    test_dataset = SyllableDataset(filenames=partition['test'], transform=numpy_to_tensor,
+                                   sylls_per_file=sylls_per_file)
+    test_dataloader = DeviceSyllableLoader(test_dataset, batch_size=batch_size, shuffle=shuffle[1],
+                                           device=device, rank=rank, world_size=world_size)
+    return {'train': train_dataloader, 'test': test_dataloader}
+
+
+if __name__ == '__main__':
+    pass

@@ -1,0 +1,175 @@
+"""GPU parity tests of the get_spec front end and the datasets against goldens generated
+by the reference's own get_spec / FixedWindowDataset (oracle/make_golden.py) and against the
+numpy oracle (oracle/spec_oracle.py).  Tolerance: 1e-5 absolute (north_star)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec_oracle
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+PKG = "autoencoded-vocal-analysis_b200"
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pre():
+    return importlib.import_module(PKG + ".preprocessing.utils")
+
+
+@pytest.fixture(scope="module")
+def win():
+    return importlib.import_module(PKG + ".models.window_vae_dataset")
+
+
+def test_get_spec_matches_reference_golden(pre):
+    g = load_golden("spec_cases")
+    p = dict(spec_oracle.MOUSE_P)
+    fs = p['fs']
+    audio = spec_oracle.synth_audio(11, int(0.6 * fs), fs)
+    for name in ["mouse_a", "mouse_b", "mouse_full", "mouse_neg", "mouse_end", "mouse_short"]:
+        t1, t2 = g[name + "_t"]
+        spec, flag = pre.get_spec(t1, t2, audio, p, fs=fs)
+        assert flag is True and spec.shape == (128, 128) and spec.dtype == np.float64
+        assert np.abs(spec - g[name]).max() <= TOL, name
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    audio2 = spec_oracle.synth_audio(12, int(4.0 * fs), fs)
+    for name in ["finch_a", "finch_b", "finch_c", "finch_d"]:
+        onset = float(g[name + "_t"][0])
+        offset = onset + p['window_length']
+        tt = np.linspace(onset, offset, 128)
+        spec, _ = pre.get_spec(max(0.0, onset - 0.05), offset + 0.05, audio2, p, fs=fs,
+                               target_times=tt)
+        assert np.abs(spec - g[name]).max() <= TOL, name
+    p3 = dict(spec_oracle.FINCH_P)
+    p3.update(mel=False, noverlap=384, max_dur=0.3, time_stretch=True)
+    audio3 = (spec_oracle.synth_audio(13, int(2.0 * fs), fs, dtype=np.float64) / 3.0).astype(np.float32)
+    spec, _ = pre.get_spec(0.5, 0.7, audio3, p3, fs=fs, remove_dc_offset=False)
+    assert np.abs(spec - g["f32_a"]).max() <= TOL
+
+
+def test_batched_engine_matches_oracle(pre):
+    """A ragged batch through SpecEngine (device-resident audio, one launch) against the
+    numpy oracle, including a too-short segment and out-of-range target times."""
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    audio = [spec_oracle.synth_audio(20 + i, int((1.0 + 0.5 * i) * fs), fs) for i in range(3)]
+    eng = pre.SpecEngine(audio, fs, p)
+    rng = np.random.default_rng(3)
+    files = rng.integers(0, 3, size=37)
+    onsets = rng.uniform(0.0, 0.85, size=37)
+    onsets[5] = 0.0
+    wl = p['window_length']
+    tt = np.linspace(onsets, onsets + wl, 128, axis=-1)
+    t1, t2 = np.maximum(0.0, onsets - 0.05), onsets + wl + 0.05
+    t2[9] = t1[9] + 0.004          # shorter than nperseg -> zeros
+    out, out64 = eng.specs(files, t1, t2, tt, want_float64=True)
+    torch.cuda.synchronize()
+    out, out64 = out.cpu().numpy(), out64.cpu().numpy()
+    for i in range(37):
+        ref, _ = spec_oracle.get_spec(t1[i], t2[i], audio[files[i]], p, fs=fs, target_times=tt[i])
+        assert np.abs(out64[i] - ref).max() <= 1e-9, i
+        assert np.abs(out[i] - ref).max() <= TOL, i
+    assert not out[9].any()
+
+
+def test_fixed_window_dataset_bit_exact_sampling(win, tmp_path):
+    from scipy.io import wavfile
+    g = load_golden("sampler_cases")
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    adir, rdir = tmp_path / "audio", tmp_path / "rois"
+    adir.mkdir()
+    rdir.mkdir()
+    names = ["b_song", "a_song", "d_song", "c_song", "e_song"]
+    rng = np.random.default_rng(5)
+    for i, nm in enumerate(names):
+        audio = spec_oracle.synth_audio(100 + i, int(3.0 * fs), fs)
+        wavfile.write(str(adir / (nm + ".wav")), fs, audio)
+        n_roi = 1 + (i % 3)
+        starts = np.sort(rng.uniform(0.1, 2.0, size=n_roi))
+        rois = np.stack([starts, starts + rng.uniform(0.2, 0.8, size=n_roi)], 1)
+        np.savetxt(str(rdir / (nm + ".txt")), rois)
+    part = win.get_window_partition([str(adir)], [str(rdir)], split=0.8)
+    assert [os.path.basename(s) for s in part['train']['audio']] == list(g["part_train_audio"])
+    assert [os.path.basename(s) for s in part['train']['rois']] == list(g["part_train_rois"])
+    assert [os.path.basename(s) for s in part['test']['audio']] == list(g["part_test_audio"])
+    part1 = win.get_window_partition([str(adir)], [str(rdir)], split=1.0)
+    assert [os.path.basename(s) for s in part1['train']['audio']] == list(g["part1_audio"])
+    ds = win.FixedWindowDataset(part1['train']['audio'], part1['train']['rois'], p)
+    assert np.array_equal(ds.file_weights, g["file_weights"])
+    for seed in (0, 1, 7):
+        specs, fidx, onsets, offsets = ds.__getitem__(np.arange(12), seed=seed, return_seg_info=True)
+        assert np.array_equal(np.array(fidx), g["seed%d_files" % seed])          # bit-exact
+        assert np.array_equal(np.array(onsets), g["seed%d_onsets" % seed])       # bit-exact
+        assert np.array_equal(np.array(offsets), g["seed%d_offsets" % seed])
+        if seed == 0:
+            got = torch.stack(specs[:3]).cpu().numpy()
+            assert np.abs(got - g["seed0_specs"]).max() <= TOL
+    # single index, loader protocol
+    one = ds[3]
+    assert one.shape == (128, 128) and one.dtype == torch.float32 and one.is_cuda
+    loaders = win.get_fixed_window_data_loaders({'train': part1['train'], 'test': part1['train']}, p,
+                                                batch_size=100)
+    batches = list(loaders['train'])
+    assert len(loaders['train'].dataset) == 2048 and len(batches) == 21
+    assert batches[0].shape == (100, 128, 128) and batches[-1].shape == (48, 128, 128)
+    # silence rejection keeps stream order: accepted windows are a subsequence of the
+    # unfiltered candidate stream
+    ds2 = win.FixedWindowDataset(part1['train']['audio'], part1['train']['rois'], p,
+                                 min_spec_val=0.0)
+    _, f2, on2, _ = ds2.__getitem__(np.arange(12), seed=7, return_seg_info=True)
+    assert np.array_equal(np.array(on2), g["seed7_onsets"])
+
+
+def test_warped_dataset_null_warp(win):
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    audio = [spec_oracle.synth_audio(40 + i, int(0.8 * fs), fs) for i in range(3)]
+    ds = win.WarpedWindowDataset(["c.wav", "a.wav", "b.wav"], p, warp_type='null', audio=audio, fs=fs)
+    specs = ds.__getitem__(np.arange(5), seed=3)
+    # oracle: same draws, identity warp, whole-file get_spec with explicit target times
+    np.random.seed(3)
+    for i in range(5):
+        fi = np.random.randint(3)
+        start = ds.start_q + np.random.rand() * (ds.stop_q - ds.start_q - ds.window_frac)
+        tv = np.linspace(start, start + ds.window_frac, 128) * ds.template_dur
+        ref, _ = spec_oracle.get_spec(0.0, ds.template_dur, audio[fi], p, fs=fs, target_times=tv)
+        assert np.abs(specs[i].cpu().numpy() - ref).max() <= TOL, i
+    np.random.seed(None)
+
+
+def test_syllable_loaders(tmp_path):
+    ds_mod = importlib.import_module(PKG + ".models.vae_dataset")
+    g = load_golden("sampler_cases")
+    hdir = tmp_path / "h5"
+    hdir.mkdir()
+    for i in range(13):
+        (hdir / ("syllables_%04d.hdf5" % i)).write_bytes(b"")
+    (hdir / "notes.txt").write_bytes(b"")
+    part = ds_mod.get_syllable_partition([str(hdir)], 0.75)
+    assert [os.path.basename(s) for s in part['train']] == list(g["syll_train"])
+    assert [os.path.basename(s) for s in part['test']] == list(g["syll_test"])
+    # device-resident loader over .npy stand-ins for the HDF5 files (h5py is not installed)
+    rng = np.random.default_rng(0)
+    files = []
+    for i in range(3):
+        fn = str(tmp_path / ("sylls_%d.npy" % i))
+        np.save(fn, rng.random((5, 128, 128)))
+        files.append(fn)
+    loaders = ds_mod.get_syllable_data_loaders({'train': files, 'test': files[:1]}, batch_size=4,
+                                               shuffle=(False, False))
+    tr = loaders['train']
+    assert len(tr.dataset) == 15 and len(tr) == 4
+    batches = list(tr)
+    assert [b.shape[0] for b in batches] == [4, 4, 4, 3] and batches[0].is_cuda
+    item = tr.dataset[7]           # file 1, row 2 (i // spf, i % spf)
+    assert torch.equal(item, torch.from_numpy(np.load(files[1])[2]).float())
+    assert torch.equal(batches[1][3].cpu(), item)
+    several = tr.dataset[np.array([0, 14])]
+    assert len(several) == 2 and several[1].shape == (128, 128)
