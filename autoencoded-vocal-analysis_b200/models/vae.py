@@ -142,6 +142,8 @@ class VAE(nn.Module):
         self._scratch = None
         self._step_host = 0
         self._graphs = {}
+        self._dp_group = None
+        self._dp_world = 1
         self.to(self.device)
 
     # ------------------------------------------------------------------ network
@@ -453,7 +455,7 @@ class VAE(nn.Module):
         call("ava_b200_bnconv_bwd_data", l, B, ptr(g_out), ptr(y), ng, ns, nd,
              self._p(name + ".weight"), ptr(x), st + 8 * 64 * l, ptr(g_in), ds + 8 * 64 * l, s)
 
-    def _backward_native(self, bufs):
+    def _backward_native(self, bufs, after_decoder=None):
         """Backward of the whole loss; leaves every parameter gradient in the flat
         gradient buffer (overwritten, not accumulated).  Replaces loss.backward(),
         ava/models/vae.py:352."""
@@ -479,6 +481,9 @@ class VAE(nn.Module):
                          B, 256, 64)
         self._linear_bwd(bufs.dt5, 64, bufs.t5, bufs.z, Z, "fc5.weight", "fc5.bias", bufs.gz, Z,
                          B, 64, Z)
+        if after_decoder is not None:
+            # decoder parameter gradients (fc5..fc8, convt1..7) are final: start reducing them
+            after_decoder()
         # ---- latent: analytic gradients of sample + prior + entropy
         call("ava_b200_latent_bwd", ptr(bufs.heads), ptr(bufs.eps_w), ptr(bufs.eps_d), ptr(bufs.z),
              ptr(bufs.gz), B, Z, ptr(bufs.gheads), s)
@@ -583,13 +588,66 @@ class VAE(nn.Module):
         no such method)."""
         return self.forward(x, noise=noise)
 
+    # ------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, process_group=None):
+        """Shard batches over the ranks of `process_group` (default: WORLD), one process
+        per GPU.  Semantics: the loss is a batch SUM, so rank
+        gradients are SUMMED (not averaged) -- the update equals the reference's at the
+        global batch; BatchNorm uses each rank's local batch statistics (every rank ==
+        the reference run on its shard) and the running buffers are averaged across ranks
+        at epoch boundaries (exactly what per-step averaging would give, since the
+        running-average recursion is linear).  Parameters are broadcast from rank 0."""
+        import torch.distributed as dist
+        self._dp_group = process_group if process_group is not None else dist.group.WORLD
+        self._dp_world = dist.get_world_size(self._dp_group)
+        self._dp_rank = dist.get_rank(self._dp_group)
+        for t in (self._flat_p, self._flat_run, self._nbt, self._flat_m, self._flat_v):
+            dist.broadcast(t, src=dist.get_global_rank(self._dp_group, 0), group=self._dp_group)
+        return self
+
+    def _grad_buckets(self):
+        """(early, late) slices of the flat gradient buffer.  `early` = fc5..convt7 (the
+        decoder, ~36 MB incl. fc8.weight) is complete after the decoder half of the
+        backward pass, so its all-reduce overlaps the encoder backward; `late` = the rest."""
+        a0 = self._off["fc5.weight"]
+        a1 = self._off["bn1.weight"]
+        return [(a0, a1)], [(0, a0), (a1, self._n_flat)]
+
+    def _allreduce(self, slices, async_op):
+        import torch.distributed as dist
+        return [dist.all_reduce(self._flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self._dp_group,
+                                async_op=async_op) for lo, hi in slices if hi > lo]
+
+    def _sync_bn_buffers(self):
+        """Average the BatchNorm running buffers over the ranks."""
+        if self._dp_world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flat_run, op=dist.ReduceOp.SUM, group=self._dp_group)
+            self._flat_run.div_(self._dp_world)
+
+    def loss_constant(self):
+        """The two Gaussian normalising constants the reference adds ONCE PER BATCH
+        (quirk F6, ava/models/vae.py:316-318)."""
+        return 0.5 * self.z_dim * math.log(2 * math.pi) + \
+            0.5 * X_DIM * math.log(2 * math.pi / self.model_precision)
+
     def train_step(self, x, noise=None):
         """zero_grad + forward + backward + Adam for one batch, entirely native
         (the body of the loop at ava/models/vae.py:347-353).  Returns the loss as a
-        0-dim device tensor (no host sync)."""
+        0-dim device tensor (no host sync).  Under data parallelism `x` is this rank's
+        shard and the gradient all-reduce overlaps the encoder half of the backward."""
         self._ensure_optimizer_state()
         bufs = self._forward_native(x, noise, True, want_grad_seed=True)
-        self._backward_native(bufs)
+        if self._dp_world > 1:
+            early, late = self._grad_buckets()
+            works = []
+            self._backward_native(bufs, after_decoder=lambda: works.extend(
+                self._allreduce(early, async_op=True)))
+            works += self._allreduce(late, async_op=True)
+            for w in works:
+                w.wait()
+        else:
+            self._backward_native(bufs)
         self._adam_native()
         return bufs.loss[0]
 
@@ -602,10 +660,12 @@ class VAE(nn.Module):
         self.train()
         self._require_cuda()
         self._loss_sum.zero_()
+        n_steps = 0
         for batch_idx, data in enumerate(train_loader):
             self.train_step(data)
+            n_steps += 1
         # one device->host read per epoch instead of loss.item() per step
-        train_loss = float(self._loss_sum.item())
+        train_loss = self._epoch_loss(n_steps)
         train_loss /= len(train_loader.dataset)
         print('Epoch: {} Average loss: {:.4f}'.format(self.epoch, train_loss))
         self.epoch += 1
@@ -616,13 +676,26 @@ class VAE(nn.Module):
         self.eval()
         self._require_cuda()
         self._loss_sum.zero_()
+        n_steps = 0
         with torch.no_grad():
             for i, data in enumerate(test_loader):
                 self._forward_native(data, None, False, want_grad_seed=False)
-        test_loss = float(self._loss_sum.item())
+                n_steps += 1
+        test_loss = self._epoch_loss(n_steps)
         test_loss /= len(test_loader.dataset)
         print('Test loss: {:.4f}'.format(test_loss))
         return test_loss
+
+    def _epoch_loss(self, n_steps):
+        """Sum of the per-batch losses of this epoch (one device->host read).  Under data
+        parallelism: summed over ranks, with the per-batch constants counted once per
+        GLOBAL batch as the reference would, and the BN running buffers re-averaged."""
+        if self._dp_world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._loss_sum, op=dist.ReduceOp.SUM, group=self._dp_group)
+            self._sync_bn_buffers()
+            return float(self._loss_sum.item()) - (self._dp_world - 1) * n_steps * self.loss_constant()
+        return float(self._loss_sum.item())
 
     def train_loop(self, loaders, epochs=100, test_freq=2, save_freq=10, vis_freq=1):
         """Train the model for multiple epochs, testing and saving along the way
@@ -690,6 +763,8 @@ class VAE(nn.Module):
         state['lr'] = self.lr
         state['save_dir'] = self.save_dir
         filename = os.path.join(self.save_dir, filename)
+        if self._dp_world > 1 and self._dp_rank != 0:
+            return  # only rank 0 writes
         torch.save(state, filename)
 
     def load_state(self, filename):

@@ -81,8 +81,9 @@ class DeviceSyllableLoader:
         self.dataset = dataset
         self.batch_size = batch_size
         self.shuffle = shuffle
-        self.device = torch.device(device) if device is not None else \
-            torch.device("cuda", torch.cuda.current_device())
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
         self.rank, self.world_size = rank, world_size
         chunks = [np.asarray(read_specs(fn), dtype=np.float32) for fn in dataset.filenames]
         for c in chunks:

@@ -144,7 +144,14 @@ class FixedWindowDataset(Dataset):
         # numpy's choice(arange(n), p=w) == searchsorted(cdf, one uniform double, 'right')
         self._file_cdf = self._cdf(self.file_weights)
         self._roi_cdf = [self._cdf(w) for w in self.roi_weights]
-        self._engine = SpecEngine(self.audio, self.fs, p, device=device)
+        self._device = device
+        self._engine_obj = None   # created on first use (needs a CUDA device)
+
+    @property
+    def _engine(self):
+        if self._engine_obj is None:
+            self._engine_obj = SpecEngine(self.audio, self.fs, self.p, device=self._device)
+        return self._engine_obj
 
     @staticmethod
     def _cdf(w):
@@ -317,7 +324,14 @@ class WarpedWindowDataset(Dataset):
                 "fitting a time warp requires the third-party `affinewarp` package (not part of "
                 "the hot path); use warp_type='null' or load_warp=True with a saved warp_fn")
         self.window_frac = self.p['window_length'] / self.template_dur
-        self._engine = SpecEngine(self.audio, self.fs, p, device=device)
+        self._device = device
+        self._engine_obj = None
+
+    @property
+    def _engine(self):
+        if self._engine_obj is None:
+            self._engine_obj = SpecEngine(self.audio, self.fs, self.p, device=self._device)
+        return self._engine_obj
 
     def __len__(self):
         """NOTE: length is arbitrary."""

@@ -1,0 +1,150 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/ava_b200.h declares
+(no compute calls), and the host-side mirror of the reference interface behaves like the
+reference's (parameter registration, checkpoint layout, loud failure without CUDA)."""
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec_oracle, vae_oracle
+from tests.helpers import ROOT, load_golden
+
+PKG = "autoencoded-vocal-analysis_b200"
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ava_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(ava_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    lib = importlib.import_module(PKG + "._lib")
+    handle = lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), "missing export " + name
+    assert sorted(lib.SIGNATURES) == declared       # the ctypes table covers the header
+    assert handle.ava_b200_abi_version() == 1
+    assert lib.launch_count() >= 0 and lib.last_error() == ""
+
+
+def test_alias_module_and_reference_surface():
+    import ava_b200
+    from ava_b200.models import vae, vae_dataset, window_vae_dataset
+    from ava_b200.preprocessing import utils as pre
+    assert vae.X_SHAPE == (128, 128) and vae.X_DIM == 16384
+    for name in ("encode", "decode", "forward", "train_epoch", "test_epoch", "train_loop",
+                 "save_state", "load_state", "visualize", "get_latent", "compute_loss"):
+        assert callable(getattr(vae.VAE, name))
+    for name in ("get_syllable_partition", "get_syllable_data_loaders", "SyllableDataset"):
+        assert hasattr(vae_dataset, name)
+    for name in ("get_window_partition", "get_fixed_window_data_loaders", "FixedWindowDataset",
+                 "get_warped_window_data_loaders", "WarpedWindowDataset"):
+        assert hasattr(window_vae_dataset, name)
+    assert callable(pre.get_spec) and pre.EPSILON == 1e-12
+    assert ava_b200.__version__
+
+
+def test_vae_container_matches_reference_layout(tmp_path):
+    vae = importlib.import_module(PKG + ".models.vae")
+    model = vae.VAE(save_dir=str(tmp_path), device_name='cpu')
+    names = [k for k, _ in model.named_parameters()]
+    want = vae_oracle.param_order()
+    assert names == [k for k, _ in want]                       # registration order (Adam index)
+    assert [tuple(p.shape) for p in model.parameters()] == [s for _, s in want]
+    assert sum(p.numel() for p in model.parameters()) == 17426323
+    assert len(model.state_dict()) == 122
+    assert set(model._get_layers()) == {'fc1', 'fc2', 'fc31', 'fc32', 'fc33', 'fc41', 'fc42',
+                                        'fc43', 'fc5', 'fc6', 'fc7', 'fc8'} | \
+        {'bn%d' % i for i in range(1, 15)} | {'conv%d' % i for i in range(1, 8)} | \
+        {'convt%d' % i for i in range(1, 8)}
+    # flat storage: parameters are views, 16-byte aligned, heads contiguous
+    base = model._flat_p.data_ptr()
+    for k, p in model.named_parameters():
+        assert p.data_ptr() == base + 4 * model._off[k]
+        if not k.startswith(("fc3", "fc4")):
+            assert model._off[k] % 4 == 0
+    assert model._off["fc32.weight"] == model._off["fc31.weight"] + 64 * 256
+    assert model._off["fc43.bias"] == model._off["fc41.bias"] + 64
+    # load seeded weights, checkpoint round trip in the reference's layout
+    P = vae_oracle.make_params(3)
+    model.load_flat_state(P)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), P[k]), k
+    model.epoch = 7
+    model.loss['train'][6] = 1.5
+    model.save_state("ck.tar")
+    ck = torch.load(os.path.join(str(tmp_path), "ck.tar"), map_location="cpu")
+    assert len(ck) == 46 and ck['z_dim'] == 32 and ck['epoch'] == 7 and ck['lr'] == 1e-3
+    assert list(ck['bn3'].keys()) == ['weight', 'bias', 'running_mean', 'running_var',
+                                      'num_batches_tracked']
+    assert ck['optimizer_state']['state'] == {}                # no step taken yet (as torch)
+    model2 = vae.VAE(save_dir=str(tmp_path), device_name='cpu')
+    model2.load_state(os.path.join(str(tmp_path), "ck.tar"))
+    assert model2.epoch == 7 and model2.loss['train'][6] == 1.5
+    for (k, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+        assert torch.equal(a, b), k
+    # a checkpoint written by torch's own Adam state (what the reference saves) is adopted
+    ref_like = vae.VAE(save_dir=str(tmp_path), device_name='cpu')
+    ref_like.load_flat_state(P)
+    for p in ref_like.parameters():
+        p.grad = torch.full_like(p, 0.01)
+    ref_like.optimizer.step()                                   # torch Adam creates its state
+    ref_like.save_state("ck2.tar")
+    model3 = vae.VAE(save_dir=str(tmp_path), device_name='cpu')
+    model3.load_state(os.path.join(str(tmp_path), "ck2.tar"))
+    assert model3._step_host == 1
+    k0 = "fc1.weight"
+    st = ref_like.optimizer.state[dict(ref_like.named_parameters())[k0]]
+    assert torch.equal(model3._views_m[k0], st['exp_avg'])
+    assert torch.equal(model3._views_v[k0], st['exp_avg_sq'])
+    # no CPU fallback
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.forward(torch.zeros(2, 128, 128))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.get_latent([torch.zeros(2, 128, 128)])
+    with pytest.raises(ValueError):
+        model._as_input(torch.zeros(2, 64, 64))
+
+
+def test_time_bracketing_matches_oracle_coordinates():
+    pre = importlib.import_module(PKG + ".preprocessing.utils")
+    rng = np.random.default_rng(0)
+    fs, nperseg, hop = 32000, 512, 256
+    n = 50
+    t1 = rng.uniform(0, 2.0, size=n)
+    seg = rng.integers(600, 9000, size=n)
+    K = pre.num_frames(seg, nperseg, hop)
+    kmax = int(K.max())
+    base = np.arange(nperseg / 2, nperseg / 2 + kmax * hop, hop) / float(fs) - (nperseg / 2) / fs
+    tt = t1[:, None] + rng.uniform(-0.05, 0.35, size=(n, 128))
+    tt[0, 0] = t1[0]                                  # exactly on the first frame time
+    idx, w = pre.bracket(t1, base, K, tt)
+    for r in range(n):
+        _, t, _ = spec_oracle.stft(np.zeros(seg[r]), fs, nperseg, nperseg - hop)
+        assert len(t) == K[r]
+        g = t + t1[r]
+        i = np.clip(np.searchsorted(g, tt[r], side='right') - 1, 0, len(g) - 2)
+        bad = (tt[r] < g[0]) | (tt[r] > g[-1])
+        assert np.array_equal(idx[r] < 0, bad)
+        ok = ~bad
+        assert np.array_equal(idx[r][ok], i[ok])
+        assert np.array_equal(w[r][ok], ((tt[r] - g[i]) / (g[i + 1] - g[i]))[ok])
+
+
+def test_window_sampler_bit_exact_on_cpu():
+    win = importlib.import_module(PKG + ".models.window_vae_dataset")
+    p = dict(spec_oracle.FINCH_P)
+    rng = np.random.default_rng(1)
+    rois = [np.sort(rng.uniform(0, 50, size=(k, 2)), axis=1) + np.array([0.0, 1.0])
+            for k in (1, 3, 2, 5)]
+    ds = win.FixedWindowDataset(["d.wav", "b.wav", "a.wav", "c.wav"], None, p,
+                                audio=[np.zeros(10, np.int16)] * 4, fs=32000, rois=rois)
+    for seed in (0, 5):
+        want_f, want_on = spec_oracle.sample_windows(40, seed, ds.rois, ds.file_weights,
+                                                     ds.roi_weights, p['window_length'])
+        np.random.seed(seed)
+        got_f, got_on = ds._draw(40)
+        assert np.array_equal(got_f, want_f) and np.array_equal(got_on, want_on)
+    g = load_golden("sampler_cases")
+    assert g["seed0_files"].shape == (12,)

@@ -1,0 +1,88 @@
+"""CPU, world_size 2 over gloo: the host-side data-parallel logic (gradient SUM buckets,
+per-batch loss-constant correction, BN-buffer averaging, loader sharding, rank-0-only
+checkpoint).  The kernels themselves need a GPU and are covered by the -m gpu tests."""
+import importlib
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+PKG = "autoencoded-vocal-analysis_b200"
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    vae = importlib.import_module(PKG + ".models.vae")
+    ds_mod = importlib.import_module(PKG + ".models.vae_dataset")
+    torch.manual_seed(100 + rank)                      # different init per rank ...
+    model = vae.VAE(save_dir=tmp, device_name='cpu')
+    model.enable_data_parallel()                       # ... rank 0's parameters win
+    ref = [torch.zeros_like(model._flat_p) for _ in range(world)]
+    dist.all_gather(ref, model._flat_p)
+    assert torch.equal(ref[0], ref[1])
+    # gradient buckets: SUM over ranks, every element reduced exactly once
+    early, late = model._grad_buckets()
+    covered = torch.zeros(model._n_flat, dtype=torch.int32)
+    for lo, hi in early + late:
+        covered[lo:hi] += 1
+    assert bool((covered == 1).all())
+    model._flat_g.copy_(torch.arange(model._n_flat, dtype=torch.float32) % 97 + rank)
+    works = model._allreduce(early, async_op=True) + model._allreduce(late, async_op=True)
+    for w in works:
+        w.wait()
+    want = 2 * (torch.arange(model._n_flat, dtype=torch.float32) % 97) + 1
+    assert torch.equal(model._flat_g, want)
+    # loss bookkeeping: per-batch constants counted once per GLOBAL batch
+    c = model.loss_constant()
+    model._loss_sum.fill_(10.0 * (rank + 1) + 3 * c)   # 3 local steps
+    model._flat_run.fill_(float(rank))
+    total = model._epoch_loss(3)
+    assert abs(total - (30.0 + 3 * c)) < 1e-6 * abs(c)
+    assert torch.allclose(model._flat_run, torch.full_like(model._flat_run, 0.5))
+    # loader sharding: the two ranks together see every global batch exactly once, in order
+    files = []
+    for i in range(2):
+        fn = os.path.join(tmp, "s%d.npy" % i)
+        if rank == 0:
+            np.save(fn, np.arange(5 * 128 * 128, dtype=np.float64).reshape(5, 128, 128) + 1e6 * i)
+        files.append(fn)
+    dist.barrier()
+    loaders = ds_mod.get_syllable_data_loaders({'train': files, 'test': []}, batch_size=4,
+                                               shuffle=(False, False), device='cpu', rank=rank,
+                                               world_size=world)
+    assert loaders['test'] is None
+    mine = [b[:, 0, 0].clone() for b in loaders['train']]
+    sizes = [len(b) for b in mine]
+    assert sizes == ([2, 2, 1] if rank == 0 else [2, 2, 1])
+    gathered = [None, None]
+    dist.all_gather_object(gathered, [b.tolist() for b in mine])
+    firsts = []
+    for step in range(3):
+        firsts += gathered[0][step] + gathered[1][step]
+    want_first = [float(np.float32(r * 128 * 128 + 1e6 * f)) for f in range(2) for r in range(5)]
+    assert firsts == want_first
+    # only rank 0 writes checkpoints
+    model.save_state("dp.tar")
+    dist.barrier()
+    assert os.path.exists(os.path.join(tmp, "dp.tar"))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_host_logic_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
