@@ -12,8 +12,10 @@
 namespace ava {
 
 int tc_gemm_supported(int M, int N, int K);
-int tc_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
-                  int act, void* ws, long long ws_bytes, cudaStream_t stream);
+long long tc_ws_bytes(int M, int N, int K);
+int tc_gemm(const float* a, int lda, bool a_trans, const float* a_mask, const float* b, int ldb, bool b_trans,
+            const float* bias, float* d, int ldd, int M, int N, int K, int act, int precision, void* ws,
+            long long ws_bytes, cudaStream_t stream);
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
@@ -218,6 +220,15 @@ colsum_kernel(const float* dy, const float* mask, int ld, int M, int N, float* d
   }
 }
 
+void launch_splitk_reduce(const float* part, int splits, int M, int N, const float* bias, float* C, int ldc, int act,
+                          cudaStream_t stream) {
+  long long total = (long long)M * N;
+  int g = (int)((total + 255) / 256);
+  if (g > 8 * kNumSMs) g = 8 * kNumSMs;
+  splitk_reduce_kernel<<<g, 256, 0, stream>>>(part, splits, 1, M, N, bias, 0, C, ldc, 0, act);
+  check_launch("splitk_reduce");
+}
+
 static int pick_splits(int M, int N, int K, int groups) {
   long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * groups;
   int splits = 1;
@@ -280,6 +291,10 @@ extern "C" long long ava_b200_linear_ws_bytes(int M, int N, int K) {
   long long a = ws_need(M, N, K, 1), b = ws_need(M, K, N, 1), c = ws_need(N, K, M, 1);
   long long m = a > b ? a : b;
   m = m > c ? m : c;
+  // tensor-core path: TF32 hi/lo copies of both operands + split-K partials
+  if (tc_gemm_supported(M, N, K)) m = m > tc_ws_bytes(M, N, K) ? m : tc_ws_bytes(M, N, K);
+  if (tc_gemm_supported(M, K, N)) m = m > tc_ws_bytes(M, K, N) ? m : tc_ws_bytes(M, K, N);
+  if (tc_gemm_supported(N, K, M)) m = m > tc_ws_bytes(N, K, M) ? m : tc_ws_bytes(N, K, M);
   return m + 256;
 }
 
@@ -288,11 +303,10 @@ extern "C" int ava_b200_linear_fwd(const float* x, int ldx, const float* w, cons
                                    long long b_gs, long long y_gs, int precision, void* ws, long long ws_bytes,
                                    void* stream) {
   AVA_REQUIRE(groups >= 1 && act >= 0 && act <= 2, "linear_fwd: bad groups/act");
-  if (precision == 1) {
-    AVA_REQUIRE(groups == 1 && tc_gemm_supported(M, N, K), "linear_fwd: tensor-core path needs groups=1 and "
-                "tile-aligned shapes (M=%d N=%d K=%d)", M, N, K);
-    return tc_linear_fwd(x, ldx, w, b, y, ldy, M, N, K, act, ws, ws_bytes, (cudaStream_t)stream);
-  }
+  // tensor cores when asked for and the shape tiles (else the exact SIMT kernel below)
+  if (precision >= 1 && groups == 1 && tc_gemm_supported(M, N, K))
+    return tc_gemm(x, ldx, false, nullptr, w, K, false, b, y, ldy, M, N, K, act, precision, ws, ws_bytes,
+                   (cudaStream_t)stream);
   GemmParams P = {};
   P.A = x; P.sam = ldx; P.sak = 1;
   P.B = w; P.sbk = 1; P.sbn = K;  // B'(k,n) = W[n*K + k]
@@ -307,8 +321,10 @@ extern "C" int ava_b200_linear_bwd_data(const float* dy, int lddy, const float* 
                                         long long w_gs, long long dx_gs, int accumulate, int precision, void* ws,
                                         long long ws_bytes, void* stream) {
   AVA_REQUIRE(accumulate == 0, "linear_bwd_data: accumulate not supported");
-  (void)precision;
-  // dX[M,K] = dY[M,N] . W[N,K]  -> gemm (M, K, N)
+  // dX[M,K] = dY[M,N] . W[N,K]  -> gemm (M, K, N); W is stored [N,K] = [contraction, out]
+  if (precision >= 1 && groups == 1 && tc_gemm_supported(M, K, N))
+    return tc_gemm(dy, lddy, false, ymask, w, K, true, nullptr, dx, lddx, M, K, N, 0, precision, ws, ws_bytes,
+                   (cudaStream_t)stream);
   GemmParams P = {};
   P.A = dy; P.Amask = ymask; P.sam = lddy; P.sak = 1;
   P.B = w; P.sbk = K; P.sbn = 1;
@@ -322,15 +338,20 @@ extern "C" int ava_b200_linear_bwd_weight(const float* dy, int lddy, const float
                                           float* dw, float* db, int M, int N, int K, int groups, long long dy_gs,
                                           long long x_gs, long long dw_gs, long long db_gs, int precision,
                                           void* ws, long long ws_bytes, void* stream) {
-  (void)precision;
   // dW[N,K] = dY^T[N,M] . X[M,K] -> gemm (N, K, M); A'(n,m) = dY[m*lddy + n]
-  GemmParams P = {};
-  P.A = dy; P.Amask = ymask; P.sam = 1; P.sak = lddy;
-  P.B = x; P.sbk = ldx; P.sbn = 1;
-  P.C = dw; P.ldc = K;
-  P.M = N; P.N = K; P.K = M; P.act = 0;
-  P.groups = groups; P.a_gs = dy_gs; P.b_gs = x_gs; P.c_gs = dw_gs;
-  if (run_gemm(P, 0, 1, ws, ws_bytes, (cudaStream_t)stream)) return 1;
+  if (precision >= 1 && groups == 1 && tc_gemm_supported(N, K, M)) {
+    if (tc_gemm(dy, lddy, true, ymask, x, ldx, true, nullptr, dw, K, N, K, M, 0, precision, ws, ws_bytes,
+                (cudaStream_t)stream))
+      return 1;
+  } else {
+    GemmParams P = {};
+    P.A = dy; P.Amask = ymask; P.sam = 1; P.sak = lddy;
+    P.B = x; P.sbk = ldx; P.sbn = 1;
+    P.C = dw; P.ldc = K;
+    P.M = N; P.N = K; P.K = M; P.act = 0;
+    P.groups = groups; P.a_gs = dy_gs; P.b_gs = x_gs; P.c_gs = dw_gs;
+    if (run_gemm(P, 0, 1, ws, ws_bytes, (cudaStream_t)stream)) return 1;
+  }
   if (db) {
     for (int g = 0; g < groups; ++g) {
       colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(

@@ -111,13 +111,17 @@ class VAE(nn.Module):
     ----------
     save_dir, lr, z_dim, model_precision, device, optimizer, epoch, loss :
         as in the reference (ava/models/vae.py:43-122).
-    precision : {'fp32', 'tc'}
-        'fp32' (default): every kernel computes in fp32 (parity rtol 1e-4).
-        'tc': fc1/fc8 run on tcgen05 tensor cores (stated tolerance 1e-2).
+    precision : {'auto', 'fp32', 'tf32x3', 'tf32'}
+        How the two 8192x1024 dense layers (fc1, fc8) are computed; everything else is
+        always fp32 SIMT.  'fp32': fp32 SIMT GEMM.  'tf32x3': tcgen05 tensor cores with
+        error-compensated 3xTF32 products and fp32 accumulation in TMEM (measured
+        parity 2e-5 vs float64, i.e. fp32-level; needs batch % 128 == 0, else falls
+        back to 'fp32').  'tf32': single-pass TF32 tensor cores (stated tolerance
+        3e-3).  'auto' (default) = 'tf32x3'.
     """
 
     def __init__(self, save_dir='', lr=1e-3, z_dim=32, model_precision=10.0,
-                 device_name="auto", *, precision='fp32'):
+                 device_name="auto", *, precision='auto'):
         super(VAE, self).__init__()
         self.save_dir = save_dir
         self.lr = lr
@@ -129,8 +133,9 @@ class VAE(nn.Module):
         self.device = torch.device(device_name)
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        assert precision in ('fp32', 'tc')
+        assert precision in ('auto', 'fp32', 'tf32x3', 'tf32')
         self.precision = precision
+        self._tc = {'auto': 2, 'fp32': 0, 'tf32x3': 2, 'tf32': 1}[precision]
         if self.save_dir != '' and not os.path.exists(self.save_dir):
             os.makedirs(self.save_dir)
         self._flat_ready = False
@@ -323,21 +328,21 @@ class VAE(nn.Module):
 
     # ------------------------------------------------------------- native passes
     def _linear(self, x, ldx, wkey, bkey, y, ldy, M, N, K, act, groups=1, x_gs=0, w_gs=0,
-                b_gs=0, y_gs=0, tc=False):
+                b_gs=0, y_gs=0, tc=0):
         ws = self._ws(self._scratch_need)
         call("ava_b200_linear_fwd", ptr(x), ldx, self._p(wkey), self._p(bkey), ptr(y), ldy, M, N,
-             K, act, groups, x_gs, w_gs, b_gs, y_gs, 1 if tc else 0, ptr(ws), ws.numel(), _stream())
+             K, act, groups, x_gs, w_gs, b_gs, y_gs, tc, ptr(ws), ws.numel(), _stream())
 
     def _linear_bwd(self, dy, lddy, ymask, x, ldx, wkey, bkey, dx, lddx, M, N, K, groups=1,
-                    dy_gs=0, x_gs=0, w_gs=0, b_gs=0, dx_gs=0):
+                    dy_gs=0, x_gs=0, w_gs=0, b_gs=0, dx_gs=0, tc=0):
         """dW, db into the flat gradient buffer; dx (if not None) = (dy*mask) W."""
         ws = self._ws(self._scratch_need)
         s = _stream()
         call("ava_b200_linear_bwd_weight", ptr(dy), lddy, ptr(ymask), ptr(x), ldx, self._g(wkey),
-             self._g(bkey), M, N, K, groups, dy_gs, x_gs, w_gs, b_gs, 0, ptr(ws), ws.numel(), s)
+             self._g(bkey), M, N, K, groups, dy_gs, x_gs, w_gs, b_gs, tc, ptr(ws), ws.numel(), s)
         if dx is not None:
             call("ava_b200_linear_bwd_data", ptr(dy), lddy, ptr(ymask), self._p(wkey), ptr(dx), lddx,
-                 M, N, K, groups, dy_gs, w_gs, dx_gs, 0, 0, ptr(ws), ws.numel(), s)
+                 M, N, K, groups, dy_gs, w_gs, dx_gs, 0, tc, ptr(ws), ws.numel(), s)
 
     def _conv_fwd(self, l, B, x, y, bufs, train, want_stats_out):
         name = _LAYERS[l][0]
@@ -356,7 +361,7 @@ class VAE(nn.Module):
         for l in range(7):
             self._conv_fwd(l, B, h, bufs.act[l], bufs, train, train and l < 6)
             h = bufs.act[l]
-        tc = self.precision == 'tc'
+        tc = self._tc
         self._linear(h, 8192, "fc1.weight", "fc1.bias", bufs.h1, 1024, B, 1024, 8192, 1, tc=tc)
         self._linear(bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.h2, 256, B, 256, 1024, 1)
         # fc31|fc32|fc33 share their input: one [192,256] layer
@@ -368,7 +373,7 @@ class VAE(nn.Module):
     def _decode_native(self, z, bufs, train):
         """z [B,Z] -> bufs.act[13] = x_rec [B,1,128,128].  ava/models/vae.py:258-270."""
         B, Z, s = bufs.B, self.z_dim, _stream()
-        tc = self.precision == 'tc'
+        tc = self._tc
         self._linear(z, Z, "fc5.weight", "fc5.bias", bufs.t5, 64, B, 64, Z, 1)
         self._linear(bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.t6, 256, B, 256, 64, 1)
         self._linear(bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.t7, 1024, B, 1024, 256, 1)
@@ -474,7 +479,7 @@ class VAE(nn.Module):
              st + 8 * 64 * 7, ds + 8 * 64 * 7, B, 32, 256, ptr(bufs.dt8), s)
         # ---- decoder dense layers
         self._linear_bwd(bufs.dt8, 8192, None, bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.dt7, 1024,
-                         B, 8192, 1024)
+                         B, 8192, 1024, tc=self._tc)
         self._linear_bwd(bufs.dt7, 1024, bufs.t7, bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.dt6, 256,
                          B, 1024, 256)
         self._linear_bwd(bufs.dt6, 256, bufs.t6, bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.dt5, 64,
@@ -495,7 +500,7 @@ class VAE(nn.Module):
         self._linear_bwd(bufs.dh2, 256, bufs.h2, bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.dh1,
                          1024, B, 256, 1024)
         self._linear_bwd(bufs.dh1, 1024, bufs.h1, bufs.act[6], 8192, "fc1.weight", "fc1.bias",
-                         bufs.da6, 8192, B, 1024, 8192)
+                         bufs.da6, 8192, B, 1024, 8192, tc=self._tc)
         # ---- encoder conv stack, layers 6..0
         g_cur = bufs.da6
         free = [bufs.g[0], bufs.g[1]]

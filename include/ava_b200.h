@@ -111,8 +111,11 @@ int ava_b200_bn_relu_bwd_apply(const float* g, const float* a, const float* gamm
  * Y[M,N] = act(X[M,K] . W[N,K]^T + b): torch.nn.Linear (+F.relu / torch.exp),
  * ava/models/vae.py:225-232,258-261.  act: 0 none, 1 relu, 2 exp.
  * `groups` > 1 runs a strided batch: group g uses X + g*x_gs, W + g*w_gs, b + g*b_gs,
- * Y + g*y_gs (the three posterior heads).  precision: 0 = fp32 SIMT (exact),
- * 1 = tcgen05 TF32 tensor cores (M,N,K multiples of the tile; rtol 1e-3). */
+ * Y + g*y_gs (the three posterior heads).  precision: 0 = fp32 SIMT,
+ * 1 = tcgen05 TF32 tensor cores (rtol 3e-3), 2 = tcgen05 3xTF32 error-compensated
+ * (fp32-level, rtol 2e-5).  The tensor-core paths need groups == 1 and M,N multiples of
+ * 128, K of 32 (for all three of fwd / bwd_data / bwd_weight); other shapes run on the SIMT
+ * kernel regardless of `precision`. */
 int ava_b200_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int N,
                         int K, int act, int groups, long long x_gs, long long w_gs, long long b_gs,
                         long long y_gs, int precision, void* ws, long long ws_bytes, void* stream);

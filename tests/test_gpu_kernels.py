@@ -334,3 +334,41 @@ def test_bn_bookkeeping(L):
         invstd = 1.0 / torch.sqrt(variances[l] + 1e-5)
         assert rel_err(gg[sl_m].numpy(), (invstd * dstats[sl_v]).numpy()) <= 1e-6
         assert rel_err(gg[sl_v].numpy(), dstats[sl_m].numpy()) <= 1e-6
+
+
+@pytest.mark.parametrize("precision,tol", [(2, 2e-5), (1, 3e-3)])
+@pytest.mark.parametrize("M,N,K", [(128, 1024, 8192), (256, 8192, 1024), (128, 128, 32)])
+def test_linear_tensor_core(L, precision, tol, M, N, K):
+    """fc1/fc8-shaped layers on the tcgen05 path: precision 2 = 3xTF32 (fp32-level parity,
+    tolerance 2e-5), precision 1 = single TF32 (stated tolerance 3e-3)."""
+    gen = torch.Generator().manual_seed(M + N + K + precision)
+    x = (torch.randn(M, K, generator=gen, dtype=torch.float64) * 0.5).float().double()
+    w = (torch.randn(N, K, generator=gen, dtype=torch.float64) / np.sqrt(K)).float().double()
+    b = (torch.randn(N, generator=gen, dtype=torch.float64) * 0.1).float().double()
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    b.requires_grad_(True)
+    y_ref = F.relu(F.linear(x, w, b))
+    dY = torch.randn(M, N, generator=gen, dtype=torch.float64).float().double()
+    (y_ref * dY).sum().backward()
+    dx_, dw_, db_, ddy = dev(x.detach()), dev(w.detach()), dev(b.detach()), dev(dY)
+    y = torch.empty(M, N, device="cuda")
+    ws_bytes = L.lib().ava_b200_linear_ws_bytes(M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    L.call("ava_b200_linear_fwd", dx_.data_ptr(), K, dw_.data_ptr(), db_.data_ptr(), y.data_ptr(), N,
+           M, N, K, 1, 1, 0, 0, 0, 0, precision, ws.data_ptr(), ws_bytes, stream())
+    gw = torch.full((N, K), 3.0, device="cuda")
+    gb = torch.full((N,), 3.0, device="cuda")
+    gx = torch.full((M, K), 3.0, device="cuda")
+    # mask from the float64 reference so that a TF32 rounding flip cannot move the ReLU mask
+    ymask = dev(y_ref.detach())
+    L.call("ava_b200_linear_bwd_weight", ddy.data_ptr(), N, ymask.data_ptr(), dx_.data_ptr(), K,
+           gw.data_ptr(), gb.data_ptr(), M, N, K, 1, 0, 0, 0, 0, precision, ws.data_ptr(), ws_bytes,
+           stream())
+    L.call("ava_b200_linear_bwd_data", ddy.data_ptr(), N, ymask.data_ptr(), dw_.data_ptr(),
+           gx.data_ptr(), K, M, N, K, 1, 0, 0, 0, 0, precision, ws.data_ptr(), ws_bytes, stream())
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu().numpy(), y_ref.detach().numpy()) <= tol
+    assert rel_err(gw.cpu().numpy(), w.grad.numpy()) <= tol
+    assert rel_err(gb.cpu().numpy(), b.grad.numpy()) <= 1e-5
+    assert rel_err(gx.cpu().numpy(), x.grad.numpy()) <= tol
