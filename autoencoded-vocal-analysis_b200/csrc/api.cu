@@ -19,6 +19,18 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+TensorMapEncodeFn get_tensor_map_encode_fn() {
+  static TensorMapEncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeFn>(p);
+  }
+  return fn;
+}
+
 }  // namespace ava
 
 extern "C" const char* ava_b200_last_error(void) { return ava::g_err; }

@@ -1,5 +1,6 @@
 // Shared helpers for the ava_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -13,6 +14,11 @@ constexpr int kStatsStride = AVA_STATS_STRIDE;  // doubles per BN layer
 constexpr int kNumSMs = 148;
 
 void set_error(const char* fmt, ...);
+// cuTensorMapEncodeTiled, fetched through the runtime (no libcuda link dependency)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn get_tensor_map_encode_fn();
 void count_launch(int n = 1);
 
 inline int check_launch(const char* what) {

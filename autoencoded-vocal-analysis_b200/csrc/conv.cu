@@ -23,6 +23,8 @@
 // Thread mapping: a warp's lanes run along x (coalesced loads/stores, conflict-free
 // shared-memory reads), each thread owns 4 output rows x COT(<=8) output channels in
 // registers; output-channel groups of 8 are warp-uniform so weight reads are broadcasts.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace ava {
@@ -78,10 +80,13 @@ struct TileGeom {
                                : (KIND == K_S2) ? (TW == 32 ? 68 : 38)
                                                 : (TW == 32 ? 36 : 24);
   static constexpr int PLANE = IN_ROWS * PITCH;
-  // raw (untransformed) staging rows filled by cp.async: same as the final layout except
-  // that S2 rows are still interleaved: [3]=left halo, [4..2TW+3]=interior
-  static constexpr int RAW_PITCH = (KIND == K_S2) ? 2 * TW + 4 : PITCH;
+  // raw (untransformed) staging tile = one dense TMA box [CIC][IN_ROWS][RAW_PITCH] whose first
+  // column is input column X0-4 (S1,S2) or X0 (UP), so that the interior quads stay 16-byte
+  // aligned: S1 [3]=left halo [4..TW+3] interior [TW+4] right halo; S2 [3]=left halo,
+  // [4..2TW+3] interleaved interior; UP [0..TW-1] interior, [TW] right halo
+  static constexpr int RAW_PITCH = (KIND == K_S1) ? TW + 8 : (KIND == K_S2 ? 2 * TW + 4 : TW + 4);
   static constexpr int RAW_PLANE = IN_ROWS * RAW_PITCH;
+  static constexpr int RAW_X_SHIFT = (KIND == K_UP) ? 0 : 4;
 };
 
 template <int KIND, int CI, int CO, int TW, int INMODE>
@@ -93,7 +98,7 @@ struct GconvCfg {
   static constexpr int NSUB = (NCOG >= 3) ? 1 : 4 / NCOG;
   static constexpr int NT = 64 * NCOG * NSUB;
   // input channels per pipeline stage: largest divisor of CI keeping a raw stage <= 37 KB
-  // (24 KB in DZ mode, which stages two raw tensors): 2 (3) stage buffers per CTA, 2 CTAs/SM
+  // (24 KB in DZ mode, which stages two raw tensors): 2 (3) stage buffers per CTA, 2+ CTAs/SM
   static constexpr int LIMIT = (INMODE == IN_DZ) ? 6144 : 9472;
   static constexpr int stage_floats(int c) { return NSUB * c * G::RAW_PLANE; }
   static constexpr int CIC = (CI % 8 == 0 && stage_floats(8) <= LIMIT)   ? 8
@@ -101,46 +106,78 @@ struct GconvCfg {
                              : (CI % 2 == 0 && stage_floats(2) <= LIMIT) ? 2
                                                                          : 1;
   static constexpr int NCHUNK = CI / CIC;
-  static constexpr int STAGE = NSUB * CIC * G::PLANE;          // floats, transformed tile
-  static constexpr int RAW_STAGE = NSUB * CIC * G::RAW_PLANE;  // floats, raw staging
+  static constexpr int STAGE = NSUB * CIC * G::PLANE;                       // floats, transformed tile
+  static constexpr int RAW_SUB = (CIC * G::RAW_PLANE + 31) / 32 * 32;       // floats, 128-byte aligned
+  static constexpr int RAW_STAGE = NSUB * RAW_SUB;
+  static constexpr int BOX_BYTES = CIC * G::RAW_PLANE * 4;
+  // transform work items per sub-tile and per thread
+  static constexpr int NQUAD = CIC * G::IN_ROWS * G::QUADS;
+  static constexpr int QITERS = (NQUAD + NT - 1) / NT;
+  static constexpr int NHALO = CIC * G::IN_ROWS;
+  static constexpr int HITERS = (NHALO + NT - 1) / NT;
+  // CTAs per SM the register budget is tuned for
+  static constexpr int MINB = (COT == 1) ? 4 : 2;
 };
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
-               "l"(gmem_src)
+__device__ __forceinline__ uint32_t cv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cv_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cv_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void cv_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cv_smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
-               "l"(gmem_src)
-               : "memory");
+__device__ __forceinline__ void cv_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "CV_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra CV_DONE;\n"
+      "bra CV_WAIT_LOOP;\n"
+      "CV_DONE:\n"
+      "}\n" ::"r"(cv_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// 3-D box [CIC][IN_ROWS][RAW_PITCH] of the [B*C, H, W] activation tensor; out-of-range
+// rows/columns (image border, negative coordinates) are zero-filled by the TMA unit
+__device__ __forceinline__ void cv_tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z,
+                                               uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(cv_smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(cv_smem_u32(bar))
+      : "memory");
+}
 
 // Software-pipelined: while the FMA loop runs on the transformed tile of stage i, the raw
-// rows of stage i+1 stream into a staging buffer with cp.async (non-blocking: the whole stage
-// is in flight at once); a short shared->shared pass then applies the BatchNorm transform /
-// BN+ReLU backward and the zero padding.  Two CTAs per SM interleave their phases.
+// rows of stage i+1 are fetched by TMA (one cp.async.bulk.tensor box per sub-tile and tensor,
+// issued by a single thread, zero register / LSU cost, completion on an mbarrier); a short
+// table-driven shared->shared pass then applies the BatchNorm transform / BN+ReLU backward
+// and the zero padding.  Two (four for CO=1) CTAs per SM interleave their phases.
 template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
-__global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, 2) gconv_kernel(const GconvParams P) {
+__global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvCfg<KIND, CI, CO, TW, INMODE>::MINB)
+    gconv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_y,
+                 const GconvParams P) {
   using G = TileGeom<KIND, TW>;
   using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
   constexpr int COT = C::COT, NCOG = C::NCOG, NSUB = C::NSUB, NT = C::NT;
   constexpr int CIC = C::CIC, NCHUNK = C::NCHUNK;
   constexpr int NOUT = (KIND == K_UP) ? 8 : 4;
 
-  extern __shared__ __align__(16) float smem[];
-  float* s_w = smem;                                // [CI][9][CO]
-  float* s_in = s_w + CI * 9 * CO;                  // [NSUB][CIC][IN_ROWS][PITCH] transformed
-  float* s_rawg = s_in + C::STAGE;                  // [RAW_STAGE] raw input (cp.async)
-  float* s_rawy = s_rawg + C::RAW_STAGE;            // [RAW_STAGE] raw saved activation (IN_DZ)
-  float* s_c0 = s_rawy + (INMODE == IN_DZ ? C::RAW_STAGE : 0);  // AFFINE scale
+  extern __shared__ __align__(128) float smem[];
+  float* s_rawg = smem;                             // [NSUB][RAW_SUB] raw input (TMA)
+  float* s_rawy = s_rawg + C::RAW_STAGE;            // [NSUB][RAW_SUB] raw saved activation (IN_DZ)
+  float* s_in = s_rawy + (INMODE == IN_DZ ? C::RAW_STAGE : 0);  // [NSUB][CIC][IN_ROWS][PITCH]
+  float* s_w = s_in + C::STAGE;                     // [CI][9][CO]
+  float* s_c0 = s_w + CI * 9 * CO;                  // AFFINE scale
   float* s_c1 = s_c0 + 32;                          // AFFINE shift
   float* s_red = s_c1 + 32;                         // [2*CO] cross-warp reduction
   float* s_bias = s_red + 64;                       // [CO]
   DzCoef* s_dz = reinterpret_cast<DzCoef*>(s_bias + 32);   // [32] (IN_DZ)
   double* s_meand = reinterpret_cast<double*>(s_dz + 32);  // [32] EPI_BWD: mean of own BN
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meand + 32);
 
   const int tid = threadIdx.x;
   const int H_in = P.H_in, W_in = P.W_in;
@@ -153,54 +190,64 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, 2) gco
   const int ntiles = P.B * tiles_per_img;
   const int ngroups = (ntiles + NSUB - 1) / NSUB;
 
-  constexpr int TPR = G::QUADS + 1;
-  constexpr int NTASK = CIC * G::IN_ROWS * TPR;
-
-  // ---- raw rows of stage (grp, ch) -> staging buffer, asynchronously
+  // ---- TMA: raw boxes of stage (grp, ch), issued by thread 0
   auto issue = [&](int grp, int ch) {
-    const int tile0 = grp * NSUB;
-#pragma unroll
-    for (int sb = 0; sb < NSUB; ++sb) {
-      const int ltile = tile0 + sb;
-      if (ltile >= ntiles) break;
+    if (tid != 0) return;
+    int nsub = ntiles - grp * NSUB;
+    if (nsub > NSUB) nsub = NSUB;
+    cv_mbar_expect_tx(s_bar, (uint32_t)(nsub * C::BOX_BYTES * (INMODE == IN_DZ ? 2 : 1)));
+    for (int sb = 0; sb < nsub; ++sb) {
+      const int ltile = grp * NSUB + sb;
       const int ln = ltile / tiles_per_img;
       const int lrem = ltile - ln * tiles_per_img;
       const int lty = lrem / tiles_x, ltx = lrem - lty * tiles_x;
       const int iy0 = (KIND == K_S1) ? lty * G::TH - 1 : (KIND == K_S2 ? 2 * lty * G::TH - 1 : lty * G::TH);
       const int X0 = (KIND == K_S2) ? 2 * ltx * TW : ltx * TW;
-      const size_t img_base = ((size_t)ln * CI + (size_t)ch * CIC) * H_in * W_in;
-      const int sbase = sb * CIC * G::RAW_PLANE;
-#pragma unroll 2
-      for (int t = tid; t < NTASK; t += NT) {
-        const int q = t % TPR;
-        const int rr = t / TPR;
-        const int r = rr % G::IN_ROWS;
-        const int ci = rr / G::IN_ROWS;
-        const int gy = iy0 + r;
-        if (gy < 0 || gy >= H_in) continue;
-        const size_t rowoff = img_base + ((size_t)ci * H_in + gy) * W_in;
-        const int so = sbase + ci * G::RAW_PLANE + r * G::RAW_PITCH;
-        if (q < G::QUADS) {
-          const size_t off = rowoff + X0 + 4 * q;
-          const int sc = (KIND == K_UP) ? 4 * q : 4 + 4 * q;
-          cp_async16(s_rawg + so + sc, P.in + off);
-          if (INMODE == IN_DZ) cp_async16(s_rawy + so + sc, P.in_y + off);
-        } else {
-          const int gx0 = (KIND == K_UP) ? X0 + TW : X0 - 1;
-          const int sc0 = (KIND == K_UP) ? TW : 3;
-          if (gx0 >= 0 && gx0 < W_in) {
-            cp_async4(s_rawg + so + sc0, P.in + rowoff + gx0);
-            if (INMODE == IN_DZ) cp_async4(s_rawy + so + sc0, P.in_y + rowoff + gx0);
-          }
-          if (KIND == K_S1 && X0 + TW < W_in) {
-            cp_async4(s_rawg + so + TW + 4, P.in + rowoff + X0 + TW);
-            if (INMODE == IN_DZ) cp_async4(s_rawy + so + TW + 4, P.in_y + rowoff + X0 + TW);
-          }
-        }
-      }
+      cv_tma_load_3d(s_rawg + sb * C::RAW_SUB, &map_in, X0 - G::RAW_X_SHIFT, iy0, ln * CI + ch * CIC, s_bar);
+      if (INMODE == IN_DZ)
+        cv_tma_load_3d(s_rawy + sb * C::RAW_SUB, &map_y, X0 - G::RAW_X_SHIFT, iy0, ln * CI + ch * CIC, s_bar);
     }
-    cp_async_commit();
   };
+
+  if (tid == 0) {
+    cv_mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if ((int)blockIdx.x < ngroups) issue(blockIdx.x, 0);
+
+  // ---- per-thread transform work list (identical for every sub-tile and stage)
+  int q_raw[C::QITERS], q_fin[C::QITERS], q_meta[C::QITERS];   // meta: row | ci<<8, -1 = none
+#pragma unroll
+  for (int j = 0; j < C::QITERS; ++j) {
+    const int t = tid + j * NT;
+    q_meta[j] = -1;
+    q_raw[j] = q_fin[j] = 0;
+    if (t < C::NQUAD) {
+      const int q = t % G::QUADS;
+      const int rr = t / G::QUADS;
+      const int r = rr % G::IN_ROWS;
+      const int ci = rr / G::IN_ROWS;
+      q_raw[j] = ci * G::RAW_PLANE + r * G::RAW_PITCH + ((KIND == K_UP) ? 4 * q : 4 + 4 * q);
+      const int frow = ci * G::PLANE + r * G::PITCH;
+      q_fin[j] = (KIND == K_S1) ? frow + 4 + 4 * q : (KIND == K_S2 ? frow + 2 * q : frow + 4 * q);
+      q_meta[j] = r | (ci << 8);
+    }
+  }
+  int h_raw[C::HITERS], h_fin[C::HITERS], h_meta[C::HITERS];
+#pragma unroll
+  for (int j = 0; j < C::HITERS; ++j) {
+    const int t = tid + j * NT;
+    h_meta[j] = -1;
+    h_raw[j] = h_fin[j] = 0;
+    if (t < C::NHALO) {
+      const int r = t % G::IN_ROWS;
+      const int ci = t / G::IN_ROWS;
+      h_raw[j] = ci * G::RAW_PLANE + r * G::RAW_PITCH;
+      h_fin[j] = ci * G::PLANE + r * G::PITCH;
+      h_meta[j] = r | (ci << 8);
+    }
+  }
 
   auto xform1 = [&](float a, float y, int cc) -> float {
     if (INMODE == IN_AFFINE) return fmaf(a, s_c0[cc], s_c1[cc]);
@@ -218,57 +265,53 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, 2) gco
       const int lty = lrem / tiles_x, ltx = lrem - lty * tiles_x;
       const int iy0 = (KIND == K_S1) ? lty * G::TH - 1 : (KIND == K_S2 ? 2 * lty * G::TH - 1 : lty * G::TH);
       const int X0 = (KIND == K_S2) ? 2 * ltx * TW : ltx * TW;
-      const int sbase = sb * CIC * G::RAW_PLANE;
+      const float* rg = s_rawg + sb * C::RAW_SUB;
+      const float* ry = s_rawy + sb * C::RAW_SUB;
       float* sdst = s_in + sb * CIC * G::PLANE;
-#pragma unroll 2
-      for (int t = tid; t < NTASK; t += NT) {
-        const int q = t % TPR;
-        const int rr = t / TPR;
-        const int r = rr % G::IN_ROWS;
-        const int ci = rr / G::IN_ROWS;
-        const int gy = iy0 + r;
-        const bool rowok = gy >= 0 && gy < H_in;
-        const int cc = ch * CIC + ci;
-        const int so = sbase + ci * G::RAW_PLANE + r * G::RAW_PITCH;
-        float* srow = sdst + ci * G::PLANE + r * G::PITCH;
-        if (q < G::QUADS) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rowok) {
-            const int sc = (KIND == K_UP) ? 4 * q : 4 + 4 * q;
-            const float4 a = *reinterpret_cast<const float4*>(s_rawg + so + sc);
-            float4 y = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (INMODE == IN_DZ) y = *reinterpret_cast<const float4*>(s_rawy + so + sc);
-            v = make_float4(xform1(a.x, y.x, cc), xform1(a.y, y.y, cc), xform1(a.z, y.z, cc),
-                            xform1(a.w, y.w, cc));
-          }
-          if (KIND == K_S1) {
-            *reinterpret_cast<float4*>(srow + 4 + 4 * q) = v;
-          } else if (KIND == K_S2) {
-            *reinterpret_cast<float2*>(srow + G::EO + 2 * q) = make_float2(v.x, v.z);  // even columns
-            *reinterpret_cast<float2*>(srow + 4 + 2 * q) = make_float2(v.y, v.w);      // odd j=2q+1,2q+2
-          } else {
-            *reinterpret_cast<float4*>(srow + 4 * q) = v;
-          }
+#pragma unroll
+      for (int j = 0; j < C::QITERS; ++j) {
+        const int m = q_meta[j];
+        if (m < 0) continue;
+        const int gy = iy0 + (m & 0xff);
+        const int cc = ch * CIC + (m >> 8);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < H_in) {
+          const float4 a = *reinterpret_cast<const float4*>(rg + q_raw[j]);
+          float4 y = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (INMODE == IN_DZ) y = *reinterpret_cast<const float4*>(ry + q_raw[j]);
+          v = make_float4(xform1(a.x, y.x, cc), xform1(a.y, y.y, cc), xform1(a.z, y.z, cc),
+                          xform1(a.w, y.w, cc));
+        }
+        float* d = sdst + q_fin[j];
+        if (KIND == K_S2) {
+          *reinterpret_cast<float2*>(d + G::EO) = make_float2(v.x, v.z);  // even columns
+          *reinterpret_cast<float2*>(d + 4) = make_float2(v.y, v.w);      // odd j=2q+1,2q+2
         } else {
-          const int gx0 = (KIND == K_UP) ? X0 + TW : X0 - 1;
-          const int sc0 = (KIND == K_UP) ? TW : 3;
-          float h0 = 0.f;
-          if (rowok && gx0 >= 0 && gx0 < W_in)
-            h0 = xform1(s_rawg[so + sc0], (INMODE == IN_DZ) ? s_rawy[so + sc0] : 1.f, cc);
-          srow[sc0] = h0;
-          if (KIND == K_S1) {
-            float h1 = 0.f;
-            if (rowok && X0 + TW < W_in)
-              h1 = xform1(s_rawg[so + TW + 4], (INMODE == IN_DZ) ? s_rawy[so + TW + 4] : 1.f, cc);
-            srow[TW + 4] = h1;
-          }
+          *reinterpret_cast<float4*>(d) = v;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < C::HITERS; ++j) {
+        const int m = h_meta[j];
+        if (m < 0) continue;
+        const int gy = iy0 + (m & 0xff);
+        const int cc = ch * CIC + (m >> 8);
+        const bool rowok = gy >= 0 && gy < H_in;
+        const int gx0 = (KIND == K_UP) ? X0 + TW : X0 - 1;
+        const int sc0 = (KIND == K_UP) ? TW : 3;
+        float h0 = 0.f;
+        if (rowok && gx0 >= 0 && gx0 < W_in)
+          h0 = xform1(rg[h_raw[j] + sc0], (INMODE == IN_DZ) ? ry[h_raw[j] + sc0] : 1.f, cc);
+        sdst[h_fin[j] + sc0] = h0;
+        if (KIND == K_S1) {
+          float h1 = 0.f;
+          if (rowok && X0 + TW < W_in)
+            h1 = xform1(rg[h_raw[j] + TW + 4], (INMODE == IN_DZ) ? ry[h_raw[j] + TW + 4] : 1.f, cc);
+          sdst[h_fin[j] + TW + 4] = h1;
         }
       }
     }
   };
-
-  // first stage's loads go out before anything else
-  if ((int)blockIdx.x < ngroups) issue(blockIdx.x, 0);
 
   // ---- one-time per CTA: weights, coefficients
   for (int idx = tid; idx < CI * 9 * CO; idx += NT) {
@@ -292,6 +335,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, 2) gco
     if (EPI == EPI_BWD) s_meand[tid] = P.stats_self[tid] / P.out_count;
   }
   if (tid < 2 * CO) s_red[tid] = 0.f;
+  __syncthreads();
 
   const int sub = tid / (64 * NCOG);
   const int t2 = tid - sub * (64 * NCOG);
@@ -304,6 +348,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, 2) gco
 #pragma unroll
   for (int c = 0; c < COT; ++c) st1[c] = st2[c] = 0.f;
 
+  uint32_t phase = 0;
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int tile = grp * NSUB + sub;
     const bool tvalid = tile < ntiles;
@@ -319,10 +364,10 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, 2) gco
 
 #pragma unroll 1
     for (int ch = 0; ch < NCHUNK; ++ch) {
-      cp_async_wait_all();
-      __syncthreads();  // this stage's raw rows have landed; previous FMA loop is done with s_in
-      transform(grp, ch);
-      __syncthreads();  // s_in ready; staging buffer free again
+      cv_mbar_wait(s_bar, phase);  // this stage's raw boxes have landed
+      phase ^= 1;
+      transform(grp, ch);          // (the previous FMA loop finished before the last barrier)
+      __syncthreads();             // s_in ready; staging buffers free again
       // prefetch the next stage while computing this one
       if (ch + 1 < NCHUNK) {
         issue(grp, ch + 1);
@@ -397,6 +442,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, 2) gco
           }
         }
       }
+      __syncthreads();  // FMA loop done with s_in before the next transform overwrites it
     }
     if (!tvalid) continue;
 
@@ -491,13 +537,35 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, 2) gco
   }
 }
 
+// [B*C, H, W] fp32 activation tensor -> boxes [CIC][IN_ROWS][RAW_PITCH], no swizzle, zero fill
+static int make_act_map(CUtensorMap* map, const float* base, long long nc, int H, int W, int box_w, int box_h,
+                        int box_c) {
+  TensorMapEncodeFn fn = get_tensor_map_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return 1;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nc};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation) failed (%d)", (int)r);
+    return 1;
+  }
+  return 0;
+}
+
 template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
 static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   using G = TileGeom<KIND, TW>;
   using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
-  const size_t smem =
-      (size_t)(CI * 9 * CO + C::STAGE + (INMODE == IN_DZ ? 2 : 1) * C::RAW_STAGE + 64 + 64 + 32) * sizeof(float) +
-      32 * sizeof(DzCoef) + 32 * sizeof(double);
+  const size_t smem = (size_t)((INMODE == IN_DZ ? 2 : 1) * C::RAW_STAGE + C::STAGE + CI * 9 * CO + 64 + 64 + 32) *
+                          sizeof(float) +
+                      32 * sizeof(DzCoef) + 32 * sizeof(double) + 16 + 128;
   auto kern = gconv_kernel<KIND, CI, CO, TW, INMODE, EPI>;
   static int max_ctas = 0;
   if (max_ctas == 0) {
@@ -517,9 +585,14 @@ static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   const int tiles_y = ((KIND == K_UP) ? P.H_in : H_out) / G::TH;
   const long long ntiles = (long long)P.B * tiles_x * tiles_y;
   if (ntiles == 0) return 0;
+  CUtensorMap map_in, map_y;
+  if (make_act_map(&map_in, P.in, (long long)P.B * CI, P.H_in, P.W_in, G::RAW_PITCH, G::IN_ROWS, C::CIC)) return 1;
+  if (make_act_map(&map_y, INMODE == IN_DZ ? P.in_y : P.in, (long long)P.B * CI, P.H_in, P.W_in, G::RAW_PITCH,
+                   G::IN_ROWS, C::CIC))
+    return 1;
   const long long ngroups = (ntiles + C::NSUB - 1) / C::NSUB;
   int grid = (int)(ngroups < max_ctas ? ngroups : max_ctas);
-  kern<<<grid, C::NT, smem, stream>>>(P);
+  kern<<<grid, C::NT, smem, stream>>>(map_in, map_y, P);
   return check_launch("gconv");
 }
 

@@ -285,25 +285,9 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 // K-major fp32 matrix [rows, K] (contiguous rows) -> 128x32 boxes, 128-byte swizzle
 static int make_map(CUtensorMap* map, const float* base, int rows, int K) {
-  EncodeTiledFn fn = get_encode_fn();
+  TensorMapEncodeFn fn = get_tensor_map_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled unavailable");
     return 1;
