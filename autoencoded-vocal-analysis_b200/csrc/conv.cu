@@ -628,33 +628,51 @@ struct WgradParams {
 
 template <int S, int TWG>
 struct WTile {
-  static constexpr int THG = (S == 1) ? 256 / TWG : 8;  // S1: 32x8 or 16x16 ; S2: 16x8
+  static constexpr int THG = (S == 1) ? 256 / TWG : 8;  // S1: 32x8 or 16x16 ; S2: TWGx8
   static constexpr int I_ROWS = S * THG + (S == 1 ? 2 : 1);
-  static constexpr int I_COLS = S * TWG + (S == 1 ? 2 : 1);
-  static constexpr int I_PITCH = (I_COLS + 3) / 4 * 4;
+  // I rows (one TMA box row, first column = input column X0-4 because the TMA start coordinate
+  // must be 16-byte aligned): [3] = left halo (X0-1), [4 .. 4+S*TWG-1] interior, then the right
+  // halo (S1).  Stride-1 pitches are padded so that the channel-plane stride is 8/24 (mod 32).
+  static constexpr int I_PITCH = (S == 1) ? (TWG == 32 ? 44 : 28) : 2 * TWG + 4;
   static constexpr int I_PLANE_RAW = I_ROWS * I_PITCH;
-  static constexpr int I_PLANE = I_PLANE_RAW + ((I_PLANE_RAW % 8 == 4) ? 0 : ((12 - I_PLANE_RAW % 8) % 8));
-  static constexpr int G_PLANE_RAW = THG * TWG;
-  static constexpr int G_PLANE = G_PLANE_RAW + 4;  // THG*TWG is a multiple of 8 -> +4 gives == 4 mod 8
+  // dense planes: the whole I tile is one TMA box (plane stride is 4 (mod 32) floats for the
+  // stride-2 tiles, i.e. conflict-free across channel planes; 8 (mod 32) for stride 1)
+  static constexpr int I_PLANE = I_PLANE_RAW;
+  static constexpr int G_PLANE = THG * TWG;  // dense: the whole G tile is one TMA box
   static constexpr int NSTRIPS = THG * TWG / 4;
 };
 
 // CONVT == 0: G uses the DZ loader, I the AFFINE loader; CONVT == 1: the other way round.
+// Staging: TMA boxes land directly in the layout the FMA loop reads (G: one [CG][THG][TWG] box;
+// I: one [CI][I_ROWS][I_PITCH] box, halo columns and image borders zero-filled by the TMA unit), then a table-driven pass transforms them IN PLACE (BN apply on one side,
+// next-BN backward + ReLU backward on the other, literal zeros for padding).
 template <int S, int CG, int CI, int TWG, int CONVT>
-__global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgradParams P) {
+__global__ void __launch_bounds__(256, 2)
+    wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_gy,
+                 const __grid_constant__ CUtensorMap map_i, const __grid_constant__ CUtensorMap map_iy,
+                 const WgradParams P) {
   using T = WTile<S, TWG>;
   constexpr int GT = (CI == 1) ? 1 : 8;   // g-channels per thread
   constexpr int NGQ = CG / GT;
   constexpr int NSLOT = NGQ * CI;         // (gq, i) pairs
   constexpr int NPG = 256 / NSLOT;        // pixel groups
   constexpr int NACT = NPG * NSLOT;       // active threads
-  constexpr int NB = CONVT ? CI : CG;     // bias length
+  constexpr int G_FLOATS = CG * T::G_PLANE;
+  constexpr int I_FLOATS = CI * T::I_PLANE;
+  constexpr int G_PAD = (G_FLOATS + 31) / 32 * 32;
+  constexpr int I_PAD = (I_FLOATS + 31) / 32 * 32;
+  constexpr int NQG = CG * T::THG * (TWG / 4);                 // G quads
+  constexpr int NQI = CI * T::I_ROWS * (T::I_PITCH / 4);       // I quads
+  constexpr int GITERS = (NQG + 255) / 256;
+  constexpr int IITERS = (NQI + 255) / 256;
 
-  extern __shared__ __align__(16) float smem[];
-  float* s_g = smem;                       // [CG][G_PLANE]
-  float* s_i = s_g + CG * T::G_PLANE;      // [CI][I_PLANE]
-  float* s_aff = s_i + CI * T::I_PLANE;    // AFFINE coefs: scale[32] | shift[32]
+  extern __shared__ __align__(128) float smem[];
+  float* s_g = smem;                                   // [CG][G_PLANE]
+  float* s_i = s_g + G_PAD;                            // [CI][I_PLANE]
+  float* s_y = s_i + I_PAD;                            // saved activation of the DZ side
+  float* s_aff = s_y + (CONVT ? I_PAD : G_PAD);        // AFFINE coefs: scale[32] | shift[32]
   DzCoef* s_dz = reinterpret_cast<DzCoef*>(s_aff + 64);  // DZ coefs [32]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dz + 32);
 
   const int tid = threadIdx.x;
   const bool active = tid < NACT;
@@ -668,6 +686,10 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgradParams P) {
   const int tiles_per_img = tiles_x * tiles_y;
   const int ntiles = P.B * tiles_per_img;
 
+  if (tid == 0) {
+    cv_mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   // coefficients
   if (tid < 32) {
     const int c = tid;
@@ -679,6 +701,35 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgradParams P) {
       s_aff[32 + c] = k.shift;
     }
     if (c < CD) s_dz[c] = dz_coef(P.next_gamma, P.next_stats, P.next_dstats, c, P.next_count);
+  }
+  // per-thread transform work lists (identical for every tile)
+  int g_off[GITERS], g_ch[GITERS];
+#pragma unroll
+  for (int j = 0; j < GITERS; ++j) {
+    const int t = tid + j * 256;
+    g_ch[j] = -1;
+    g_off[j] = 0;
+    if (t < NQG) {
+      const int q = t % (TWG / 4);
+      const int y = (t / (TWG / 4)) % T::THG;
+      const int c = t / ((TWG / 4) * T::THG);
+      g_off[j] = c * T::G_PLANE + y * TWG + 4 * q;
+      g_ch[j] = c;
+    }
+  }
+  int i_off[IITERS], i_meta[IITERS];   // meta: channel | row<<8 | quad<<16, -1 = none
+#pragma unroll
+  for (int j = 0; j < IITERS; ++j) {
+    const int t = tid + j * 256;
+    i_meta[j] = -1;
+    i_off[j] = 0;
+    if (t < NQI) {
+      const int q = t % (T::I_PITCH / 4);
+      const int y = (t / (T::I_PITCH / 4)) % T::I_ROWS;
+      const int c = t / ((T::I_PITCH / 4) * T::I_ROWS);
+      i_off[j] = c * T::I_PLANE + y * T::I_PITCH + 4 * q;
+      i_meta[j] = c | (y << 8) | (q << 16);
+    }
   }
 
   float acc[GT][9];
@@ -692,140 +743,80 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgradParams P) {
 #pragma unroll
   for (int g = 0; g < GT; ++g) bs[g] = 0.f;
 
+  uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int n = tile / tiles_per_img;
     const int trem = tile - n * tiles_per_img;
     const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
     const int gy0 = ty * T::THG, gx0 = tx * TWG;
     const int iy0 = S * gy0 - 1;
-    __syncthreads();
-    // ---- stage G tile (no halo, always in range): aligned float4 quads, loads batched so
-    // that U (x2 for the DZ side) 16-byte loads per thread are in flight
-    {
-      constexpr int QG = TWG / 4;
-      constexpr int NTASK = CG * T::THG * QG;
-      constexpr int U = CONVT ? 8 : 4;
-#pragma unroll 1
-      for (int t0 = tid; t0 < NTASK; t0 += 256 * U) {
-        float4 ra[U], ry[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int t = t0 + u * 256;
-          if (t < NTASK) {
-            const int q = t % QG;
-            const int y = (t / QG) % T::THG;
-            const int c = t / (QG * T::THG);
-            const size_t off = (((size_t)n * CG + c) * Hg + gy0 + y) * Wg + gx0 + 4 * q;
-            ra[u] = __ldg(reinterpret_cast<const float4*>(P.g_a + off));
-            if (!CONVT) ry[u] = __ldg(reinterpret_cast<const float4*>(P.g_y + off));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int t = t0 + u * 256;
-          if (t < NTASK) {
-            const int q = t % QG;
-            const int y = (t / QG) % T::THG;
-            const int c = t / (QG * T::THG);
-            const float4 a = ra[u];
-            float4 v;
-            if (CONVT) {
-              const float sc = s_aff[c], sh = s_aff[32 + c];
-              v = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
-            } else {
-              const float4 yv = ry[u];
-              const DzCoef k = s_dz[c];
-              const bool m = P.relu_mask != 0;
-              v.x = (m && !(yv.x > 0.f)) ? 0.f : dz_apply(k, a.x, yv.x);
-              v.y = (m && !(yv.y > 0.f)) ? 0.f : dz_apply(k, a.y, yv.y);
-              v.z = (m && !(yv.z > 0.f)) ? 0.f : dz_apply(k, a.z, yv.z);
-              v.w = (m && !(yv.w > 0.f)) ? 0.f : dz_apply(k, a.w, yv.w);
-            }
-            *reinterpret_cast<float4*>(s_g + c * T::G_PLANE + y * TWG + 4 * q) = v;
-          }
-        }
-      }
+    const int X0 = S * gx0;
+    __syncthreads();  // previous tile's FMA loop is done with the buffers
+    if (tid == 0) {
+      constexpr uint32_t BYTES = (uint32_t)(G_FLOATS * 4 * (CONVT ? 1 : 2) +
+                                            CI * T::I_PLANE_RAW * 4 * (CONVT ? 2 : 1));
+      cv_mbar_expect_tx(s_bar, BYTES);
+      cv_tma_load_3d(s_g, &map_g, gx0, gy0, n * CG, s_bar);
+      if (!CONVT) cv_tma_load_3d(s_y, &map_gy, gx0, gy0, n * CG, s_bar);
+      cv_tma_load_3d(s_i, &map_i, X0 - 4, iy0, n * CI, s_bar);
+      if (CONVT) cv_tma_load_3d(s_y, &map_iy, X0 - 4, iy0, n * CI, s_bar);
     }
-    // ---- stage I tile: aligned interior quads (stored one column to the right of the left
-    // halo), scalar halo columns, zero rows/cols outside the image (padding AFTER the transform)
-    {
-      constexpr int QI = S * TWG / 4;
-      constexpr int TPR = QI + 1;
-      constexpr int NTASK = CI * T::I_ROWS * TPR;
-      constexpr int U = CONVT ? 4 : 8;
-      const int X0 = S * gx0;
-#pragma unroll 1
-      for (int t0 = tid; t0 < NTASK; t0 += 256 * U) {
-        float4 ra[U], ry[U];
+    cv_mbar_wait(s_bar, phase);
+    phase ^= 1;
+    // ---- in-place transform of the G tile (always in range)
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int t = t0 + u * 256;
-          ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          ry[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (t < NTASK) {
-            const int q = t % TPR;
-            const int y = (t / TPR) % T::I_ROWS;
-            const int c = t / (TPR * T::I_ROWS);
-            const int gy = iy0 + y;
-            if (gy >= 0 && gy < Hi) {
-              const size_t rowoff = (((size_t)n * CI + c) * Hi + gy) * Wi;
-              if (q < QI) {
-                const size_t off = rowoff + X0 + 4 * q;
-                ra[u] = __ldg(reinterpret_cast<const float4*>(P.i_a + off));
-                if (CONVT) ry[u] = __ldg(reinterpret_cast<const float4*>(P.i_y + off));
-              } else {
-                if (X0 - 1 >= 0) {
-                  ra[u].x = __ldg(P.i_a + rowoff + X0 - 1);
-                  if (CONVT) ry[u].x = __ldg(P.i_y + rowoff + X0 - 1);
-                }
-                if (S == 1 && X0 + TWG < Wi) {
-                  ra[u].y = __ldg(P.i_a + rowoff + X0 + TWG);
-                  if (CONVT) ry[u].y = __ldg(P.i_y + rowoff + X0 + TWG);
-                }
-              }
-            }
-          }
+    for (int j = 0; j < GITERS; ++j) {
+      const int c = g_ch[j];
+      if (c < 0) continue;
+      float4* p = reinterpret_cast<float4*>(s_g + g_off[j]);
+      const float4 a = *p;
+      float4 v;
+      if (CONVT) {
+        const float sc = s_aff[c], sh = s_aff[32 + c];
+        v = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
+      } else {
+        const float4 yv = *reinterpret_cast<const float4*>(s_y + g_off[j]);
+        const DzCoef k = s_dz[c];
+        const bool m = P.relu_mask != 0;
+        v.x = (m && !(yv.x > 0.f)) ? 0.f : dz_apply(k, a.x, yv.x);
+        v.y = (m && !(yv.y > 0.f)) ? 0.f : dz_apply(k, a.y, yv.y);
+        v.z = (m && !(yv.z > 0.f)) ? 0.f : dz_apply(k, a.z, yv.z);
+        v.w = (m && !(yv.w > 0.f)) ? 0.f : dz_apply(k, a.w, yv.w);
+      }
+      *p = v;
+    }
+    // ---- in-place transform of the I tile; zero rows/cols outside the image AFTER the transform
+#pragma unroll
+    for (int j = 0; j < IITERS; ++j) {
+      const int m = i_meta[j];
+      if (m < 0) continue;
+      const int c = m & 0xff;
+      const int gy = iy0 + ((m >> 8) & 0xff);
+      const int gx = X0 - 4 + 4 * (m >> 16);
+      float4* p = reinterpret_cast<float4*>(s_i + i_off[j]);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < Hi) {
+        const float4 a = *p;
+        if (CONVT) {
+          const float4 yv = *reinterpret_cast<const float4*>(s_y + i_off[j]);
+          const DzCoef k = s_dz[c];
+          const bool mk = P.relu_mask != 0;
+          v.x = (mk && !(yv.x > 0.f)) ? 0.f : dz_apply(k, a.x, yv.x);
+          v.y = (mk && !(yv.y > 0.f)) ? 0.f : dz_apply(k, a.y, yv.y);
+          v.z = (mk && !(yv.z > 0.f)) ? 0.f : dz_apply(k, a.z, yv.z);
+          v.w = (mk && !(yv.w > 0.f)) ? 0.f : dz_apply(k, a.w, yv.w);
+        } else {
+          const float sc = s_aff[c], sh = s_aff[32 + c];
+          v = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int t = t0 + u * 256;
-          if (t < NTASK) {
-            const int q = t % TPR;
-            const int y = (t / TPR) % T::I_ROWS;
-            const int c = t / (TPR * T::I_ROWS);
-            const int gy = iy0 + y;
-            const bool rowok = gy >= 0 && gy < Hi;
-            const float4 a = ra[u];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rowok) {
-              if (CONVT) {
-                const float4 yv = ry[u];
-                const DzCoef k = s_dz[c];
-                const bool m = P.relu_mask != 0;
-                v.x = (m && !(yv.x > 0.f)) ? 0.f : dz_apply(k, a.x, yv.x);
-                v.y = (m && !(yv.y > 0.f)) ? 0.f : dz_apply(k, a.y, yv.y);
-                if (q < QI) {
-                  v.z = (m && !(yv.z > 0.f)) ? 0.f : dz_apply(k, a.z, yv.z);
-                  v.w = (m && !(yv.w > 0.f)) ? 0.f : dz_apply(k, a.w, yv.w);
-                }
-              } else {
-                const float sc = s_aff[c], sh = s_aff[32 + c];
-                v = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
-              }
-            }
-            float* srow = s_i + c * T::I_PLANE + y * T::I_PITCH;
-            if (q < QI) {
-              srow[1 + 4 * q] = v.x;
-              srow[2 + 4 * q] = v.y;
-              srow[3 + 4 * q] = v.z;
-              srow[4 + 4 * q] = v.w;
-            } else {
-              srow[0] = (X0 - 1 >= 0) ? v.x : 0.f;
-              if (S == 1) srow[TWG + 1] = (X0 + TWG < Wi) ? v.y : 0.f;
-            }
-          }
+        if (gx < 0 || gx >= Wi) v = make_float4(0.f, 0.f, 0.f, (gx + 3 >= 0 && gx + 3 < Wi) ? v.w : 0.f);
+        if (gx >= 0) {
+          if (gx + 1 >= Wi) v.y = 0.f;
+          if (gx + 2 >= Wi) v.z = 0.f;
+          if (gx + 3 >= Wi) v.w = 0.f;
         }
       }
+      *p = v;
     }
     __syncthreads();
     if (!active) continue;
@@ -837,19 +828,22 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgradParams P) {
       constexpr int WR = 3;
       constexpr int WC = (S == 1) ? 6 : 9;
       float iv[WR][WC];
+      // window of the strip: tile columns 3 + S*sx .. (left halo sits in column 3)
       const float* ip = s_i + ti * T::I_PLANE + (S * sy) * T::I_PITCH + S * sx;
 #pragma unroll
       for (int r = 0; r < WR; ++r) {
+        const float* rp = ip + r * T::I_PITCH;
         if (S == 1) {
-          float4 a = *reinterpret_cast<const float4*>(ip + r * T::I_PITCH);
-          float2 b = *reinterpret_cast<const float2*>(ip + r * T::I_PITCH + 4);
-          iv[r][0] = a.x; iv[r][1] = a.y; iv[r][2] = a.z; iv[r][3] = a.w; iv[r][4] = b.x; iv[r][5] = b.y;
+          float4 a = *reinterpret_cast<const float4*>(rp + 4);
+          iv[r][0] = rp[3];
+          iv[r][1] = a.x; iv[r][2] = a.y; iv[r][3] = a.z; iv[r][4] = a.w;
+          iv[r][5] = rp[8];
         } else {
-          float4 a = *reinterpret_cast<const float4*>(ip + r * T::I_PITCH);
-          float4 b = *reinterpret_cast<const float4*>(ip + r * T::I_PITCH + 4);
-          iv[r][0] = a.x; iv[r][1] = a.y; iv[r][2] = a.z; iv[r][3] = a.w;
-          iv[r][4] = b.x; iv[r][5] = b.y; iv[r][6] = b.z; iv[r][7] = b.w;
-          iv[r][8] = ip[r * T::I_PITCH + 8];
+          float4 a = *reinterpret_cast<const float4*>(rp + 4);
+          float4 b = *reinterpret_cast<const float4*>(rp + 8);
+          iv[r][0] = rp[3];
+          iv[r][1] = a.x; iv[r][2] = a.y; iv[r][3] = a.z; iv[r][4] = a.w;
+          iv[r][5] = b.x; iv[r][6] = b.y; iv[r][7] = b.z; iv[r][8] = b.w;
         }
       }
       if (CONVT && gq == 0) {
@@ -893,7 +887,7 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(const WgradParams P) {
   __syncthreads();
   float* dst = P.partial + (size_t)blockIdx.x * (CG * CI * 9 + 32);
   for (int idx = tid; idx < CG * CI * 9 + 32; idx += 256) dst[idx] = s_red[idx];
-  (void)NB;
+
 }
 
 // second stage: out[j] = sum_p partial[p][j]
@@ -909,13 +903,19 @@ __global__ void reduce_partials_kernel(const float* partial, int nparts, int str
 template <int S, int CG, int CI, int TWG, int CONVT>
 static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStream_t stream) {
   using T = WTile<S, TWG>;
-  size_t smem_f = (size_t)CG * T::G_PLANE + (size_t)CI * T::I_PLANE + 64 + 32 * sizeof(DzCoef) / sizeof(float);
+  constexpr int G_PAD = (CG * T::G_PLANE + 31) / 32 * 32;
+  constexpr int I_PAD = (CI * T::I_PLANE + 31) / 32 * 32;
+  size_t smem_f = (size_t)G_PAD + I_PAD + (CONVT ? I_PAD : G_PAD) + 64 + 32 * sizeof(DzCoef) / sizeof(float) + 8;
   if (smem_f < (size_t)CG * CI * 9 + 32) smem_f = (size_t)CG * CI * 9 + 32;
-  const size_t smem = smem_f * sizeof(float);
+  const size_t smem = smem_f * sizeof(float) + 128;
   auto kern = wgrad_kernel<S, CG, CI, TWG, CONVT>;
   static int max_ctas = 0;
   if (max_ctas == 0) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("wgrad: cannot reserve %zu bytes of shared memory", smem);
+      return 1;
+    }
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
     if (per_sm < 1) per_sm = 1;
@@ -924,9 +924,16 @@ static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStrea
   const long long ntiles = (long long)P.B * (P.Wg / TWG) * (P.Hg / T::THG);
   int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
   if (grid > 296) grid = 296;  // workspace bound, see ava_b200_bnconv_bwd_weight_ws
+  CUtensorMap map_g, map_gy, map_i, map_iy;
+  if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, TWG, T::THG, CG)) return 1;
+  if (make_act_map(&map_gy, CONVT ? P.g_a : P.g_y, (long long)P.B * CG, P.Hg, P.Wg, TWG, T::THG, CG)) return 1;
+  if (make_act_map(&map_i, P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS, CI)) return 1;
+  if (make_act_map(&map_iy, CONVT ? P.i_y : P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS,
+                   CI))
+    return 1;
   P.partial = reinterpret_cast<float*>(ws);
   const int stride = CG * CI * 9 + 32;
-  kern<<<grid, 256, smem, stream>>>(P);
+  kern<<<grid, 256, smem, stream>>>(map_g, map_gy, map_i, map_iy, P);
   if (check_launch("wgrad")) return 1;
   reduce_partials_kernel<<<(CG * CI * 9 + 127) / 128, 128, 0, stream>>>(P.partial, grid, stride, CG * CI * 9, dw,
                                                                         0);

@@ -139,7 +139,8 @@ def test_autograd_backward_and_torch_seeded_noise(vae_mod):
     torch.manual_seed(123)
     with torch.no_grad():
         l_drawn = model3.forward(x).item()
-    assert l_inj == l_drawn
+    # (equal up to the summation order of the statistics atomics)
+    assert abs(l_inj - l_drawn) <= 1e-6 * abs(l_inj)
 
 
 def test_train_steps_match_reference_adam_trajectory(vae_mod):
