@@ -19,11 +19,11 @@ SIGNATURES = {
     "ava_b200_channel_stats": (P, I, I, I, P, P),
     "ava_b200_bn_update_running": (P, P, P, P, P, P, P, F, P),
     "ava_b200_bnconv_fwd": (I, I, P, P, P, P, P, P, P, P, P, I, P, P),
-    "ava_b200_bnconv_bwd_data": (I, I, P, P, P, P, P, P, P, P, P, P, P),
-    "ava_b200_bnconv_bwd_weight": (I, I, P, P, P, P, P, P, P, P, P, P, P, P, P),
+    "ava_b200_bnconv_bwd_data": (I, I, P, P, P, P, P, P, P),
+    "ava_b200_bnconv_bwd_weight": (I, I, P, P, P, P, P, P, P, P, P),
     "ava_b200_bnconv_bwd_weight_ws": (I, I),
     "ava_b200_bn_param_grads": (P, P, P, P, P, P, P, P),
-    "ava_b200_bn_relu_bwd_apply": (P, P, P, P, P, I, I, I, P, P),
+    "ava_b200_bn_relu_bwd_apply": (P, P, P, P, P, I, I, I, I, P, P),
     "ava_b200_linear_fwd": (P, I, P, P, P, I, I, I, I, I, I, LL, LL, LL, LL, I, P, LL, P),
     "ava_b200_linear_bwd_data": (P, I, P, P, P, I, I, I, I, I, LL, LL, LL, I, I, P, LL, P),
     "ava_b200_linear_bwd_weight": (P, I, P, P, I, P, P, I, I, I, I, LL, LL, LL, LL, I, P, LL, P),

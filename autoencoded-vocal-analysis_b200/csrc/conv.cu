@@ -14,7 +14,8 @@
 //
 // Prologue (while staging the input tile in shared memory):
 //   IN_AFFINE: v = x*scale[c] + shift[c]  (BatchNorm apply; zero padding AFTER bn)
-//   IN_DZ:     v = [y>0] * (p[c]*g + q[c]*y + r[c])  (next BN's backward + ReLU backward)
+//   IN_PLAIN:  v = g  (a gradient already pushed through the next BN's backward and this layer's
+//              ReLU by ava_b200_bn_relu_bwd_apply; its zero padding is TMA's out-of-bounds fill)
 // Epilogue:
 //   EPI_FWD: + bias, ReLU, store, and per-channel sum / sum-of-squares of the output
 //            (the next BatchNorm's batch statistics) via warp shuffles -> smem -> fp64 atomics
@@ -30,12 +31,11 @@
 namespace ava {
 
 enum { K_S1 = 0, K_S2 = 1, K_UP = 2 };
-enum { IN_AFFINE = 0, IN_DZ = 1 };
+enum { IN_AFFINE = 0, IN_PLAIN = 1 };
 enum { EPI_FWD = 0, EPI_BWD = 1 };
 
 struct GconvParams {
-  const float* in;    // AFFINE: x;  DZ: g_out
-  const float* in_y;  // DZ: saved activation (same shape as in)
+  const float* in;    // AFFINE: x;  PLAIN: dz
   // coefficient sources for the input transform
   const float* gamma;
   const float* beta;
@@ -43,8 +43,6 @@ struct GconvParams {
   const float* rmean;
   const float* rvar;
   int train;
-  const double* dstats_next;  // DZ only
-  int relu_mask;              // DZ only
   double in_count;
   // weights
   const float* w;
@@ -97,20 +95,28 @@ struct GconvCfg {
   // threads: 64 slots x NCOG channel groups x NSUB sub-tiles (256, or 192 for CO=24)
   static constexpr int NSUB = (NCOG >= 3) ? 1 : 4 / NCOG;
   static constexpr int NT = 64 * NCOG * NSUB;
-  // input channels per pipeline stage: largest divisor of CI keeping a raw stage <= 37 KB
-  // (24 KB in DZ mode, which stages two raw tensors): 2 (3) stage buffers per CTA, 2+ CTAs/SM
-  static constexpr int LIMIT = (INMODE == IN_DZ) ? 6144 : 9472;
-  static constexpr int stage_floats(int c) { return NSUB * c * G::RAW_PLANE; }
+  // IN_PLAIN input (an already materialised gradient) needs no per-element transform and its
+  // zero padding is exactly TMA's out-of-bounds fill: for the stride-1 / up kernels the boxes
+  // land DIRECTly in the layout the FMA loop reads (double buffered, no staging pass at all).
+  // The stride-2 kernels still de-interleave even/odd columns through a staging buffer.
+  static constexpr bool DIRECT = (INMODE == IN_PLAIN) && (KIND != K_S2);
+  static constexpr int BOX_W = DIRECT ? G::PITCH : G::RAW_PITCH;
+  static constexpr int BOX_PLANE = G::IN_ROWS * BOX_W;
+  // input channels per pipeline stage: largest divisor of CI keeping a stage <= 37 KB
+  static constexpr int LIMIT = 9472;
+  static constexpr int stage_floats(int c) { return NSUB * c * BOX_PLANE; }
   static constexpr int CIC = (CI % 8 == 0 && stage_floats(8) <= LIMIT)   ? 8
                              : (CI % 4 == 0 && stage_floats(4) <= LIMIT) ? 4
                              : (CI % 2 == 0 && stage_floats(2) <= LIMIT) ? 2
                                                                          : 1;
   static constexpr int NCHUNK = CI / CIC;
-  static constexpr int STAGE = NSUB * CIC * G::PLANE;                       // floats, transformed tile
-  static constexpr int RAW_SUB = (CIC * G::RAW_PLANE + 31) / 32 * 32;       // floats, 128-byte aligned
-  static constexpr int RAW_STAGE = NSUB * RAW_SUB;
-  static constexpr int BOX_BYTES = CIC * G::RAW_PLANE * 4;
-  // transform work items per sub-tile and per thread
+  static constexpr int FIN_SUB = (CIC * G::PLANE + 31) / 32 * 32;           // floats, 128-byte aligned
+  static constexpr int RAW_SUB = (CIC * G::RAW_PLANE + 31) / 32 * 32;
+  static constexpr int STAGE = NSUB * FIN_SUB;                              // transformed tile(s)
+  static constexpr int RAW_STAGE = NSUB * RAW_SUB;                          // staging (non-DIRECT)
+  static constexpr int BUF_FLOATS = DIRECT ? 2 * STAGE : RAW_STAGE + STAGE;
+  static constexpr int BOX_BYTES = CIC * BOX_PLANE * 4;
+  // transform work items per sub-tile and per thread (non-DIRECT)
   static constexpr int NQUAD = CIC * G::IN_ROWS * G::QUADS;
   static constexpr int QITERS = (NQUAD + NT - 1) / NT;
   static constexpr int NHALO = CIC * G::IN_ROWS;
@@ -140,8 +146,8 @@ __device__ __forceinline__ void cv_mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// 3-D box [CIC][IN_ROWS][RAW_PITCH] of the [B*C, H, W] activation tensor; out-of-range
-// rows/columns (image border, negative coordinates) are zero-filled by the TMA unit
+// 3-D box [channels][rows][cols] of a [B*C, H, W] activation tensor; out-of-range rows/columns
+// (image border, negative coordinates) are zero-filled by the TMA unit
 __device__ __forceinline__ void cv_tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z,
                                                uint64_t* bar) {
   asm volatile(
@@ -151,32 +157,31 @@ __device__ __forceinline__ void cv_tma_load_3d(void* smem_dst, const CUtensorMap
       : "memory");
 }
 
-// Software-pipelined: while the FMA loop runs on the transformed tile of stage i, the raw
-// rows of stage i+1 are fetched by TMA (one cp.async.bulk.tensor box per sub-tile and tensor,
-// issued by a single thread, zero register / LSU cost, completion on an mbarrier); a short
-// table-driven shared->shared pass then applies the BatchNorm transform / BN+ReLU backward
-// and the zero padding.  Two (four for CO=1) CTAs per SM interleave their phases.
+// Software-pipelined: while the FMA loop runs on stage i, the boxes of stage i+1 are fetched
+// by TMA (one cp.async.bulk.tensor box per sub-tile, issued by a single thread: no register or
+// LSU cost, completion on an mbarrier).  IN_AFFINE: a short table-driven shared->shared pass
+// applies the BatchNorm scale/shift and writes literal zeros for the padding (padding is
+// applied AFTER BatchNorm).  IN_PLAIN: see GconvCfg::DIRECT.  2 (4 for CO=1) CTAs per SM.
 template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
 __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvCfg<KIND, CI, CO, TW, INMODE>::MINB)
-    gconv_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_y,
-                 const GconvParams P) {
+    gconv_kernel(const __grid_constant__ CUtensorMap map_in, const GconvParams P) {
   using G = TileGeom<KIND, TW>;
   using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
   constexpr int COT = C::COT, NCOG = C::NCOG, NSUB = C::NSUB, NT = C::NT;
   constexpr int CIC = C::CIC, NCHUNK = C::NCHUNK;
+  constexpr bool DIRECT = C::DIRECT;
   constexpr int NOUT = (KIND == K_UP) ? 8 : 4;
 
   extern __shared__ __align__(128) float smem[];
-  float* s_rawg = smem;                             // [NSUB][RAW_SUB] raw input (TMA)
-  float* s_rawy = s_rawg + C::RAW_STAGE;            // [NSUB][RAW_SUB] raw saved activation (IN_DZ)
-  float* s_in = s_rawy + (INMODE == IN_DZ ? C::RAW_STAGE : 0);  // [NSUB][CIC][IN_ROWS][PITCH]
-  float* s_w = s_in + C::STAGE;                     // [CI][9][CO]
+  // DIRECT: [2][STAGE] ring of ready-to-use tiles; else [RAW_STAGE] staging + [STAGE] transformed
+  float* s_raw = smem;
+  float* s_in = DIRECT ? smem : smem + C::RAW_STAGE;
+  float* s_w = smem + C::BUF_FLOATS;                // [CI][9][CO]
   float* s_c0 = s_w + CI * 9 * CO;                  // AFFINE scale
   float* s_c1 = s_c0 + 32;                          // AFFINE shift
   float* s_red = s_c1 + 32;                         // [2*CO] cross-warp reduction
   float* s_bias = s_red + 64;                       // [CO]
-  DzCoef* s_dz = reinterpret_cast<DzCoef*>(s_bias + 32);   // [32] (IN_DZ)
-  double* s_meand = reinterpret_cast<double*>(s_dz + 32);  // [32] EPI_BWD: mean of own BN
+  double* s_meand = reinterpret_cast<double*>(s_bias + 32);  // [32] EPI_BWD: mean of own BN
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meand + 32);
 
   const int tid = threadIdx.x;
@@ -190,12 +195,14 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
   const int ntiles = P.B * tiles_per_img;
   const int ngroups = (ntiles + NSUB - 1) / NSUB;
 
-  // ---- TMA: raw boxes of stage (grp, ch), issued by thread 0
-  auto issue = [&](int grp, int ch) {
+  // ---- TMA: boxes of stage (grp, ch) into ring slot `buf`, issued by thread 0
+  auto issue = [&](int grp, int ch, int buf) {
     if (tid != 0) return;
     int nsub = ntiles - grp * NSUB;
     if (nsub > NSUB) nsub = NSUB;
-    cv_mbar_expect_tx(s_bar, (uint32_t)(nsub * C::BOX_BYTES * (INMODE == IN_DZ ? 2 : 1)));
+    cv_mbar_expect_tx(s_bar, (uint32_t)(nsub * C::BOX_BYTES));
+    float* dst = DIRECT ? s_in + buf * C::STAGE : s_raw;
+    constexpr int SUBF = DIRECT ? C::FIN_SUB : C::RAW_SUB;
     for (int sb = 0; sb < nsub; ++sb) {
       const int ltile = grp * NSUB + sb;
       const int ln = ltile / tiles_per_img;
@@ -203,9 +210,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
       const int lty = lrem / tiles_x, ltx = lrem - lty * tiles_x;
       const int iy0 = (KIND == K_S1) ? lty * G::TH - 1 : (KIND == K_S2 ? 2 * lty * G::TH - 1 : lty * G::TH);
       const int X0 = (KIND == K_S2) ? 2 * ltx * TW : ltx * TW;
-      cv_tma_load_3d(s_rawg + sb * C::RAW_SUB, &map_in, X0 - G::RAW_X_SHIFT, iy0, ln * CI + ch * CIC, s_bar);
-      if (INMODE == IN_DZ)
-        cv_tma_load_3d(s_rawy + sb * C::RAW_SUB, &map_y, X0 - G::RAW_X_SHIFT, iy0, ln * CI + ch * CIC, s_bar);
+      cv_tma_load_3d(dst + sb * SUBF, &map_in, X0 - G::RAW_X_SHIFT, iy0, ln * CI + ch * CIC, s_bar);
     }
   };
 
@@ -214,47 +219,49 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if ((int)blockIdx.x < ngroups) issue(blockIdx.x, 0);
+  if ((int)blockIdx.x < ngroups) issue(blockIdx.x, 0, 0);
 
   // ---- per-thread transform work list (identical for every sub-tile and stage)
   int q_raw[C::QITERS], q_fin[C::QITERS], q_meta[C::QITERS];   // meta: row | ci<<8, -1 = none
-#pragma unroll
-  for (int j = 0; j < C::QITERS; ++j) {
-    const int t = tid + j * NT;
-    q_meta[j] = -1;
-    q_raw[j] = q_fin[j] = 0;
-    if (t < C::NQUAD) {
-      const int q = t % G::QUADS;
-      const int rr = t / G::QUADS;
-      const int r = rr % G::IN_ROWS;
-      const int ci = rr / G::IN_ROWS;
-      q_raw[j] = ci * G::RAW_PLANE + r * G::RAW_PITCH + ((KIND == K_UP) ? 4 * q : 4 + 4 * q);
-      const int frow = ci * G::PLANE + r * G::PITCH;
-      q_fin[j] = (KIND == K_S1) ? frow + 4 + 4 * q : (KIND == K_S2 ? frow + 2 * q : frow + 4 * q);
-      q_meta[j] = r | (ci << 8);
-    }
-  }
   int h_raw[C::HITERS], h_fin[C::HITERS], h_meta[C::HITERS];
+  if (!DIRECT) {
 #pragma unroll
-  for (int j = 0; j < C::HITERS; ++j) {
-    const int t = tid + j * NT;
-    h_meta[j] = -1;
-    h_raw[j] = h_fin[j] = 0;
-    if (t < C::NHALO) {
-      const int r = t % G::IN_ROWS;
-      const int ci = t / G::IN_ROWS;
-      h_raw[j] = ci * G::RAW_PLANE + r * G::RAW_PITCH;
-      h_fin[j] = ci * G::PLANE + r * G::PITCH;
-      h_meta[j] = r | (ci << 8);
+    for (int j = 0; j < C::QITERS; ++j) {
+      const int t = tid + j * NT;
+      q_meta[j] = -1;
+      q_raw[j] = q_fin[j] = 0;
+      if (t < C::NQUAD) {
+        const int q = t % G::QUADS;
+        const int rr = t / G::QUADS;
+        const int r = rr % G::IN_ROWS;
+        const int ci = rr / G::IN_ROWS;
+        q_raw[j] = ci * G::RAW_PLANE + r * G::RAW_PITCH + ((KIND == K_UP) ? 4 * q : 4 + 4 * q);
+        const int frow = ci * G::PLANE + r * G::PITCH;
+        q_fin[j] = (KIND == K_S1) ? frow + 4 + 4 * q : (KIND == K_S2 ? frow + 2 * q : frow + 4 * q);
+        q_meta[j] = r | (ci << 8);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < C::HITERS; ++j) {
+      const int t = tid + j * NT;
+      h_meta[j] = -1;
+      h_raw[j] = h_fin[j] = 0;
+      if (t < C::NHALO) {
+        const int r = t % G::IN_ROWS;
+        const int ci = t / G::IN_ROWS;
+        h_raw[j] = ci * G::RAW_PLANE + r * G::RAW_PITCH;
+        h_fin[j] = ci * G::PLANE + r * G::PITCH;
+        h_meta[j] = r | (ci << 8);
+      }
     }
   }
 
-  auto xform1 = [&](float a, float y, int cc) -> float {
+  auto xform1 = [&](float a, int cc) -> float {
     if (INMODE == IN_AFFINE) return fmaf(a, s_c0[cc], s_c1[cc]);
-    return (P.relu_mask && !(y > 0.f)) ? 0.f : dz_apply(s_dz[cc], a, y);
+    return a;
   };
 
-  // ---- staging buffer -> transformed tile (BN apply / BN+ReLU backward; zero padding AFTER)
+  // ---- staging buffer -> tile the FMA loop reads (BN apply; zero padding AFTER; even/odd split)
   auto transform = [&](int grp, int ch) {
     const int tile0 = grp * NSUB;
 #pragma unroll
@@ -265,9 +272,8 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
       const int lty = lrem / tiles_x, ltx = lrem - lty * tiles_x;
       const int iy0 = (KIND == K_S1) ? lty * G::TH - 1 : (KIND == K_S2 ? 2 * lty * G::TH - 1 : lty * G::TH);
       const int X0 = (KIND == K_S2) ? 2 * ltx * TW : ltx * TW;
-      const float* rg = s_rawg + sb * C::RAW_SUB;
-      const float* ry = s_rawy + sb * C::RAW_SUB;
-      float* sdst = s_in + sb * CIC * G::PLANE;
+      const float* rg = s_raw + sb * C::RAW_SUB;
+      float* sdst = s_in + sb * C::FIN_SUB;
 #pragma unroll
       for (int j = 0; j < C::QITERS; ++j) {
         const int m = q_meta[j];
@@ -277,10 +283,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gy >= 0 && gy < H_in) {
           const float4 a = *reinterpret_cast<const float4*>(rg + q_raw[j]);
-          float4 y = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (INMODE == IN_DZ) y = *reinterpret_cast<const float4*>(ry + q_raw[j]);
-          v = make_float4(xform1(a.x, y.x, cc), xform1(a.y, y.y, cc), xform1(a.z, y.z, cc),
-                          xform1(a.w, y.w, cc));
+          v = make_float4(xform1(a.x, cc), xform1(a.y, cc), xform1(a.z, cc), xform1(a.w, cc));
         }
         float* d = sdst + q_fin[j];
         if (KIND == K_S2) {
@@ -300,13 +303,11 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
         const int gx0 = (KIND == K_UP) ? X0 + TW : X0 - 1;
         const int sc0 = (KIND == K_UP) ? TW : 3;
         float h0 = 0.f;
-        if (rowok && gx0 >= 0 && gx0 < W_in)
-          h0 = xform1(rg[h_raw[j] + sc0], (INMODE == IN_DZ) ? ry[h_raw[j] + sc0] : 1.f, cc);
+        if (rowok && gx0 >= 0 && gx0 < W_in) h0 = xform1(rg[h_raw[j] + sc0], cc);
         sdst[h_fin[j] + sc0] = h0;
         if (KIND == K_S1) {
           float h1 = 0.f;
-          if (rowok && X0 + TW < W_in)
-            h1 = xform1(rg[h_raw[j] + TW + 4], (INMODE == IN_DZ) ? ry[h_raw[j] + TW + 4] : 1.f, cc);
+          if (rowok && X0 + TW < W_in) h1 = xform1(rg[h_raw[j] + TW + 4], cc);
           sdst[h_fin[j] + TW + 4] = h1;
         }
       }
@@ -321,14 +322,10 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
     int kk = P.w_flip ? 8 - k : k;
     s_w[idx] = P.w[(size_t)co * P.w_so + (size_t)ci * P.w_si + kk];
   }
-  if (tid < CI) {
-    if (INMODE == IN_AFFINE) {
-      BnCoef k = bn_coef(P.stats, tid, P.in_count, P.gamma, P.beta, P.rmean, P.rvar, P.train != 0);
-      s_c0[tid] = k.scale;
-      s_c1[tid] = k.shift;
-    } else {
-      s_dz[tid] = dz_coef(P.gamma, P.stats, P.dstats_next, tid, P.in_count);
-    }
+  if (INMODE == IN_AFFINE && tid < CI) {
+    BnCoef k = bn_coef(P.stats, tid, P.in_count, P.gamma, P.beta, P.rmean, P.rvar, P.train != 0);
+    s_c0[tid] = k.scale;
+    s_c1[tid] = k.shift;
   }
   if (tid < CO) {
     s_bias[tid] = (EPI == EPI_FWD && P.bias) ? P.bias[tid] : 0.f;
@@ -349,6 +346,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
   for (int c = 0; c < COT; ++c) st1[c] = st2[c] = 0.f;
 
   uint32_t phase = 0;
+  int it = 0;
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int tile = grp * NSUB + sub;
     const bool tvalid = tile < ntiles;
@@ -363,19 +361,20 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
       for (int c = 0; c < COT; ++c) acc[o][c] = 0.f;
 
 #pragma unroll 1
-    for (int ch = 0; ch < NCHUNK; ++ch) {
-      cv_mbar_wait(s_bar, phase);  // this stage's raw boxes have landed
+    for (int ch = 0; ch < NCHUNK; ++ch, ++it) {
+      const int buf = DIRECT ? (it & 1) : 0;
+      cv_mbar_wait(s_bar, phase);  // this stage's boxes have landed
       phase ^= 1;
-      transform(grp, ch);          // (the previous FMA loop finished before the last barrier)
-      __syncthreads();             // s_in ready; staging buffers free again
+      if (!DIRECT) transform(grp, ch);
+      __syncthreads();  // everyone has seen this phase (and, if staged, the tile is ready)
       // prefetch the next stage while computing this one
       if (ch + 1 < NCHUNK) {
-        issue(grp, ch + 1);
+        issue(grp, ch + 1, buf ^ 1);
       } else if (grp + (int)gridDim.x < ngroups) {
-        issue(grp + gridDim.x, 0);
+        issue(grp + gridDim.x, 0, buf ^ 1);
       }
       if (tvalid) {
-        const float* s_mine = s_in + sub * CIC * G::PLANE;
+        const float* s_mine = s_in + (DIRECT ? buf * C::STAGE : 0) + sub * C::FIN_SUB;
 #pragma unroll 2
         for (int ci = 0; ci < CIC; ++ci) {
           const float* tw = s_w + ((ch * CIC + ci) * 9) * CO + cog * COT;
@@ -442,7 +441,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
           }
         }
       }
-      __syncthreads();  // FMA loop done with s_in before the next transform overwrites it
+      __syncthreads();  // FMA loop done with this tile before it is overwritten
     }
     if (!tvalid) continue;
 
@@ -563,9 +562,8 @@ template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
 static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   using G = TileGeom<KIND, TW>;
   using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
-  const size_t smem = (size_t)((INMODE == IN_DZ ? 2 : 1) * C::RAW_STAGE + C::STAGE + CI * 9 * CO + 64 + 64 + 32) *
-                          sizeof(float) +
-                      32 * sizeof(DzCoef) + 32 * sizeof(double) + 16 + 128;
+  const size_t smem = (size_t)(C::BUF_FLOATS + CI * 9 * CO + 64 + 64 + 32) * sizeof(float) + 32 * sizeof(double) +
+                      16 + 128;
   auto kern = gconv_kernel<KIND, CI, CO, TW, INMODE, EPI>;
   static int max_ctas = 0;
   if (max_ctas == 0) {
@@ -585,14 +583,11 @@ static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   const int tiles_y = ((KIND == K_UP) ? P.H_in : H_out) / G::TH;
   const long long ntiles = (long long)P.B * tiles_x * tiles_y;
   if (ntiles == 0) return 0;
-  CUtensorMap map_in, map_y;
-  if (make_act_map(&map_in, P.in, (long long)P.B * CI, P.H_in, P.W_in, G::RAW_PITCH, G::IN_ROWS, C::CIC)) return 1;
-  if (make_act_map(&map_y, INMODE == IN_DZ ? P.in_y : P.in, (long long)P.B * CI, P.H_in, P.W_in, G::RAW_PITCH,
-                   G::IN_ROWS, C::CIC))
-    return 1;
+  CUtensorMap map_in;
+  if (make_act_map(&map_in, P.in, (long long)P.B * CI, P.H_in, P.W_in, C::BOX_W, G::IN_ROWS, C::CIC)) return 1;
   const long long ngroups = (ntiles + C::NSUB - 1) / C::NSUB;
   int grid = (int)(ngroups < max_ctas ? ngroups : max_ctas);
-  kern<<<grid, C::NT, smem, stream>>>(map_in, map_y, P);
+  kern<<<grid, C::NT, smem, stream>>>(map_in, P);
   return check_launch("gconv");
 }
 
@@ -605,24 +600,14 @@ static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
 // across the CTA's whole persistent loop and are reduced once at the end
 // (smem -> per-CTA partial in the workspace -> deterministic second-stage sum).
 struct WgradParams {
-  // "G" tensor (low resolution when S == 2)
-  const float* g_a;      // AFFINE: x ; DZ: g_out
-  const float* g_y;      // DZ: saved activation
-  // "I" tensor
-  const float* i_a;
-  const float* i_y;
-  // AFFINE coefficient sources (bn of this layer)
+  const float* g_a;  // "G" tensor (low resolution when S == 2): conv layers dz, convT layers x
+  const float* i_a;  // "I" tensor: conv layers x, convT layers dz
+  // BatchNorm of this layer (applied to x on load)
   const float* gamma;
   const float* beta;
   const double* stats;
   double bn_count;
-  // DZ coefficient sources (next bn)
-  const float* next_gamma;
-  const double* next_stats;
-  const double* next_dstats;
-  double next_count;
-  int relu_mask;
-  float* partial;  // [grid][CG*CI*9 + nbias]
+  float* partial;  // [grid][CG*CI*9 + 32]
   int B, Hg, Wg;   // dims of the G tensor
 };
 
@@ -648,8 +633,7 @@ struct WTile {
 // next-BN backward + ReLU backward on the other, literal zeros for padding).
 template <int S, int CG, int CI, int TWG, int CONVT>
 __global__ void __launch_bounds__(256, 2)
-    wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_gy,
-                 const __grid_constant__ CUtensorMap map_i, const __grid_constant__ CUtensorMap map_iy,
+    wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_i,
                  const WgradParams P) {
   using T = WTile<S, TWG>;
   constexpr int GT = (CI == 1) ? 1 : 8;   // g-channels per thread
@@ -669,10 +653,8 @@ __global__ void __launch_bounds__(256, 2)
   extern __shared__ __align__(128) float smem[];
   float* s_g = smem;                                   // [CG][G_PLANE]
   float* s_i = s_g + G_PAD;                            // [CI][I_PLANE]
-  float* s_y = s_i + I_PAD;                            // saved activation of the DZ side
-  float* s_aff = s_y + (CONVT ? I_PAD : G_PAD);        // AFFINE coefs: scale[32] | shift[32]
-  DzCoef* s_dz = reinterpret_cast<DzCoef*>(s_aff + 64);  // DZ coefs [32]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dz + 32);
+  float* s_aff = s_i + I_PAD;                          // BN coefs: scale[32] | shift[32]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_aff + 64);
 
   const int tid = threadIdx.x;
   const bool active = tid < NACT;
@@ -693,19 +675,17 @@ __global__ void __launch_bounds__(256, 2)
   // coefficients
   if (tid < 32) {
     const int c = tid;
-    constexpr int CA = CONVT ? CG : CI;  // channels on the AFFINE side
-    constexpr int CD = CONVT ? CI : CG;  // channels on the DZ side
+    constexpr int CA = CONVT ? CG : CI;  // channels of x
     if (c < CA) {
       BnCoef k = bn_coef(P.stats, c, P.bn_count, P.gamma, P.beta, nullptr, nullptr, true);
       s_aff[c] = k.scale;
       s_aff[32 + c] = k.shift;
     }
-    if (c < CD) s_dz[c] = dz_coef(P.next_gamma, P.next_stats, P.next_dstats, c, P.next_count);
   }
   // per-thread transform work lists (identical for every tile)
   int g_off[GITERS], g_ch[GITERS];
 #pragma unroll
-  for (int j = 0; j < GITERS; ++j) {
+  for (int j = 0; j < (CONVT ? GITERS : 0); ++j) {
     const int t = tid + j * 256;
     g_ch[j] = -1;
     g_off[j] = 0;
@@ -719,7 +699,7 @@ __global__ void __launch_bounds__(256, 2)
   }
   int i_off[IITERS], i_meta[IITERS];   // meta: channel | row<<8 | quad<<16, -1 = none
 #pragma unroll
-  for (int j = 0; j < IITERS; ++j) {
+  for (int j = 0; j < (CONVT ? 0 : IITERS); ++j) {
     const int t = tid + j * 256;
     i_meta[j] = -1;
     i_off[j] = 0;
@@ -753,70 +733,42 @@ __global__ void __launch_bounds__(256, 2)
     const int X0 = S * gx0;
     __syncthreads();  // previous tile's FMA loop is done with the buffers
     if (tid == 0) {
-      constexpr uint32_t BYTES = (uint32_t)(G_FLOATS * 4 * (CONVT ? 1 : 2) +
-                                            CI * T::I_PLANE_RAW * 4 * (CONVT ? 2 : 1));
+      constexpr uint32_t BYTES = (uint32_t)(G_FLOATS * 4 + CI * T::I_PLANE_RAW * 4);
       cv_mbar_expect_tx(s_bar, BYTES);
       cv_tma_load_3d(s_g, &map_g, gx0, gy0, n * CG, s_bar);
-      if (!CONVT) cv_tma_load_3d(s_y, &map_gy, gx0, gy0, n * CG, s_bar);
       cv_tma_load_3d(s_i, &map_i, X0 - 4, iy0, n * CI, s_bar);
-      if (CONVT) cv_tma_load_3d(s_y, &map_iy, X0 - 4, iy0, n * CI, s_bar);
     }
     cv_mbar_wait(s_bar, phase);
     phase ^= 1;
-    // ---- in-place transform of the G tile (always in range)
+    if (CONVT) {
+      // ---- G = x: BatchNorm in place (no halo, always in range)
 #pragma unroll
-    for (int j = 0; j < GITERS; ++j) {
-      const int c = g_ch[j];
-      if (c < 0) continue;
-      float4* p = reinterpret_cast<float4*>(s_g + g_off[j]);
-      const float4 a = *p;
-      float4 v;
-      if (CONVT) {
-        const float sc = s_aff[c], sh = s_aff[32 + c];
-        v = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
-      } else {
-        const float4 yv = *reinterpret_cast<const float4*>(s_y + g_off[j]);
-        const DzCoef k = s_dz[c];
-        const bool m = P.relu_mask != 0;
-        v.x = (m && !(yv.x > 0.f)) ? 0.f : dz_apply(k, a.x, yv.x);
-        v.y = (m && !(yv.y > 0.f)) ? 0.f : dz_apply(k, a.y, yv.y);
-        v.z = (m && !(yv.z > 0.f)) ? 0.f : dz_apply(k, a.z, yv.z);
-        v.w = (m && !(yv.w > 0.f)) ? 0.f : dz_apply(k, a.w, yv.w);
-      }
-      *p = v;
-    }
-    // ---- in-place transform of the I tile; zero rows/cols outside the image AFTER the transform
-#pragma unroll
-    for (int j = 0; j < IITERS; ++j) {
-      const int m = i_meta[j];
-      if (m < 0) continue;
-      const int c = m & 0xff;
-      const int gy = iy0 + ((m >> 8) & 0xff);
-      const int gx = X0 - 4 + 4 * (m >> 16);
-      float4* p = reinterpret_cast<float4*>(s_i + i_off[j]);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy >= 0 && gy < Hi) {
+      for (int j = 0; j < GITERS; ++j) {
+        const int c = g_ch[j];
+        if (c < 0) continue;
+        float4* p = reinterpret_cast<float4*>(s_g + g_off[j]);
         const float4 a = *p;
-        if (CONVT) {
-          const float4 yv = *reinterpret_cast<const float4*>(s_y + i_off[j]);
-          const DzCoef k = s_dz[c];
-          const bool mk = P.relu_mask != 0;
-          v.x = (mk && !(yv.x > 0.f)) ? 0.f : dz_apply(k, a.x, yv.x);
-          v.y = (mk && !(yv.y > 0.f)) ? 0.f : dz_apply(k, a.y, yv.y);
-          v.z = (mk && !(yv.z > 0.f)) ? 0.f : dz_apply(k, a.z, yv.z);
-          v.w = (mk && !(yv.w > 0.f)) ? 0.f : dz_apply(k, a.w, yv.w);
-        } else {
+        const float sc = s_aff[c], sh = s_aff[32 + c];
+        *p = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
+      }
+    } else {
+      // ---- I = x: BatchNorm in place; rows/cols outside the image are zero AFTER the transform
+#pragma unroll
+      for (int j = 0; j < IITERS; ++j) {
+        const int m = i_meta[j];
+        if (m < 0) continue;
+        const int c = m & 0xff;
+        const int gy = iy0 + ((m >> 8) & 0xff);
+        const int gx = X0 - 4 + 4 * (m >> 16);   // quads are entirely inside or outside the image
+        float4* p = reinterpret_cast<float4*>(s_i + i_off[j]);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < Hi && gx >= 0 && gx < Wi) {
+          const float4 a = *p;
           const float sc = s_aff[c], sh = s_aff[32 + c];
           v = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
         }
-        if (gx < 0 || gx >= Wi) v = make_float4(0.f, 0.f, 0.f, (gx + 3 >= 0 && gx + 3 < Wi) ? v.w : 0.f);
-        if (gx >= 0) {
-          if (gx + 1 >= Wi) v.y = 0.f;
-          if (gx + 2 >= Wi) v.z = 0.f;
-          if (gx + 3 >= Wi) v.w = 0.f;
-        }
+        *p = v;
       }
-      *p = v;
     }
     __syncthreads();
     if (!active) continue;
@@ -905,7 +857,7 @@ static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStrea
   using T = WTile<S, TWG>;
   constexpr int G_PAD = (CG * T::G_PLANE + 31) / 32 * 32;
   constexpr int I_PAD = (CI * T::I_PLANE + 31) / 32 * 32;
-  size_t smem_f = (size_t)G_PAD + I_PAD + (CONVT ? I_PAD : G_PAD) + 64 + 32 * sizeof(DzCoef) / sizeof(float) + 8;
+  size_t smem_f = (size_t)G_PAD + I_PAD + 64 + 8;
   if (smem_f < (size_t)CG * CI * 9 + 32) smem_f = (size_t)CG * CI * 9 + 32;
   const size_t smem = smem_f * sizeof(float) + 128;
   auto kern = wgrad_kernel<S, CG, CI, TWG, CONVT>;
@@ -924,16 +876,12 @@ static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStrea
   const long long ntiles = (long long)P.B * (P.Wg / TWG) * (P.Hg / T::THG);
   int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
   if (grid > 296) grid = 296;  // workspace bound, see ava_b200_bnconv_bwd_weight_ws
-  CUtensorMap map_g, map_gy, map_i, map_iy;
+  CUtensorMap map_g, map_i;
   if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, TWG, T::THG, CG)) return 1;
-  if (make_act_map(&map_gy, CONVT ? P.g_a : P.g_y, (long long)P.B * CG, P.Hg, P.Wg, TWG, T::THG, CG)) return 1;
   if (make_act_map(&map_i, P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS, CI)) return 1;
-  if (make_act_map(&map_iy, CONVT ? P.i_y : P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS,
-                   CI))
-    return 1;
   P.partial = reinterpret_cast<float*>(ws);
   const int stride = CG * CI * 9 + 32;
-  kern<<<grid, 256, smem, stream>>>(map_g, map_gy, map_i, map_iy, P);
+  kern<<<grid, 256, smem, stream>>>(map_g, map_i, P);
   if (check_launch("wgrad")) return 1;
   reduce_partials_kernel<<<(CG * CI * 9 + 127) / 128, 128, 0, stream>>>(P.partial, grid, stride, CG * CI * 9, dw,
                                                                         0);
@@ -1018,9 +966,7 @@ extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, c
   return 1;
 }
 
-extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* g_out, const float* y,
-                                        const float* next_gamma, const double* next_stats,
-                                        const double* next_dstats, const float* w, const float* x,
+extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const float* w, const float* x,
                                         const double* stats_in, float* g_in, double* dstats, void* stream_) {
   AVA_REQUIRE(layer >= 0 && layer < 14, "bnconv_bwd_data: bad layer %d", layer);
   if (B <= 0) return 0;
@@ -1028,13 +974,7 @@ extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* g_out, co
   const LayerGeom& L = kLayers[layer];
   const int ho = h_out_of(L);
   GconvParams P = {};
-  P.in = g_out;
-  P.in_y = y;
-  P.gamma = next_gamma;
-  P.stats = next_stats;
-  P.dstats_next = next_dstats;
-  P.relu_mask = L.relu;
-  P.in_count = (double)B * ho * ho;
+  P.in = dz;
   P.w = w;
   P.out = g_in;
   P.x_self = x;
@@ -1053,20 +993,20 @@ extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* g_out, co
     P.w_flip = 0;
   }
   switch (layer) {
-    case 0: return launch_gconv<K_S1, 8, 1, 32, IN_DZ, EPI_BWD>(P, stream);
-    case 1: return launch_gconv<K_UP, 8, 8, 32, IN_DZ, EPI_BWD>(P, stream);
-    case 2: return launch_gconv<K_S1, 16, 8, 32, IN_DZ, EPI_BWD>(P, stream);
-    case 3: return launch_gconv<K_UP, 16, 16, 32, IN_DZ, EPI_BWD>(P, stream);
-    case 4: return launch_gconv<K_S1, 24, 16, 32, IN_DZ, EPI_BWD>(P, stream);
-    case 5: return launch_gconv<K_UP, 24, 24, 16, IN_DZ, EPI_BWD>(P, stream);
-    case 6: return launch_gconv<K_S1, 32, 24, 16, IN_DZ, EPI_BWD>(P, stream);
-    case 7: return launch_gconv<K_S1, 24, 32, 16, IN_DZ, EPI_BWD>(P, stream);
-    case 8: return launch_gconv<K_S2, 24, 24, 16, IN_DZ, EPI_BWD>(P, stream);
-    case 9: return launch_gconv<K_S1, 16, 24, 32, IN_DZ, EPI_BWD>(P, stream);
-    case 10: return launch_gconv<K_S2, 16, 16, 32, IN_DZ, EPI_BWD>(P, stream);
-    case 11: return launch_gconv<K_S1, 8, 16, 32, IN_DZ, EPI_BWD>(P, stream);
-    case 12: return launch_gconv<K_S2, 8, 8, 32, IN_DZ, EPI_BWD>(P, stream);
-    case 13: return launch_gconv<K_S1, 1, 8, 32, IN_DZ, EPI_BWD>(P, stream);
+    case 0: return launch_gconv<K_S1, 8, 1, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 1: return launch_gconv<K_UP, 8, 8, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 2: return launch_gconv<K_S1, 16, 8, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 3: return launch_gconv<K_UP, 16, 16, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 4: return launch_gconv<K_S1, 24, 16, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 5: return launch_gconv<K_UP, 24, 24, 16, IN_PLAIN, EPI_BWD>(P, stream);
+    case 6: return launch_gconv<K_S1, 32, 24, 16, IN_PLAIN, EPI_BWD>(P, stream);
+    case 7: return launch_gconv<K_S1, 24, 32, 16, IN_PLAIN, EPI_BWD>(P, stream);
+    case 8: return launch_gconv<K_S2, 24, 24, 16, IN_PLAIN, EPI_BWD>(P, stream);
+    case 9: return launch_gconv<K_S1, 16, 24, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 10: return launch_gconv<K_S2, 16, 16, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 11: return launch_gconv<K_S1, 8, 16, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 12: return launch_gconv<K_S2, 8, 8, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 13: return launch_gconv<K_S1, 1, 8, 32, IN_PLAIN, EPI_BWD>(P, stream);
   }
   return 1;
 }
@@ -1079,9 +1019,7 @@ extern "C" long long ava_b200_bnconv_bwd_weight_ws(int layer, int B) {
   return (long long)296 * (L.cin * L.cout * 9 + 32) * (long long)sizeof(float);
 }
 
-extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* g_out, const float* y,
-                                          const float* next_gamma, const double* next_stats,
-                                          const double* next_dstats, const float* x, const float* gamma,
+extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, const float* x, const float* gamma,
                                           const float* beta, const double* stats_in, float* dw, float* db,
                                           void* ws, void* stream_) {
   AVA_REQUIRE(layer >= 0 && layer < 14, "bnconv_bwd_weight: bad layer %d", layer);
@@ -1095,17 +1033,11 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* g_out, 
   P.beta = beta;
   P.stats = stats_in;
   P.bn_count = (double)B * L.h_in * L.h_in;
-  P.next_gamma = next_gamma;
-  P.next_stats = next_stats;
-  P.next_dstats = next_dstats;
-  P.next_count = (double)B * ho * ho;
-  P.relu_mask = L.relu;
   P.B = B;
   int rc = 1;
   if (!L.transposed) {
     // G = dz (output resolution), I = bn(x) (input resolution)
-    P.g_a = g_out;
-    P.g_y = y;
+    P.g_a = dz;
     P.i_a = x;
     P.Hg = P.Wg = ho;
     switch (layer) {
@@ -1121,8 +1053,7 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* g_out, 
   } else {
     // G = bn(x) (input resolution), I = dz (output resolution)
     P.g_a = x;
-    P.i_a = g_out;
-    P.i_y = y;
+    P.i_a = dz;
     P.Hg = P.Wg = L.h_in;
     switch (layer) {
       case 7: rc = launch_wgrad<1, 32, 24, 16, 1>(P, dw, db, ws, stream); break;

@@ -84,9 +84,9 @@ __global__ void bn_param_grads_kernel(const double* stats, const double* dstats,
 }
 
 __global__ void __launch_bounds__(256)
-bn_relu_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ a, const float* gamma,
+bn_relu_bwd_apply_kernel(const float* g, const float* __restrict__ a, const float* gamma,
                          const double* stats, const double* dstats, int C, int HW, double count, long long n4,
-                         float* __restrict__ out) {
+                         int relu, float* out) {
   // HW is a multiple of 4, so a float4 never straddles a channel
   __shared__ DzCoef s_k[32];
   if (threadIdx.x < C) s_k[threadIdx.x] = dz_coef(gamma, stats, dstats, threadIdx.x, count);
@@ -95,13 +95,13 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ 
        i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(((i * 4) / HW) % C);
     const DzCoef k = s_k[c];
-    float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 gv = reinterpret_cast<const float4*>(g)[i];
     float4 av = __ldg(reinterpret_cast<const float4*>(a) + i);
     float4 o;
-    o.x = av.x > 0.f ? dz_apply(k, gv.x, av.x) : 0.f;
-    o.y = av.y > 0.f ? dz_apply(k, gv.y, av.y) : 0.f;
-    o.z = av.z > 0.f ? dz_apply(k, gv.z, av.z) : 0.f;
-    o.w = av.w > 0.f ? dz_apply(k, gv.w, av.w) : 0.f;
+    o.x = (relu && !(av.x > 0.f)) ? 0.f : dz_apply(k, gv.x, av.x);
+    o.y = (relu && !(av.y > 0.f)) ? 0.f : dz_apply(k, gv.y, av.y);
+    o.z = (relu && !(av.z > 0.f)) ? 0.f : dz_apply(k, gv.z, av.z);
+    o.w = (relu && !(av.w > 0.f)) ? 0.f : dz_apply(k, gv.w, av.w);
     reinterpret_cast<float4*>(out)[i] = o;
   }
 }
@@ -263,14 +263,15 @@ extern "C" int ava_b200_bn_param_grads(const double* stats, const double* dstats
 }
 
 extern "C" int ava_b200_bn_relu_bwd_apply(const float* g, const float* a, const float* gamma, const double* stats,
-                                          const double* dstats, int B, int C, int HW, float* out, void* stream) {
+                                          const double* dstats, int B, int C, int HW, int relu, float* out,
+                                          void* stream) {
   AVA_REQUIRE(HW % 4 == 0, "bn_relu_bwd_apply: HW=%d must be a multiple of 4", HW);
   if (B <= 0) return 0;
   long long n4 = (long long)B * C * HW / 4;
   int grid = (int)((n4 + 255) / 256);
   if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
   bn_relu_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, a, gamma, stats, dstats, C, HW,
-                                                                   (double)B * HW, n4, out);
+                                                                   (double)B * HW, n4, relu, out);
   return check_launch("bn_relu_bwd_apply");
 }
 

@@ -444,21 +444,26 @@ class VAE(nn.Module):
         return cache[B]
 
     def _conv_bwd(self, l, bufs, g_out, y, x, g_in, has_next_bn):
-        """Backward of fused layer l: weight/bias grads into the flat gradient buffer,
-        data gradient (w.r.t. this layer's BN output) into g_in, dstats[l]."""
+        """Backward of fused layer l.  (1) g_out -> dz IN PLACE: next BatchNorm's backward +
+        this layer's ReLU backward, one elementwise pass; (2) weight/bias gradients into the
+        flat gradient buffer; (3) data gradient (w.r.t. this layer's BN output) into g_in
+        and dstats[l] (this BN's dbeta / dgamma sums)."""
         B = bufs.B
-        name = _LAYERS[l][0]
+        name, _, co, _, _ = _LAYERS[l]
+        relu = 0 if l == 13 else 1
         st, ds = bufs.stats.data_ptr(), bufs.dstats.data_ptr()
-        ng = self._p("bn%d.weight" % (l + 2)) if has_next_bn else None
-        ns = st + 8 * 64 * (l + 1) if has_next_bn else None
-        nd = ds + 8 * 64 * (l + 1) if has_next_bn else None
-        ws = self._ws(self._scratch_need)
         s = _stream()
-        call("ava_b200_bnconv_bwd_weight", l, B, ptr(g_out), ptr(y), ng, ns, nd, ptr(x),
-             self._p("bn%d.weight" % (l + 1)), self._p("bn%d.bias" % (l + 1)), st + 8 * 64 * l,
-             self._g(name + ".weight"), self._g(name + ".bias"), ptr(ws), s)
-        call("ava_b200_bnconv_bwd_data", l, B, ptr(g_out), ptr(y), ng, ns, nd,
-             self._p(name + ".weight"), ptr(x), st + 8 * 64 * l, ptr(g_in), ds + 8 * 64 * l, s)
+        if relu or has_next_bn:
+            hw = _out_hw(l) ** 2
+            ng = self._p("bn%d.weight" % (l + 2)) if has_next_bn else None
+            call("ava_b200_bn_relu_bwd_apply", ptr(g_out), ptr(y), ng, st + 8 * 64 * (l + 1),
+                 ds + 8 * 64 * (l + 1), B, co, hw, relu, ptr(g_out), s)
+        ws = self._ws(self._scratch_need)
+        call("ava_b200_bnconv_bwd_weight", l, B, ptr(g_out), ptr(x), self._p("bn%d.weight" % (l + 1)),
+             self._p("bn%d.bias" % (l + 1)), st + 8 * 64 * l, self._g(name + ".weight"),
+             self._g(name + ".bias"), ptr(ws), s)
+        call("ava_b200_bnconv_bwd_data", l, B, ptr(g_out), self._p(name + ".weight"), ptr(x),
+             st + 8 * 64 * l, ptr(g_in), ds + 8 * 64 * l, s)
 
     def _backward_native(self, bufs, after_decoder=None):
         """Backward of the whole loss; leaves every parameter gradient in the flat
@@ -476,7 +481,7 @@ class VAE(nn.Module):
         # ---- bn8 backward + fc8's ReLU
         st, ds = bufs.stats.data_ptr(), bufs.dstats.data_ptr()
         call("ava_b200_bn_relu_bwd_apply", ptr(g_cur), ptr(bufs.t8), self._p("bn8.weight"),
-             st + 8 * 64 * 7, ds + 8 * 64 * 7, B, 32, 256, ptr(bufs.dt8), s)
+             st + 8 * 64 * 7, ds + 8 * 64 * 7, B, 32, 256, 1, ptr(bufs.dt8), s)
         # ---- decoder dense layers
         self._linear_bwd(bufs.dt8, 8192, None, bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.dt7, 1024,
                          B, 8192, 1024, tc=self._tc)

@@ -60,10 +60,10 @@ def algorithmic(key, args, B):
         if name.endswith("fwd"):
             return 4.0 * B * (n_in + n_out), 2.0 * B * macs
         if name.endswith("bwd_data"):
-            # reads g_out, y (out-shaped), x (in-shaped, for dgamma); writes g_in
+            # reads dz (out-shaped), x (in-shaped, for dgamma); writes g_in
             w = 0 if l == 0 else n_in
-            return 4.0 * B * (2 * n_out + n_in + w), 2.0 * B * macs
-        return 4.0 * B * (2 * n_out + n_in), 2.0 * B * macs   # reads g_out, y, x
+            return 4.0 * B * (n_out + n_in + w), 2.0 * B * macs
+        return 4.0 * B * (n_out + n_in), 2.0 * B * macs   # reads dz, x
     if name == "ava_b200_linear_fwd":
         M, N, K, groups = args[6], args[7], args[8], args[10]
         return 4.0 * groups * (M * K + N * K + M * N), 2.0 * groups * M * N * K
@@ -84,7 +84,7 @@ def algorithmic(key, args, B):
         return 4.0 * Bn * C * HW, 3.0 * Bn * C * HW
     if name == "ava_b200_bn_relu_bwd_apply":
         Bn, C, HW = args[5], args[6], args[7]
-        return 4.0 * 3 * Bn * C * HW, 6.0 * Bn * C * HW
+        return 4.0 * 3 * Bn * C * HW, 8.0 * Bn * C * HW
     return 0.0, 0.0
 
 

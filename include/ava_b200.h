@@ -72,28 +72,25 @@ int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float*
                         const float* running_mean, const float* running_var, int train,
                         double* stats_out, void* stream);
 
-/* Backward-data of layer `layer`.  Inputs: g_out = gradient w.r.t. the NEXT BN's
- * output (or w.r.t. y itself when next_* are NULL), y = this layer's saved output.
- * The incoming gradient is first pushed through the next BN's backward and this
- * layer's ReLU on load:  dz = [y>0] * (p*g_out + q*y + r)  with p,q,r derived from
- * (next_gamma, next_stats, next_dstats, count).  Output: g_in = gradient w.r.t.
- * THIS layer's BN output (same shape as x), and dstats (this BN's dbeta=sum g_in,
- * dgamma=sum g_in*xhat) accumulated in the epilogue.  g_in may be NULL (layer 0:
- * only the bn1 parameter gradients are needed).  Replaces autograd's
- * cudnn_convolution_backward(input) + native_batch_norm_backward + threshold_backward
- * for ava/models/vae.py:352. */
-int ava_b200_bnconv_bwd_data(int layer, int B, const float* g_out, const float* y, const float* next_gamma,
-                             const double* next_stats, const double* next_dstats, const float* w,
-                             const float* x, const double* stats_in, float* g_in, double* dstats,
-                             void* stream);
+/* Backward of layer `layer`.  `dz` is the gradient w.r.t. this layer's PRE-activation
+ * conv output: the gradient arriving from the next layer already pushed through the next
+ * BatchNorm's backward and this layer's ReLU by ava_b200_bn_relu_bwd_apply (in place is
+ * fine).  For layer 13 (no ReLU, nothing after it) dz is the loss gradient itself.
+ *
+ * Backward-data: g_in = gradient w.r.t. THIS layer's BN output (same shape as x) and dstats
+ * (this BN's dbeta = sum g_in, sum g_in*(x-mean) = dgamma/invstd) accumulated in the
+ * epilogue.  g_in may be NULL (layer 0: only the bn1 parameter gradients are needed).
+ * Replaces autograd's cudnn_convolution_backward(input) + the statistics half of
+ * native_batch_norm_backward for ava/models/vae.py:352. */
+int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const float* w, const float* x,
+                             const double* stats_in, float* g_in, double* dstats, void* stream);
 
 /* Backward-weight of layer `layer`: dw (same layout as w) and db, OVERWRITTEN (not
- * accumulated).  x/gamma/beta/stats_in give bn(x) (recomputed on load); g_out/y/next_*
- * give dz as above.  ws: scratch of ava_b200_bnconv_bwd_weight_ws(layer,B) bytes. */
-int ava_b200_bnconv_bwd_weight(int layer, int B, const float* g_out, const float* y, const float* next_gamma,
-                               const double* next_stats, const double* next_dstats, const float* x,
-                               const float* gamma, const float* beta, const double* stats_in, float* dw,
-                               float* db, void* ws, void* stream);
+ * accumulated).  x/gamma/beta/stats_in give bn(x) (recomputed on load).
+ * ws: scratch of ava_b200_bnconv_bwd_weight_ws(layer,B) bytes. */
+int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, const float* x, const float* gamma,
+                               const float* beta, const double* stats_in, float* dw, float* db, void* ws,
+                               void* stream);
 long long ava_b200_bnconv_bwd_weight_ws(int layer, int B);
 
 /* BN backward finalisation: dgamma[c] = invstd*dstats[32+c], dbeta[c] = dstats[c]
@@ -102,10 +99,13 @@ int ava_b200_bn_param_grads(const double* stats, const double* dstats, const int
                             const long long* h_counts, float* grads, const int* h_dgamma_off,
                             const int* h_dbeta_off, void* stream);
 
-/* out = [a>0] * (p*g + q*a + r), per channel c = (i / HW) % C: BN backward + ReLU
- * backward as one elementwise pass (used at the fc8 -> bn8 seam). */
+/* out = [a>0] * (p*(g - c1) + q*(a - mean)), per channel c = (i / HW) % C: the backward of
+ * the BatchNorm that consumes `a` (train mode; fp64 coefficient math) followed by the ReLU
+ * backward of the layer that produced `a`, as one elementwise pass; out may alias g.
+ * gamma == NULL: no BatchNorm, only the ReLU mask.  relu == 0: no mask.  Produces the `dz`
+ * the conv backward kernels and the dense backward (fc8 -> bn8 seam) consume. */
 int ava_b200_bn_relu_bwd_apply(const float* g, const float* a, const float* gamma, const double* stats,
-                               const double* dstats, int B, int C, int HW, float* out, void* stream);
+                               const double* dstats, int B, int C, int HW, int relu, float* out, void* stream);
 
 /* ------------------------------------------------------------- dense (Linear) layers
  * Y[M,N] = act(X[M,K] . W[N,K]^T + b): torch.nn.Linear (+F.relu / torch.exp),

@@ -27,10 +27,8 @@ for job in jobs:
             L.call("ava_b200_bnconv_fwd", l, B, x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), gam.data_ptr(), bet.data_ptr(),
                    stats.data_ptr(), gam.data_ptr(), gam.data_ptr(), 1, stats.data_ptr()+8*128, s)
         elif kind == "bwdd":
-            L.call("ava_b200_bnconv_bwd_data", l, B, g.data_ptr(), y.data_ptr(), gam.data_ptr(), stats.data_ptr()+8*64, stats.data_ptr()+8*192,
-                   w.data_ptr(), x.data_ptr(), stats.data_ptr(), gin.data_ptr(), stats.data_ptr()+8*128, s)
+            L.call("ava_b200_bnconv_bwd_data", l, B, g.data_ptr(), w.data_ptr(), x.data_ptr(), stats.data_ptr(), gin.data_ptr(), stats.data_ptr()+8*128, s)
         else:
-            L.call("ava_b200_bnconv_bwd_weight", l, B, g.data_ptr(), y.data_ptr(), gam.data_ptr(), stats.data_ptr()+8*64, stats.data_ptr()+8*192,
-                   x.data_ptr(), gam.data_ptr(), bet.data_ptr(), stats.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), s)
+            L.call("ava_b200_bnconv_bwd_weight", l, B, g.data_ptr(), x.data_ptr(), gam.data_ptr(), bet.data_ptr(), stats.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), s)
     torch.cuda.synchronize()
 print("done")

@@ -130,19 +130,22 @@ def test_bnconv_bwd(L, l, next_bn):
     ng = dg2.data_ptr() if next_bn else None
     ns = dnstats.data_ptr() if next_bn else None
     nd = dndstats.data_ptr() if next_bn else None
+    # --- dz: next BN's backward + this layer's ReLU backward, in place over the gradient
+    relu = 0 if l == 13 else 1
+    L.call("ava_b200_bn_relu_bwd_apply", dR.data_ptr(), dy.data_ptr(), ng, ns, nd, B, co, ho * ho, relu,
+           dR.data_ptr(), stream())
     # --- weight gradient
     ws_bytes = L.lib().ava_b200_bnconv_bwd_weight_ws(l, B)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
     gw = torch.full(w.shape, 7.0, device="cuda")
     gb = torch.full((co,), 7.0, device="cuda")
-    L.call("ava_b200_bnconv_bwd_weight", l, B, dR.data_ptr(), dy.data_ptr(), ng, ns, nd, dx.data_ptr(),
-           dg.data_ptr(), dbeta.data_ptr(), dstats.data_ptr(), gw.data_ptr(), gb.data_ptr(),
-           ws.data_ptr(), stream())
+    L.call("ava_b200_bnconv_bwd_weight", l, B, dR.data_ptr(), dx.data_ptr(), dg.data_ptr(),
+           dbeta.data_ptr(), dstats.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), stream())
     # --- data gradient
     gin = torch.empty(B, ci, h, h, device="cuda")
     dst = torch.zeros(64, dtype=torch.float64, device="cuda")
-    L.call("ava_b200_bnconv_bwd_data", l, B, dR.data_ptr(), dy.data_ptr(), ng, ns, nd, dw_.data_ptr(),
-           dx.data_ptr(), dstats.data_ptr(), gin.data_ptr(), dst.data_ptr(), stream())
+    L.call("ava_b200_bnconv_bwd_data", l, B, dR.data_ptr(), dw_.data_ptr(), dx.data_ptr(),
+           dstats.data_ptr(), gin.data_ptr(), dst.data_ptr(), stream())
     torch.cuda.synchronize()
     assert rel_err(gw.cpu().numpy(), w.grad.numpy()) <= TOL, "dw"
     # a bias in front of a BatchNorm has (nearly) zero gradient: absolute tolerance scaled by
