@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
   float* s_w = smem + C::BUF_FLOATS;                // [CI][9][CO]
   float* s_c0 = s_w + CI * 9 * CO;                  // AFFINE scale
   float* s_c1 = s_c0 + 32;                          // AFFINE shift
-  float* s_red = s_c1 + 32;                         // [2*CO] cross-warp reduction
-  float* s_bias = s_red + 64;                       // [CO]
+  float* s_red = s_c1 + 32;                         // [8 warps][2*COT] per-warp partial sums
+  float* s_bias = s_red + 128;                      // [CO]
   double* s_meand = reinterpret_cast<double*>(s_bias + 32);  // [32] EPI_BWD: mean of own BN
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meand + 32);
 
@@ -331,7 +331,6 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
     s_bias[tid] = (EPI == EPI_FWD && P.bias) ? P.bias[tid] : 0.f;
     if (EPI == EPI_BWD) s_meand[tid] = P.stats_self[tid] / P.out_count;
   }
-  if (tid < 2 * CO) s_red[tid] = 0.f;
   __syncthreads();
 
   const int sub = tid / (64 * NCOG);
@@ -514,24 +513,34 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
     }
   }
 
-  // ---- per-channel statistics: warp shuffle -> smem atomics -> one fp64 atomic per channel
+  // ---- per-channel statistics: warp shuffle -> per-warp smem slots -> fixed-order sum ->
+  // one fp64 atomic per channel per CTA (the in-CTA part is deterministic)
   double* dst = (EPI == EPI_FWD) ? P.stats_out : P.dstats;
   if (dst != nullptr) {
+    const int warp = tid >> 5;
 #pragma unroll
     for (int c = 0; c < COT; ++c) {
       float a = warp_sum(st1[c]);
       float b = warp_sum(st2[c]);
       if ((tid & 31) == 0) {
-        atomicAdd(&s_red[cog * COT + c], a);
-        atomicAdd(&s_red[CO + cog * COT + c], b);
+        s_red[warp * 16 + c] = a;
+        s_red[warp * 16 + 8 + c] = b;
       }
     }
     __syncthreads();
     if (tid < CO) {
-      const double a = (double)s_red[tid], b = (double)s_red[CO + tid];
-      atomicAdd(&dst[tid], a);
+      const int mycog = tid / COT, c = tid % COT;
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < NT / 32; ++w) {
+        const int wcog = ((w * 32) % (64 * NCOG)) >> 6;
+        if (wcog == mycog) {
+          a += s_red[w * 16 + c];
+          b += s_red[w * 16 + 8 + c];
+        }
+      }
+      atomicAdd(&dst[tid], (double)a);
       // EPI_BWD: sum g*(x - mean) = sum g*x - mean * sum g, centred in fp64
-      atomicAdd(&dst[32 + tid], (EPI == EPI_BWD) ? b - s_meand[tid] * a : b);
+      atomicAdd(&dst[32 + tid], (EPI == EPI_BWD) ? (double)b - s_meand[tid] * (double)a : (double)b);
     }
   }
 }
@@ -562,7 +571,7 @@ template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
 static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   using G = TileGeom<KIND, TW>;
   using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
-  const size_t smem = (size_t)(C::BUF_FLOATS + CI * 9 * CO + 64 + 64 + 32) * sizeof(float) + 32 * sizeof(double) +
+  const size_t smem = (size_t)(C::BUF_FLOATS + CI * 9 * CO + 64 + 128 + 32) * sizeof(float) + 32 * sizeof(double) +
                       16 + 128;
   auto kern = gconv_kernel<KIND, CI, CO, TW, INMODE, EPI>;
   static int max_ctas = 0;
@@ -820,23 +829,26 @@ __global__ void __launch_bounds__(256, 2)
     }
   }
 
-  // ---- cross-group reduction in shared memory, then one partial per CTA
+  // ---- cross-group reduction in shared memory (pixel groups add in a fixed order, so the
+  // result is deterministic), then one partial per CTA
   __syncthreads();
-  float* s_red = smem;  // reuse: [CG*CI*9]
+  float* s_red = smem;  // reuse: [CG*CI*9 + 32]
   for (int idx = tid; idx < CG * CI * 9 + 32; idx += 256) s_red[idx] = 0.f;
   __syncthreads();
-  if (active) {
+  for (int turn = 0; turn < NPG; ++turn) {
+    if (active && pg == turn) {
 #pragma unroll
-    for (int g = 0; g < GT; ++g)
+      for (int g = 0; g < GT; ++g)
 #pragma unroll
-      for (int k = 0; k < 9; ++k) atomicAdd(&s_red[((gq * GT + g) * CI + ti) * 9 + k], acc[g][k]);
-    if (CONVT && gq == 0) atomicAdd(&s_red[CG * CI * 9 + ti], bs[0]);
-    if (!CONVT && ti == 0) {
+        for (int k = 0; k < 9; ++k) s_red[((gq * GT + g) * CI + ti) * 9 + k] += acc[g][k];
+      if (CONVT && gq == 0) s_red[CG * CI * 9 + ti] += bs[0];
+      if (!CONVT && ti == 0) {
 #pragma unroll
-      for (int g = 0; g < GT; ++g) atomicAdd(&s_red[CG * CI * 9 + gq * GT + g], bs[g]);
+        for (int g = 0; g < GT; ++g) s_red[CG * CI * 9 + gq * GT + g] += bs[g];
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
   float* dst = P.partial + (size_t)blockIdx.x * (CG * CI * 9 + 32);
   for (int idx = tid; idx < CG * CI * 9 + 32; idx += 256) dst[idx] = s_red[idx];
 

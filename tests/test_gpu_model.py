@@ -214,10 +214,12 @@ def test_epoch_loops_get_latent_and_checkpoint(vae_mod, tmp_path):
     la = model.train_step(x, noise=noise).item()
     lb = model2.train_step(x, noise=noise).item()
     assert abs(la - lb) <= 1e-6 * abs(la)
-    # (run-to-run bitwise equality is not guaranteed: the statistics reductions use atomics,
-    # and Adam's early, sign-like steps amplify that noise in near-zero gradients)
+    # (run-to-run bitwise equality is not guaranteed: cross-CTA statistics use fp64 atomics,
+    # and Adam's early, sign-like steps turn a sign flip of a near-zero gradient into a
+    # 2*lr difference of that weight -- so compare in the L2 sense)
+    from tests.helpers import l2_err
     for (k, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
-        assert rel_err(a.double().cpu().numpy(), b.double().cpu().numpy()) <= 5e-3, k
+        assert l2_err(a.double().cpu().numpy(), b.double().cpu().numpy()) <= 1e-2, k
     # get_latent: float64 [N, z], loader order, train-mode BN as in the reference (F8)
     lat = model.get_latent(loader)
     assert lat.shape == (20, 32) and lat.dtype == np.float64
