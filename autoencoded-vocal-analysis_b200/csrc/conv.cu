@@ -854,14 +854,24 @@ __global__ void __launch_bounds__(256, 2)
 
 }
 
-// second stage: out[j] = sum_p partial[p][j]
-__global__ void reduce_partials_kernel(const float* partial, int nparts, int stride, int n, float* out,
-                                       int out_off) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * stride + j];
-  out[out_off + j] = (float)s;
+constexpr int kWgradMaxCtas = 8 * kNumSMs;  // per-CTA partial slots in the workspace
+
+// second stage: out[j] = sum_p partial[p][j] for the weights (j < nw -> dw[j]) and the bias slots
+// (j >= nw -> db[j-nw]) in one launch; one warp per output element, lanes stride over the
+// partials and combine with a fixed-order shuffle tree (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int nparts, int stride, int nw, int nb,
+                       float* __restrict__ dw, float* __restrict__ db) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= nw + nb) return;
+  float s = 0.f;
+  for (int p = lane; p < nparts; p += 32) s += partial[(size_t)p * stride + j];
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (j < nw) dw[j] = s;
+    else db[j - nw] = s;
+  }
 }
 
 template <int S, int CG, int CI, int TWG, int CONVT>
@@ -887,7 +897,7 @@ static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStrea
   }
   const long long ntiles = (long long)P.B * (P.Wg / TWG) * (P.Hg / T::THG);
   int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
-  if (grid > 296) grid = 296;  // workspace bound, see ava_b200_bnconv_bwd_weight_ws
+  if (grid > kWgradMaxCtas) grid = kWgradMaxCtas;  // workspace bound, see ava_b200_bnconv_bwd_weight_ws
   CUtensorMap map_g, map_i;
   if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, TWG, T::THG, CG)) return 1;
   if (make_act_map(&map_i, P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS, CI)) return 1;
@@ -895,11 +905,9 @@ static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStrea
   const int stride = CG * CI * 9 + 32;
   kern<<<grid, 256, smem, stream>>>(map_g, map_i, P);
   if (check_launch("wgrad")) return 1;
-  reduce_partials_kernel<<<(CG * CI * 9 + 127) / 128, 128, 0, stream>>>(P.partial, grid, stride, CG * CI * 9, dw,
-                                                                        0);
-  if (check_launch("wgrad_reduce")) return 1;
-  reduce_partials_kernel<<<1, 32, 0, stream>>>(P.partial + CG * CI * 9, grid, stride, CONVT ? CI : CG, db, 0);
-  return check_launch("wgrad_bias_reduce");
+  constexpr int NW = CG * CI * 9, NB = CONVT ? CI : CG;
+  reduce_partials_kernel<<<(NW + NB + 7) / 8, 256, 0, stream>>>(P.partial, grid, stride, NW, NB, dw, db);
+  return check_launch("wgrad_reduce");
 }
 
 // ------------------------------------------------------------------------------------
@@ -1027,8 +1035,8 @@ extern "C" long long ava_b200_bnconv_bwd_weight_ws(int layer, int B) {
   (void)B;
   if (layer < 0 || layer >= 14) return 0;
   const LayerGeom& L = kLayers[layer];
-  // 296 per-CTA partials of (weights + 32 bias slots) floats
-  return (long long)296 * (L.cin * L.cout * 9 + 32) * (long long)sizeof(float);
+  // one partial of (weights + 32 bias slots) floats per resident CTA (up to 8 per SM)
+  return (long long)kWgradMaxCtas * (L.cin * L.cout * 9 + 32) * (long long)sizeof(float);
 }
 
 extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, const float* x, const float* gamma,

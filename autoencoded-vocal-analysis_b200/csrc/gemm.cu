@@ -197,15 +197,20 @@ splitk_reduce_kernel(const float* part, int splits, int groups, int M, int N, co
   }
 }
 
-// db[n] = sum_m (mask>0 ? dy : 0)[m, n]
+// db[n] = sum_m (mask>0 ? dy : 0)[m, n].  grid (ceil(N/32), row splits): each block sums its
+// slice of rows for 32 columns; with more than one split the per-split sums go to `part`
+// [splits][N] and colsum_finish_kernel adds them in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* dy, const float* mask, int ld, int M, int N, float* db) {
+colsum_kernel(const float* __restrict__ dy, const float* __restrict__ mask, int ld, int M, int N, int rows_per_split,
+              float* __restrict__ out) {
   __shared__ float s[8][33];
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int r = threadIdx.x >> 5;
+  const int m0 = blockIdx.y * rows_per_split;
+  const int m1 = min(M, m0 + rows_per_split);
   float acc = 0.f;
   if (n < N) {
-    for (int m = r; m < M; m += 8) {
+    for (int m = m0 + r; m < m1; m += 8) {
       float v = dy[(size_t)m * ld + n];
       if (mask && !(mask[(size_t)m * ld + n] > 0.f)) v = 0.f;
       acc += v;
@@ -216,8 +221,32 @@ colsum_kernel(const float* dy, const float* mask, int ld, int M, int N, float* d
   if (r == 0 && n < N) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x];
-    db[n] = t;
+    out[(size_t)blockIdx.y * N + n] = t;
   }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int splits, int N, float* __restrict__ db) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int sp = 0; sp < splits; ++sp) t += part[(size_t)sp * N + n];
+  db[n] = t;
+}
+
+static int launch_colsum(const float* dy, const float* mask, int ld, int M, int N, float* db, void* ws,
+                         long long ws_bytes, cudaStream_t stream) {
+  int splits = 1;
+  const int col_blocks = (N + 31) / 32;
+  while (col_blocks * splits < 2 * kNumSMs && M / (splits * 2) >= 64) splits *= 2;
+  if (ws == nullptr || ws_bytes < (long long)splits * N * 4) splits = 1;
+  const int rows = (M + splits - 1) / splits;
+  float* out = splits > 1 ? reinterpret_cast<float*>(ws) : db;
+  colsum_kernel<<<dim3(col_blocks, splits), 256, 0, stream>>>(dy, mask, ld, M, N, rows, out);
+  if (check_launch("colsum")) return 1;
+  if (splits > 1) {
+    colsum_finish_kernel<<<(N + 255) / 256, 256, 0, stream>>>(out, splits, N, db);
+    return check_launch("colsum_finish");
+  }
+  return 0;
 }
 
 void launch_splitk_reduce(const float* part, int splits, int M, int N, const float* bias, float* C, int ldc, int act,
@@ -354,9 +383,9 @@ extern "C" int ava_b200_linear_bwd_weight(const float* dy, int lddy, const float
   }
   if (db) {
     for (int g = 0; g < groups; ++g) {
-      colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
-          dy + (size_t)g * dy_gs, ymask ? ymask + (size_t)g * dy_gs : nullptr, lddy, M, N, db + (size_t)g * db_gs);
-      if (check_launch("colsum")) return 1;
+      if (launch_colsum(dy + (size_t)g * dy_gs, ymask ? ymask + (size_t)g * dy_gs : nullptr, lddy, M, N,
+                        db + (size_t)g * db_gs, ws, ws_bytes, (cudaStream_t)stream))
+        return 1;
     }
   }
   return 0;

@@ -121,7 +121,7 @@ class VAE(nn.Module):
     """
 
     def __init__(self, save_dir='', lr=1e-3, z_dim=32, model_precision=10.0,
-                 device_name="auto", *, precision='auto'):
+                 device_name="auto", *, precision='auto', cuda_graphs='auto'):
         super(VAE, self).__init__()
         self.save_dir = save_dir
         self.lr = lr
@@ -136,6 +136,9 @@ class VAE(nn.Module):
         assert precision in ('auto', 'fp32', 'tf32x3', 'tf32')
         self.precision = precision
         self._tc = {'auto': 2, 'fp32': 0, 'tf32x3': 2, 'tf32': 1}[precision]
+        # CUDA graphs for the train step: 'auto' = when the step is host-bound (batch <= 256)
+        assert cuda_graphs in ('auto', True, False)
+        self.cuda_graphs = cuda_graphs
         if self.save_dir != '' and not os.path.exists(self.save_dir):
             os.makedirs(self.save_dir)
         self._flat_ready = False
@@ -641,12 +644,66 @@ class VAE(nn.Module):
         return 0.5 * self.z_dim * math.log(2 * math.pi) + \
             0.5 * X_DIM * math.log(2 * math.pi / self.model_precision)
 
+    def _graph_wanted(self, B):
+        if self._dp_world > 1 or self._flat_p.device.type != "cuda":
+            return False
+        if self.cuda_graphs == 'auto':
+            return B <= 256
+        return bool(self.cuda_graphs)
+
+    def _train_step_graph(self, x, noise):
+        """The whole step (~140 launches) replayed as one CUDA graph per batch size: at
+        batch 64 the step is otherwise bound by host launch overhead.  The first two steps
+        at a new batch size run eagerly (they also warm up lazy initialisation), the third
+        is captured.  Inputs and noise are copied into static buffers before each replay."""
+        B = x.shape[0]
+        st = self._graphs.get(B)
+        if st is None:
+            dev = self._flat_p.device
+            st = self._graphs[B] = {
+                "count": 0, "graph": None,
+                "x": torch.empty(B, X_SHAPE[0], X_SHAPE[1], dtype=torch.float32, device=dev),
+                "ew": torch.empty(B, 1, dtype=torch.float32, device=dev),
+                "ed": torch.empty(B, self.z_dim, dtype=torch.float32, device=dev)}
+        st["x"].copy_(x, non_blocking=True)
+        if noise is not None:
+            st["ew"].copy_(noise[0].reshape(B, 1))
+            st["ed"].copy_(noise[1].reshape(B, self.z_dim))
+        else:
+            st["ew"].normal_()     # same draw order as rsample: eps_W first, then eps_D
+            st["ed"].normal_()
+        if st["graph"] is None:
+            st["count"] += 1
+            if st["count"] <= 2:
+                return self._train_step_eager(st["x"], (st["ew"], st["ed"]))
+            try:
+                g = torch.cuda.CUDAGraph()
+                host_step = self._step_host
+                with torch.cuda.graph(g):
+                    loss = self._train_step_eager(st["x"], (st["ew"], st["ed"]))
+                self._step_host = host_step      # capture records, it does not execute
+                st["graph"], st["loss"] = g, loss
+            except Exception:
+                self.cuda_graphs = False
+                torch.cuda.synchronize()
+                return self._train_step_eager(st["x"], (st["ew"], st["ed"]))
+        st["graph"].replay()
+        self._step_host += 1
+        return st["loss"]
+
     def train_step(self, x, noise=None):
         """zero_grad + forward + backward + Adam for one batch, entirely native
         (the body of the loop at ava/models/vae.py:347-353).  Returns the loss as a
         0-dim device tensor (no host sync).  Under data parallelism `x` is this rank's
         shard and the gradient all-reduce overlaps the encoder half of the backward."""
         self._ensure_optimizer_state()
+        self._require_cuda()
+        x = self._as_input(x)
+        if self._graph_wanted(x.shape[0]):
+            return self._train_step_graph(x, noise)
+        return self._train_step_eager(x, noise)
+
+    def _train_step_eager(self, x, noise):
         bufs = self._forward_native(x, noise, True, want_grad_seed=True)
         if self._dp_world > 1:
             early, late = self._grad_buckets()

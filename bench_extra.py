@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""
+Secondary measurements for the other BASELINE.json configs (one JSON object per line):
+
+  * train step at batch 64 (configs[1], CUDA-graph replay) and 256
+  * get_latent-style inference (configs[4]): encode-only specs/s, eval-mode BN, batch 1024
+  * shotgun front end (configs[3]): GPU get_spec windows/s on a synthetic finch-style corpus
+    (kernel only, and including the host-side sampling + coordinate tables), and end-to-end
+    train samples/s with windows generated on the fly
+
+    python bench_extra.py > profiles/r01_extra.jsonl
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "autoencoded-vocal-analysis_b200"
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FINCH_P = {  # examples/finch_window_mwe.py:29-49
+    'fs': 32000, 'num_freq_bins': 128, 'num_time_bins': 128, 'nperseg': 512, 'noverlap': 256,
+    'max_dur': 1e9, 'window_length': 0.12, 'min_freq': 400, 'max_freq': 10e3, 'spec_min_val': 2.0,
+    'spec_max_val': 6.5, 'mel': True, 'time_stretch': False, 'within_syll_normalize': False,
+}
+
+
+def timed(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, 1e3 * (time.perf_counter() - t0) / iters
+
+
+def main():
+    vae_mod = importlib.import_module(PKG + ".models.vae")
+    win_mod = importlib.import_module(PKG + ".models.window_vae_dataset")
+    torch.manual_seed(0)
+    out = []
+    # ---- train step at small batches
+    for B, graphs in ((64, True), (64, False), (256, True)):
+        model = vae_mod.VAE(device_name='cuda', cuda_graphs=graphs)
+        model.train()
+        x = torch.rand(B, 128, 128, device="cuda")
+        ms, wall = timed(lambda: model.train_step(x), 100, warmup=6)
+        out.append({"what": "train_step", "batch": B, "cuda_graph": graphs, "us_per_step": 1e3 * ms,
+                    "samples_per_s": B / (wall * 1e-3)})
+        del model
+    # ---- inference: encode only, eval-mode BN (get_latent inner loop)
+    model = vae_mod.VAE(device_name='cuda')
+    model.eval()
+    B = 1024
+    xs = [torch.rand(B, 128, 128, device="cuda") for _ in range(2)]
+    i = [0]
+
+    def enc():
+        bufs = model._buffers_for(B)
+        model._cur = bufs
+        model._scratch_need = model._scratch_need_for(B)
+        model._encode_native(xs[i[0] & 1], bufs, False)
+        i[0] += 1
+    with torch.no_grad():
+        ms, wall = timed(enc, 30)
+    out.append({"what": "get_latent encode (eval BN)", "batch": B, "ms_per_batch": ms,
+                "specs_per_s": B / (ms * 1e-3),
+                "hbm_GBps_layer_granular": 2.36e6 * B / (ms * 1e-3) / 1e9})
+    # ---- shotgun: synthetic corpus 16 files x 60 s @ 32 kHz int16, 2 ROIs per file
+    rng = np.random.default_rng(0)
+    fs = FINCH_P['fs']
+    n_files, dur = 16, 60.0
+    audio = [(3000 * rng.standard_normal(int(dur * fs))).astype(np.int16) for _ in range(n_files)]
+    rois = [np.array([[1.0, 25.0], [30.0, 58.0]]) for _ in range(n_files)]
+    names = ["f%02d.wav" % k for k in range(n_files)]
+    ds = win_mod.FixedWindowDataset(names, None, dict(FINCH_P), audio=audio, fs=fs, rois=rois)
+    for nb in (128, 1024):
+        ms, wall = timed(lambda: ds.sample_batch(nb), 20)
+        out.append({"what": "shotgun windows (host sampling + tables + GPU get_spec)", "batch": nb,
+                    "ms_per_batch_gpu": ms, "ms_per_batch_wall": wall, "windows_per_s": nb / (wall * 1e-3)})
+    # kernel only: same windows re-issued (tables already on the device)
+    nb = 1024
+    np.random.seed(0)
+    files, onsets = ds._draw(nb)
+    np.random.seed(None)
+    eng = ds._engine
+    wl = FINCH_P['window_length']
+    tt = np.linspace(onsets, onsets + wl, 128, axis=-1)
+    outbuf = torch.empty(nb, 128, 128, device="cuda")
+    lib = importlib.import_module(PKG + "._lib")
+    eng.specs(files, np.maximum(0, onsets - 0.05), onsets + wl + 0.05, tt, out=outbuf)
+    torch.cuda.synchronize()
+    captured = {}
+    orig_call = lib.call
+
+    def spy(name, *a):
+        captured["args"] = (name, a)
+        return orig_call(name, *a)
+    pre = importlib.import_module(PKG + ".preprocessing.utils")
+    pre.call = spy
+    eng.specs(files, np.maximum(0, onsets - 0.05), onsets + wl + 0.05, tt, out=outbuf)
+    pre.call = orig_call
+    keep = eng._keepalive
+    name, a = captured["args"]
+    ms, _ = timed(lambda: orig_call(name, *a), 50)
+    seg_bytes = int((0.22 * fs)) * 2
+    out.append({"what": "get_spec kernel only (fp64 STFT+log+resample)", "batch": nb, "us_per_launch": 1e3 * ms,
+                "windows_per_s": nb / (ms * 1e-3),
+                "hbm_GBps_algorithmic": nb * (seg_bytes + 65536) / (ms * 1e-3) / 1e9})
+    del keep
+    # end to end: windows generated on the fly feeding the train step
+    model = vae_mod.VAE(device_name='cuda')
+    model.train()
+    for nb in (128, 1024):
+        ms, wall = timed(lambda: model.train_step(ds.sample_batch(nb)), 15)
+        out.append({"what": "shotgun train step with on-the-fly GPU get_spec", "batch": nb,
+                    "ms_per_step_wall": wall, "samples_per_s": nb / (wall * 1e-3)})
+    for o in out:
+        print(json.dumps(o))
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,14 @@ LAYERS = [(1, 8, 1, 128, 0), (8, 8, 2, 128, 0), (8, 16, 1, 64, 0), (16, 16, 2, 6
 B = int(sys.argv[1]); jobs = sys.argv[2:]   # e.g. fwd:13 bwdd:13 bwdw:12
 s = torch.cuda.current_stream().cuda_stream
 for job in jobs:
+    if job == "fc1":
+        M, N, K = B, 1024, 8192
+        x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") * 0.01; bb = torch.zeros(N, device="cuda")
+        y = torch.empty(M, N, device="cuda")
+        wsb = L.lib().ava_b200_linear_ws_bytes(M, N, K); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        for rep in range(2):
+            L.call("ava_b200_linear_fwd", x.data_ptr(), K, w.data_ptr(), bb.data_ptr(), y.data_ptr(), N, M, N, K, 1, 1, 0, 0, 0, 0, 2, ws.data_ptr(), wsb, s)
+        torch.cuda.synchronize(); continue
     kind, l = job.split(":"); l = int(l)
     ci, co, st, h, tr = LAYERS[l]
     ho = h if st == 1 else (h*2 if tr else h//2)
@@ -23,7 +31,9 @@ for job in jobs:
     ws = torch.empty(L.lib().ava_b200_bnconv_bwd_weight_ws(l, B), dtype=torch.uint8, device="cuda")
     dw = torch.empty(ci*co*9, device="cuda"); db = torch.empty(32, device="cuda")
     for rep in range(2):
-        if kind == "fwd":
+        if kind == "ew":
+            L.call("ava_b200_bn_relu_bwd_apply", g.data_ptr(), y.data_ptr(), gam.data_ptr(), stats.data_ptr()+8*64, stats.data_ptr()+8*192, B, co, ho*ho, 1, g.data_ptr(), s)
+        elif kind == "fwd":
             L.call("ava_b200_bnconv_fwd", l, B, x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), gam.data_ptr(), bet.data_ptr(),
                    stats.data_ptr(), gam.data_ptr(), gam.data_ptr(), 1, stats.data_ptr()+8*128, s)
         elif kind == "bwdd":
