@@ -162,7 +162,7 @@ __device__ __forceinline__ void cv_tma_load_3d(void* smem_dst, const CUtensorMap
 // LSU cost, completion on an mbarrier).  IN_AFFINE: a short table-driven shared->shared pass
 // applies the BatchNorm scale/shift and writes literal zeros for the padding (padding is
 // applied AFTER BatchNorm).  IN_PLAIN: see GconvCfg::DIRECT.  2 (4 for CO=1) CTAs per SM.
-template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
+template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN>
 __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvCfg<KIND, CI, CO, TW, INMODE>::MINB)
     gconv_kernel(const __grid_constant__ CUtensorMap map_in, const GconvParams P) {
   using G = TileGeom<KIND, TW>;
@@ -185,13 +185,15 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meand + 32);
 
   const int tid = threadIdx.x;
-  const int H_in = P.H_in, W_in = P.W_in;
-  const int H_out = (KIND == K_S1) ? H_in : (KIND == K_S2 ? H_in / 2 : H_in * 2);
-  const int W_out = (KIND == K_S1) ? W_in : (KIND == K_S2 ? W_in / 2 : W_in * 2);
+  // every instantiation serves exactly one layer, so the image size is a compile-time constant
+  // (tile decoding and all address arithmetic fold to shifts / immediates)
+  constexpr int H_in = HIN, W_in = HIN;
+  constexpr int H_out = (KIND == K_S1) ? H_in : (KIND == K_S2 ? H_in / 2 : H_in * 2);
+  constexpr int W_out = (KIND == K_S1) ? W_in : (KIND == K_S2 ? W_in / 2 : W_in * 2);
   // tiles are counted in output space for S1/S2 and in input space for UP
-  const int tiles_x = ((KIND == K_UP) ? W_in : W_out) / TW;
-  const int tiles_y = ((KIND == K_UP) ? H_in : H_out) / G::TH;
-  const int tiles_per_img = tiles_x * tiles_y;
+  constexpr int tiles_x = ((KIND == K_UP) ? W_in : W_out) / TW;
+  constexpr int tiles_y = ((KIND == K_UP) ? H_in : H_out) / G::TH;
+  constexpr int tiles_per_img = tiles_x * tiles_y;
   const int ntiles = P.B * tiles_per_img;
   const int ngroups = (ntiles + NSUB - 1) / NSUB;
 
@@ -567,13 +569,17 @@ static int make_act_map(CUtensorMap* map, const float* base, long long nc, int H
   return 0;
 }
 
-template <int KIND, int CI, int CO, int TW, int INMODE, int EPI>
+template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN>
 static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   using G = TileGeom<KIND, TW>;
   using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
   const size_t smem = (size_t)(C::BUF_FLOATS + CI * 9 * CO + 64 + 128 + 32) * sizeof(float) + 32 * sizeof(double) +
                       16 + 128;
-  auto kern = gconv_kernel<KIND, CI, CO, TW, INMODE, EPI>;
+  if (P.H_in != HIN || P.W_in != HIN) {
+    set_error("gconv: layer geometry mismatch");
+    return 1;
+  }
+  auto kern = gconv_kernel<KIND, CI, CO, TW, INMODE, EPI, HIN>;
   static int max_ctas = 0;
   if (max_ctas == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -968,20 +974,20 @@ extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, c
     P.w_flip = (L.stride == 1) ? 1 : 0;
   }
   switch (layer) {
-    case 0: return launch_gconv<K_S1, 1, 8, 32, IN_AFFINE, EPI_FWD>(P, stream);
-    case 1: return launch_gconv<K_S2, 8, 8, 32, IN_AFFINE, EPI_FWD>(P, stream);
-    case 2: return launch_gconv<K_S1, 8, 16, 32, IN_AFFINE, EPI_FWD>(P, stream);
-    case 3: return launch_gconv<K_S2, 16, 16, 32, IN_AFFINE, EPI_FWD>(P, stream);
-    case 4: return launch_gconv<K_S1, 16, 24, 32, IN_AFFINE, EPI_FWD>(P, stream);
-    case 5: return launch_gconv<K_S2, 24, 24, 16, IN_AFFINE, EPI_FWD>(P, stream);
-    case 6: return launch_gconv<K_S1, 24, 32, 16, IN_AFFINE, EPI_FWD>(P, stream);
-    case 7: return launch_gconv<K_S1, 32, 24, 16, IN_AFFINE, EPI_FWD>(P, stream);
-    case 8: return launch_gconv<K_UP, 24, 24, 16, IN_AFFINE, EPI_FWD>(P, stream);
-    case 9: return launch_gconv<K_S1, 24, 16, 32, IN_AFFINE, EPI_FWD>(P, stream);
-    case 10: return launch_gconv<K_UP, 16, 16, 32, IN_AFFINE, EPI_FWD>(P, stream);
-    case 11: return launch_gconv<K_S1, 16, 8, 32, IN_AFFINE, EPI_FWD>(P, stream);
-    case 12: return launch_gconv<K_UP, 8, 8, 32, IN_AFFINE, EPI_FWD>(P, stream);
-    case 13: return launch_gconv<K_S1, 8, 1, 32, IN_AFFINE, EPI_FWD>(P, stream);
+    case 0: return launch_gconv<K_S1, 1, 8, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
+    case 1: return launch_gconv<K_S2, 8, 8, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
+    case 2: return launch_gconv<K_S1, 8, 16, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
+    case 3: return launch_gconv<K_S2, 16, 16, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
+    case 4: return launch_gconv<K_S1, 16, 24, 32, IN_AFFINE, EPI_FWD, 32>(P, stream);
+    case 5: return launch_gconv<K_S2, 24, 24, 16, IN_AFFINE, EPI_FWD, 32>(P, stream);
+    case 6: return launch_gconv<K_S1, 24, 32, 16, IN_AFFINE, EPI_FWD, 16>(P, stream);
+    case 7: return launch_gconv<K_S1, 32, 24, 16, IN_AFFINE, EPI_FWD, 16>(P, stream);
+    case 8: return launch_gconv<K_UP, 24, 24, 16, IN_AFFINE, EPI_FWD, 16>(P, stream);
+    case 9: return launch_gconv<K_S1, 24, 16, 32, IN_AFFINE, EPI_FWD, 32>(P, stream);
+    case 10: return launch_gconv<K_UP, 16, 16, 32, IN_AFFINE, EPI_FWD, 32>(P, stream);
+    case 11: return launch_gconv<K_S1, 16, 8, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
+    case 12: return launch_gconv<K_UP, 8, 8, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
+    case 13: return launch_gconv<K_S1, 8, 1, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
   }
   return 1;
 }
@@ -1013,20 +1019,20 @@ extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const
     P.w_flip = 0;
   }
   switch (layer) {
-    case 0: return launch_gconv<K_S1, 8, 1, 32, IN_PLAIN, EPI_BWD>(P, stream);
-    case 1: return launch_gconv<K_UP, 8, 8, 32, IN_PLAIN, EPI_BWD>(P, stream);
-    case 2: return launch_gconv<K_S1, 16, 8, 32, IN_PLAIN, EPI_BWD>(P, stream);
-    case 3: return launch_gconv<K_UP, 16, 16, 32, IN_PLAIN, EPI_BWD>(P, stream);
-    case 4: return launch_gconv<K_S1, 24, 16, 32, IN_PLAIN, EPI_BWD>(P, stream);
-    case 5: return launch_gconv<K_UP, 24, 24, 16, IN_PLAIN, EPI_BWD>(P, stream);
-    case 6: return launch_gconv<K_S1, 32, 24, 16, IN_PLAIN, EPI_BWD>(P, stream);
-    case 7: return launch_gconv<K_S1, 24, 32, 16, IN_PLAIN, EPI_BWD>(P, stream);
-    case 8: return launch_gconv<K_S2, 24, 24, 16, IN_PLAIN, EPI_BWD>(P, stream);
-    case 9: return launch_gconv<K_S1, 16, 24, 32, IN_PLAIN, EPI_BWD>(P, stream);
-    case 10: return launch_gconv<K_S2, 16, 16, 32, IN_PLAIN, EPI_BWD>(P, stream);
-    case 11: return launch_gconv<K_S1, 8, 16, 32, IN_PLAIN, EPI_BWD>(P, stream);
-    case 12: return launch_gconv<K_S2, 8, 8, 32, IN_PLAIN, EPI_BWD>(P, stream);
-    case 13: return launch_gconv<K_S1, 1, 8, 32, IN_PLAIN, EPI_BWD>(P, stream);
+    case 0: return launch_gconv<K_S1, 8, 1, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
+    case 1: return launch_gconv<K_UP, 8, 8, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
+    case 2: return launch_gconv<K_S1, 16, 8, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
+    case 3: return launch_gconv<K_UP, 16, 16, 32, IN_PLAIN, EPI_BWD, 32>(P, stream);
+    case 4: return launch_gconv<K_S1, 24, 16, 32, IN_PLAIN, EPI_BWD, 32>(P, stream);
+    case 5: return launch_gconv<K_UP, 24, 24, 16, IN_PLAIN, EPI_BWD, 16>(P, stream);
+    case 6: return launch_gconv<K_S1, 32, 24, 16, IN_PLAIN, EPI_BWD, 16>(P, stream);
+    case 7: return launch_gconv<K_S1, 24, 32, 16, IN_PLAIN, EPI_BWD, 16>(P, stream);
+    case 8: return launch_gconv<K_S2, 24, 24, 16, IN_PLAIN, EPI_BWD, 32>(P, stream);
+    case 9: return launch_gconv<K_S1, 16, 24, 32, IN_PLAIN, EPI_BWD, 32>(P, stream);
+    case 10: return launch_gconv<K_S2, 16, 16, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
+    case 11: return launch_gconv<K_S1, 8, 16, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
+    case 12: return launch_gconv<K_S2, 8, 8, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
+    case 13: return launch_gconv<K_S1, 1, 8, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
   }
   return 1;
 }
