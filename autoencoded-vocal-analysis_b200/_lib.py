@@ -22,6 +22,8 @@ SIGNATURES = {
     "ava_b200_bnconv_bwd_data": (I, I, P, P, P, P, P, P, P),
     "ava_b200_bnconv_bwd_weight": (I, I, P, P, P, P, P, P, P, P, P),
     "ava_b200_bnconv_bwd_weight_ws": (I, I),
+    "ava_b200_set_conv_precision": (I,),
+    "ava_b200_get_conv_precision": (),
     "ava_b200_bn_param_grads": (P, P, P, P, P, P, P, P),
     "ava_b200_bn_relu_bwd_apply": (P, P, P, P, P, I, I, I, I, P, P),
     "ava_b200_linear_fwd": (P, I, P, P, P, I, I, I, I, I, I, LL, LL, LL, LL, I, P, LL, P),
@@ -45,7 +47,7 @@ _RESTYPES = {
     "ava_b200_linear_ws_bytes": LL,
 }
 # entry points whose int return value is a status code
-_STATUS = {n for n in SIGNATURES if n not in _RESTYPES and n != "ava_b200_abi_version"}
+_STATUS = {n for n in SIGNATURES if n not in _RESTYPES and n not in ("ava_b200_abi_version", "ava_b200_get_conv_precision")}
 
 
 class AvaB200Error(RuntimeError):

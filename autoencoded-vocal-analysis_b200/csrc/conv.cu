@@ -72,9 +72,10 @@ struct TileGeom {
   //   S2: odd input columns at [3..TW+3] (j=0 is the left halo), even columns at [EO..EO+TW-1]
   //   UP: [0..TW-1]=interior, [TW]=right halo
   // pitches: interior 16-byte aligned, and for TW=16 (two row groups per warp) the second
-  // group lands 16 banks away from the first
+  // group lands 16 banks away from the first; stride-1 planes (IN_ROWS*PITCH) are 24 (mod 32)
+  // floats so that the tensor-core fragment loads (4 channels x 8 pixels per warp) hit 32 banks
   static constexpr int EO = TW + 4;
-  static constexpr int PITCH = (KIND == K_S1) ? (TW == 32 ? 40 : 28)
+  static constexpr int PITCH = (KIND == K_S1) ? (TW == 32 ? 44 : 28)
                                : (KIND == K_S2) ? (TW == 32 ? 68 : 38)
                                                 : (TW == 32 ? 36 : 24);
   static constexpr int PLANE = IN_ROWS * PITCH;
@@ -87,14 +88,23 @@ struct TileGeom {
   static constexpr int RAW_X_SHIFT = (KIND == K_UP) ? 0 : 4;
 };
 
-template <int KIND, int CI, int CO, int TW, int INMODE>
+// TERMS == 0: fp32 SIMT FMA loop.  TERMS == 1 / 3: the inner product runs on the tensor cores as
+// mma.sync m16n8k8 TF32 (1 term: operands rounded to TF32; 3 terms: error-compensated
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with x = x_hi + x_lo, fp32-level accuracy); every warp then
+// owns 4 output rows x 16 pixels x all output channels, one 8-input-channel chunk per stage;
+// a CTA is 4 warps on one 256-pixel sub-tile, 4 (3 for the widest layers) CTAs per SM, so that
+// the load / transform / MMA / epilogue phases of independent CTAs overlap.
+template <int KIND, int CI, int CO, int TW, int INMODE, int TERMS = 0>
 struct GconvCfg {
   using G = TileGeom<KIND, TW>;
+  static constexpr bool MMA = TERMS > 0;
   static constexpr int COT = (CO >= 8) ? 8 : CO;
   static constexpr int NCOG = CO / COT;
-  // threads: 64 slots x NCOG channel groups x NSUB sub-tiles (256, or 192 for CO=24)
-  static constexpr int NSUB = (NCOG >= 3) ? 1 : 4 / NCOG;
-  static constexpr int NT = 64 * NCOG * NSUB;
+  static constexpr int NTL = CO / 8;  // MMA: n-tiles of 8 output channels per warp
+  // threads: 64 slots x NCOG channel groups x NSUB sub-tiles (256, or 192 for CO=24);
+  // MMA: 4 warps on one sub-tile
+  static constexpr int NSUB = MMA ? 1 : (NCOG >= 3) ? 1 : 4 / NCOG;
+  static constexpr int NT = MMA ? 128 : 64 * NCOG * NSUB;
   // IN_PLAIN input (an already materialised gradient) needs no per-element transform and its
   // zero padding is exactly TMA's out-of-bounds fill: for the stride-1 / up kernels the boxes
   // land DIRECTly in the layout the FMA loop reads (double buffered, no staging pass at all).
@@ -105,7 +115,7 @@ struct GconvCfg {
   // input channels per pipeline stage: largest divisor of CI keeping a stage <= 37 KB
   static constexpr int LIMIT = 9472;
   static constexpr int stage_floats(int c) { return NSUB * c * BOX_PLANE; }
-  static constexpr int CIC = (CI % 8 == 0 && stage_floats(8) <= LIMIT)   ? 8
+  static constexpr int CIC = (MMA || (CI % 8 == 0 && stage_floats(8) <= LIMIT)) ? 8
                              : (CI % 4 == 0 && stage_floats(4) <= LIMIT) ? 4
                              : (CI % 2 == 0 && stage_floats(2) <= LIMIT) ? 2
                                                                          : 1;
@@ -122,8 +132,30 @@ struct GconvCfg {
   static constexpr int NHALO = CIC * G::IN_ROWS;
   static constexpr int HITERS = (NHALO + NT - 1) / NT;
   // CTAs per SM the register budget is tuned for
-  static constexpr int MINB = (COT == 1) ? 4 : 2;
+  static constexpr int MINB = (MMA || COT == 1) ? 4 : 2;
+  // staged weights: SIMT [CI][9][CO]; MMA: B fragments in register order
+  // [CI/8][9][NTL][32 lanes]: {b0,b1} TF32-rounded (TERMS 1); {b0_hi,b1_hi,b0_lo,b1_lo}
+  // (TERMS 3, PRESPLIT) or, for the widest layers, {b0,b1} in full fp32 split where used
+  static constexpr bool PRESPLIT = (TERMS == 3) && (CI * CO <= 384);
+  static constexpr int WF = PRESPLIT ? 4 : 2;   // floats per lane per fragment
+  static constexpr int W_FLOATS = CI * 9 * CO * (PRESPLIT ? 2 : 1);
+  static constexpr int RED_FLOATS = MMA ? 4 * 64 : 128;
+  static_assert(!MMA || (CI % 8 == 0 && CO % 8 == 0 && KIND == K_S1), "tensor-core path: stride-1, channels % 8");
 };
+
+__device__ __forceinline__ uint32_t cv_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// x with the low 13 mantissa bits cleared: exactly representable in TF32
+__device__ __forceinline__ uint32_t cv_tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+__device__ __forceinline__ void cv_mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 __device__ __forceinline__ uint32_t cv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cv_mbar_init(uint64_t* bar, uint32_t count) {
@@ -162,11 +194,12 @@ __device__ __forceinline__ void cv_tma_load_3d(void* smem_dst, const CUtensorMap
 // LSU cost, completion on an mbarrier).  IN_AFFINE: a short table-driven shared->shared pass
 // applies the BatchNorm scale/shift and writes literal zeros for the padding (padding is
 // applied AFTER BatchNorm).  IN_PLAIN: see GconvCfg::DIRECT.  2 (4 for CO=1) CTAs per SM.
-template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN>
-__global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvCfg<KIND, CI, CO, TW, INMODE>::MINB)
+template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN, int TERMS>
+__global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
+                                  GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::MINB)
     gconv_kernel(const __grid_constant__ CUtensorMap map_in, const GconvParams P) {
   using G = TileGeom<KIND, TW>;
-  using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
+  using C = GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>;
   constexpr int COT = C::COT, NCOG = C::NCOG, NSUB = C::NSUB, NT = C::NT;
   constexpr int CIC = C::CIC, NCHUNK = C::NCHUNK;
   constexpr bool DIRECT = C::DIRECT;
@@ -176,11 +209,11 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
   // DIRECT: [2][STAGE] ring of ready-to-use tiles; else [RAW_STAGE] staging + [STAGE] transformed
   float* s_raw = smem;
   float* s_in = DIRECT ? smem : smem + C::RAW_STAGE;
-  float* s_w = smem + C::BUF_FLOATS;                // [CI][9][CO]
-  float* s_c0 = s_w + CI * 9 * CO;                  // AFFINE scale
+  float* s_w = smem + C::BUF_FLOATS;                // [CI][9][CO] (MMA: B fragments, see GconvCfg)
+  float* s_c0 = s_w + C::W_FLOATS;                  // AFFINE scale
   float* s_c1 = s_c0 + 32;                          // AFFINE shift
-  float* s_red = s_c1 + 32;                         // [8 warps][2*COT] per-warp partial sums
-  float* s_bias = s_red + 128;                      // [CO]
+  float* s_red = s_c1 + 32;                         // per-warp partial sums
+  float* s_bias = s_red + C::RED_FLOATS;            // [CO]
   double* s_meand = reinterpret_cast<double*>(s_bias + 32);  // [32] EPI_BWD: mean of own BN
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meand + 32);
 
@@ -317,12 +350,37 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
   };
 
   // ---- one-time per CTA: weights, coefficients
-  for (int idx = tid; idx < CI * 9 * CO; idx += NT) {
-    int co = idx % CO;
-    int k = (idx / CO) % 9;
-    int ci = idx / (9 * CO);
-    int kk = P.w_flip ? 8 - k : k;
-    s_w[idx] = P.w[(size_t)co * P.w_so + (size_t)ci * P.w_si + kk];
+  if constexpr (C::MMA) {
+    // B fragments of mma.m16n8k8 (col): lane (g = lane>>2, t = lane&3) holds b0 = W[k=t][n=g],
+    // b1 = W[k=t+4][n=g], k = input channel within the 8-channel chunk, n = output channel
+    for (int idx = tid; idx < (CI / 8) * 9 * C::NTL * 32; idx += NT) {
+      const int ln = idx & 31;
+      int rest = idx >> 5;
+      const int nt = rest % C::NTL;
+      rest /= C::NTL;
+      const int k = rest % 9, ks = rest / 9;
+      const int co = nt * 8 + (ln >> 2), ci0 = ks * 8 + (ln & 3);
+      const int kk = P.w_flip ? 8 - k : k;
+      const float w0 = P.w[(size_t)co * P.w_so + (size_t)ci0 * P.w_si + kk];
+      const float w1 = P.w[(size_t)co * P.w_so + (size_t)(ci0 + 4) * P.w_si + kk];
+      if (C::PRESPLIT) {
+        const float h0 = __uint_as_float(cv_tf32(w0)), h1 = __uint_as_float(cv_tf32(w1));
+        *reinterpret_cast<float4*>(s_w + 4 * idx) = make_float4(h0, h1, w0 - h0, w1 - h1);
+      } else if (TERMS == 3) {
+        *reinterpret_cast<float2*>(s_w + 2 * idx) = make_float2(w0, w1);
+      } else {
+        *reinterpret_cast<float2*>(s_w + 2 * idx) =
+            make_float2(__uint_as_float(cv_tf32(w0)), __uint_as_float(cv_tf32(w1)));
+      }
+    }
+  } else {
+    for (int idx = tid; idx < CI * 9 * CO; idx += NT) {
+      int co = idx % CO;
+      int k = (idx / CO) % 9;
+      int ci = idx / (9 * CO);
+      int kk = P.w_flip ? 8 - k : k;
+      s_w[idx] = P.w[(size_t)co * P.w_so + (size_t)ci * P.w_si + kk];
+    }
   }
   if (INMODE == IN_AFFINE && tid < CI) {
     BnCoef k = bn_coef(P.stats, tid, P.in_count, P.gamma, P.beta, P.rmean, P.rvar, P.train != 0);
@@ -335,6 +393,201 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
   }
   __syncthreads();
 
+  if constexpr (C::MMA) {
+    // ---------------------------------------------------------------- tensor-core path (K_S1)
+    // warp -> (sub-tile, 16-pixel half xh, 4 output rows from r0); lane -> (g, t) of the fragments
+    constexpr int NTL = C::NTL;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int sub = 0;
+    const int wq = warp;
+    const int xh = (TW == 32) ? (wq & 1) : 0;
+    const int r0 = (TW == 32) ? 4 * (wq >> 1) : 4 * wq;
+    float st1[NTL][2], st2[NTL][2];
+#pragma unroll
+    for (int i = 0; i < NTL; ++i) st1[i][0] = st1[i][1] = st2[i][0] = st2[i][1] = 0.f;
+
+    uint32_t phase = 0;
+    int it = 0;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+      const int tile = grp * NSUB + sub;
+      const bool tvalid = tile < ntiles;
+      const int n = tile / tiles_per_img;
+      const int trem = tile - n * tiles_per_img;
+      const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+
+      float acc[4][NTL][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < NTL; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[r][i][j] = 0.f;
+
+#pragma unroll 1
+      for (int ch = 0; ch < NCHUNK; ++ch, ++it) {
+        const int buf = DIRECT ? (it & 1) : 0;
+        cv_mbar_wait(s_bar, phase);
+        phase ^= 1;
+        if (!DIRECT) transform(grp, ch);
+        __syncthreads();
+        if (ch + 1 < NCHUNK) {
+          issue(grp, ch + 1, buf ^ 1);
+        } else if (grp + (int)gridDim.x < ngroups) {
+          issue(grp + gridDim.x, 0, buf ^ 1);
+        }
+        if (tvalid) {
+          // A fragment (row-major 16 pixels x 8 channels): a0 = (pixel g, channel t),
+          // a1 = (g+8, t), a2 = (g, t+4), a3 = (g+8, t+4); tile column 3 is the left halo
+          const float* tin = s_in + (DIRECT ? buf * C::STAGE : 0) + sub * C::FIN_SUB + t * G::PLANE + r0 * G::PITCH +
+                             3 + xh * 16 + g;
+          const float* wf = s_w + (ch * 9) * NTL * 32 * C::WF + lane * C::WF;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {   // input rows r0 + r (tile row 0 is the top halo)
+              const float* p = tin + r * G::PITCH + kx;
+              const float av[4] = {p[0], p[8], p[4 * G::PLANE], p[4 * G::PLANE + 8]};
+              // TF32 operands: the tensor core reads the top 19 bits of an fp32 register.  3 terms:
+              // hi = x with the low 13 mantissa bits cleared, lo = x - hi (exact; its own low bits
+              // fall off at 2^-21 relative)
+              uint32_t ah[4], al[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                ah[j] = (TERMS == 3) ? cv_tf32_hi(av[j]) : __float_as_uint(av[j]);
+                if (TERMS == 3) al[j] = __float_as_uint(av[j] - __uint_as_float(ah[j]));
+              }
+              // the taps (ky) that use this input row feed different output rows: independent
+              // accumulators, issued term by term so that dependent MMAs are 3 apart
+#pragma unroll
+              for (int i = 0; i < NTL; ++i) {
+                uint32_t bh[3][2], bl[3][2];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                  if (r - ky < 0 || r - ky > 3) continue;
+                  const float* wp = wf + ((ky * 3 + kx) * NTL + i) * 32 * C::WF;
+                  if (C::PRESPLIT) {
+                    const float4 b = *reinterpret_cast<const float4*>(wp);
+                    bh[ky][0] = __float_as_uint(b.x);
+                    bh[ky][1] = __float_as_uint(b.y);
+                    bl[ky][0] = __float_as_uint(b.z);
+                    bl[ky][1] = __float_as_uint(b.w);
+                  } else {
+                    const float2 b = *reinterpret_cast<const float2*>(wp);
+                    if (TERMS == 3) {
+                      bh[ky][0] = cv_tf32_hi(b.x);
+                      bh[ky][1] = cv_tf32_hi(b.y);
+                      bl[ky][0] = __float_as_uint(b.x - __uint_as_float(bh[ky][0]));
+                      bl[ky][1] = __float_as_uint(b.y - __uint_as_float(bh[ky][1]));
+                    } else {
+                      bh[ky][0] = __float_as_uint(b.x);
+                      bh[ky][1] = __float_as_uint(b.y);
+                    }
+                  }
+                }
+                if (TERMS == 3) {
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky)
+                    if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], al, bh[ky][0], bh[ky][1]);
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky)
+                    if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], ah, bl[ky][0], bl[ky][1]);
+                }
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+                  if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], ah, bh[ky][0], bh[ky][1]);
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (!tvalid) continue;
+
+      // ---- epilogue on the accumulator fragments: c0 = (pixel g, channel 2t), c1 = (g, 2t+1),
+      // c2 = (g+8, 2t), c3 = (g+8, 2t+1)
+      const int oy0 = ty * G::TH + r0, ox0 = tx * TW + xh * 16 + g;
+      if (EPI == EPI_BWD) {
+        // sum g and sum g*x per channel (centred with the exact mean at the very end)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float xs[NTL][4];
+#pragma unroll
+          for (int i = 0; i < NTL; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int co = i * 8 + 2 * t + (j & 1);
+              const float* px = P.x_self + (((size_t)n * CO + co) * H_out + oy0 + r) * W_out + ox0 + 8 * (j >> 1);
+              asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(xs[i][j]) : "l"(px));
+            }
+#pragma unroll
+          for (int i = 0; i < NTL; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              st1[i][j & 1] += acc[r][i][j];
+              st2[i][j & 1] = fmaf(acc[r][i][j], xs[i][j], st2[i][j & 1]);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int i = 0; i < NTL; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float v = acc[r][i][j] + s_bias[i * 8 + 2 * t + (j & 1)];
+              if (P.relu_out) v = fmaxf(v, 0.f);
+              st1[i][j & 1] += v;
+              st2[i][j & 1] = fmaf(v, v, st2[i][j & 1]);
+              acc[r][i][j] = v;
+            }
+      }
+      if (P.out) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int i = 0; i < NTL; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int co = i * 8 + 2 * t + (j & 1);
+              P.out[(((size_t)n * CO + co) * H_out + oy0 + r) * W_out + ox0 + 8 * (j >> 1)] = acc[r][i][j];
+            }
+      }
+    }
+
+    // ---- per-channel statistics: lanes sharing t hold the same channels -> xor-shuffle over g,
+    // per-warp smem slots, fixed-order sum over the 4 warps, one fp64 atomic per channel per CTA
+    double* dst = (EPI == EPI_FWD) ? P.stats_out : P.dstats;
+    if (dst != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NTL; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float a = st1[i][j], b = st2[i][j];
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          if (g == 0) {
+            s_red[warp * 64 + i * 8 + 2 * t + j] = a;
+            s_red[warp * 64 + 32 + i * 8 + 2 * t + j] = b;
+          }
+        }
+      __syncthreads();
+      if (tid < CO) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          a += s_red[w * 64 + tid];
+          b += s_red[w * 64 + 32 + tid];
+        }
+        atomicAdd(&dst[tid], (double)a);
+        atomicAdd(&dst[32 + tid], (EPI == EPI_BWD) ? (double)b - s_meand[tid] * (double)a : (double)b);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- fp32 SIMT path
   const int sub = tid / (64 * NCOG);
   const int t2 = tid - sub * (64 * NCOG);
   const int slot = t2 & 63;
@@ -545,6 +798,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE>::NT, GconvC
       atomicAdd(&dst[32 + tid], (EPI == EPI_BWD) ? (double)b - s_meand[tid] * (double)a : (double)b);
     }
   }
+  }
 }
 
 // [B*C, H, W] fp32 activation tensor -> boxes [CIC][IN_ROWS][RAW_PITCH], no swizzle, zero fill
@@ -569,17 +823,20 @@ static int make_act_map(CUtensorMap* map, const float* base, long long nc, int H
   return 0;
 }
 
-template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN>
+// 0: fp32 SIMT; 1: TF32 tensor cores; 3: error-compensated 3xTF32 (layers the tensor-core path covers)
+static int g_conv_terms = 0;
+
+template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN, int TERMS = 0>
 static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   using G = TileGeom<KIND, TW>;
-  using C = GconvCfg<KIND, CI, CO, TW, INMODE>;
-  const size_t smem = (size_t)(C::BUF_FLOATS + CI * 9 * CO + 64 + 128 + 32) * sizeof(float) + 32 * sizeof(double) +
-                      16 + 128;
+  using C = GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>;
+  const size_t smem = (size_t)(C::BUF_FLOATS + C::W_FLOATS + 64 + C::RED_FLOATS + 32) * sizeof(float) +
+                      32 * sizeof(double) + 16 + 128;
   if (P.H_in != HIN || P.W_in != HIN) {
     set_error("gconv: layer geometry mismatch");
     return 1;
   }
-  auto kern = gconv_kernel<KIND, CI, CO, TW, INMODE, EPI, HIN>;
+  auto kern = gconv_kernel<KIND, CI, CO, TW, INMODE, EPI, HIN, TERMS>;
   static int max_ctas = 0;
   if (max_ctas == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -939,6 +1196,19 @@ static inline int h_out_of(const LayerGeom& L) {
 
 using namespace ava;
 
+// stride-1 layers with channel counts that are multiples of 8 can run on the tensor cores
+#define GCONV_TC(CI, CO, TW, INMODE, EPI, HIN)                                                     \
+  (g_conv_terms == 3   ? launch_gconv<K_S1, CI, CO, TW, INMODE, EPI, HIN, 3>(P, stream)            \
+   : g_conv_terms == 1 ? launch_gconv<K_S1, CI, CO, TW, INMODE, EPI, HIN, 1>(P, stream)            \
+                       : launch_gconv<K_S1, CI, CO, TW, INMODE, EPI, HIN, 0>(P, stream))
+
+extern "C" int ava_b200_set_conv_precision(int mode) {
+  AVA_REQUIRE(mode == 0 || mode == 1 || mode == 2, "set_conv_precision: mode %d (0 fp32, 1 tf32, 2 tf32x3)", mode);
+  g_conv_terms = (mode == 2) ? 3 : mode;
+  return 0;
+}
+extern "C" int ava_b200_get_conv_precision(void) { return g_conv_terms == 3 ? 2 : g_conv_terms; }
+
 extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float* w, const float* b,
                                    const float* gamma, const float* beta, const double* stats_in,
                                    const float* running_mean, const float* running_var, int train,
@@ -976,16 +1246,16 @@ extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, c
   switch (layer) {
     case 0: return launch_gconv<K_S1, 1, 8, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
     case 1: return launch_gconv<K_S2, 8, 8, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
-    case 2: return launch_gconv<K_S1, 8, 16, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
+    case 2: return GCONV_TC(8, 16, 32, IN_AFFINE, EPI_FWD, 64);
     case 3: return launch_gconv<K_S2, 16, 16, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
-    case 4: return launch_gconv<K_S1, 16, 24, 32, IN_AFFINE, EPI_FWD, 32>(P, stream);
+    case 4: return GCONV_TC(16, 24, 32, IN_AFFINE, EPI_FWD, 32);
     case 5: return launch_gconv<K_S2, 24, 24, 16, IN_AFFINE, EPI_FWD, 32>(P, stream);
-    case 6: return launch_gconv<K_S1, 24, 32, 16, IN_AFFINE, EPI_FWD, 16>(P, stream);
-    case 7: return launch_gconv<K_S1, 32, 24, 16, IN_AFFINE, EPI_FWD, 16>(P, stream);
+    case 6: return GCONV_TC(24, 32, 16, IN_AFFINE, EPI_FWD, 16);
+    case 7: return GCONV_TC(32, 24, 16, IN_AFFINE, EPI_FWD, 16);
     case 8: return launch_gconv<K_UP, 24, 24, 16, IN_AFFINE, EPI_FWD, 16>(P, stream);
-    case 9: return launch_gconv<K_S1, 24, 16, 32, IN_AFFINE, EPI_FWD, 32>(P, stream);
+    case 9: return GCONV_TC(24, 16, 32, IN_AFFINE, EPI_FWD, 32);
     case 10: return launch_gconv<K_UP, 16, 16, 32, IN_AFFINE, EPI_FWD, 32>(P, stream);
-    case 11: return launch_gconv<K_S1, 16, 8, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
+    case 11: return GCONV_TC(16, 8, 32, IN_AFFINE, EPI_FWD, 64);
     case 12: return launch_gconv<K_UP, 8, 8, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
     case 13: return launch_gconv<K_S1, 8, 1, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
   }
@@ -1021,16 +1291,16 @@ extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const
   switch (layer) {
     case 0: return launch_gconv<K_S1, 8, 1, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
     case 1: return launch_gconv<K_UP, 8, 8, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
-    case 2: return launch_gconv<K_S1, 16, 8, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
+    case 2: return GCONV_TC(16, 8, 32, IN_PLAIN, EPI_BWD, 64);
     case 3: return launch_gconv<K_UP, 16, 16, 32, IN_PLAIN, EPI_BWD, 32>(P, stream);
-    case 4: return launch_gconv<K_S1, 24, 16, 32, IN_PLAIN, EPI_BWD, 32>(P, stream);
+    case 4: return GCONV_TC(24, 16, 32, IN_PLAIN, EPI_BWD, 32);
     case 5: return launch_gconv<K_UP, 24, 24, 16, IN_PLAIN, EPI_BWD, 16>(P, stream);
-    case 6: return launch_gconv<K_S1, 32, 24, 16, IN_PLAIN, EPI_BWD, 16>(P, stream);
-    case 7: return launch_gconv<K_S1, 24, 32, 16, IN_PLAIN, EPI_BWD, 16>(P, stream);
+    case 6: return GCONV_TC(32, 24, 16, IN_PLAIN, EPI_BWD, 16);
+    case 7: return GCONV_TC(24, 32, 16, IN_PLAIN, EPI_BWD, 16);
     case 8: return launch_gconv<K_S2, 24, 24, 16, IN_PLAIN, EPI_BWD, 32>(P, stream);
-    case 9: return launch_gconv<K_S1, 16, 24, 32, IN_PLAIN, EPI_BWD, 32>(P, stream);
+    case 9: return GCONV_TC(16, 24, 32, IN_PLAIN, EPI_BWD, 32);
     case 10: return launch_gconv<K_S2, 16, 16, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
-    case 11: return launch_gconv<K_S1, 8, 16, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
+    case 11: return GCONV_TC(8, 16, 32, IN_PLAIN, EPI_BWD, 64);
     case 12: return launch_gconv<K_S2, 8, 8, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
     case 13: return launch_gconv<K_S1, 1, 8, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
   }

@@ -72,6 +72,16 @@ int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float*
                         const float* running_mean, const float* running_var, int train,
                         double* stats_out, void* stream);
 
+/* Arithmetic of the conv inner products (process-wide, like the reference side's
+ * torch.backends.cudnn.allow_tf32 switch that governs the same layers on a GPU):
+ *   0  fp32 FMA (default)
+ *   1  TF32 tensor cores (mma.sync m16n8k8), operands rounded to TF32: rtol ~2e-3
+ *   2  error-compensated 3xTF32 on the tensor cores (x = x_hi + x_lo; a_lo*b_hi + a_hi*b_lo +
+ *      a_hi*b_hi, fp32 accumulate): fp32-level accuracy (rtol 1e-4 parity holds)
+ * Layers whose channel counts are not multiples of 8 always use fp32 FMA. */
+int ava_b200_set_conv_precision(int mode);
+int ava_b200_get_conv_precision(void);
+
 /* Backward of layer `layer`.  `dz` is the gradient w.r.t. this layer's PRE-activation
  * conv output: the gradient arriving from the next layer already pushed through the next
  * BatchNorm's backward and this layer's ReLU by ava_b200_bn_relu_bwd_apply (in place is
