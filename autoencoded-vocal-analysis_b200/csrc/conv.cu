@@ -138,6 +138,8 @@ struct GconvCfg {
   // (TERMS 3, PRESPLIT) or, for the widest layers, {b0,b1} in full fp32 split where used
   static constexpr bool PRESPLIT = (TERMS == 3) && (CI * CO <= 384);
   static constexpr int WF = PRESPLIT ? 4 : 2;   // floats per lane per fragment
+  // A-resident loop order when the fragments of 6 input rows fit next to the accumulators
+  static constexpr bool ARES = (TERMS == 1) ? (NTL <= 3) : (NTL <= 2);
   static constexpr int W_FLOATS = CI * 9 * CO * (PRESPLIT ? 2 : 1);
   static constexpr int RED_FLOATS = MMA ? 4 * 64 : 128;
   static_assert(!MMA || (CI % 8 == 0 && CO % 8 == 0 && KIND == K_S1), "tensor-core path: stride-1, channels % 8");
@@ -442,60 +444,85 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
           const float* tin = s_in + (DIRECT ? buf * C::STAGE : 0) + sub * C::FIN_SUB + t * G::PLANE + r0 * G::PITCH +
                              3 + xh * 16 + g;
           const float* wf = s_w + (ch * 9) * NTL * 32 * C::WF + lane * C::WF;
+          // TF32 operands: the tensor core reads the top 19 bits of an fp32 register.  3 terms:
+          // hi = x with the low 13 mantissa bits cleared, lo = x - hi (exact; its own low bits fall
+          // off at 2^-21 relative)
+          auto load_a = [&](const float* p, uint32_t (&ah)[4], uint32_t (&al)[4]) {
+            const float av[4] = {p[0], p[8], p[4 * G::PLANE], p[4 * G::PLANE + 8]};
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
+            for (int j = 0; j < 4; ++j) {
+              ah[j] = (TERMS == 3) ? cv_tf32_hi(av[j]) : __float_as_uint(av[j]);
+              al[j] = (TERMS == 3) ? __float_as_uint(av[j] - __uint_as_float(ah[j])) : 0u;
+            }
+          };
+          auto load_b = [&](int k, int i, uint32_t (&bh)[2], uint32_t (&bl)[2]) {
+            const float* wp = wf + (k * NTL + i) * 32 * C::WF;
+            if (C::PRESPLIT) {
+              const float4 b = *reinterpret_cast<const float4*>(wp);
+              bh[0] = __float_as_uint(b.x);
+              bh[1] = __float_as_uint(b.y);
+              bl[0] = __float_as_uint(b.z);
+              bl[1] = __float_as_uint(b.w);
+            } else {
+              const float2 b = *reinterpret_cast<const float2*>(wp);
+              bh[0] = (TERMS == 3) ? cv_tf32_hi(b.x) : __float_as_uint(b.x);
+              bh[1] = (TERMS == 3) ? cv_tf32_hi(b.y) : __float_as_uint(b.y);
+              bl[0] = (TERMS == 3) ? __float_as_uint(b.x - __uint_as_float(bh[0])) : 0u;
+              bl[1] = (TERMS == 3) ? __float_as_uint(b.y - __uint_as_float(bh[1])) : 0u;
+            }
+          };
+          if constexpr (C::ARES) {
+            // A-resident order: the 6 input-row fragments of one kx stay in registers, every B
+            // fragment is loaded once per tap and feeds the 4 output rows (independent accumulators,
+            // issued term by term)
 #pragma unroll
-            for (int r = 0; r < 6; ++r) {   // input rows r0 + r (tile row 0 is the top halo)
-              const float* p = tin + r * G::PITCH + kx;
-              const float av[4] = {p[0], p[8], p[4 * G::PLANE], p[4 * G::PLANE + 8]};
-              // TF32 operands: the tensor core reads the top 19 bits of an fp32 register.  3 terms:
-              // hi = x with the low 13 mantissa bits cleared, lo = x - hi (exact; its own low bits
-              // fall off at 2^-21 relative)
-              uint32_t ah[4], al[4];
+            for (int kx = 0; kx < 3; ++kx) {
+              uint32_t ah[6][4], al[6][4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                ah[j] = (TERMS == 3) ? cv_tf32_hi(av[j]) : __float_as_uint(av[j]);
-                if (TERMS == 3) al[j] = __float_as_uint(av[j] - __uint_as_float(ah[j]));
-              }
-              // the taps (ky) that use this input row feed different output rows: independent
-              // accumulators, issued term by term so that dependent MMAs are 3 apart
+              for (int r = 0; r < 6; ++r) load_a(tin + r * G::PITCH + kx, ah[r], al[r]);
 #pragma unroll
-              for (int i = 0; i < NTL; ++i) {
-                uint32_t bh[3][2], bl[3][2];
+              for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                  if (r - ky < 0 || r - ky > 3) continue;
-                  const float* wp = wf + ((ky * 3 + kx) * NTL + i) * 32 * C::WF;
-                  if (C::PRESPLIT) {
-                    const float4 b = *reinterpret_cast<const float4*>(wp);
-                    bh[ky][0] = __float_as_uint(b.x);
-                    bh[ky][1] = __float_as_uint(b.y);
-                    bl[ky][0] = __float_as_uint(b.z);
-                    bl[ky][1] = __float_as_uint(b.w);
-                  } else {
-                    const float2 b = *reinterpret_cast<const float2*>(wp);
-                    if (TERMS == 3) {
-                      bh[ky][0] = cv_tf32_hi(b.x);
-                      bh[ky][1] = cv_tf32_hi(b.y);
-                      bl[ky][0] = __float_as_uint(b.x - __uint_as_float(bh[ky][0]));
-                      bl[ky][1] = __float_as_uint(b.y - __uint_as_float(bh[ky][1]));
-                    } else {
-                      bh[ky][0] = __float_as_uint(b.x);
-                      bh[ky][1] = __float_as_uint(b.y);
-                    }
+                for (int i = 0; i < NTL; ++i) {
+                  uint32_t bh[2], bl[2];
+                  load_b(ky * 3 + kx, i, bh, bl);
+                  if (TERMS == 3) {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) cv_mma_tf32(acc[o][i], al[o + ky], bh[0], bh[1]);
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) cv_mma_tf32(acc[o][i], ah[o + ky], bl[0], bl[1]);
                   }
+#pragma unroll
+                  for (int o = 0; o < 4; ++o) cv_mma_tf32(acc[o][i], ah[o + ky], bh[0], bh[1]);
                 }
-                if (TERMS == 3) {
+            }
+          } else {
+            // rolling order (register-light): one input-row fragment at a time; the taps (ky) that
+            // use it feed different output rows
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+              for (int r = 0; r < 6; ++r) {   // input rows r0 + r (tile row 0 is the top halo)
+                uint32_t ah[4], al[4];
+                load_a(tin + r * G::PITCH + kx, ah, al);
+#pragma unroll
+                for (int i = 0; i < NTL; ++i) {
+                  uint32_t bh[3][2], bl[3][2];
 #pragma unroll
                   for (int ky = 0; ky < 3; ++ky)
-                    if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], al, bh[ky][0], bh[ky][1]);
+                    if (r - ky >= 0 && r - ky <= 3) load_b(ky * 3 + kx, i, bh[ky], bl[ky]);
+                  if (TERMS == 3) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                      if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], al, bh[ky][0], bh[ky][1]);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                      if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], ah, bl[ky][0], bl[ky][1]);
+                  }
 #pragma unroll
                   for (int ky = 0; ky < 3; ++ky)
-                    if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], ah, bl[ky][0], bl[ky][1]);
+                    if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], ah, bh[ky][0], bh[ky][1]);
                 }
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
-                  if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], ah, bh[ky][0], bh[ky][1]);
               }
             }
           }
@@ -1117,6 +1144,214 @@ __global__ void __launch_bounds__(256, 2)
 
 }
 
+// ------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores (mma.sync m16n8k8 TF32, 1 or 3 terms as in gconv_kernel).
+// Per tap (ky,kx):  D_tap[g][i] += sum_p G[g][p] * I[i][p + tap]   ->  M = 16 g-channels,
+// N = 8 i-channels, K = 8 consecutive pixels of one tile row.  A warp owns one (M-tile, N-tile)
+// pair and all 9 taps (36 accumulator registers) for its share of a tile's 32 k-steps;
+// accumulators persist over the CTA's whole persistent loop.  Fragments are read straight from
+// the channel-planar TMA tiles; the planes are 4 (mod 8) floats apart (spare box rows / columns)
+// so that the fragment loads (8 channels x 4 pixels per warp) are bank-conflict free.
+template <int S, int TWG>
+struct WTileM : WTile<S, TWG> {
+  using B = WTile<S, TWG>;
+  static constexpr int I_ROWS_BOX = B::I_ROWS + (S == 1 ? 1 : 0);
+  static constexpr int I_PLANE = I_ROWS_BOX * B::I_PITCH;
+  // G box: 4 spare columns and one spare row, for the same reason (A-fragment loads)
+  static constexpr int G_W = TWG + 4, G_ROWS_BOX = B::THG + 1;
+  static constexpr int G_PLANE = G_ROWS_BOX * G_W;
+  static_assert(I_PLANE % 8 == 4 && G_PLANE % 8 == 4, "plane strides must be 4 (mod 8) floats");
+};
+
+template <int S, int CG, int CI, int TWG, int CONVT, int TERMS>
+__global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256, 2)
+    wgrad_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_i,
+                     const WgradParams P) {
+  using T = WTileM<S, TWG>;
+  constexpr int MT = (CG + 15) / 16, NTI = CI / 8, NPAIR = MT * NTI;
+  constexpr int KS = (NPAIR == 6) ? 1 : 8 / NPAIR;     // k-splits (warps per pair)
+  constexpr int NTHR = NPAIR * KS * 32;
+  constexpr int G_FLOATS = CG * T::G_PLANE;
+  constexpr int I_FLOATS = CI * T::I_PLANE;
+  constexpr int G_PAD = (G_FLOATS + 31) / 32 * 32;
+  constexpr int I_PAD = (I_FLOATS + 31) / 32 * 32;
+  constexpr int NQG = CG * T::THG * (T::G_W / 4);
+  constexpr int NQI = CI * T::I_ROWS * (T::I_PITCH / 4);
+  constexpr int GITERS = (NQG + NTHR - 1) / NTHR;
+  constexpr int IITERS = (NQI + NTHR - 1) / NTHR;
+  constexpr int KSTEPS = T::THG * TWG / 8;
+
+  extern __shared__ __align__(128) float smem[];
+  float* s_g = smem;
+  float* s_i = s_g + G_PAD;
+  float* s_aff = s_i + I_PAD;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_aff + 64);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int pair = warp % NPAIR, ks = warp / NPAIR;
+  const int mt = pair / NTI, nt = pair % NTI;
+
+  const int Hg = P.Hg, Wg = P.Wg, Hi = S * Hg, Wi = S * Wg;
+  const int tiles_x = Wg / TWG, tiles_y = Hg / T::THG;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int ntiles = P.B * tiles_per_img;
+
+  if (tid == 0) {
+    cv_mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) {
+    constexpr int CA = CONVT ? CG : CI;
+    if (tid < CA) {
+      BnCoef k = bn_coef(P.stats, tid, P.bn_count, P.gamma, P.beta, nullptr, nullptr, true);
+      s_aff[tid] = k.scale;
+      s_aff[32 + tid] = k.shift;
+    }
+  }
+
+  float acc[9][4];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+  float bs0 = 0.f, bs1 = 0.f;   // bias-gradient partial sums (see below)
+  // rows g+8 of the last M-tile do not exist when CG is not a multiple of 16
+  const bool hi_rows = (CG % 16 == 0) || (mt + 1 < MT);
+
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / tiles_per_img;
+    const int trem = tile - n * tiles_per_img;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    const int gy0 = ty * T::THG, gx0 = tx * TWG;
+    const int iy0 = S * gy0 - 1;
+    const int X0 = S * gx0;
+    __syncthreads();
+    if (tid == 0) {
+      constexpr uint32_t BYTES = (uint32_t)(G_FLOATS * 4 + I_FLOATS * 4);
+      cv_mbar_expect_tx(s_bar, BYTES);
+      cv_tma_load_3d(s_g, &map_g, gx0, gy0, n * CG, s_bar);
+      cv_tma_load_3d(s_i, &map_i, X0 - 4, iy0, n * CI, s_bar);
+    }
+    cv_mbar_wait(s_bar, phase);
+    phase ^= 1;
+    if (CONVT) {
+      // G = x: BatchNorm in place
+#pragma unroll
+      for (int j = 0; j < GITERS; ++j) {
+        const int q = tid + j * NTHR;
+        if (q < NQG) {
+          const int c = q / ((T::G_W / 4) * T::THG);
+          const int rq = q - c * ((T::G_W / 4) * T::THG);
+          float4* p = reinterpret_cast<float4*>(s_g + c * T::G_PLANE + 4 * rq);
+          const float4 a = *p;
+          const float sc = s_aff[c], sh = s_aff[32 + c];
+          *p = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
+        }
+      }
+    } else {
+      // I = x: BatchNorm in place; rows / columns outside the image are zero AFTER the transform
+#pragma unroll
+      for (int j = 0; j < IITERS; ++j) {
+        const int q = tid + j * NTHR;
+        if (q < NQI) {
+          const int qx = q % (T::I_PITCH / 4);
+          const int y = (q / (T::I_PITCH / 4)) % T::I_ROWS;
+          const int c = q / ((T::I_PITCH / 4) * T::I_ROWS);
+          const int gy = iy0 + y, gx = X0 - 4 + 4 * qx;
+          float4* p = reinterpret_cast<float4*>(s_i + c * T::I_PLANE + y * T::I_PITCH + 4 * qx);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gy >= 0 && gy < Hi && gx >= 0 && gx < Wi) {
+            const float4 a = *p;
+            const float sc = s_aff[c], sh = s_aff[32 + c];
+            v = make_float4(fmaf(a.x, sc, sh), fmaf(a.y, sc, sh), fmaf(a.z, sc, sh), fmaf(a.w, sc, sh));
+          }
+          *p = v;
+        }
+      }
+    }
+    __syncthreads();
+
+    const float* gbase = s_g + (mt * 16 + g) * T::G_PLANE + t;
+    const float* ibase = s_i + (nt * 8 + g) * T::I_PLANE + 3 + S * t;
+#pragma unroll 2
+    for (int j = ks; j < KSTEPS; j += KS) {
+      const int y = j / (TWG / 8), x0 = (j % (TWG / 8)) * 8;
+      // A fragment: a0 = G[g][p+t], a1 = G[g+8][p+t], a2 = G[g][p+t+4], a3 = G[g+8][p+t+4]
+      const float* gp = gbase + y * T::G_W + x0;
+      float av[4];
+      av[0] = gp[0];
+      av[2] = gp[4];
+      av[1] = hi_rows ? gp[8 * T::G_PLANE] : 0.f;
+      av[3] = hi_rows ? gp[8 * T::G_PLANE + 4] : 0.f;
+      if (!CONVT && nt == 0) {   // conv layers: db = sum of dz = G
+        bs0 += av[0] + av[2];
+        bs1 += av[1] + av[3];
+      }
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ah[q] = (TERMS == 3) ? cv_tf32_hi(av[q]) : __float_as_uint(av[q]);
+        al[q] = (TERMS == 3) ? __float_as_uint(av[q] - __uint_as_float(ah[q])) : 0u;
+      }
+      const float* ip = ibase + (S * y) * T::I_PITCH + S * x0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int ky = k / 3, kx = k % 3;
+        // B fragment: b0 = I[g][pixel t + tap], b1 = I[g][pixel t+4 + tap]
+        const float b0 = ip[ky * T::I_PITCH + kx], b1 = ip[ky * T::I_PITCH + kx + 4 * S];
+        if (CONVT && mt == 0) {   // convT layers: db = sum of dz = I over the pixels of this strip
+          if (S == 1 ? (k == 4) : (ky >= 1 && kx >= 1)) bs0 += b0 + b1;
+        }
+        if (TERMS == 3) {
+          const uint32_t bh0 = cv_tf32_hi(b0), bh1 = cv_tf32_hi(b1);
+          const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
+          const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
+          cv_mma_tf32(acc[k], al, bh0, bh1);
+          cv_mma_tf32(acc[k], ah, bl0, bl1);
+          cv_mma_tf32(acc[k], ah, bh0, bh1);
+        } else {
+          cv_mma_tf32(acc[k], ah, __float_as_uint(b0), __float_as_uint(b1));
+        }
+      }
+    }
+  }
+
+  // ---- k-split warps add in a fixed order (deterministic), then one partial per CTA
+  // D fragment: c0 = (g, 2t), c1 = (g, 2t+1), c2 = (g+8, 2t), c3 = (g+8, 2t+1)
+  bs0 += __shfl_xor_sync(0xffffffffu, bs0, 1);
+  bs0 += __shfl_xor_sync(0xffffffffu, bs0, 2);
+  bs1 += __shfl_xor_sync(0xffffffffu, bs1, 1);
+  bs1 += __shfl_xor_sync(0xffffffffu, bs1, 2);
+  __syncthreads();
+  float* s_red = smem;  // reuse: [CG*CI*9 + 32]
+  for (int idx = tid; idx < CG * CI * 9 + 32; idx += NTHR) s_red[idx] = 0.f;
+  __syncthreads();
+  for (int turn = 0; turn < KS; ++turn) {
+    if (ks == turn) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int gc = mt * 16 + g + 8 * (q >> 1), ic = nt * 8 + 2 * t + (q & 1);
+          if (gc < CG) s_red[(gc * CI + ic) * 9 + k] += acc[k][q];
+        }
+      if (t == 0) {
+        if (!CONVT && nt == 0) {
+          s_red[CG * CI * 9 + mt * 16 + g] += bs0;
+          if (hi_rows) s_red[CG * CI * 9 + mt * 16 + g + 8] += bs1;
+        }
+        if (CONVT && mt == 0) s_red[CG * CI * 9 + nt * 8 + g] += bs0;
+      }
+    }
+    __syncthreads();
+  }
+  float* dst = P.partial + (size_t)blockIdx.x * (CG * CI * 9 + 32);
+  for (int idx = tid; idx < CG * CI * 9 + 32; idx += NTHR) dst[idx] = s_red[idx];
+}
+
 constexpr int kWgradMaxCtas = 8 * kNumSMs;  // per-CTA partial slots in the workspace
 
 // second stage: out[j] = sum_p partial[p][j] for the weights (j < nw -> dw[j]) and the bias slots
@@ -1172,6 +1407,50 @@ static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStrea
   reduce_partials_kernel<<<(NW + NB + 7) / 8, 256, 0, stream>>>(P.partial, grid, stride, NW, NB, dw, db);
   return check_launch("wgrad_reduce");
 }
+
+template <int S, int CG, int CI, int TWG, int CONVT, int TERMS>
+static int launch_wgrad_mma(WgradParams P, float* dw, float* db, void* ws, cudaStream_t stream) {
+  using T = WTileM<S, TWG>;
+  constexpr int NPAIR = ((CG + 15) / 16) * (CI / 8);
+  constexpr int NTHR = (NPAIR == 6) ? 192 : 256;
+  constexpr int G_PAD = (CG * T::G_PLANE + 31) / 32 * 32;
+  constexpr int I_PAD = (CI * T::I_PLANE + 31) / 32 * 32;
+  size_t smem_f = (size_t)G_PAD + I_PAD + 64 + 8;
+  if (smem_f < (size_t)CG * CI * 9 + 32) smem_f = (size_t)CG * CI * 9 + 32;
+  const size_t smem = smem_f * sizeof(float) + 128;
+  auto kern = wgrad_mma_kernel<S, CG, CI, TWG, CONVT, TERMS>;
+  static int max_ctas = 0;
+  if (max_ctas == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("wgrad_mma: cannot reserve %zu bytes of shared memory", smem);
+      return 1;
+    }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NTHR, smem);
+    if (per_sm < 1) per_sm = 1;
+    max_ctas = per_sm * kNumSMs;
+  }
+  const long long ntiles = (long long)P.B * (P.Wg / TWG) * (P.Hg / T::THG);
+  int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
+  if (grid > kWgradMaxCtas) grid = kWgradMaxCtas;
+  CUtensorMap map_g, map_i;
+  if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, T::G_W, T::G_ROWS_BOX, CG)) return 1;
+  if (make_act_map(&map_i, P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS_BOX, CI)) return 1;
+  P.partial = reinterpret_cast<float*>(ws);
+  const int stride = CG * CI * 9 + 32;
+  kern<<<grid, NTHR, smem, stream>>>(map_g, map_i, P);
+  if (check_launch("wgrad_mma")) return 1;
+  constexpr int NW = CG * CI * 9, NB = CONVT ? CI : CG;
+  reduce_partials_kernel<<<(NW + NB + 7) / 8, 256, 0, stream>>>(P.partial, grid, stride, NW, NB, dw, db);
+  return check_launch("wgrad_reduce");
+}
+
+// tensor-core weight gradient for the layers with >= 16 "G" channels, else the fp32 FMA kernel
+#define WGRAD_TC(S, CG, CI, TWG, CONVT)                                                              \
+  (g_conv_terms == 3   ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 3>(P, dw, db, ws, stream)          \
+   : g_conv_terms == 1 ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 1>(P, dw, db, ws, stream)          \
+                       : launch_wgrad<S, CG, CI, TWG, CONVT>(P, dw, db, ws, stream))
 
 // ------------------------------------------------------------------------------------
 struct LayerGeom {
@@ -1339,11 +1618,11 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, con
     switch (layer) {
       case 0: rc = launch_wgrad<1, 8, 1, 32, 0>(P, dw, db, ws, stream); break;
       case 1: rc = launch_wgrad<2, 8, 8, 32, 0>(P, dw, db, ws, stream); break;
-      case 2: rc = launch_wgrad<1, 16, 8, 32, 0>(P, dw, db, ws, stream); break;
-      case 3: rc = launch_wgrad<2, 16, 16, 32, 0>(P, dw, db, ws, stream); break;
-      case 4: rc = launch_wgrad<1, 24, 16, 32, 0>(P, dw, db, ws, stream); break;
-      case 5: rc = launch_wgrad<2, 24, 24, 16, 0>(P, dw, db, ws, stream); break;
-      case 6: rc = launch_wgrad<1, 32, 24, 16, 0>(P, dw, db, ws, stream); break;
+      case 2: rc = WGRAD_TC(1, 16, 8, 32, 0); break;
+      case 3: rc = WGRAD_TC(2, 16, 16, 32, 0); break;
+      case 4: rc = WGRAD_TC(1, 24, 16, 32, 0); break;
+      case 5: rc = WGRAD_TC(2, 24, 24, 16, 0); break;
+      case 6: rc = WGRAD_TC(1, 32, 24, 16, 0); break;
     }
     return rc;
   } else {
@@ -1352,11 +1631,11 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, con
     P.i_a = dz;
     P.Hg = P.Wg = L.h_in;
     switch (layer) {
-      case 7: rc = launch_wgrad<1, 32, 24, 16, 1>(P, dw, db, ws, stream); break;
-      case 8: rc = launch_wgrad<2, 24, 24, 16, 1>(P, dw, db, ws, stream); break;
-      case 9: rc = launch_wgrad<1, 24, 16, 32, 1>(P, dw, db, ws, stream); break;
-      case 10: rc = launch_wgrad<2, 16, 16, 32, 1>(P, dw, db, ws, stream); break;
-      case 11: rc = launch_wgrad<1, 16, 8, 32, 1>(P, dw, db, ws, stream); break;
+      case 7: rc = WGRAD_TC(1, 32, 24, 16, 1); break;
+      case 8: rc = WGRAD_TC(2, 24, 24, 16, 1); break;
+      case 9: rc = WGRAD_TC(1, 24, 16, 32, 1); break;
+      case 10: rc = WGRAD_TC(2, 16, 16, 32, 1); break;
+      case 11: rc = WGRAD_TC(1, 16, 8, 32, 1); break;
       case 12: rc = launch_wgrad<2, 8, 8, 32, 1>(P, dw, db, ws, stream); break;
       case 13: rc = launch_wgrad<1, 8, 1, 32, 1>(P, dw, db, ws, stream); break;
     }
