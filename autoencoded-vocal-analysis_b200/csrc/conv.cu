@@ -150,8 +150,20 @@ __device__ __forceinline__ uint32_t cv_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
-// x with the low 13 mantissa bits cleared: exactly representable in TF32
-__device__ __forceinline__ uint32_t cv_tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+// x rounded to the nearest TF32 value (ties away from zero, like cvt.rna, in two integer ops):
+// exactly representable in TF32, and |x - hi| <= 2^-12 |x|, so the dropped lo*lo term of the
+// 3-term product is 2^-24 relative and unbiased
+__device__ __forceinline__ uint32_t cv_tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+// The tensor core adds into its fp32 accumulator with truncation (measured: 2000 chained
+// accumulations drift by 1.6e-4), a bias that BatchNorm backward amplifies.  The 3-term product
+// is therefore evaluated as a short chain on a fresh accumulator, smallest terms first
+// (t = a_lo*b_hi; t += a_hi*b_lo; t += a_hi*b_hi), and t is added to the running sum with an
+// ordinary round-to-nearest FADD.
+__device__ __forceinline__ void cv_mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
 __device__ __forceinline__ void cv_mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -445,8 +457,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
                              3 + xh * 16 + g;
           const float* wf = s_w + (ch * 9) * NTL * 32 * C::WF + lane * C::WF;
           // TF32 operands: the tensor core reads the top 19 bits of an fp32 register.  3 terms:
-          // hi = x with the low 13 mantissa bits cleared, lo = x - hi (exact; its own low bits fall
-          // off at 2^-21 relative)
+          // hi = x rounded to TF32, lo = x - hi (exact; its own low bits fall off at 2^-22 relative)
           auto load_a = [&](const float* p, uint32_t (&ah)[4], uint32_t (&al)[4]) {
             const float av[4] = {p[0], p[8], p[4 * G::PLANE], p[4 * G::PLANE + 8]};
 #pragma unroll
@@ -480,21 +491,46 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
               uint32_t ah[6][4], al[6][4];
 #pragma unroll
               for (int r = 0; r < 6; ++r) load_a(tin + r * G::PITCH + kx, ah[r], al[r]);
-#pragma unroll
-              for (int ky = 0; ky < 3; ++ky)
+              if constexpr (TERMS == 3) {
+                // chain over the 3 taps of this kernel column on a fresh accumulator (6 small-term
+                // MMAs, then the 3 main terms), then one round-to-nearest add into the running sum
 #pragma unroll
                 for (int i = 0; i < NTL; ++i) {
-                  uint32_t bh[2], bl[2];
-                  load_b(ky * 3 + kx, i, bh, bl);
-                  if (TERMS == 3) {
+                  uint32_t bh[3][2], bl[3][2];
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) cv_mma_tf32(acc[o][i], al[o + ky], bh[0], bh[1]);
+                  for (int ky = 0; ky < 3; ++ky) load_b(ky * 3 + kx, i, bh[ky], bl[ky]);
+                  float tq[4][4];
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) cv_mma_tf32(acc[o][i], ah[o + ky], bl[0], bl[1]);
+                  for (int o = 0; o < 4; ++o) cv_mma_tf32_zero(tq[o], al[o], bh[0][0], bh[0][1]);
+#pragma unroll
+                  for (int o = 0; o < 4; ++o) cv_mma_tf32(tq[o], ah[o], bl[0][0], bl[0][1]);
+#pragma unroll
+                  for (int ky = 1; ky < 3; ++ky) {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) cv_mma_tf32(tq[o], al[o + ky], bh[ky][0], bh[ky][1]);
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) cv_mma_tf32(tq[o], ah[o + ky], bl[ky][0], bl[ky][1]);
                   }
 #pragma unroll
-                  for (int o = 0; o < 4; ++o) cv_mma_tf32(acc[o][i], ah[o + ky], bh[0], bh[1]);
+                  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) cv_mma_tf32(tq[o], ah[o + ky], bh[ky][0], bh[ky][1]);
+#pragma unroll
+                  for (int o = 0; o < 4; ++o)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[o][i][q] += tq[o][q];
                 }
+              } else {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                  for (int i = 0; i < NTL; ++i) {
+                    uint32_t bh[2], bl[2];
+                    load_b(ky * 3 + kx, i, bh, bl);
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) cv_mma_tf32(acc[o][i], ah[o + ky], bh[0], bh[1]);
+                  }
+              }
             }
           } else {
             // rolling order (register-light): one input-row fragment at a time; the taps (ky) that
@@ -512,16 +548,27 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
                   for (int ky = 0; ky < 3; ++ky)
                     if (r - ky >= 0 && r - ky <= 3) load_b(ky * 3 + kx, i, bh[ky], bl[ky]);
                   if (TERMS == 3) {
+                    float tq[3][4];
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
-                      if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], al, bh[ky][0], bh[ky][1]);
+                      if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32_zero(tq[ky], al, bh[ky][0], bh[ky][1]);
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
-                      if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], ah, bl[ky][0], bl[ky][1]);
+                      if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(tq[ky], ah, bl[ky][0], bl[ky][1]);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                      if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(tq[ky], ah, bh[ky][0], bh[ky][1]);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                      if (r - ky >= 0 && r - ky <= 3) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[r - ky][i][q] += tq[ky][q];
+                      }
+                  } else {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                      if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], ah, bh[ky][0], bh[ky][1]);
                   }
-#pragma unroll
-                  for (int ky = 0; ky < 3; ++ky)
-                    if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(acc[r - ky][i], ah, bh[ky][0], bh[ky][1]);
                 }
               }
             }
@@ -1298,22 +1345,42 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
       }
       const float* ip = ibase + (S * y) * T::I_PITCH + S * x0;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const int ky = k / 3, kx = k % 3;
-        // B fragment: b0 = I[g][pixel t + tap], b1 = I[g][pixel t+4 + tap]
-        const float b0 = ip[ky * T::I_PITCH + kx], b1 = ip[ky * T::I_PITCH + kx + 4 * S];
-        if (CONVT && mt == 0) {   // convT layers: db = sum of dz = I over the pixels of this strip
-          if (S == 1 ? (k == 4) : (ky >= 1 && kx >= 1)) bs0 += b0 + b1;
+      for (int ky = 0; ky < 3; ++ky) {
+        // B fragments of the three taps of this kernel row: b0 = I[g][pixel t + tap],
+        // b1 = I[g][pixel t+4 + tap]
+        float bv[3][2];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          bv[kx][0] = ip[ky * T::I_PITCH + kx];
+          bv[kx][1] = ip[ky * T::I_PITCH + kx + 4 * S];
+          if (CONVT && mt == 0) {   // convT layers: db = sum of dz = I over the pixels of this strip
+            if (S == 1 ? (ky == 1 && kx == 1) : (ky >= 1 && kx >= 1)) bs0 += bv[kx][0] + bv[kx][1];
+          }
         }
         if (TERMS == 3) {
-          const uint32_t bh0 = cv_tf32_hi(b0), bh1 = cv_tf32_hi(b1);
-          const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
-          const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
-          cv_mma_tf32(acc[k], al, bh0, bh1);
-          cv_mma_tf32(acc[k], ah, bl0, bl1);
-          cv_mma_tf32(acc[k], ah, bh0, bh1);
+          uint32_t bh[3][2], bl[3][2];
+          float tq[3][4];
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              bh[kx][q] = cv_tf32_hi(bv[kx][q]);
+              bl[kx][q] = __float_as_uint(bv[kx][q] - __uint_as_float(bh[kx][q]));
+            }
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32_zero(tq[kx], al, bh[kx][0], bh[kx][1]);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32(tq[kx], ah, bl[kx][0], bl[kx][1]);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32(tq[kx], ah, bh[kx][0], bh[kx][1]);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[ky * 3 + kx][q] += tq[kx][q];
         } else {
-          cv_mma_tf32(acc[k], ah, __float_as_uint(b0), __float_as_uint(b1));
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            cv_mma_tf32(acc[ky * 3 + kx], ah, __float_as_uint(bv[kx][0]), __float_as_uint(bv[kx][1]));
         }
       }
     }

@@ -52,6 +52,13 @@ def _out_hw(layer):
     return h // 2 if layer < 7 else h * 2
 
 
+def _set_conv_precision(mode):
+    """Process-wide conv arithmetic of the native library (0 fp32 FMA, 1 TF32, 2 3xTF32); the
+    reference-side analogue is torch.backends.cudnn.allow_tf32.  A host-side switch, no launch."""
+    if _lib.lib().ava_b200_set_conv_precision(mode) != 0:
+        raise _lib.AvaB200Error(_lib.last_error())
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -350,6 +357,7 @@ class VAE(nn.Module):
     def _conv_fwd(self, l, B, x, y, bufs, train, want_stats_out):
         name = _LAYERS[l][0]
         st = bufs.stats.data_ptr()
+        _set_conv_precision(self._tc)
         call("ava_b200_bnconv_fwd", l, B, ptr(x), ptr(y), self._p(name + ".weight"),
              self._p(name + ".bias"), self._p("bn%d.weight" % (l + 1)), self._p("bn%d.bias" % (l + 1)),
              st + 8 * 64 * l, self._rm(l), self._rv(l), 1 if train else 0,
@@ -462,6 +470,7 @@ class VAE(nn.Module):
             call("ava_b200_bn_relu_bwd_apply", ptr(g_out), ptr(y), ng, st + 8 * 64 * (l + 1),
                  ds + 8 * 64 * (l + 1), B, co, hw, relu, ptr(g_out), s)
         ws = self._ws(self._scratch_need)
+        _set_conv_precision(self._tc)
         call("ava_b200_bnconv_bwd_weight", l, B, ptr(g_out), ptr(x), self._p("bn%d.weight" % (l + 1)),
              self._p("bn%d.bias" % (l + 1)), st + 8 * 64 * l, self._g(name + ".weight"),
              self._g(name + ".bias"), ptr(ws), s)
