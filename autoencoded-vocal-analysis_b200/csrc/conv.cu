@@ -996,11 +996,15 @@ __global__ void __launch_bounds__(256, 2)
   constexpr int GITERS = (NQG + 255) / 256;
   constexpr int IITERS = (NQI + 255) / 256;
 
+  // double buffering (the next tile's boxes fly while this one is transformed and consumed) when
+  // two stages leave room for >= 2 CTAs per SM
+  // (measured: pays for the small tiles and for the convT layers, whose in-place transform only
+  // touches the small G tile)
+  constexpr bool DB = (G_PAD + I_PAD) * 4 <= (CONVT ? 48 : 40) * 1024;
+  constexpr int NSTG = DB ? 2 : 1;
   extern __shared__ __align__(128) float smem[];
-  float* s_g = smem;                                   // [CG][G_PLANE]
-  float* s_i = s_g + G_PAD;                            // [CI][I_PLANE]
-  float* s_aff = s_i + I_PAD;                          // BN coefs: scale[32] | shift[32]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_aff + 64);
+  float* s_aff = smem + NSTG * (G_PAD + I_PAD);        // BN coefs: scale[32] | shift[32]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_aff + 64);   // [NSTG]
 
   const int tid = threadIdx.x;
   const bool active = tid < NACT;
@@ -1015,9 +1019,21 @@ __global__ void __launch_bounds__(256, 2)
   const int ntiles = P.B * tiles_per_img;
 
   if (tid == 0) {
-    cv_mbar_init(s_bar, 1);
+    cv_mbar_init(&s_bar[0], 1);
+    if (DB) cv_mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // TMA: boxes of `tile` into stage `st` (thread 0)
+  auto issue = [&](int tile, int st) {
+    const int n = tile / tiles_per_img;
+    const int trem = tile - n * tiles_per_img;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    constexpr uint32_t BYTES = (uint32_t)(G_FLOATS * 4 + CI * T::I_PLANE_RAW * 4);
+    float* sg = smem + st * (G_PAD + I_PAD);
+    cv_mbar_expect_tx(&s_bar[st], BYTES);
+    cv_tma_load_3d(sg, &map_g, tx * TWG, ty * T::THG, n * CG, &s_bar[st]);
+    cv_tma_load_3d(sg + G_PAD, &map_i, S * tx * TWG - 4, S * ty * T::THG - 1, n * CI, &s_bar[st]);
+  };
   // coefficients
   if (tid < 32) {
     const int c = tid;
@@ -1069,23 +1085,26 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
   for (int g = 0; g < GT; ++g) bs[g] = 0.f;
 
-  uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  __syncthreads();   // barriers initialised
+  if (DB && tid == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int st = DB ? (it & 1) : 0;
     const int n = tile / tiles_per_img;
     const int trem = tile - n * tiles_per_img;
     const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
     const int gy0 = ty * T::THG, gx0 = tx * TWG;
     const int iy0 = S * gy0 - 1;
     const int X0 = S * gx0;
+    (void)gy0;
+    float* s_g = smem + st * (G_PAD + I_PAD);           // [CG][G_PLANE]
+    float* s_i = s_g + G_PAD;                            // [CI][I_PLANE]
     __syncthreads();  // previous tile's FMA loop is done with the buffers
     if (tid == 0) {
-      constexpr uint32_t BYTES = (uint32_t)(G_FLOATS * 4 + CI * T::I_PLANE_RAW * 4);
-      cv_mbar_expect_tx(s_bar, BYTES);
-      cv_tma_load_3d(s_g, &map_g, gx0, gy0, n * CG, s_bar);
-      cv_tma_load_3d(s_i, &map_i, X0 - 4, iy0, n * CI, s_bar);
+      if (!DB) issue(tile, 0);
+      else if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, st ^ 1);
     }
-    cv_mbar_wait(s_bar, phase);
-    phase ^= 1;
+    cv_mbar_wait(&s_bar[st], DB ? ((it >> 1) & 1) : (it & 1));
     if (CONVT) {
       // ---- G = x: BatchNorm in place (no halo, always in range)
 #pragma unroll
@@ -1228,10 +1247,10 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
   constexpr int IITERS = (NQI + NTHR - 1) / NTHR;
   constexpr int KSTEPS = T::THG * TWG / 8;
 
+  constexpr bool DB = (G_PAD + I_PAD) * 4 <= 40 * 1024;   // see wgrad_kernel
+  constexpr int NSTG = DB ? 2 : 1;
   extern __shared__ __align__(128) float smem[];
-  float* s_g = smem;
-  float* s_i = s_g + G_PAD;
-  float* s_aff = s_i + I_PAD;
+  float* s_aff = smem + NSTG * (G_PAD + I_PAD);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_aff + 64);
 
   const int tid = threadIdx.x;
@@ -1246,9 +1265,20 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
   const int ntiles = P.B * tiles_per_img;
 
   if (tid == 0) {
-    cv_mbar_init(s_bar, 1);
+    cv_mbar_init(&s_bar[0], 1);
+    if (DB) cv_mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  auto issue = [&](int tile, int st) {
+    const int n = tile / tiles_per_img;
+    const int trem = tile - n * tiles_per_img;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    constexpr uint32_t BYTES = (uint32_t)(G_FLOATS * 4 + I_FLOATS * 4);
+    float* sg = smem + st * (G_PAD + I_PAD);
+    cv_mbar_expect_tx(&s_bar[st], BYTES);
+    cv_tma_load_3d(sg, &map_g, tx * TWG, ty * T::THG, n * CG, &s_bar[st]);
+    cv_tma_load_3d(sg + G_PAD, &map_i, S * tx * TWG - 4, S * ty * T::THG - 1, n * CI, &s_bar[st]);
+  };
   if (tid < 32) {
     constexpr int CA = CONVT ? CG : CI;
     if (tid < CA) {
@@ -1267,23 +1297,26 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
   // rows g+8 of the last M-tile do not exist when CG is not a multiple of 16
   const bool hi_rows = (CG % 16 == 0) || (mt + 1 < MT);
 
-  uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  __syncthreads();   // barriers initialised
+  if (DB && tid == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int st = DB ? (it & 1) : 0;
     const int n = tile / tiles_per_img;
     const int trem = tile - n * tiles_per_img;
     const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
     const int gy0 = ty * T::THG, gx0 = tx * TWG;
     const int iy0 = S * gy0 - 1;
     const int X0 = S * gx0;
-    __syncthreads();
+    (void)n;
+    float* s_g = smem + st * (G_PAD + I_PAD);
+    float* s_i = s_g + G_PAD;
+    __syncthreads();   // previous tile's MMA loop is done with the buffers
     if (tid == 0) {
-      constexpr uint32_t BYTES = (uint32_t)(G_FLOATS * 4 + I_FLOATS * 4);
-      cv_mbar_expect_tx(s_bar, BYTES);
-      cv_tma_load_3d(s_g, &map_g, gx0, gy0, n * CG, s_bar);
-      cv_tma_load_3d(s_i, &map_i, X0 - 4, iy0, n * CI, s_bar);
+      if (!DB) issue(tile, 0);
+      else if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, st ^ 1);
     }
-    cv_mbar_wait(s_bar, phase);
-    phase ^= 1;
+    cv_mbar_wait(&s_bar[st], DB ? ((it >> 1) & 1) : (it & 1));
     if (CONVT) {
       // G = x: BatchNorm in place
 #pragma unroll
@@ -1444,7 +1477,8 @@ static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStrea
   using T = WTile<S, TWG>;
   constexpr int G_PAD = (CG * T::G_PLANE + 31) / 32 * 32;
   constexpr int I_PAD = (CI * T::I_PLANE + 31) / 32 * 32;
-  size_t smem_f = (size_t)G_PAD + I_PAD + 64 + 8;
+  constexpr int NSTG = ((G_PAD + I_PAD) * 4 <= (CONVT ? 48 : 40) * 1024) ? 2 : 1;   // as in the kernel
+  size_t smem_f = (size_t)NSTG * (G_PAD + I_PAD) + 64 + 8;
   if (smem_f < (size_t)CG * CI * 9 + 32) smem_f = (size_t)CG * CI * 9 + 32;
   const size_t smem = smem_f * sizeof(float) + 128;
   auto kern = wgrad_kernel<S, CG, CI, TWG, CONVT>;
@@ -1482,7 +1516,8 @@ static int launch_wgrad_mma(WgradParams P, float* dw, float* db, void* ws, cudaS
   constexpr int NTHR = (NPAIR == 6) ? 192 : 256;
   constexpr int G_PAD = (CG * T::G_PLANE + 31) / 32 * 32;
   constexpr int I_PAD = (CI * T::I_PLANE + 31) / 32 * 32;
-  size_t smem_f = (size_t)G_PAD + I_PAD + 64 + 8;
+  constexpr int NSTG = ((G_PAD + I_PAD) * 4 <= 40 * 1024) ? 2 : 1;   // as in the kernel
+  size_t smem_f = (size_t)NSTG * (G_PAD + I_PAD) + 64 + 8;
   if (smem_f < (size_t)CG * CI * 9 + 32) smem_f = (size_t)CG * CI * 9 + 32;
   const size_t smem = smem_f * sizeof(float) + 128;
   auto kern = wgrad_mma_kernel<S, CG, CI, TWG, CONVT, TERMS>;
@@ -1513,7 +1548,7 @@ static int launch_wgrad_mma(WgradParams P, float* dw, float* db, void* ws, cudaS
   return check_launch("wgrad_reduce");
 }
 
-// tensor-core weight gradient for the layers with >= 16 "G" channels, else the fp32 FMA kernel
+// tensor-core weight gradient (all layers with >= 8 channels on both sides), else the fp32 FMA kernel
 #define WGRAD_TC(S, CG, CI, TWG, CONVT)                                                              \
   (g_conv_terms == 3   ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 3>(P, dw, db, ws, stream)          \
    : g_conv_terms == 1 ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 1>(P, dw, db, ws, stream)          \
@@ -1684,7 +1719,7 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, con
     P.Hg = P.Wg = ho;
     switch (layer) {
       case 0: rc = launch_wgrad<1, 8, 1, 32, 0>(P, dw, db, ws, stream); break;
-      case 1: rc = launch_wgrad<2, 8, 8, 32, 0>(P, dw, db, ws, stream); break;
+      case 1: rc = WGRAD_TC(2, 8, 8, 32, 0); break;
       case 2: rc = WGRAD_TC(1, 16, 8, 32, 0); break;
       case 3: rc = WGRAD_TC(2, 16, 16, 32, 0); break;
       case 4: rc = WGRAD_TC(1, 24, 16, 32, 0); break;
@@ -1703,7 +1738,7 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, con
       case 9: rc = WGRAD_TC(1, 24, 16, 32, 1); break;
       case 10: rc = WGRAD_TC(2, 16, 16, 32, 1); break;
       case 11: rc = WGRAD_TC(1, 16, 8, 32, 1); break;
-      case 12: rc = launch_wgrad<2, 8, 8, 32, 1>(P, dw, db, ws, stream); break;
+      case 12: rc = launch_wgrad<2, 8, 8, 32, 1>(P, dw, db, ws, stream); break;  // HBM-bound: FMA kernel wins
       case 13: rc = launch_wgrad<1, 8, 1, 32, 1>(P, dw, db, ws, stream); break;
     }
     return rc;

@@ -321,7 +321,7 @@ def main():
     sampler.join(timeout=2)
     if rank == 0:
         peak, peak_src = measured_peaks()
-        roof, kernels = None, []
+        roof, kernels, families = None, [], []
         if prof is not None:
             agg = prof.summary(B, args.steps)
             tot = sum(d["ms"] for d in agg.values())
@@ -333,18 +333,34 @@ def main():
                                 "us_per_launch": round(1e3 * d["ms"] / d["n"], 2),
                                 "GBps": round(gbs, 1), "hbm_frac": round(gbs / peak, 4),
                                 "fp32_TFLOPs": round(tf, 2)})
-            key, d = top[0]
-            traffic = None
+            # the dominant kernel = the native entry point (all its launches in the step, every
+            # layer it serves) with the largest share of the step
+            fam = {}
+            for key, d in agg.items():
+                f = fam.setdefault(key.split("[")[0], {"ms": 0.0, "n": 0, "bytes": 0.0, "flops": 0.0})
+                for kk in ("ms", "n", "bytes", "flops"):
+                    f[kk] += d[kk]
+            ftop = sorted(fam.items(), key=lambda kv: -kv[1]["ms"])
             tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+            tmap = {}
             if os.path.exists(tpath) and B == 1024:
                 with open(tpath) as f:
-                    traffic = json.load(f).get(key.replace("ava_b200_", ""))
+                    tmap = json.load(f)
+            for key, d in ftop[:8]:
+                gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+                families.append({"call": key.replace("ava_b200_", ""), "share": round(d["ms"] / tot, 4),
+                                 "launches_per_step": d["n"] // args.steps,
+                                 "us_per_step": round(1e3 * d["ms"] / args.steps, 1),
+                                 "GBps": round(gbs, 1), "hbm_frac": round(gbs / peak, 4),
+                                 "fp32_TFLOPs": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2)})
+            key, d = ftop[0]
             ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             roof = {"kernel": key.replace("ava_b200_", ""), "bound": "hbm", "achieved": round(ach, 1),
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4),
-                    "traffic": traffic,
+                    "traffic": tmap.get(key.replace("ava_b200_", "")),
                     "algorithmic_bytes_per_launch": d["bytes"] / d["n"],
                     "us_per_launch": round(1e3 * d["ms"] / d["n"], 2),
+                    "launches_per_step": d["n"] // args.steps,
                     "fp32_TFLOPs": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2),
                     "share_of_step": round(d["ms"] / tot, 4)}
         cpu = None
@@ -357,15 +373,18 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "dtype_note": "fp32 storage and accumulation everywhere; fc1/fc8 products as "
-                          "error-compensated 3xTF32 on tcgen05 (parity 2e-5 vs float64) when "
-                          "precision is auto/tf32x3",
+            "dtype_note": "fp32 storage and accumulation everywhere; with precision auto/tf32x3 the "
+                          "fc1/fc8 products (tcgen05) and the conv inner products of the layers with "
+                          ">= 8 channels (mma.sync) are error-compensated 3xTF32 = fp32-level accuracy "
+                          "(whole-model gradient parity equal to the fp32 FMA path); 'tf32' is the "
+                          "opt-in reduced-precision mode (the reference's own GPU default)",
             "config": make_config(B, world, args.precision),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 128 * 128 * 4,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "roofline": roof,
+            "kernel_families": families,
             "kernels": kernels,
             "cpu_baseline": cpu,
         }
