@@ -374,7 +374,7 @@ class VAE(nn.Module):
             h = bufs.act[l]
         tc = self._tc
         self._linear(h, 8192, "fc1.weight", "fc1.bias", bufs.h1, 1024, B, 1024, 8192, 1, tc=tc)
-        self._linear(bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.h2, 256, B, 256, 1024, 1)
+        self._linear(bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.h2, 256, B, 256, 1024, 1, tc=tc)
         # fc31|fc32|fc33 share their input: one [192,256] layer
         self._linear(bufs.h2, 256, "fc31.weight", "fc31.bias", bufs.h3, 192, B, 192, 256, 1)
         # fc41|fc42|fc43: three [Z,64] layers on the three 64-wide slices (strided batch)
@@ -387,7 +387,7 @@ class VAE(nn.Module):
         tc = self._tc
         self._linear(z, Z, "fc5.weight", "fc5.bias", bufs.t5, 64, B, 64, Z, 1)
         self._linear(bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.t6, 256, B, 256, 64, 1)
-        self._linear(bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.t7, 1024, B, 1024, 256, 1)
+        self._linear(bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.t7, 1024, B, 1024, 256, 1, tc=tc)
         self._linear(bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.t8, 8192, B, 8192, 1024, 1, tc=tc)
         if train:
             call("ava_b200_channel_stats", ptr(bufs.t8), B, 32, 256,
@@ -498,7 +498,7 @@ class VAE(nn.Module):
         self._linear_bwd(bufs.dt8, 8192, None, bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.dt7, 1024,
                          B, 8192, 1024, tc=self._tc)
         self._linear_bwd(bufs.dt7, 1024, bufs.t7, bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.dt6, 256,
-                         B, 1024, 256)
+                         B, 1024, 256, tc=self._tc)
         self._linear_bwd(bufs.dt6, 256, bufs.t6, bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.dt5, 64,
                          B, 256, 64)
         self._linear_bwd(bufs.dt5, 64, bufs.t5, bufs.z, Z, "fc5.weight", "fc5.bias", bufs.gz, Z,
@@ -515,7 +515,7 @@ class VAE(nn.Module):
         self._linear_bwd(bufs.dh3, 192, bufs.h3, bufs.h2, 256, "fc31.weight", "fc31.bias", bufs.dh2,
                          256, B, 192, 256)
         self._linear_bwd(bufs.dh2, 256, bufs.h2, bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.dh1,
-                         1024, B, 256, 1024)
+                         1024, B, 256, 1024, tc=self._tc)
         self._linear_bwd(bufs.dh1, 1024, bufs.h1, bufs.act[6], 8192, "fc1.weight", "fc1.bias",
                          bufs.da6, 8192, B, 1024, 8192, tc=self._tc)
         # ---- encoder conv stack, layers 6..0
