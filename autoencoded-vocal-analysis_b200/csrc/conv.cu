@@ -987,7 +987,11 @@ __global__ void __launch_bounds__(256, 2)
   constexpr int NSLOT = NGQ * CI;         // (gq, i) pairs
   constexpr int NPG = 256 / NSLOT;        // pixel groups
   constexpr int NACT = NPG * NSLOT;       // active threads
-  constexpr int G_FLOATS = CG * T::G_PLANE;
+  // one g-channel per thread (CI == 1): lanes differ in the g-channel, so the G planes are padded
+  // to 4 (mod 32) floats (box with 4 spare columns and one spare row) against bank conflicts
+  constexpr int GW = (CI == 1) ? TWG + 4 : TWG, GROWS = (CI == 1) ? T::THG + 1 : T::THG;
+  constexpr int GPL = GW * GROWS;
+  constexpr int G_FLOATS = CG * GPL;
   constexpr int I_FLOATS = CI * T::I_PLANE;
   constexpr int G_PAD = (G_FLOATS + 31) / 32 * 32;
   constexpr int I_PAD = (I_FLOATS + 31) / 32 * 32;
@@ -1055,7 +1059,7 @@ __global__ void __launch_bounds__(256, 2)
       const int q = t % (TWG / 4);
       const int y = (t / (TWG / 4)) % T::THG;
       const int c = t / ((TWG / 4) * T::THG);
-      g_off[j] = c * T::G_PLANE + y * TWG + 4 * q;
+      g_off[j] = c * GPL + y * GW + 4 * q;
       g_ch[j] = c;
     }
   }
@@ -1174,7 +1178,7 @@ __global__ void __launch_bounds__(256, 2)
       }
 #pragma unroll
       for (int g = 0; g < GT; ++g) {
-        float4 gv = *reinterpret_cast<const float4*>(s_g + (gq * GT + g) * T::G_PLANE + sy * TWG + sx);
+        float4 gv = *reinterpret_cast<const float4*>(s_g + (gq * GT + g) * GPL + sy * GW + sx);
         const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
         if (!CONVT && ti == 0) bs[g] += (gg[0] + gg[1]) + (gg[2] + gg[3]);
 #pragma unroll
@@ -1475,7 +1479,8 @@ reduce_partials_kernel(const float* __restrict__ partial, int nparts, int stride
 template <int S, int CG, int CI, int TWG, int CONVT>
 static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStream_t stream) {
   using T = WTile<S, TWG>;
-  constexpr int G_PAD = (CG * T::G_PLANE + 31) / 32 * 32;
+  constexpr int GW = (CI == 1) ? TWG + 4 : TWG, GROWS = (CI == 1) ? T::THG + 1 : T::THG;   // as in the kernel
+  constexpr int G_PAD = (CG * GW * GROWS + 31) / 32 * 32;
   constexpr int I_PAD = (CI * T::I_PLANE + 31) / 32 * 32;
   constexpr int NSTG = ((G_PAD + I_PAD) * 4 <= (CONVT ? 48 : 40) * 1024) ? 2 : 1;   // as in the kernel
   size_t smem_f = (size_t)NSTG * (G_PAD + I_PAD) + 64 + 8;
@@ -1498,7 +1503,7 @@ static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStrea
   int grid = (int)(ntiles < max_ctas ? ntiles : max_ctas);
   if (grid > kWgradMaxCtas) grid = kWgradMaxCtas;  // workspace bound, see ava_b200_bnconv_bwd_weight_ws
   CUtensorMap map_g, map_i;
-  if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, TWG, T::THG, CG)) return 1;
+  if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, GW, GROWS, CG)) return 1;
   if (make_act_map(&map_i, P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS, CI)) return 1;
   P.partial = reinterpret_cast<float*>(ws);
   const int stride = CG * CI * 9 + 32;
