@@ -111,6 +111,77 @@ class _Buffers:
         self.da6 = torch.empty(B, 8192, **f32)
 
 
+_PREFETCH_STATE = {}
+
+
+def prefetch_to_device(batches, device=None, depth=1):
+    """Iterate over host batches with the host->device copy of batch i+1 in flight on a side
+    stream while batch i is being consumed (the reference copies synchronously inside the step,
+    ava/models/vae.py:349).  Batches that are already on the device pass through.  Copies land
+    in a small ring of preallocated device buffers (no allocator traffic in the loop); pageable
+    CPU tensors are staged through pinned memory so that the copy is asynchronous."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    nslots = depth + 1
+    # the side stream and the staging ring persist across calls (one set per device): epochs
+    # after the first allocate nothing
+    state = _PREFETCH_STATE.setdefault((device.index, nslots), {"stream": None, "ring": {}})
+    if state["stream"] is None:
+        state["stream"] = torch.cuda.Stream(device=device)
+    copy_stream, ring = state["stream"], state["ring"]
+    done = [None] * nslots          # consumer-finished events per slot
+    copy_stream.wait_stream(torch.cuda.current_stream(device))   # earlier readers of the ring
+    queue = []
+    count = 0
+
+    def enqueue(b):
+        nonlocal count
+        if not torch.is_tensor(b):
+            b = torch.as_tensor(b)
+        if b.is_cuda:
+            queue.append((b, None, -1))
+            return
+        if b.dtype != torch.float32:
+            b = b.float()
+        if not b.is_pinned():
+            b = b.pin_memory()
+        slot = count % nslots
+        count += 1
+        bufs = ring.setdefault(tuple(b.shape), [None] * nslots)
+        if bufs[slot] is None:
+            bufs[slot] = torch.empty(b.shape, dtype=torch.float32, device=device)
+        if done[slot] is not None:
+            copy_stream.wait_event(done[slot])      # the step that read this slot has been issued
+        with torch.cuda.stream(copy_stream):
+            bufs[slot].copy_(b, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        queue.append((bufs[slot], ev, slot))
+
+    def pop():
+        d, ev, slot = queue.pop(0)
+        if ev is not None:
+            torch.cuda.current_stream(device).wait_event(ev)
+        return d, slot
+
+    def release(slot):
+        if slot >= 0:
+            done[slot] = torch.cuda.Event()
+            done[slot].record(torch.cuda.current_stream(device))
+
+    for b in batches:
+        enqueue(b)
+        if len(queue) > depth:
+            d, slot = pop()
+            yield d
+            release(slot)
+    while queue:
+        d, slot = pop()
+        yield d
+        release(slot)
+
+
 class VAE(nn.Module):
     """Variational Autoencoder class for single-channel images (B200-native).
 
@@ -737,7 +808,7 @@ class VAE(nn.Module):
         self._require_cuda()
         self._loss_sum.zero_()
         n_steps = 0
-        for batch_idx, data in enumerate(train_loader):
+        for batch_idx, data in enumerate(prefetch_to_device(train_loader, self._flat_p.device)):
             self.train_step(data)
             n_steps += 1
         # one device->host read per epoch instead of loss.item() per step
@@ -754,7 +825,7 @@ class VAE(nn.Module):
         self._loss_sum.zero_()
         n_steps = 0
         with torch.no_grad():
-            for i, data in enumerate(test_loader):
+            for i, data in enumerate(prefetch_to_device(test_loader, self._flat_p.device)):
                 self._forward_native(data, None, False, want_grad_seed=False)
                 n_steps += 1
         test_loss = self._epoch_loss(n_steps)
@@ -898,7 +969,7 @@ class VAE(nn.Module):
         dev_latent = torch.zeros(n, Z, dtype=torch.float32, device=self._flat_p.device)
         i = 0
         with torch.no_grad():
-            for data in loader:
+            for data in prefetch_to_device(loader, self._flat_p.device):
                 x = self._as_input(data)
                 B = x.shape[0]
                 bufs = self._buffers_for(B)
