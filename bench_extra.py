@@ -49,6 +49,20 @@ def main():
     win_mod = importlib.import_module(PKG + ".models.window_vae_dataset")
     torch.manual_seed(0)
     out = []
+    # ---- train step at batch 1024 per precision mode (bench.py's headline is 'auto' = tf32x3)
+    for prec in ("fp32", "tf32x3", "tf32"):
+        model = vae_mod.VAE(device_name='cuda', precision=prec, cuda_graphs=False)
+        model.train()
+        xs = [torch.rand(1024, 128, 128, device="cuda") for _ in range(2)]
+        k = [0]
+
+        def step():
+            k[0] += 1
+            return model.train_step(xs[k[0] & 1])
+        ms, wall = timed(step, 10, warmup=3)
+        out.append({"what": "train_step", "batch": 1024, "precision": prec, "ms_per_step": ms,
+                    "samples_per_s": 1024 / (ms * 1e-3)})
+        del model, xs
     # ---- train step at small batches
     for B, graphs in ((64, True), (64, False), (256, True)):
         model = vae_mod.VAE(device_name='cuda', cuda_graphs=graphs)
