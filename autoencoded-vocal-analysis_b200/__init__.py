@@ -7,6 +7,8 @@ module layout for that path:
     ava.models.vae_dataset         -> <this package>.models.vae_dataset
     ava.models.window_vae_dataset  -> <this package>.models.window_vae_dataset
     ava.preprocessing.utils        -> <this package>.preprocessing.utils
+    ava.preprocessing.preprocess   -> <this package>.preprocessing.preprocess  (process_sylls)
+    ava.plotting.mmd_plots         -> <this package>.plotting.mmd_plots        (MMD^2 estimators)
 
 The directory name contains hyphens, so import it with
 ``importlib.import_module("autoencoded-vocal-analysis_b200")`` or through the

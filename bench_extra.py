@@ -139,6 +139,53 @@ def main():
         ms, wall = timed(lambda: model.train_step(ds.sample_batch(nb)), 15)
         out.append({"what": "shotgun train step with on-the-fly GPU get_spec", "batch": nb,
                     "ms_per_step_wall": wall, "samples_per_s": nb / (wall * 1e-3)})
+    # ---- syllable preprocessing driver (all syllables of a file in one launch)
+    pp = importlib.import_module(PKG + ".preprocessing.preprocess")
+    from oracle import spec_oracle
+    ps = dict(FINCH_P)
+    ps.update(max_dur=0.2, time_stretch=True)
+    fs = ps['fs']
+    audio = spec_oracle.synth_audio(5, int(120 * fs), fs)
+    rng = np.random.default_rng(0)
+    on = np.sort(rng.uniform(0.1, 119.0, size=2000))
+    off = on + rng.uniform(0.03, 0.19, size=2000)
+    tf = pp._inv_mel(np.linspace(pp._mel(ps['min_freq']), pp._mel(ps['max_freq']), ps['num_freq_bins']))
+    pp._syll_specs_batched(on[:64], off[:64], audio, fs, ps, tf)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    specs, _ = pp._syll_specs_batched(on, off, audio, fs, ps, tf)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for i in range(40):
+        spec_oracle.get_spec(on[i], off[i], audio, ps, fs=fs, target_freqs=tf)
+    cpu = (time.perf_counter() - t0) / 40
+    out.append({"what": "process_sylls: get_syll_specs of one file (2000 syllables, incl. upload of 120 s "
+                        "audio and float64 download)", "syllables_per_s": len(specs) / dt,
+                "cpu_port_syllables_per_s_1core": 1.0 / cpu,
+                "cpu_sample": "40 syllables through oracle/spec_oracle.get_spec (numpy float64)"})
+    # ---- MMD^2 matrix between conditions of a corpus of latent means
+    mmd = importlib.import_module(PKG + ".plotting.mmd_plots")
+    from oracle import mmd_oracle
+    N, ncond = 18020, 8            # corpus size of docs/source/data_management.rst:73
+    lat = rng.standard_normal((N, 32))
+    cond = rng.integers(0, ncond, size=N)
+    mmd.mmd2_matrix(lat[:512], cond[:512], sigma=8.0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m, _ = mmd.mmd2_matrix(lat, cond, sigma=8.0)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    i1, i2 = np.argwhere(cond == 0).flatten()[:600], np.argwhere(cond == 1).flatten()[:600]
+    t0 = time.perf_counter()
+    mmd_oracle.estimate_mmd2(lat, i1, i2, 8.0)
+    cpu = time.perf_counter() - t0
+    cpu_pairs = (600 * 599 + 600 * 600)
+    out.append({"what": "mmd2_matrix: all %d condition pairs of %d latent means (fp64, incl. upload)" % (ncond * (ncond - 1) // 2, N),
+                "ms": 1e3 * dt, "kernel_evals_per_s": N * N / dt,
+                "cpu_port_kernel_evals_per_s": cpu_pairs / cpu,
+                "cpu_sample": "one pair of 600-point conditions through oracle/mmd_oracle.estimate_mmd2 (vectorised numpy; "
+                              "the reference itself is a Python double loop)"})
     for o in out:
         print(json.dumps(o))
 

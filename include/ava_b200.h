@@ -192,6 +192,17 @@ int ava_b200_get_spec_batch(const void* audio, int is_f32, const long long* seg_
                             const double* f_frac, int n_f, int max_frames, double spec_min, double spec_max,
                             float* out, double* out64, void* stream);
 
+/* ------------------------------------------------- MMD^2 between sets of latent means
+ * Downstream statistic on get_latent's output, ava/plotting/mmd_plots.py:255-312, 450-476.
+ * x: [N,D] float64 latent means; seg[i] in [0,n_seg) = condition of row i.
+ * S[a*n_seg+b] = sum_{i in a, j in b} exp(A*||x_i-x_j||^2), A = -0.5/sigma^2 (S is zeroed by
+ * the call).  MMD^2(a,b) = (S_aa-n_a)/(n_a(n_a-1)) + (S_bb-n_b)/(n_b(n_b-1)) - 2 S_ab/(n_a n_b). */
+int ava_b200_mmd_block_sums(const double* x, int N, int D, const int* seg, int n_seg, double A, double* S,
+                            void* stream);
+/* out[k] = ||x[ia[k]]-x[ib[k]]||^2 (mode 0) or exp(A * that) (mode 1); numpy summation order. */
+int ava_b200_pair_kernel(const double* x, int D, const long long* ia, const long long* ib, long long n,
+                         double A, int mode, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

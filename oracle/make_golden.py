@@ -300,11 +300,113 @@ def sampler_cases(ref_win, ref_ds, ref_pre):
     print("sampler cases ok")
 
 
+class _FakeH5File:
+    """Stand-in for h5py.File("...", "w") that records create_dataset calls (h5py is not
+    installed here; the reference's process_sylls only uses this much of it)."""
+    written = {}
+
+    def __init__(self, filename, mode="r"):
+        self.filename = filename
+        self.data = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        _FakeH5File.written[os.path.basename(self.filename)] = self.data
+
+    def create_dataset(self, key, data=None):
+        self.data[key] = np.asarray(data)
+
+
+PROCESS_P = dict(spec_oracle.FINCH_P)
+PROCESS_P.update(max_dur=0.2, time_stretch=True, sylls_per_file=4, max_num_syllables=None)
+
+
+def write_process_corpus(root):
+    """Two synthetic int16 wav files + segment files (shared by the generator and the test)."""
+    from scipy.io import wavfile
+    adir, sdir = os.path.join(root, "audio"), os.path.join(root, "segs")
+    os.makedirs(adir, exist_ok=True)
+    os.makedirs(sdir, exist_ok=True)
+    fs = PROCESS_P['fs']
+    segs = {
+        "a.wav": [(0.10, 0.18), (0.30, 0.45), (0.600, 0.6100), (0.95, 1.10)],   # 3rd: < nperseg samples
+        "b.wav": [(0.05, 0.20), (0.50, 0.56), (1.42, 1.52), (0.80, 0.93), (1.10, 1.21)],  # 3rd runs off the end
+    }
+    for k, (name, sg) in enumerate(segs.items()):
+        wavfile.write(os.path.join(adir, name), fs, spec_oracle.synth_audio(21 + k, int(1.5 * fs), fs))
+        np.savetxt(os.path.join(sdir, name[:-4] + ".txt"), np.array(sg), header="onset offset")
+    return adir, sdir
+
+
+def process_case(ref_pre):
+    import tempfile
+    _ref_import.install_stubs()
+    import ava.preprocessing.preprocess as ref_pp
+    ref_pp.h5py.File = _FakeH5File
+    _FakeH5File.written = {}
+    p = dict(PROCESS_P)
+    p['get_spec'] = ref_pre.get_spec
+    with tempfile.TemporaryDirectory() as root:
+        adir, sdir = write_process_corpus(root)
+        ref_pp.process_sylls(adir, sdir, os.path.join(root, "out"), p, shuffle=True, verbose=False)
+    out = {"versions": np.array(versions())}
+    for fn, d in sorted(_FakeH5File.written.items()):
+        for key, v in d.items():
+            if key == 'audio_filenames':
+                v = np.array([os.path.basename(i.decode()) for i in v]).astype('S')
+            out[fn + ":" + key] = v
+    np.savez_compressed(os.path.join(GOLDEN, "process_sylls.npz"), **out)
+    print("process_sylls files:", sorted(_FakeH5File.written))
+
+
+def mmd_latent(seed=31):
+    rng = np.random.default_rng(seed)
+    sizes, shifts = (120, 150, 130), (0.0, 0.35, -0.5)
+    latent = np.concatenate([rng.standard_normal((n, 32)) + s for n, s in zip(sizes, shifts)])
+    condition = np.concatenate([np.full(n, 10 * (k + 1)) for k, n in enumerate(sizes)])
+    perm = rng.permutation(len(latent))
+    return latent[perm], condition[perm]
+
+
+def mmd_case():
+    _ref_import.install_stubs()
+    import types
+    for name, attrs in (("matplotlib.collections", {"PolyCollection": None}),
+                        ("matplotlib.colors", {"cnames": {}, "to_rgba": None})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+    import ava.plotting.mmd_plots as ref_mmd
+    latent, condition = mmd_latent()
+    out = {"versions": np.array(versions())}
+    sigma = ref_mmd.estimate_median_sigma(latent)
+    out["sigma"] = np.array(sigma)
+    conds = np.unique(condition)
+    groups = [np.argwhere(condition == c).flatten() for c in conds]
+    m = np.zeros((3, 3))
+    lin = np.zeros((3, 3))
+    sub = np.zeros((3, 3))
+    for i in range(2):
+        for j in range(i + 1, 3):
+            m[i, j] = m[j, i] = ref_mmd._estimate_mmd2(latent, groups[i], groups[j], sigma=sigma)
+            lin[i, j] = lin[j, i] = ref_mmd._estimate_mmd2_linear_time(latent, groups[i], groups[j], sigma=sigma)
+            sub[i, j] = sub[j, i] = ref_mmd._estimate_mmd2(latent, groups[i].copy(), groups[j].copy(),
+                                                           sigma=sigma, max_n=64, seed=5)
+    out["mmd2"], out["mmd2_linear"], out["mmd2_max64_seed5"] = m, lin, sub
+    out["sigma_n500_seed7"] = np.array(ref_mmd.estimate_median_sigma(latent, n=500, seed=7))
+    np.savez_compressed(os.path.join(GOLDEN, "mmd_cases.npz"), **out)
+    print("mmd cases: sigma", sigma, "mmd2", m[0, 1], m[0, 2], m[1, 2])
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
     ref_vae, ref_pre, ref_win, ref_ds = _ref_import.import_reference()
-    which = sys.argv[1:] or ["vae", "adam", "spec", "sampler"]
+    which = sys.argv[1:] or ["vae", "adam", "spec", "sampler", "process", "mmd"]
     if "vae" in which:
         vae_case(ref_vae, "vae_train_b7", seed=0, batch=7, train=True)
         vae_case(ref_vae, "vae_eval_b7", seed=1, batch=7, train=False)
@@ -316,6 +418,10 @@ def main():
         spec_cases(ref_pre)
     if "sampler" in which:
         sampler_cases(ref_win, ref_ds, ref_pre)
+    if "process" in which:
+        process_case(ref_pre)
+    if "mmd" in which:
+        mmd_case()
 
 
 if __name__ == "__main__":

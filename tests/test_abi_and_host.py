@@ -148,3 +148,47 @@ def test_window_sampler_bit_exact_on_cpu():
         assert np.array_equal(got_f, want_f) and np.array_equal(got_on, want_on)
     g = load_golden("sampler_cases")
     assert g["seed0_files"].shape == (12,)
+
+
+def test_next_rows_host_logic_and_no_cpu_fallback(tmp_path):
+    """process_sylls / mmd_plots: file pairing and parsing follow the
+    reference; compute raises without a CUDA device instead of falling back."""
+    import importlib
+    import numpy as np
+    import pytest
+    import torch
+    pp = importlib.import_module(PKG + ".preprocessing.preprocess")
+    mmd = importlib.import_module(PKG + ".plotting.mmd_plots")
+    adir, sdir = tmp_path / "audio", tmp_path / "segs"
+    adir.mkdir()
+    sdir.mkdir()
+    for name in ("b.wav", "a.wav", "c.wav", "notes.md"):
+        (adir / name).write_bytes(b"")
+    np.savetxt(sdir / "a.txt", np.array([[0.1, 0.2], [0.3, 0.45]]), header="onset offset")
+    np.savetxt(sdir / "c.txt", np.zeros((0, 2)), header="none")
+    a, s = pp.get_audio_seg_filenames(str(adir), str(sdir), {})
+    assert [os.path.basename(i) for i in a] == ["a.wav", "c.wav"]       # b.wav has no segment file
+    assert [os.path.basename(i) for i in s] == ["a.txt", "c.txt"]
+    assert [os.path.basename(i) for i in pp.get_audio_filenames(str(adir))] == ["a.wav", "b.wav", "c.wav"]
+    on, off = pp.read_onsets_offsets_from_file(str(sdir / "a.txt"), {})
+    assert list(on) == [0.1, 0.3] and list(off) == [0.2, 0.45]
+    on, off = pp.read_onsets_offsets_from_file(str(sdir / "c.txt"), {})
+    assert len(on) == 0 and len(off) == 0
+    assert pp.is_audio_file("x.wav") and not pp.is_audio_file("x.WAV") and not pp.is_audio_file("wav")
+    # MMD^2 from Gram block sums == the reference's three-term estimator
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal((7, 4)), rng.standard_normal((9, 4)) + 0.3
+    A = -0.5 / 1.7 ** 2
+    k = lambda u, v: np.exp(A * ((u[:, None] - v[None]) ** 2).sum(-1))     # noqa: E731
+    S = np.array([[k(x, x).sum(), k(x, y).sum()], [k(y, x).sum(), k(y, y).sum()]])
+    from oracle import mmd_oracle
+    lat = np.concatenate([x, y])
+    want = mmd_oracle.estimate_mmd2(lat, np.arange(7), np.arange(7, 16), 1.7)
+    assert abs(mmd._mmd2_from_sums(S, [7, 9], 0, 1) - want) <= 1e-12
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            mmd.estimate_median_sigma(lat)
+        with pytest.raises(RuntimeError):
+            pp._syll_specs_batched(np.array([0.1]), np.array([0.2]), np.zeros(32000, np.int16), 32000,
+                                   {'max_dur': 0.2, 'time_stretch': False, 'num_time_bins': 128,
+                                    'nperseg': 512, 'noverlap': 256, 'within_syll_normalize': False}, None)

@@ -99,3 +99,22 @@ def test_get_spec_oracle_matches_reference_golden():
                                    remove_dc_offset=False)
     # the reference computes this one in float32 (complex64 STFT)
     assert np.abs(spec - g["f32_a"]).max() <= 1e-5
+
+
+def test_mmd_oracle_matches_reference_golden():
+    """oracle/mmd_oracle.py (numpy restatement of ava/plotting/mmd_plots.py:255-312,450-476)
+    against outputs of the reference itself."""
+    from oracle import make_golden, mmd_oracle
+    g = load_golden("mmd_cases")
+    latent, condition = make_golden.mmd_latent()
+    assert mmd_oracle.estimate_median_sigma(latent) == float(g["sigma"])
+    sigma = float(g["sigma"])
+    groups = [np.argwhere(condition == c).flatten() for c in np.unique(condition)]
+    for i in range(2):
+        for j in range(i + 1, 3):
+            a = mmd_oracle.estimate_mmd2(latent, groups[i], groups[j], sigma)
+            assert abs(a - g["mmd2"][i, j]) <= 1e-10 * abs(g["mmd2"][i, j])
+            b = mmd_oracle.estimate_mmd2_linear_time(latent, groups[i], groups[j], sigma)
+            assert abs(b - g["mmd2_linear"][i, j]) <= 1e-12
+            c = mmd_oracle.estimate_mmd2(latent, groups[i].copy(), groups[j].copy(), sigma, max_n=64, seed=5)
+            assert abs(c - g["mmd2_max64_seed5"][i, j]) <= 1e-10 * abs(g["mmd2_max64_seed5"][i, j])
