@@ -60,10 +60,11 @@ struct GconvParams {
   int B, H_in, W_in;
 };
 
-template <int KIND, int TW>
+template <int KIND, int TW, bool MMA = false>
 struct TileGeom {
-  // sub-tile handled by 64 thread slots: output tile (S1,S2) or input tile (UP)
-  static constexpr int TH = (KIND == K_UP) ? 128 / TW : 256 / TW;
+  // sub-tile handled by 64 thread slots: output tile (S1,S2) or input tile (UP); the stride-2
+  // tensor-core tile is 128 output pixels (its staging buffers are twice as large per pixel)
+  static constexpr int TH = (KIND == K_UP || (MMA && KIND == K_S2)) ? 128 / TW : 256 / TW;
   static constexpr int IN_ROWS = (KIND == K_S1) ? TH + 2 : (KIND == K_S2 ? 2 * TH + 1 : TH + 1);
   // aligned interior of a staged row, loaded as float4 quads; halo columns are scalars
   static constexpr int QUADS = (KIND == K_S2) ? TW / 2 : TW / 4;
@@ -76,7 +77,7 @@ struct TileGeom {
   // floats so that the tensor-core fragment loads (4 channels x 8 pixels per warp) hit 32 banks
   static constexpr int EO = TW + 4;
   static constexpr int PITCH = (KIND == K_S1) ? (TW == 32 ? 44 : 28)
-                               : (KIND == K_S2) ? (TW == 32 ? 68 : 38)
+                               : (KIND == K_S2) ? (MMA ? (TW == 32 ? 72 : 40) : (TW == 32 ? 68 : 38))
                                                 : (TW == 32 ? 36 : 24);
   static constexpr int PLANE = IN_ROWS * PITCH;
   // raw (untransformed) staging tile = one dense TMA box [CIC][IN_ROWS][RAW_PITCH] whose first
@@ -96,7 +97,7 @@ struct TileGeom {
 // the load / transform / MMA / epilogue phases of independent CTAs overlap.
 template <int KIND, int CI, int CO, int TW, int INMODE, int TERMS = 0>
 struct GconvCfg {
-  using G = TileGeom<KIND, TW>;
+  using G = TileGeom<KIND, TW, (TERMS > 0)>;
   static constexpr bool MMA = TERMS > 0;
   static constexpr int COT = (CO >= 8) ? 8 : CO;
   static constexpr int NCOG = CO / COT;
@@ -142,7 +143,10 @@ struct GconvCfg {
   static constexpr bool ARES = (TERMS == 1) ? (NTL <= 3) : (NTL <= 2);
   static constexpr int W_FLOATS = CI * 9 * CO * (PRESPLIT ? 2 : 1);
   static constexpr int RED_FLOATS = MMA ? 4 * 64 : 128;
-  static_assert(!MMA || (CI % 8 == 0 && CO % 8 == 0 && KIND == K_S1), "tensor-core path: stride-1, channels % 8");
+  static_assert(!MMA || (CI % 8 == 0 && CO % 8 == 0 && KIND != K_UP), "tensor-core path: stride 1 / 2 down, channels % 8");
+  static_assert(!MMA || (G::PLANE % 32 == 8 || G::PLANE % 32 == 24), "tensor-core path: conflict-free channel planes");
+  // output rows per warp (16 pixels wide)
+  static constexpr int R = (KIND == K_S1) ? 4 : 2;
 };
 
 __device__ __forceinline__ uint32_t cv_tf32(float x) {
@@ -212,8 +216,8 @@ template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN, int TE
 __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
                                   GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::MINB)
     gconv_kernel(const __grid_constant__ CUtensorMap map_in, const GconvParams P) {
-  using G = TileGeom<KIND, TW>;
   using C = GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>;
+  using G = typename C::G;
   constexpr int COT = C::COT, NCOG = C::NCOG, NSUB = C::NSUB, NT = C::NT;
   constexpr int CIC = C::CIC, NCHUNK = C::NCHUNK;
   constexpr bool DIRECT = C::DIRECT;
@@ -408,15 +412,15 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
   __syncthreads();
 
   if constexpr (C::MMA) {
-    // ---------------------------------------------------------------- tensor-core path (K_S1)
-    // warp -> (sub-tile, 16-pixel half xh, 4 output rows from r0); lane -> (g, t) of the fragments
-    constexpr int NTL = C::NTL;
+    // ---------------------------------------------------------------- tensor-core path (K_S1, K_S2)
+    // warp -> (sub-tile, 16-pixel half xh, R output rows from r0); lane -> (g, t) of the fragments
+    constexpr int NTL = C::NTL, R = C::R;
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     constexpr int sub = 0;
     const int wq = warp;
     const int xh = (TW == 32) ? (wq & 1) : 0;
-    const int r0 = (TW == 32) ? 4 * (wq >> 1) : 4 * wq;
+    const int r0 = (TW == 32) ? R * (wq >> 1) : R * wq;
     float st1[NTL][2], st2[NTL][2];
 #pragma unroll
     for (int i = 0; i < NTL; ++i) st1[i][0] = st1[i][1] = st2[i][0] = st2[i][1] = 0.f;
@@ -430,9 +434,9 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       const int trem = tile - n * tiles_per_img;
       const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
 
-      float acc[4][NTL][4];
+      float acc[R][NTL][4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int i = 0; i < NTL; ++i)
 #pragma unroll
@@ -453,8 +457,8 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
         if (tvalid) {
           // A fragment (row-major 16 pixels x 8 channels): a0 = (pixel g, channel t),
           // a1 = (g+8, t), a2 = (g, t+4), a3 = (g+8, t+4); tile column 3 is the left halo
-          const float* tin = s_in + (DIRECT ? buf * C::STAGE : 0) + sub * C::FIN_SUB + t * G::PLANE + r0 * G::PITCH +
-                             3 + xh * 16 + g;
+          const float* tin = s_in + (DIRECT ? buf * C::STAGE : 0) + sub * C::FIN_SUB + t * G::PLANE +
+                             (KIND == K_S2 ? 2 * r0 : r0) * G::PITCH + (KIND == K_S2 ? 0 : 3) + xh * 16 + g;
           const float* wf = s_w + (ch * 9) * NTL * 32 * C::WF + lane * C::WF;
           // TF32 operands: the tensor core reads the top 19 bits of an fp32 register.  3 terms:
           // hi = x rounded to TF32, lo = x - hi (exact; its own low bits fall off at 2^-22 relative)
@@ -482,7 +486,53 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
               bl[1] = (TERMS == 3) ? __float_as_uint(b.y - __uint_as_float(bh[1])) : 0u;
             }
           };
-          if constexpr (C::ARES) {
+          if constexpr (KIND == K_S2) {
+            // stride 2: output row o reads input rows 2o+ky of the tile (5 rows for the warp's 2
+            // output rows); the staged rows hold odd columns at [3..], even columns at [EO..], so
+            // tap kx reads column offset 3 / EO / 4 with unit stride across the 16 pixels.
+            // Per kernel column: the 5 row fragments stay resident, the 3 taps of the column are
+            // chained on a fresh accumulator and flushed with one round-to-nearest add.
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int off = (kx == 0) ? 3 : (kx == 1 ? G::EO : 4);
+              uint32_t ah[5][4], al[5][4];
+#pragma unroll
+              for (int ir = 0; ir < 5; ++ir) load_a(tin + ir * G::PITCH + off, ah[ir], al[ir]);
+#pragma unroll
+              for (int i = 0; i < NTL; ++i) {
+                uint32_t bh[3][2], bl[3][2];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) load_b(ky * 3 + kx, i, bh[ky], bl[ky]);
+                if (TERMS == 3) {
+                  float tq[2][4];
+#pragma unroll
+                  for (int o = 0; o < 2; ++o) cv_mma_tf32_zero(tq[o], al[2 * o], bh[0][0], bh[0][1]);
+#pragma unroll
+                  for (int o = 0; o < 2; ++o) cv_mma_tf32(tq[o], ah[2 * o], bl[0][0], bl[0][1]);
+#pragma unroll
+                  for (int ky = 1; ky < 3; ++ky) {
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) cv_mma_tf32(tq[o], al[2 * o + ky], bh[ky][0], bh[ky][1]);
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) cv_mma_tf32(tq[o], ah[2 * o + ky], bl[ky][0], bl[ky][1]);
+                  }
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) cv_mma_tf32(tq[o], ah[2 * o + ky], bh[ky][0], bh[ky][1]);
+#pragma unroll
+                  for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[o][i][q] += tq[o][q];
+                } else {
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) cv_mma_tf32(acc[o][i], ah[2 * o + ky], bh[ky][0], bh[ky][1]);
+                }
+              }
+            }
+          } else if constexpr (C::ARES) {
             // A-resident order: the 6 input-row fragments of one kx stay in registers, every B
             // fragment is loaded once per tap and feeds the 4 output rows (independent accumulators,
             // issued term by term)
@@ -584,7 +634,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       if (EPI == EPI_BWD) {
         // sum g and sum g*x per channel (centred with the exact mean at the very end)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < R; ++r) {
           float xs[NTL][4];
 #pragma unroll
           for (int i = 0; i < NTL; ++i)
@@ -604,7 +654,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int i = 0; i < NTL; ++i)
 #pragma unroll
@@ -618,7 +668,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       }
       if (P.out) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int i = 0; i < NTL; ++i)
 #pragma unroll
@@ -902,8 +952,8 @@ static int g_conv_terms = 0;
 
 template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN, int TERMS = 0>
 static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
-  using G = TileGeom<KIND, TW>;
   using C = GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>;
+  using G = typename C::G;
   const size_t smem = (size_t)(C::BUF_FLOATS + C::W_FLOATS + 64 + C::RED_FLOATS + 32) * sizeof(float) +
                       32 * sizeof(double) + 16 + 128;
   if (P.H_in != HIN || P.W_in != HIN) {
@@ -1582,11 +1632,12 @@ static inline int h_out_of(const LayerGeom& L) {
 
 using namespace ava;
 
-// stride-1 layers with channel counts that are multiples of 8 can run on the tensor cores
-#define GCONV_TC(CI, CO, TW, INMODE, EPI, HIN)                                                     \
-  (g_conv_terms == 3   ? launch_gconv<K_S1, CI, CO, TW, INMODE, EPI, HIN, 3>(P, stream)            \
-   : g_conv_terms == 1 ? launch_gconv<K_S1, CI, CO, TW, INMODE, EPI, HIN, 1>(P, stream)            \
-                       : launch_gconv<K_S1, CI, CO, TW, INMODE, EPI, HIN, 0>(P, stream))
+// stride-1 / stride-2-down layers with channel counts that are multiples of 8 can run on the
+// tensor cores
+#define GCONV_TC(KIND, CI, CO, TW, INMODE, EPI, HIN)                                               \
+  (g_conv_terms == 3   ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 3>(P, stream)            \
+   : g_conv_terms == 1 ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 1>(P, stream)            \
+                       : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 0>(P, stream))
 
 extern "C" int ava_b200_set_conv_precision(int mode) {
   AVA_REQUIRE(mode == 0 || mode == 1 || mode == 2, "set_conv_precision: mode %d (0 fp32, 1 tf32, 2 tf32x3)", mode);
@@ -1631,17 +1682,17 @@ extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, c
   }
   switch (layer) {
     case 0: return launch_gconv<K_S1, 1, 8, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
-    case 1: return launch_gconv<K_S2, 8, 8, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
-    case 2: return GCONV_TC(8, 16, 32, IN_AFFINE, EPI_FWD, 64);
-    case 3: return launch_gconv<K_S2, 16, 16, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
-    case 4: return GCONV_TC(16, 24, 32, IN_AFFINE, EPI_FWD, 32);
-    case 5: return launch_gconv<K_S2, 24, 24, 16, IN_AFFINE, EPI_FWD, 32>(P, stream);
-    case 6: return GCONV_TC(24, 32, 16, IN_AFFINE, EPI_FWD, 16);
-    case 7: return GCONV_TC(32, 24, 16, IN_AFFINE, EPI_FWD, 16);
+    case 1: return GCONV_TC(K_S2, 8, 8, 32, IN_AFFINE, EPI_FWD, 128);
+    case 2: return GCONV_TC(K_S1, 8, 16, 32, IN_AFFINE, EPI_FWD, 64);
+    case 3: return GCONV_TC(K_S2, 16, 16, 32, IN_AFFINE, EPI_FWD, 64);
+    case 4: return GCONV_TC(K_S1, 16, 24, 32, IN_AFFINE, EPI_FWD, 32);
+    case 5: return GCONV_TC(K_S2, 24, 24, 16, IN_AFFINE, EPI_FWD, 32);
+    case 6: return GCONV_TC(K_S1, 24, 32, 16, IN_AFFINE, EPI_FWD, 16);
+    case 7: return GCONV_TC(K_S1, 32, 24, 16, IN_AFFINE, EPI_FWD, 16);
     case 8: return launch_gconv<K_UP, 24, 24, 16, IN_AFFINE, EPI_FWD, 16>(P, stream);
-    case 9: return GCONV_TC(24, 16, 32, IN_AFFINE, EPI_FWD, 32);
+    case 9: return GCONV_TC(K_S1, 24, 16, 32, IN_AFFINE, EPI_FWD, 32);
     case 10: return launch_gconv<K_UP, 16, 16, 32, IN_AFFINE, EPI_FWD, 32>(P, stream);
-    case 11: return GCONV_TC(16, 8, 32, IN_AFFINE, EPI_FWD, 64);
+    case 11: return GCONV_TC(K_S1, 16, 8, 32, IN_AFFINE, EPI_FWD, 64);
     case 12: return launch_gconv<K_UP, 8, 8, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
     case 13: return launch_gconv<K_S1, 8, 1, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
   }
@@ -1677,17 +1728,17 @@ extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const
   switch (layer) {
     case 0: return launch_gconv<K_S1, 8, 1, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
     case 1: return launch_gconv<K_UP, 8, 8, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
-    case 2: return GCONV_TC(16, 8, 32, IN_PLAIN, EPI_BWD, 64);
+    case 2: return GCONV_TC(K_S1, 16, 8, 32, IN_PLAIN, EPI_BWD, 64);
     case 3: return launch_gconv<K_UP, 16, 16, 32, IN_PLAIN, EPI_BWD, 32>(P, stream);
-    case 4: return GCONV_TC(24, 16, 32, IN_PLAIN, EPI_BWD, 32);
+    case 4: return GCONV_TC(K_S1, 24, 16, 32, IN_PLAIN, EPI_BWD, 32);
     case 5: return launch_gconv<K_UP, 24, 24, 16, IN_PLAIN, EPI_BWD, 16>(P, stream);
-    case 6: return GCONV_TC(32, 24, 16, IN_PLAIN, EPI_BWD, 16);
-    case 7: return GCONV_TC(24, 32, 16, IN_PLAIN, EPI_BWD, 16);
-    case 8: return launch_gconv<K_S2, 24, 24, 16, IN_PLAIN, EPI_BWD, 32>(P, stream);
-    case 9: return GCONV_TC(16, 24, 32, IN_PLAIN, EPI_BWD, 32);
-    case 10: return launch_gconv<K_S2, 16, 16, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
-    case 11: return GCONV_TC(8, 16, 32, IN_PLAIN, EPI_BWD, 64);
-    case 12: return launch_gconv<K_S2, 8, 8, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
+    case 6: return GCONV_TC(K_S1, 32, 24, 16, IN_PLAIN, EPI_BWD, 16);
+    case 7: return GCONV_TC(K_S1, 24, 32, 16, IN_PLAIN, EPI_BWD, 16);
+    case 8: return GCONV_TC(K_S2, 24, 24, 16, IN_PLAIN, EPI_BWD, 32);
+    case 9: return GCONV_TC(K_S1, 16, 24, 32, IN_PLAIN, EPI_BWD, 32);
+    case 10: return GCONV_TC(K_S2, 16, 16, 32, IN_PLAIN, EPI_BWD, 64);
+    case 11: return GCONV_TC(K_S1, 8, 16, 32, IN_PLAIN, EPI_BWD, 64);
+    case 12: return GCONV_TC(K_S2, 8, 8, 32, IN_PLAIN, EPI_BWD, 128);
     case 13: return launch_gconv<K_S1, 1, 8, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
   }
   return 1;
