@@ -78,7 +78,7 @@ struct TileGeom {
   static constexpr int EO = TW + 4;
   static constexpr int PITCH = (KIND == K_S1) ? (TW == 32 ? 44 : 28)
                                : (KIND == K_S2) ? (MMA ? (TW == 32 ? 72 : 40) : (TW == 32 ? 68 : 38))
-                                                : (TW == 32 ? 36 : 24);
+                                                : (TW == 32 ? (MMA ? 40 : 36) : 24);
   static constexpr int PLANE = IN_ROWS * PITCH;
   // raw (untransformed) staging tile = one dense TMA box [CIC][IN_ROWS][RAW_PITCH] whose first
   // column is input column X0-4 (S1,S2) or X0 (UP), so that the interior quads stay 16-byte
@@ -105,7 +105,9 @@ struct GconvCfg {
   // threads: 64 slots x NCOG channel groups x NSUB sub-tiles (256, or 192 for CO=24);
   // MMA: 4 warps on one sub-tile
   static constexpr int NSUB = MMA ? 1 : (NCOG >= 3) ? 1 : 4 / NCOG;
-  static constexpr int NT = MMA ? 128 : 64 * NCOG * NSUB;
+  // (the stride-2-up tensor-core CTA is 8 warps: one input row x 16 pixels and its 2x2 output
+  // parity classes per warp)
+  static constexpr int NT = MMA ? (KIND == K_UP ? 256 : 128) : 64 * NCOG * NSUB;
   // IN_PLAIN input (an already materialised gradient) needs no per-element transform and its
   // zero padding is exactly TMA's out-of-bounds fill: for the stride-1 / up kernels the boxes
   // land DIRECTly in the layout the FMA loop reads (double buffered, no staging pass at all).
@@ -133,7 +135,7 @@ struct GconvCfg {
   static constexpr int NHALO = CIC * G::IN_ROWS;
   static constexpr int HITERS = (NHALO + NT - 1) / NT;
   // CTAs per SM the register budget is tuned for
-  static constexpr int MINB = (MMA || COT == 1) ? 4 : 2;
+  static constexpr int MINB = (MMA && KIND == K_UP) ? 2 : (MMA || COT == 1) ? 4 : 2;
   // staged weights: SIMT [CI][9][CO]; MMA: B fragments in register order
   // [CI/8][9][NTL][32 lanes]: {b0,b1} TF32-rounded (TERMS 1); {b0_hi,b1_hi,b0_lo,b1_lo}
   // (TERMS 3, PRESPLIT) or, for the widest layers, {b0,b1} in full fp32 split where used
@@ -142,11 +144,11 @@ struct GconvCfg {
   // A-resident loop order when the fragments of 6 input rows fit next to the accumulators
   static constexpr bool ARES = (TERMS == 1) ? (NTL <= 3) : (NTL <= 2);
   static constexpr int W_FLOATS = CI * 9 * CO * (PRESPLIT ? 2 : 1);
-  static constexpr int RED_FLOATS = MMA ? 4 * 64 : 128;
-  static_assert(!MMA || (CI % 8 == 0 && CO % 8 == 0 && KIND != K_UP), "tensor-core path: stride 1 / 2 down, channels % 8");
+  static constexpr int RED_FLOATS = MMA ? (NT / 32) * 128 : 128;   // MMA: [warps][64] doubles
+  static_assert(!MMA || (CI % 8 == 0 && CO % 8 == 0), "tensor-core path: channels % 8");
   static_assert(!MMA || (G::PLANE % 32 == 8 || G::PLANE % 32 == 24), "tensor-core path: conflict-free channel planes");
   // output rows per warp (16 pixels wide)
-  static constexpr int R = (KIND == K_S1) ? 4 : 2;
+  static constexpr int R = (KIND == K_S1) ? 4 : (KIND == K_S2 ? 2 : 4);   // K_UP: the 4 parity classes
 };
 
 __device__ __forceinline__ uint32_t cv_tf32(float x) {
@@ -420,14 +422,26 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
     constexpr int sub = 0;
     const int wq = warp;
     const int xh = (TW == 32) ? (wq & 1) : 0;
-    const int r0 = (TW == 32) ? R * (wq >> 1) : R * wq;
-    float st1[NTL][2], st2[NTL][2];
+    // K_UP: r0 = the warp's input row; its accumulator index is the output parity class 2*oa+ob
+    const int r0 = (KIND == K_UP) ? ((TW == 32) ? (wq >> 1) : wq) : (TW == 32) ? R * (wq >> 1) : R * wq;
+    // per-channel statistics: fp32 only within one tile (8 values per thread and channel slot);
+    // every tile's warp-level partial sums are added to per-warp fp64 slots in shared memory
+    // (fixed order: deterministic), so no fp32 rounding accumulates over the CTA's many tiles
+    double* s_accd = reinterpret_cast<double*>(s_red) + warp * 64;
+    const bool want_stats = ((EPI == EPI_FWD) ? P.stats_out : P.dstats) != nullptr;
+    if (lane < 4) {
 #pragma unroll
-    for (int i = 0; i < NTL; ++i) st1[i][0] = st1[i][1] = st2[i][0] = st2[i][1] = 0.f;
+      for (int i = 0; i < NTL; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) s_accd[i * 8 + 2 * t + j] = s_accd[32 + i * 8 + 2 * t + j] = 0.0;
+    }
 
     uint32_t phase = 0;
     int it = 0;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+      float st1[NTL][2], st2[NTL][2];
+#pragma unroll
+      for (int i = 0; i < NTL; ++i) st1[i][0] = st1[i][1] = st2[i][0] = st2[i][1] = 0.f;
       const int tile = grp * NSUB + sub;
       const bool tvalid = tile < ntiles;
       const int n = tile / tiles_per_img;
@@ -458,7 +472,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
           // A fragment (row-major 16 pixels x 8 channels): a0 = (pixel g, channel t),
           // a1 = (g+8, t), a2 = (g, t+4), a3 = (g+8, t+4); tile column 3 is the left halo
           const float* tin = s_in + (DIRECT ? buf * C::STAGE : 0) + sub * C::FIN_SUB + t * G::PLANE +
-                             (KIND == K_S2 ? 2 * r0 : r0) * G::PITCH + (KIND == K_S2 ? 0 : 3) + xh * 16 + g;
+                             (KIND == K_S2 ? 2 * r0 : r0) * G::PITCH + (KIND == K_S1 ? 3 : 0) + xh * 16 + g;
           const float* wf = s_w + (ch * 9) * NTL * 32 * C::WF + lane * C::WF;
           // TF32 operands: the tensor core reads the top 19 bits of an fp32 register.  3 terms:
           // hi = x rounded to TF32, lo = x - hi (exact; its own low bits fall off at 2^-22 relative)
@@ -486,7 +500,62 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
               bl[1] = (TERMS == 3) ? __float_as_uint(b.y - __uint_as_float(bh[1])) : 0u;
             }
           };
-          if constexpr (KIND == K_S2) {
+          if constexpr (KIND == K_UP) {
+            // stride 2 up (gather form): input pixel (a, x) feeds the outputs (2a+oa, 2x+ob); tap
+            // (ky,kx) belongs to class oa = (ky != 1), ob = (kx != 1) and reads the input at
+            // (a + (ky == 0), x + (kx == 0)).  The four neighbour fragments stay resident.
+            uint32_t ah[2][2][4], al[2][2][4];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) load_a(tin + dy * G::PITCH + dx, ah[dy][dx], al[dy][dx]);
+#pragma unroll
+            for (int i = 0; i < NTL; ++i) {
+#pragma unroll
+              for (int pass = 0; pass < 2; ++pass) {
+                // pass 0: classes (0,0) [tap 4] and (1,1) [taps 0,2,6,8]; pass 1: (0,1) [3,5] and (1,0) [1,7]
+                constexpr int NTAP = 5;
+                const int taps[2][NTAP] = {{4, 0, 2, 6, 8}, {3, 5, 1, 7, -1}};
+                uint32_t bh[NTAP][2], bl[NTAP][2];
+#pragma unroll
+                for (int q = 0; q < NTAP; ++q)
+                  if (taps[pass][q] >= 0) load_b(taps[pass][q], i, bh[q], bl[q]);
+                if (TERMS == 3) {
+                  // one short chain per tap (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi on a fresh accumulator:
+                  // a single truncating add at full magnitude), the taps of the pass interleaved
+                  float tq[NTAP][4];
+#pragma unroll
+                  for (int term = 0; term < 3; ++term)
+#pragma unroll
+                    for (int q = 0; q < NTAP; ++q) {
+                      const int k = taps[pass][q];
+                      if (k < 0) continue;
+                      const int dy = (k / 3 == 0) ? 1 : 0, dx = (k % 3 == 0) ? 1 : 0;
+                      if (term == 0) cv_mma_tf32_zero(tq[q], al[dy][dx], bh[q][0], bh[q][1]);
+                      else if (term == 1) cv_mma_tf32(tq[q], ah[dy][dx], bl[q][0], bl[q][1]);
+                      else cv_mma_tf32(tq[q], ah[dy][dx], bh[q][0], bh[q][1]);
+                    }
+#pragma unroll
+                  for (int q = 0; q < NTAP; ++q) {
+                    const int k = taps[pass][q];
+                    if (k < 0) continue;
+                    const int cls = 2 * ((k / 3 == 1) ? 0 : 1) + ((k % 3 == 1) ? 0 : 1);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[cls][i][e] += tq[q][e];
+                  }
+                } else {
+#pragma unroll
+                  for (int q = 0; q < NTAP; ++q) {
+                    const int k = taps[pass][q];
+                    if (k < 0) continue;
+                    const int dy = (k / 3 == 0) ? 1 : 0, dx = (k % 3 == 0) ? 1 : 0;
+                    const int cls = 2 * ((k / 3 == 1) ? 0 : 1) + ((k % 3 == 1) ? 0 : 1);
+                    cv_mma_tf32(acc[cls][i], ah[dy][dx], bh[q][0], bh[q][1]);
+                  }
+                }
+              }
+            }
+          } else if constexpr (KIND == K_S2) {
             // stride 2: output row o reads input rows 2o+ky of the tile (5 rows for the warp's 2
             // output rows); the staged rows hold odd columns at [3..], even columns at [EO..], so
             // tap kx reads column offset 3 / EO / 4 with unit stride across the 16 pixels.
@@ -628,86 +697,121 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       }
       if (!tvalid) continue;
 
-      // ---- epilogue on the accumulator fragments: c0 = (pixel g, channel 2t), c1 = (g, 2t+1),
-      // c2 = (g+8, 2t), c3 = (g+8, 2t+1)
-      const int oy0 = ty * G::TH + r0, ox0 = tx * TW + xh * 16 + g;
-      if (EPI == EPI_BWD) {
-        // sum g and sum g*x per channel (centred with the exact mean at the very end)
+      if constexpr (KIND == K_UP) {
+        // ---- epilogue, stride-2 up: acc[2*oa+ob][i][j] -> output (2a+oa, 2x+ob), pixel x = ox_in
+        // (+8 for j >= 2), channel i*8 + 2t + (j&1); the two column parities form one float2
+        const int a_in = ty * G::TH + r0, x_in = tx * TW + xh * 16 + g;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          float xs[NTL][4];
+        for (int oa = 0; oa < 2; ++oa)
 #pragma unroll
           for (int i = 0; i < NTL; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int co = i * 8 + 2 * t + (j & 1);
-              const float* px = P.x_self + (((size_t)n * CO + co) * H_out + oy0 + r) * W_out + ox0 + 8 * (j >> 1);
-              asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(xs[i][j]) : "l"(px));
+              const size_t o = (((size_t)n * CO + co) * H_out + 2 * a_in + oa) * W_out + 2 * (x_in + 8 * (j >> 1));
+              float v0 = acc[2 * oa][i][j], v1 = acc[2 * oa + 1][i][j];
+              if (EPI == EPI_BWD) {
+                const float2 xv = *reinterpret_cast<const float2*>(P.x_self + o);
+                st1[i][j & 1] += v0 + v1;
+                st2[i][j & 1] = fmaf(v0, xv.x, fmaf(v1, xv.y, st2[i][j & 1]));
+              } else {
+                v0 += s_bias[co];
+                v1 += s_bias[co];
+                if (P.relu_out) {
+                  v0 = fmaxf(v0, 0.f);
+                  v1 = fmaxf(v1, 0.f);
+                }
+                st1[i][j & 1] += v0 + v1;
+                st2[i][j & 1] = fmaf(v0, v0, fmaf(v1, v1, st2[i][j & 1]));
+              }
+              if (P.out) *reinterpret_cast<float2*>(P.out + o) = make_float2(v0, v1);
             }
-#pragma unroll
-          for (int i = 0; i < NTL; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              st1[i][j & 1] += acc[r][i][j];
-              st2[i][j & 1] = fmaf(acc[r][i][j], xs[i][j], st2[i][j & 1]);
-            }
-        }
       } else {
+        // ---- epilogue on the accumulator fragments: c0 = (pixel g, channel 2t), c1 = (g, 2t+1),
+        // c2 = (g+8, 2t), c3 = (g+8, 2t+1)
+        const int oy0 = ty * G::TH + r0, ox0 = tx * TW + xh * 16 + g;
+        if (EPI == EPI_BWD) {
+          // sum g and sum g*x per channel (centred with the exact mean at the very end)
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+          for (int r = 0; r < R; ++r) {
+            float xs[NTL][4];
 #pragma unroll
-          for (int i = 0; i < NTL; ++i)
+            for (int i = 0; i < NTL; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float v = acc[r][i][j] + s_bias[i * 8 + 2 * t + (j & 1)];
-              if (P.relu_out) v = fmaxf(v, 0.f);
-              st1[i][j & 1] += v;
-              st2[i][j & 1] = fmaf(v, v, st2[i][j & 1]);
-              acc[r][i][j] = v;
-            }
+              for (int j = 0; j < 4; ++j) {
+                const int co = i * 8 + 2 * t + (j & 1);
+                const float* px = P.x_self + (((size_t)n * CO + co) * H_out + oy0 + r) * W_out + ox0 + 8 * (j >> 1);
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(xs[i][j]) : "l"(px));
+              }
+#pragma unroll
+            for (int i = 0; i < NTL; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                st1[i][j & 1] += acc[r][i][j];
+                st2[i][j & 1] = fmaf(acc[r][i][j], xs[i][j], st2[i][j & 1]);
+              }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < NTL; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v = acc[r][i][j] + s_bias[i * 8 + 2 * t + (j & 1)];
+                if (P.relu_out) v = fmaxf(v, 0.f);
+                st1[i][j & 1] += v;
+                st2[i][j & 1] = fmaf(v, v, st2[i][j & 1]);
+                acc[r][i][j] = v;
+              }
+        }
+        if (P.out) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < NTL; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int co = i * 8 + 2 * t + (j & 1);
+                P.out[(((size_t)n * CO + co) * H_out + oy0 + r) * W_out + ox0 + 8 * (j >> 1)] = acc[r][i][j];
+              }
+        }
       }
-      if (P.out) {
+      // this tile's statistics: lanes sharing t hold the same channels -> xor-shuffle over g, then
+      // lanes 0..3 add to the warp's fp64 slots
+      if (want_stats) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int i = 0; i < NTL; ++i)
 #pragma unroll
-          for (int i = 0; i < NTL; ++i)
+          for (int j = 0; j < 2; ++j) {
+            float a = st1[i][j], b = st2[i][j];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int co = i * 8 + 2 * t + (j & 1);
-              P.out[(((size_t)n * CO + co) * H_out + oy0 + r) * W_out + ox0 + 8 * (j >> 1)] = acc[r][i][j];
+            for (int o = 4; o < 32; o <<= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, o);
+              b += __shfl_xor_sync(0xffffffffu, b, o);
             }
+            if (g == 0) {
+              s_accd[i * 8 + 2 * t + j] += (double)a;
+              s_accd[32 + i * 8 + 2 * t + j] += (double)b;
+            }
+          }
       }
     }
 
-    // ---- per-channel statistics: lanes sharing t hold the same channels -> xor-shuffle over g,
-    // per-warp smem slots, fixed-order sum over the 4 warps, one fp64 atomic per channel per CTA
+    // ---- fixed-order sum over the warps, one fp64 atomic per channel per CTA
     double* dst = (EPI == EPI_FWD) ? P.stats_out : P.dstats;
     if (dst != nullptr) {
-#pragma unroll
-      for (int i = 0; i < NTL; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float a = st1[i][j], b = st2[i][j];
-#pragma unroll
-          for (int o = 4; o < 32; o <<= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-          }
-          if (g == 0) {
-            s_red[warp * 64 + i * 8 + 2 * t + j] = a;
-            s_red[warp * 64 + 32 + i * 8 + 2 * t + j] = b;
-          }
-        }
       __syncthreads();
       if (tid < CO) {
-        float a = 0.f, b = 0.f;
+        const double* sd = reinterpret_cast<const double*>(s_red);
+        double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          a += s_red[w * 64 + tid];
-          b += s_red[w * 64 + 32 + tid];
+        for (int w = 0; w < NT / 32; ++w) {
+          a += sd[w * 64 + tid];
+          b += sd[w * 64 + 32 + tid];
         }
-        atomicAdd(&dst[tid], (double)a);
-        atomicAdd(&dst[32 + tid], (EPI == EPI_BWD) ? (double)b - s_meand[tid] * (double)a : (double)b);
+        atomicAdd(&dst[tid], a);
+        atomicAdd(&dst[32 + tid], (EPI == EPI_BWD) ? b - s_meand[tid] * a : b);
       }
     }
   } else {
@@ -1632,12 +1736,17 @@ static inline int h_out_of(const LayerGeom& L) {
 
 using namespace ava;
 
-// stride-1 / stride-2-down layers with channel counts that are multiples of 8 can run on the
-// tensor cores
+// layers with channel counts that are multiples of 8 on both sides can run on the tensor cores
 #define GCONV_TC(KIND, CI, CO, TW, INMODE, EPI, HIN)                                               \
   (g_conv_terms == 3   ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 3>(P, stream)            \
    : g_conv_terms == 1 ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 1>(P, stream)            \
                        : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 0>(P, stream))
+
+// (HBM-bound layer where the 3-term tensor-core kernel loses to the FMA kernel: tensor cores only
+// in plain TF32 mode)
+#define GCONV_TC1(KIND, CI, CO, TW, INMODE, EPI, HIN)                                              \
+  (g_conv_terms == 1 ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 1>(P, stream)              \
+                     : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 0>(P, stream))
 
 extern "C" int ava_b200_set_conv_precision(int mode) {
   AVA_REQUIRE(mode == 0 || mode == 1 || mode == 2, "set_conv_precision: mode %d (0 fp32, 1 tf32, 2 tf32x3)", mode);
@@ -1689,11 +1798,11 @@ extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, c
     case 5: return GCONV_TC(K_S2, 24, 24, 16, IN_AFFINE, EPI_FWD, 32);
     case 6: return GCONV_TC(K_S1, 24, 32, 16, IN_AFFINE, EPI_FWD, 16);
     case 7: return GCONV_TC(K_S1, 32, 24, 16, IN_AFFINE, EPI_FWD, 16);
-    case 8: return launch_gconv<K_UP, 24, 24, 16, IN_AFFINE, EPI_FWD, 16>(P, stream);
+    case 8: return GCONV_TC(K_UP, 24, 24, 16, IN_AFFINE, EPI_FWD, 16);
     case 9: return GCONV_TC(K_S1, 24, 16, 32, IN_AFFINE, EPI_FWD, 32);
-    case 10: return launch_gconv<K_UP, 16, 16, 32, IN_AFFINE, EPI_FWD, 32>(P, stream);
+    case 10: return GCONV_TC(K_UP, 16, 16, 32, IN_AFFINE, EPI_FWD, 32);
     case 11: return GCONV_TC(K_S1, 16, 8, 32, IN_AFFINE, EPI_FWD, 64);
-    case 12: return launch_gconv<K_UP, 8, 8, 32, IN_AFFINE, EPI_FWD, 64>(P, stream);
+    case 12: return GCONV_TC(K_UP, 8, 8, 32, IN_AFFINE, EPI_FWD, 64);
     case 13: return launch_gconv<K_S1, 8, 1, 32, IN_AFFINE, EPI_FWD, 128>(P, stream);
   }
   return 1;
@@ -1727,11 +1836,11 @@ extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const
   }
   switch (layer) {
     case 0: return launch_gconv<K_S1, 8, 1, 32, IN_PLAIN, EPI_BWD, 128>(P, stream);
-    case 1: return launch_gconv<K_UP, 8, 8, 32, IN_PLAIN, EPI_BWD, 64>(P, stream);
+    case 1: return GCONV_TC1(K_UP, 8, 8, 32, IN_PLAIN, EPI_BWD, 64);
     case 2: return GCONV_TC(K_S1, 16, 8, 32, IN_PLAIN, EPI_BWD, 64);
-    case 3: return launch_gconv<K_UP, 16, 16, 32, IN_PLAIN, EPI_BWD, 32>(P, stream);
+    case 3: return GCONV_TC(K_UP, 16, 16, 32, IN_PLAIN, EPI_BWD, 32);
     case 4: return GCONV_TC(K_S1, 24, 16, 32, IN_PLAIN, EPI_BWD, 32);
-    case 5: return launch_gconv<K_UP, 24, 24, 16, IN_PLAIN, EPI_BWD, 16>(P, stream);
+    case 5: return GCONV_TC(K_UP, 24, 24, 16, IN_PLAIN, EPI_BWD, 16);
     case 6: return GCONV_TC(K_S1, 32, 24, 16, IN_PLAIN, EPI_BWD, 16);
     case 7: return GCONV_TC(K_S1, 24, 32, 16, IN_PLAIN, EPI_BWD, 16);
     case 8: return GCONV_TC(K_S2, 24, 24, 16, IN_PLAIN, EPI_BWD, 32);
