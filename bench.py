@@ -9,8 +9,9 @@ synthetic 128x128 spectrograms, `--batch` per GPU (default 1024, the per-GPU bat
 BASELINE.json's configs[1]/[2]).  Prints ONE JSON line (see the contract in the task
 statement): `value` = whole-job samples/s with inputs resident in HBM, `e2e` = the same
 through the public API with pinned host batches (H2D inside the timed region and a D2H
-read of the loss every step), `roofline` for the dominant kernel (CUDA-event timed per
-native call on the launching stream), `cpu_baseline` = the oracle's CPU train step timed
+read of the loss every step), `roofline` for the dominant entry point (CUDA-event timed per
+native call on the launching stream, in a second identical K-step loop so that the event
+records do not slow the `value` loop), `cpu_baseline` = the oracle's CPU train step timed
 on the host cores (rank 0, N=1 only).
 
 `--impl reference`: the CPU restatement of the reference train step (oracle/, torch CPU,
@@ -138,7 +139,30 @@ class ClockSampler(threading.Thread):
         self.stop_flag = False
         self.samples = []
 
+    def _run_nvml(self):
+        """Fast path: NVML through nvidia_ml_py (same counters as the nvidia-smi query below)."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        bits = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.samples.append([str(sm), str(mx)] + ["Active" if r & bits[n] else "Not Active" for n in
+                                                     ("hw_slowdown", "hw_thermal_slowdown",
+                                                      "sw_thermal_slowdown", "sw_power_cap")])
+            time.sleep(0.01)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -279,11 +303,9 @@ def main():
     for i in range(args.warmup):
         model.train_step(xs[i % 2])
     barrier()
-    prof = None if args.no_profile else EventProfiler(torch)
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = lib.launch_count()
-    lib.PROFILER = prof
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -291,9 +313,23 @@ def main():
         model.train_step(xs[i % 2])
     ev1.record()
     barrier()
-    lib.PROFILER = None
     launches = lib.launch_count() - launches0
-    sampler.stop_flag = True
+    # the same K steps again with a CUDA-event pair around every native call (roofline /
+    # kernel_families / kernels); the event records cost ~5 %, so `value` is taken from the
+    # loop above and this loop's own time is reported as profiled_ms_per_step
+    prof = None if args.no_profile else EventProfiler(torch)
+    ms_prof = None
+    if prof is not None:
+        lib.PROFILER = prof
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        p0.record()
+        for i in range(args.steps):
+            model.train_step(xs[i % 2])
+        p1.record()
+        barrier()
+        lib.PROFILER = None
+        ms_prof = p0.elapsed_time(p1) / args.steps
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -322,6 +358,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
 
+    sampler.stop_flag = True      # sampled through both timed regions (device-resident and e2e)
     sampler.join(timeout=2)
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -375,7 +412,8 @@ def main():
                              "torch CPU, %d threads)" % cores}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_step, "profiled_ms_per_step": ms_prof,
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "dtype_note": "fp32 storage and accumulation everywhere; with precision auto/tf32x3 the "
                           "fc1/fc8 products (tcgen05) and the conv inner products of the layers with "
