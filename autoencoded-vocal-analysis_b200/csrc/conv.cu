@@ -1514,6 +1514,13 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
 
     const float* gbase = s_g + (mt * 16 + g) * T::G_PLANE + t;
     const float* ibase = s_i + (nt * 8 + g) * T::I_PLANE + 3 + S * t;
+    float tq[9][4];
+    if (TERMS == 3) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tq[k][q] = 0.f;
+    }
 #pragma unroll 2
     for (int j = ks; j < KSTEPS; j += KS) {
       const int y = j / (TWG / 8), x0 = (j % (TWG / 8)) * 8;
@@ -1549,8 +1556,10 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
           }
         }
         if (TERMS == 3) {
+          // the tile's k-steps are chained in the tensor-core accumulators tq (a weight gradient is
+          // not amplified downstream, unlike an activation: a few dozen truncating adds per tile
+          // are harmless) and flushed into the running sums once per tile
           uint32_t bh[3][2], bl[3][2];
-          float tq[3][4];
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
@@ -1559,21 +1568,23 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
               bl[kx][q] = __float_as_uint(bv[kx][q] - __uint_as_float(bh[kx][q]));
             }
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32_zero(tq[kx], al, bh[kx][0], bh[kx][1]);
+          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32(tq[ky * 3 + kx], al, bh[kx][0], bh[kx][1]);
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32(tq[kx], ah, bl[kx][0], bl[kx][1]);
+          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32(tq[ky * 3 + kx], ah, bl[kx][0], bl[kx][1]);
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32(tq[kx], ah, bh[kx][0], bh[kx][1]);
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[ky * 3 + kx][q] += tq[kx][q];
+          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32(tq[ky * 3 + kx], ah, bh[kx][0], bh[kx][1]);
         } else {
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)
             cv_mma_tf32(acc[ky * 3 + kx], ah, __float_as_uint(bv[kx][0]), __float_as_uint(bv[kx][1]));
         }
       }
+    }
+    if (TERMS == 3) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[k][q] += tq[k][q];
     }
   }
 
