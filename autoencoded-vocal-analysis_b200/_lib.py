@@ -38,6 +38,9 @@ SIGNATURES = {
     "ava_b200_get_spec_batch": (P, I, P, P, I, I, I, I, P, D, P, P, I, P, P, I, I, D, D, P, P, P),
     "ava_b200_mmd_block_sums": (P, I, I, P, I, D, P, P),
     "ava_b200_pair_kernel": (P, I, P, P, LL, D, I, P, P),
+    "ava_b200_pca_ws_bytes": (I,),
+    "ava_b200_pca_fit": (P, I, LL, I, P, P, P, P, P, LL, P),
+    "ava_b200_pca_transform": (P, I, LL, I, P, P, I, P, P),
     "ava_b200_last_error": (),
     "ava_b200_abi_version": (),
     "ava_b200_launch_count": (),
@@ -47,6 +50,7 @@ _RESTYPES = {
     "ava_b200_launch_count": LL,
     "ava_b200_bnconv_bwd_weight_ws": LL,
     "ava_b200_linear_ws_bytes": LL,
+    "ava_b200_pca_ws_bytes": LL,
 }
 # entry points whose int return value is a status code
 _STATUS = {n for n in SIGNATURES if n not in _RESTYPES and n not in ("ava_b200_abi_version", "ava_b200_get_conv_precision")}

@@ -44,7 +44,87 @@ def timed(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters, 1e3 * (time.perf_counter() - t0) / iters
 
 
+def n1_section(out):
+    """PCA of latent means (csrc/pca.cu) and the DataContainer latent-mean
+    path on a synthetic corpus of syllable files."""
+    import tempfile
+    dcm = importlib.import_module(PKG + ".data.data_container")
+    mu = importlib.import_module(PKG + ".models.utils")
+    vae_mod = importlib.import_module(PKG + ".models.vae")
+    from oracle import pca_oracle
+    N, D = 4_000_000, 32
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(N, D, device="cuda", dtype=torch.float64, generator=g) * \
+        torch.linspace(3.0, 0.2, D, device="cuda", dtype=torch.float64)
+    pca = dcm.LatentPCA(2)
+    pca.fit_transform_device(x[:4096])
+    torch.cuda.synchronize()
+    lib = importlib.import_module(PKG + "._lib")
+    ws_bytes = int(lib.lib().ava_b200_pca_ws_bytes(D))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    mean, ev = (torch.empty(D, dtype=torch.float64, device="cuda") for _ in range(2))
+    cov, comps = (torch.empty(D, D, dtype=torch.float64, device="cuda") for _ in range(2))
+    emb = torch.empty(N, 2, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    fit = lambda: lib.call("ava_b200_pca_fit", x.data_ptr(), 0, N, D, mean.data_ptr(), cov.data_ptr(),  # noqa: E731
+                           ev.data_ptr(), comps.data_ptr(), ws.data_ptr(), ws_bytes, st)
+    tr = lambda: lib.call("ava_b200_pca_transform", x.data_ptr(), 0, N, D, mean.data_ptr(),  # noqa: E731
+                          comps.data_ptr(), 2, emb.data_ptr(), st)
+    ms_fit, _ = timed(fit, 10)
+    ms_tr, _ = timed(tr, 10)
+    xs = x[:200000].cpu().numpy()
+    t0 = time.perf_counter()
+    pca_oracle.pca_fit_transform(xs, 2)
+    cpu = time.perf_counter() - t0
+    out.append({"what": "LatentPCA fit + transform of %d x %d float64 latent means (device resident)" % (N, D),
+                "fit_ms": ms_fit, "transform_ms": ms_tr,
+                "fit_GBps": N * D * 8 / (ms_fit * 1e-3) / 1e9,
+                "transform_GBps": N * (D + 2) * 8 / (ms_tr * 1e-3) / 1e9,
+                "rows_per_s": N / ((ms_fit + ms_tr) * 1e-3),
+                "cpu_port_rows_per_s": len(xs) / cpu,
+                "cpu_sample": "200000 rows through oracle/pca_oracle.pca_fit_transform (numpy float64, all cores)"})
+    del x, emb
+    # DataContainer.request('latent_means'): 64 files x 512 syllables, reference semantics
+    # (train-mode BN, batches of 64) and the eval-mode / batch-1024 variant
+    ext = ".npz"
+    try:
+        import h5py  # noqa: F401
+        ext = ".hdf5"
+    except ImportError:
+        pass
+    nf, spf = 64, 512
+    rng = np.random.default_rng(0)
+    with tempfile.TemporaryDirectory() as root:
+        sd, pd = os.path.join(root, "specs"), os.path.join(root, "proj")
+        os.makedirs(sd)
+        for j in range(nf):
+            mu.append_field(os.path.join(sd, "syllables_%04d%s" % (j, ext)), 'specs',
+                            rng.random((spf, 128, 128), dtype=np.float32).astype(np.float64))
+        model = vae_mod.VAE(save_dir=root)
+        model.save_state("checkpoint_000.tar")
+        del model
+        for kw in ({}, {"latent_batch_size": 1024, "latent_eval": True}):
+            dc = dcm.DataContainer(spec_dirs=[sd], projection_dirs=[pd], verbose=False,
+                                   model_filename=os.path.join(root, "checkpoint_000.tar"), **kw)
+            dc.clear_projections() if os.path.exists(pd) else None
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lat = dc.request('latent_mean_pca')
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out.append({"what": "DataContainer latent_means + latent_mean_pca, %d files x %d syllables "
+                                "(float64 spec files read from disk, projections written)" % (nf, spf),
+                        "options": kw or "reference semantics (train-mode BN, batch 64)",
+                        "seconds": dt, "syllables_per_s": len(lat) / dt})
+
+
 def main():
+    if "n1" in sys.argv[1:]:
+        out = []
+        n1_section(out)
+        for o in out:
+            print(json.dumps(o))
+        return
     vae_mod = importlib.import_module(PKG + ".models.vae")
     win_mod = importlib.import_module(PKG + ".models.window_vae_dataset")
     torch.manual_seed(0)
@@ -186,6 +266,7 @@ def main():
                 "cpu_port_kernel_evals_per_s": cpu_pairs / cpu,
                 "cpu_sample": "one pair of 600-point conditions through oracle/mmd_oracle.estimate_mmd2 (vectorised numpy; "
                               "the reference itself is a Python double loop)"})
+    n1_section(out)
     for o in out:
         print(json.dumps(o))
 

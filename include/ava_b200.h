@@ -203,6 +203,20 @@ int ava_b200_mmd_block_sums(const double* x, int N, int D, const int* seg, int n
 int ava_b200_pair_kernel(const double* x, int D, const long long* ia, const long long* ib, long long n,
                          double A, int mode, double* out, void* stream);
 
+/* ------------------------------------------------- PCA of the latent means
+ * sklearn.decomposition.PCA(n_components=K).fit_transform on get_latent's output,
+ * ava/data/data_container.py:538-551 (_make_latent_mean_pca_projection).
+ * x: [N,D] rows, float64 (is_f32 = 0) or the encoder's float32 latents (is_f32 = 1), D <= 64.
+ * fit: mean[D]; cov[D*D] = sample covariance (divisor N-1); evals[D] descending, clipped at 0;
+ * comps[D*D]: row k = unit eigenvector k, its largest-magnitude entry positive (scikit-learn's
+ * svd_flip with u_based_decision=False).  ws: ava_b200_pca_ws_bytes(D) bytes of scratch.
+ * transform: out[N,K] = (x - mean) . comps[:K]^T. */
+long long ava_b200_pca_ws_bytes(int D);
+int ava_b200_pca_fit(const void* x, int is_f32, long long N, int D, double* mean, double* cov, double* evals,
+                     double* comps, void* ws, long long ws_bytes, void* stream);
+int ava_b200_pca_transform(const void* x, int is_f32, long long N, int D, const double* mean, const double* comps,
+                           int K, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -402,11 +402,150 @@ def mmd_case():
     print("mmd cases: sigma", sigma, "mmd2", m[0, 1], m[0, 2], m[1, 2])
 
 
+# ---------------------------------------------------------------- SURVEY 8(f) N1
+class _MemH5File:
+    """In-memory stand-in for h5py.File (h5py is not installed here): datasets live in a
+    process-global store keyed by path; an empty file of the same name is kept on disk so
+    that os.listdir-based discovery (get_hdf5s_from_dir) works.  Covers what the reference's
+    DataContainer / SyllableDataset use: open modes r/a/w, f[key], key in f, f.keys(),
+    create_dataset."""
+    store = {}
+
+    def __init__(self, filename, mode="r"):
+        self.filename = os.path.abspath(filename)
+        if mode == "w" or (mode == "a" and self.filename not in _MemH5File.store):
+            _MemH5File.store[self.filename] = {}
+            open(self.filename, "a").close()
+        assert self.filename in _MemH5File.store, "no such file: " + filename
+        self.data = _MemH5File.store[self.filename]
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def __getitem__(self, key):
+        return self.data[key]
+
+    def __contains__(self, key):
+        return key in self.data
+
+    def keys(self):
+        return self.data.keys()
+
+    def create_dataset(self, key, data=None):
+        assert key not in self.data, "name already exists"
+        self.data[key] = np.asarray(data)
+
+
+CONTAINER_SEED = 11
+CONTAINER_SPF = 24            # syllables per file
+CONTAINER_FILES = (3, 2)      # files in spec dir 0 / 1
+
+
+def container_corpus():
+    """The synthetic syllable corpus of the DataContainer case: per spec dir a list of
+    (basename, specs float64 [spf,128,128]); shared by the generator and the test."""
+    n = CONTAINER_SPF * sum(CONTAINER_FILES)
+    specs = vae_oracle.make_input(CONTAINER_SEED, n).double().numpy()
+    dirs, k = [], 0
+    for d, nf in enumerate(CONTAINER_FILES):
+        files = []
+        for j in range(nf):
+            files.append(("syllables_%04d" % j, specs[k:k + CONTAINER_SPF]))
+            k += CONTAINER_SPF
+        dirs.append(files)
+    return dirs
+
+
+def container_case(ref_vae):
+    """The reference's DataContainer.request('latent_means') and request('latent_mean_pca')
+    (ava/data/data_container.py:435-487, 538-551) run unmodified on the synthetic corpus,
+    with the in-memory h5py stand-in and the reference VAE on the CPU."""
+    import tempfile
+    import types
+    _ref_import.install_stubs()
+    for name, attrs in (("umap", {"UMAP": None}), ("numba", None), ("numba.errors", None)):
+        if name not in sys.modules and attrs is not None:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+    import h5py
+    h5py.File = _MemH5File
+    import ava.data.data_container as ref_dc
+    import ava.models.vae_dataset as ref_ds
+    import ava.models.utils as ref_mu
+    ref_dc.h5py.File = ref_ds.h5py.File = ref_mu.h5py.File = _MemH5File
+    _MemH5File.store = {}
+    out = {"versions": np.array(versions())}
+    with tempfile.TemporaryDirectory() as root:
+        spec_dirs = [os.path.join(root, "specs%d" % d) for d in range(len(CONTAINER_FILES))]
+        proj_dirs = [os.path.join(root, "proj%d" % d) for d in range(len(CONTAINER_FILES))]
+        for sd, files in zip(spec_dirs, container_corpus()):
+            os.makedirs(sd)
+            for base, specs in files:
+                with _MemH5File(os.path.join(sd, base + ".hdf5"), "w") as f:
+                    f.create_dataset("specs", data=specs)
+        model = ref_vae.VAE(save_dir=root, device_name='cpu')
+        load_into_reference(model, vae_oracle.make_params(CONTAINER_SEED))
+        model.save_state("checkpoint_000.tar")
+        # torch >= 2.6 defaults torch.load to weights_only=True; the reference predates it
+        orig_load = torch.load
+        torch.load = lambda *a, **k: orig_load(*a, **{**k, "weights_only": False})
+        orig_loaders = ref_dc.get_syllable_data_loaders
+        # forked DataLoader workers are not needed for a 120-syllable corpus
+        ref_dc.get_syllable_data_loaders = lambda part, **k: orig_loaders(part, num_workers=0, **k)
+        try:
+            dc = ref_dc.DataContainer(spec_dirs=spec_dirs, projection_dirs=proj_dirs,
+                                      model_filename=os.path.join(root, "checkpoint_000.tar"),
+                                      verbose=False)
+            pca = dc.request('latent_mean_pca')
+            latent = dc.request('latent_means')   # now read back from the projection files
+        finally:
+            torch.load = orig_load
+            ref_dc.get_syllable_data_loaders = orig_loaders
+        out["latent_means"] = latent
+        out["latent_mean_pca"] = pca
+        for d, pd in enumerate(proj_dirs):
+            for fn in sorted(os.listdir(pd)):
+                data = _MemH5File.store[os.path.abspath(os.path.join(pd, fn))]
+                out["proj%d/%s:keys" % (d, fn)] = np.array(sorted(data.keys())).astype('S')
+                out["proj%d/%s:latent_means" % (d, fn)] = data['latent_means']
+    np.savez_compressed(os.path.join(GOLDEN, "container_case.npz"), **out)
+    print("container case: latent", latent.shape, "pca", pca.shape, "first", pca[0])
+
+
+def pca_case():
+    """scikit-learn's PCA exactly as the reference constructs it (data_container.py:543),
+    on synthetic latent clouds: one above 500 rows (covariance_eigh route) and one below
+    (full-SVD route)."""
+    import sklearn
+    from sklearn.decomposition import PCA
+    from oracle import pca_oracle
+    out = {"versions": np.array(versions() + " sklearn " + sklearn.__version__)}
+    for name, seed, n, d in (("big", 5, 3000, 32), ("small", 6, 200, 32), ("z8", 7, 1000, 8),
+                             ("z64", 8, 1500, 64)):
+        x = pca_oracle.synth_latents(seed, n, d)
+        transform = PCA(n_components=2, copy=False, random_state=42)
+        emb = transform.fit_transform(x.copy())
+        out[name + ":embedding"] = emb
+        out[name + ":mean"] = transform.mean_
+        out[name + ":components"] = transform.components_
+        out[name + ":explained_variance"] = transform.explained_variance_
+        out[name + ":explained_variance_ratio"] = transform.explained_variance_ratio_
+        out[name + ":shape"] = np.array([seed, n, d])
+        o_emb, _ = pca_oracle.pca_fit_transform(x, 2)
+        print("pca case", name, "oracle vs sklearn:", np.abs(o_emb - emb).max())
+    np.savez_compressed(os.path.join(GOLDEN, "pca_cases.npz"), **out)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
     ref_vae, ref_pre, ref_win, ref_ds = _ref_import.import_reference()
-    which = sys.argv[1:] or ["vae", "adam", "spec", "sampler", "process", "mmd"]
+    which = sys.argv[1:] or ["vae", "adam", "spec", "sampler", "process", "mmd", "container", "pca"]
     if "vae" in which:
         vae_case(ref_vae, "vae_train_b7", seed=0, batch=7, train=True)
         vae_case(ref_vae, "vae_eval_b7", seed=1, batch=7, train=False)
@@ -422,6 +561,10 @@ def main():
         process_case(ref_pre)
     if "mmd" in which:
         mmd_case()
+    if "container" in which:
+        container_case(ref_vae)
+    if "pca" in which:
+        pca_case()
 
 
 if __name__ == "__main__":

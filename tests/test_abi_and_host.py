@@ -192,3 +192,67 @@ def test_next_rows_host_logic_and_no_cpu_fallback(tmp_path):
             pp._syll_specs_batched(np.array([0.1]), np.array([0.2]), np.zeros(32000, np.int16), 32000,
                                    {'max_dur': 0.2, 'time_stretch': False, 'num_time_bins': 128,
                                     'nperseg': 512, 'noverlap': 256, 'within_syll_normalize': False}, None)
+
+
+def test_data_container_host_logic_and_no_cpu_fallback(tmp_path):
+    """the DataContainer request/read/write protocol follows the reference
+    (ava/data/data_container.py:251-373, 652-716); computing latent means or the PCA without
+    a CUDA device raises instead of falling back."""
+    import importlib
+    import numpy as np
+    import pytest
+    import torch
+    dcm = importlib.import_module(PKG + ".data.data_container")
+    mu = importlib.import_module(PKG + ".models.utils")
+    assert dcm.PROJECTION_FIELDS == ['latent_means', 'latent_mean_pca', 'latent_mean_umap']
+    assert dcm.SPEC_FIELDS == ['specs', 'onsets', 'offsets', 'audio_filenames']
+    assert len(dcm.ALL_FIELDS) == 1 + 1 + 2 + 3 + 4 + 14 + 16 + 15
+    try:
+        import h5py  # noqa: F401
+        ext = ".hdf5"
+    except ImportError:
+        ext = ".npz"
+    sdirs = [str(tmp_path / "s0"), str(tmp_path / "s1")]
+    pdirs = [str(tmp_path / "p0"), str(tmp_path / "p1")]
+    rng = np.random.default_rng(0)
+    k = 0
+    for sd, nf in zip(sdirs, (2, 1)):
+        os.makedirs(sd)
+        for j in range(nf):
+            fn = os.path.join(sd, "syllables_%04d%s" % (j, ext))
+            mu.append_field(fn, 'specs', rng.random((3, 128, 128)))
+            mu.append_field(fn, 'onsets', np.arange(3) + 10.0 * k)
+            mu.append_field(fn, 'offsets', np.arange(3) + 10.0 * k + 0.5)
+            mu.append_field(fn, 'audio_filenames', np.array(["f%d.wav" % k] * 3).astype('S'))
+            k += 1
+    with pytest.raises(Exception):
+        mu.append_field(fn, 'specs', np.zeros(3))            # like h5py: no overwrite
+    assert mu.stored_fields(fn) == {'specs': 3, 'onsets': 3, 'offsets': 3, 'audio_filenames': 3}
+    dc = dcm.DataContainer(spec_dirs=sdirs, projection_dirs=pdirs, model_filename="none.tar",
+                           verbose=False, plots_dir=str(tmp_path / "plots"))
+    assert os.path.isdir(tmp_path / "plots")
+    assert set(dc.fields) == set(dcm.SPEC_FIELDS) and dc.sylls_per_file is None
+    assert list(dc.request('onsets')) == [0., 1., 2., 10., 11., 12., 20., 21., 22.]
+    assert list(dc.request('audio_filenames')) == ["f0.wav"] * 3 + ["f1.wav"] * 3 + ["f2.wav"] * 3
+    assert dc.request('specs').shape == (9, 128, 128)
+    with pytest.raises(NotImplementedError):
+        dc.request('not_a_field')
+    with pytest.raises(NotImplementedError):
+        dc.request('latent_mean_umap')
+    with pytest.raises(AssertionError):
+        dcm.DataContainer(spec_dirs=sdirs, verbose=False).request('latent_means')
+    # projections written file by file in directory order, picked up by a new container
+    dc.sylls_per_file = 3
+    for pd in pdirs:
+        os.makedirs(pd)
+    emb = np.arange(18.0).reshape(9, 2)
+    dc._write_projection('latent_mean_pca', emb)
+    assert sorted(os.listdir(pdirs[0])) == ["syllables_0000" + ext, "syllables_0001" + ext]
+    dc2 = dcm.DataContainer(spec_dirs=sdirs, projection_dirs=pdirs, verbose=False)
+    assert 'latent_mean_pca' in dc2.fields and dc2.sylls_per_file == 3
+    np.testing.assert_array_equal(dc2.request('latent_mean_pca'), emb)
+    dc2.clear_projections()
+    assert os.listdir(pdirs[0]) == [] and 'latent_mean_pca' not in dc2.fields
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            dcm.LatentPCA(2).fit_transform(rng.standard_normal((50, 32)))

@@ -118,3 +118,38 @@ def test_mmd_oracle_matches_reference_golden():
             assert abs(b - g["mmd2_linear"][i, j]) <= 1e-12
             c = mmd_oracle.estimate_mmd2(latent, groups[i].copy(), groups[j].copy(), sigma, max_n=64, seed=5)
             assert abs(c - g["mmd2_max64_seed5"][i, j]) <= 1e-10 * abs(g["mmd2_max64_seed5"][i, j])
+
+
+@pytest.mark.parametrize("name", ["big", "small", "z8", "z64"])
+def test_pca_oracle_matches_sklearn_golden(name):
+    """oracle/pca_oracle.py against scikit-learn's PCA run as the reference constructs it
+    (ava/data/data_container.py:543; tests/golden/pca_cases.npz)."""
+    from oracle import pca_oracle
+    g = load_golden("pca_cases")
+    seed, n, d = (int(v) for v in g[name + ":shape"])
+    x = pca_oracle.synth_latents(seed, n, d)
+    emb, fit = pca_oracle.pca_fit_transform(x, 2)
+    assert np.abs(emb - g[name + ":embedding"]).max() <= TOL64 * np.abs(g[name + ":embedding"]).max()
+    assert np.abs(fit["mean"] - g[name + ":mean"]).max() <= 1e-12
+    assert np.abs(fit["components"] - g[name + ":components"]).max() <= TOL64
+    assert rel_err(fit["explained_variance"], g[name + ":explained_variance"]) <= TOL64
+    assert rel_err(fit["explained_variance_ratio"], g[name + ":explained_variance_ratio"]) <= TOL64
+
+
+def test_container_golden_is_self_consistent():
+    """tests/golden/container_case.npz (the reference's DataContainer run unmodified): the
+    latent means read back equal the per-file datasets in directory / file order, and the
+    PCA oracle applied to them reproduces the reference's embedding."""
+    from oracle import make_golden, pca_oracle
+    g = load_golden("container_case")
+    n = make_golden.CONTAINER_SPF * sum(make_golden.CONTAINER_FILES)
+    assert g["latent_means"].shape == (n, 32) and g["latent_means"].dtype == np.float64
+    parts = []
+    for d, nf in enumerate(make_golden.CONTAINER_FILES):
+        for j in range(nf):
+            key = "proj%d/syllables_%04d.hdf5" % (d, j)
+            assert sorted(k.decode() for k in g[key + ":keys"]) == ["latent_mean_pca", "latent_means"]
+            parts.append(g[key + ":latent_means"])
+    np.testing.assert_array_equal(np.concatenate(parts), g["latent_means"])
+    emb, _ = pca_oracle.pca_fit_transform(g["latent_means"], 2)
+    assert np.abs(emb - g["latent_mean_pca"]).max() <= TOL64 * np.abs(g["latent_mean_pca"]).max()
