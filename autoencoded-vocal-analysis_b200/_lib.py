@@ -36,6 +36,7 @@ SIGNATURES = {
     "ava_b200_elbo_finalize": (P, I, I, F, P, P, P),
     "ava_b200_adam_step": (P, P, P, P, LL, P, D, D, D, D, F, P),
     "ava_b200_get_spec_batch": (P, I, P, P, I, I, I, I, P, D, P, P, I, P, P, I, I, D, D, P, P, P),
+    "ava_b200_window_time_tables": (P, P, P, I, P, P, I, I, P, P, P),
     "ava_b200_mmd_block_sums": (P, I, I, P, I, D, P, P),
     "ava_b200_pair_kernel": (P, I, P, P, LL, D, I, P, P),
     "ava_b200_pca_ws_bytes": (I,),

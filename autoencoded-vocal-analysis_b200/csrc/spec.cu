@@ -160,6 +160,59 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P) {
 
 }  // namespace ava
 
+// Target-time tables of a batch of fixed-duration windows, on the device.  Bit-for-bit the
+// float64 arithmetic of the host path (preprocessing/utils.py::bracket), which follows
+// ava/models/window_vae_dataset.py:231-235 (target_times = np.linspace(onset, offset, n_t)) and
+// the scipy interp2d bracketing / fill rule behind ava/preprocessing/utils.py:80-81,99:
+//   T_j   = fl(fl(j * step) + tstart), step = fl(fl(tstop - tstart) / (n_t-1)), T_{n_t-1} = tstop
+//   g_k   = fl(base[k] + grid0)                     (frame times, the reference's t += max(0,t1))
+//   i     = the interval [g_i, g_{i+1}] containing T (i <= K-2), w = (T-g_i)/(g_{i+1}-g_i)
+//   T < g_0 or T > g_{K-1}: i = -1, w = 0 (fill value)
+// No FMA contraction anywhere (numpy multiplies, then adds).
+namespace ava {
+__global__ void __launch_bounds__(128)
+time_tables_kernel(const double* __restrict__ grid0, const int* __restrict__ K, const double* __restrict__ base,
+                   const double* __restrict__ tstart, const double* __restrict__ tstop, int n, int n_t,
+                   int* __restrict__ t_idx, double* __restrict__ t_frac) {
+  const int w = blockIdx.x;
+  if (w >= n) return;
+  const double g0 = grid0[w];
+  const int Kw = K[w];
+  const long long km2 = Kw - 2;
+  const double start = tstart[w], stop = tstop[w];
+  const double step = __ddiv_rn(__dsub_rn(stop, start), (double)(n_t - 1));
+  const double dt = __dsub_rn(base[1], base[0]);
+  const double first = __dadd_rn(base[0], g0);
+  const double last = __dadd_rn(base[Kw - 1], g0);
+  for (int j = threadIdx.x; j < n_t; j += blockDim.x) {
+    const double T = (j == n_t - 1 && n_t > 1) ? stop : __dadd_rn(__dmul_rn((double)j, step), start);
+    double f = floor(__ddiv_rn(__dsub_rn(T, first), dt));
+    f = fmin(fmax(f, 0.0), (double)km2);
+    long long i = (long long)f;
+    for (int it = 0; it < 2; ++it) {
+      if (__dadd_rn(base[i], g0) > T) --i;
+      i = i < 0 ? 0 : (i > km2 ? km2 : i);
+      if (__dadd_rn(base[i + 1], g0) <= T && i < km2) ++i;
+    }
+    const double lo = __dadd_rn(base[i], g0), hi = __dadd_rn(base[i + 1], g0);
+    const double wgt = __ddiv_rn(__dsub_rn(T, lo), __dsub_rn(hi, lo));
+    const bool bad = (T < first) || (T > last);
+    t_idx[(size_t)w * n_t + j] = bad ? -1 : (int)i;
+    t_frac[(size_t)w * n_t + j] = bad ? 0.0 : wgt;
+  }
+}
+}  // namespace ava
+
+extern "C" int ava_b200_window_time_tables(const double* grid0, const int* K, const double* base, int kmax,
+                                           const double* tstart, const double* tstop, int n, int n_t, int* t_idx,
+                                           double* t_frac, void* stream) {
+  using namespace ava;
+  AVA_REQUIRE(kmax >= 3 && n_t >= 2, "window_time_tables: kmax=%d n_t=%d", kmax, n_t);
+  if (n <= 0) return 0;
+  time_tables_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(grid0, K, base, tstart, tstop, n, n_t, t_idx, t_frac);
+  return check_launch("window_time_tables");
+}
+
 extern "C" int ava_b200_get_spec_batch(const void* audio, int is_f32, const long long* seg_start,
                                        const int* seg_len, int n, int nperseg, int noverlap, int remove_dc,
                                        const double* window, double scale, const int* t_idx,

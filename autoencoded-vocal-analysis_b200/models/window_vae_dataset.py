@@ -180,8 +180,9 @@ class FixedWindowDataset(Dataset):
     def _specs(self, files, onsets, shoulder):
         wl = self.p['window_length']
         offsets = onsets + wl
-        tt = np.linspace(onsets, offsets, self.p['num_time_bins'], axis=-1)
-        return self._engine.specs(files, np.maximum(0.0, onsets - shoulder), offsets + shoulder, tt)
+        # target_times = np.linspace(onset, offset, num_time_bins), built on the device
+        return self._engine.specs_linspace(files, np.maximum(0.0, onsets - shoulder), offsets + shoulder,
+                                           onsets, offsets)
 
     def sample(self, n, seed=None, shoulder=0.05):
         """n accepted windows: (specs [n,128,128] fp32 on the device, file_indices, onsets,

@@ -128,6 +128,7 @@ class SpecEngine:
         self.scale = float(1.0 / win.sum())
         self.window_dev = torch.from_numpy(win).to(self.device)
         self._freq_cache = None
+        self._base_cache = None
 
     def _freq_tables(self, target_freqs):
         f = np.fft.rfftfreq(self.nperseg, 1 / self.fs)
@@ -140,18 +141,12 @@ class SpecEngine:
         idx, w = bracket_1d(f, np.asarray(target_freqs, dtype=np.float64))
         return torch.from_numpy(idx).to(self.device), torch.from_numpy(w).to(self.device), idx
 
-    def specs(self, file_index, t1, t2, target_times, target_freqs=None, remove_dc_offset=True,
-              out=None, want_float64=False):
-        """Spectrograms of n segments [t1_i, t2_i] of files file_index_i with explicit
-        target times [n, n_t].  Returns fp32 [n, n_f, n_t] on the device (and the float64
-        version if want_float64).  Mirrors ava/preprocessing/utils.py:59-104 per segment."""
-        p, fs = self.p, self.fs
-        file_index = np.asarray(file_index, dtype=np.int64)
-        t1 = np.asarray(t1, dtype=np.float64)
-        t2 = np.asarray(t2, dtype=np.float64)
-        tt = np.asarray(target_times, dtype=np.float64)
-        n, n_t = tt.shape
-        n_f = int(p['num_freq_bins']) if target_freqs is None else len(target_freqs)
+    def _segments(self, file_index, t1, t2):
+        """Sample ranges and STFT frame counts of n segments [t1_i, t2_i]
+        (ava/preprocessing/utils.py:66-72): (seg_start int64 [n] into the concatenated audio,
+        seg_len int32 [n] with 0 for the reference's "too short" branch, K frames [n], kmax,
+        base frame times [kmax] of a segment starting at t = 0)."""
+        fs = self.fs
         # int(round(t*fs)): Python round == numpy rint (half to even)
         s1 = np.rint(t1 * fs).astype(np.int64)
         s2 = np.rint(t2 * fs).astype(np.int64)
@@ -162,16 +157,16 @@ class SpecEngine:
         short = (seg_len < self.nperseg) | (s2 <= 0) | (s1 >= flen)     # utils.py:69-71
         seg_len = np.where(short, 0, seg_len)
         K = np.where(short, 3, num_frames(np.maximum(seg_len, self.nperseg), self.nperseg, self.hop))
-        kmax = int(K.max()) if n else 3
+        kmax = int(K.max()) if len(K) else 3
         base = np.arange(self.nperseg / 2, self.nperseg / 2 + kmax * self.hop, self.hop) / float(fs)
         base = base - (self.nperseg / 2) / fs
-        t_idx, t_frac = bracket(np.maximum(0.0, t1), base, K, tt)
+        return self.offsets[file_index] + lo, seg_len.astype(np.int32), K, kmax, base
+
+    def _launch(self, seg_start, seg_len_d, n, t_idx_d, t_frac_d, n_t, target_freqs, kmax,
+                remove_dc_offset, out, want_float64):
+        p, dev = self.p, self.device
         f_idx_dev, f_frac_dev, _ = self._freq_tables(target_freqs)
-        dev = self.device
-        seg_start = torch.from_numpy(self.offsets[file_index] + lo).to(dev)
-        seg_len_d = torch.from_numpy(seg_len.astype(np.int32)).to(dev)
-        t_idx_d = torch.from_numpy(np.ascontiguousarray(t_idx)).to(dev)
-        t_frac_d = torch.from_numpy(np.ascontiguousarray(t_frac)).to(dev)
+        n_f = int(p['num_freq_bins']) if target_freqs is None else len(target_freqs)
         if out is None:
             out = torch.empty(n, n_f, n_t, dtype=torch.float32, device=dev)
         out64 = torch.empty(n, n_f, n_t, dtype=torch.float64, device=dev) if want_float64 else None
@@ -182,9 +177,81 @@ class SpecEngine:
              f_frac_dev.data_ptr(), n_f, kmax + 1, float(p['spec_min_val']), float(p['spec_max_val']),
              out.data_ptr(), out64.data_ptr() if out64 is not None else None,
              torch.cuda.current_stream().cuda_stream)
+        return (out, out64) if want_float64 else out
+
+    def specs(self, file_index, t1, t2, target_times, target_freqs=None, remove_dc_offset=True,
+              out=None, want_float64=False):
+        """Spectrograms of n segments [t1_i, t2_i] of files file_index_i with explicit
+        target times [n, n_t].  Returns fp32 [n, n_f, n_t] on the device (and the float64
+        version if want_float64).  Mirrors ava/preprocessing/utils.py:59-104 per segment."""
+        file_index = np.asarray(file_index, dtype=np.int64)
+        t1 = np.asarray(t1, dtype=np.float64)
+        t2 = np.asarray(t2, dtype=np.float64)
+        tt = np.asarray(target_times, dtype=np.float64)
+        n, n_t = tt.shape
+        seg_start, seg_len, K, kmax, base = self._segments(file_index, t1, t2)
+        t_idx, t_frac = bracket(np.maximum(0.0, t1), base, K, tt)
+        dev = self.device
+        seg_start = torch.from_numpy(seg_start).to(dev)
+        seg_len_d = torch.from_numpy(seg_len).to(dev)
+        t_idx_d = torch.from_numpy(np.ascontiguousarray(t_idx)).to(dev)
+        t_frac_d = torch.from_numpy(np.ascontiguousarray(t_frac)).to(dev)
         # keep the argument tensors alive until the kernel has consumed them
         self._keepalive = (seg_start, seg_len_d, t_idx_d, t_frac_d)
-        return (out, out64) if want_float64 else out
+        return self._launch(seg_start, seg_len_d, n, t_idx_d, t_frac_d, n_t, target_freqs, kmax,
+                            remove_dc_offset, out, want_float64)
+
+    def specs_linspace(self, file_index, t1, t2, tstart, tstop, n_t=None, remove_dc_offset=True,
+                       out=None, want_float64=False):
+        """Same as ``specs`` with ``target_times[i] = np.linspace(tstart_i, tstop_i, n_t)`` (the
+        fixed-window sampler, ava/models/window_vae_dataset.py:231-235), the [n, n_t] tables
+        being built on the device by ``ava_b200_window_time_tables`` -- the same float64
+        operations as ``bracket``, bit for bit -- so that the host only handles O(n) numbers
+        per batch: one packed upload of 40 bytes per window."""
+        file_index = np.asarray(file_index, dtype=np.int64)
+        t1 = np.asarray(t1, dtype=np.float64)
+        t2 = np.asarray(t2, dtype=np.float64)
+        tstart = np.asarray(tstart, dtype=np.float64)
+        tstop = np.asarray(tstop, dtype=np.float64)
+        n = len(file_index)
+        n_t = int(self.p['num_time_bins']) if n_t is None else int(n_t)
+        if n_t < 2 or n == 0 or np.any(tstop == tstart):
+            # numpy's linspace switches formula when a step is zero; keep one code path for that
+            tt = np.linspace(tstart, tstop, n_t, axis=-1).reshape(n, n_t)
+            return self.specs(file_index, t1, t2, tt, remove_dc_offset=remove_dc_offset, out=out,
+                              want_float64=want_float64)
+        seg_start, seg_len, K, kmax, base = self._segments(file_index, t1, t2)
+        dev = self.device
+        # one upload: rows [seg_start i64 | grid0 f64 | tstart f64 | tstop f64 | seg_len, K i32]
+        m = n + (n & 1)
+        packed = np.zeros((5, m), dtype=np.int64)
+        packed[0, :n] = seg_start
+        packed[1, :n] = np.maximum(0.0, t1).view(np.int64)
+        packed[2, :n] = np.ascontiguousarray(tstart).view(np.int64)
+        packed[3, :n] = np.ascontiguousarray(tstop).view(np.int64)
+        tail = packed[4].view(np.int32)                          # 2m int32 slots
+        tail[:n] = seg_len
+        tail[m:m + n] = K
+        packed_d = torch.from_numpy(packed).to(dev)
+        if self._base_cache is None or self._base_cache[0] < kmax:
+            # frame times do not depend on the batch: element k of a longer table is the same
+            # number, so a cached table of at least kmax entries serves every batch
+            kcap = max(kmax, 64)
+            b = np.arange(self.nperseg / 2, self.nperseg / 2 + kcap * self.hop, self.hop) / float(self.fs)
+            b = b - (self.nperseg / 2) / self.fs
+            assert np.array_equal(b[:kmax], base)
+            self._base_cache = (kcap, torch.from_numpy(b).to(dev))
+        base_d = self._base_cache[1]
+        tail_d = packed_d[4].view(torch.int32)
+        seg_len_d, K_d = tail_d[:n], tail_d[m:m + n]
+        t_idx_d = torch.empty(n, n_t, dtype=torch.int32, device=dev)
+        t_frac_d = torch.empty(n, n_t, dtype=torch.float64, device=dev)
+        call("ava_b200_window_time_tables", packed_d[1].data_ptr(), K_d.data_ptr(), base_d.data_ptr(), kmax,
+             packed_d[2].data_ptr(), packed_d[3].data_ptr(), n, n_t, t_idx_d.data_ptr(),
+             t_frac_d.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        self._keepalive = (packed_d, seg_len_d, K_d, t_idx_d, t_frac_d)
+        return self._launch(packed_d[0], seg_len_d, n, t_idx_d, t_frac_d, n_t, None, kmax,
+                            remove_dc_offset, out, want_float64)
 
 
 def get_spec(t1, t2, audio, p, fs=32000, target_freqs=None, target_times=None,

@@ -118,12 +118,45 @@ def n1_section(out):
                         "seconds": dt, "syllables_per_s": len(lat) / dt})
 
 
+def shotgun_section(out):
+    """BASELINE configs[3] / SURVEY 8(d) config 4: synthetic corpus of 16 files x 600 s @ 32 kHz
+    int16, 2 ROIs per file, finch parameters; windows/s of the sampler + GPU get_spec, and the
+    train step fed with windows generated on the fly next to the same step on a resident batch
+    ("training never waits" <=> the two rates agree)."""
+    vae_mod = importlib.import_module(PKG + ".models.vae")
+    win_mod = importlib.import_module(PKG + ".models.window_vae_dataset")
+    rng = np.random.default_rng(0)
+    fs = FINCH_P['fs']
+    n_files, dur = 16, 600.0
+    audio = [(3000 * rng.standard_normal(int(dur * fs), dtype=np.float32)).astype(np.int16)
+             for _ in range(n_files)]
+    rois = [np.array([[1.0, 250.0], [300.0, 598.0]]) for _ in range(n_files)]
+    names = ["f%02d.wav" % k for k in range(n_files)]
+    ds = win_mod.FixedWindowDataset(names, None, dict(FINCH_P), audio=audio, fs=fs, rois=rois)
+    for nb in (128, 1024):
+        ms, wall = timed(lambda: ds.sample_batch(nb), 20)
+        out.append({"what": "shotgun windows (host sampling + device tables + GPU get_spec)", "batch": nb,
+                    "ms_per_batch_gpu": ms, "ms_per_batch_wall": wall, "windows_per_s": nb / (wall * 1e-3)})
+    model = vae_mod.VAE(device_name='cuda')
+    model.train()
+    for nb in (128, 1024):
+        x = ds.sample_batch(nb)
+        ms0, wall0 = timed(lambda: model.train_step(x), 15)
+        ms, wall = timed(lambda: model.train_step(ds.sample_batch(nb)), 15)
+        out.append({"what": "shotgun train step with on-the-fly GPU get_spec", "batch": nb,
+                    "ms_per_step_wall": wall, "samples_per_s": nb / (wall * 1e-3),
+                    "resident_batch_ms_per_step": ms0, "resident_batch_samples_per_s": nb / (ms0 * 1e-3),
+                    "ratio_vs_resident": ms0 / wall})
+
+
 def main():
-    if "n1" in sys.argv[1:]:
-        out = []
-        n1_section(out)
-        for o in out:
-            print(json.dumps(o))
+    for key, fn in (("n1", n1_section), ("shotgun", shotgun_section)):
+        if key in sys.argv[1:]:
+            out = []
+            fn(out)
+            for o in out:
+                print(json.dumps(o))
+    if len(sys.argv) > 1:
         return
     vae_mod = importlib.import_module(PKG + ".models.vae")
     win_mod = importlib.import_module(PKG + ".models.window_vae_dataset")

@@ -192,6 +192,17 @@ int ava_b200_get_spec_batch(const void* audio, int is_f32, const long long* seg_
                             const double* f_frac, int n_f, int max_frames, double spec_min, double spec_max,
                             float* out, double* out64, void* stream);
 
+/* Target-time tables of a batch of fixed-duration windows computed on the device (the
+ * shotgun path, ava/models/window_vae_dataset.py:231-235: target_times = linspace(onset,
+ * offset, n_t); bracketing and fill rule of scipy interp2d, ava/preprocessing/utils.py:80-81,99).
+ * Same float64 operations as the host tables, bit for bit.
+ *   grid0 [n]: max(0, t1) of each window; K [n]: STFT frames of each window (>= 3);
+ *   base [kmax]: frame times of a segment starting at 0; tstart/tstop [n]: first / last target
+ *   t_idx/t_frac [n,n_t]: outputs in the layout ava_b200_get_spec_batch consumes. */
+int ava_b200_window_time_tables(const double* grid0, const int* K, const double* base, int kmax,
+                                const double* tstart, const double* tstop, int n, int n_t, int* t_idx,
+                                double* t_frac, void* stream);
+
 /* ------------------------------------------------- MMD^2 between sets of latent means
  * Downstream statistic on get_latent's output, ava/plotting/mmd_plots.py:255-312, 450-476.
  * x: [N,D] float64 latent means; seg[i] in [0,n_seg) = condition of row i.

@@ -78,6 +78,46 @@ def test_batched_engine_matches_oracle(pre):
     assert not out[9].any()
 
 
+def test_device_time_tables_bit_exact(pre):
+    """ava_b200_window_time_tables (target times + bracketing built on the device for the
+    fixed-window sampler) reproduces the host float64 tables bit for bit, so specs_linspace
+    and specs give identical spectrograms -- windows at the file start, running off the file
+    end (out-of-range targets -> fill) and too-short segments included."""
+    lib = importlib.import_module(PKG + "._lib")
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    audio = [spec_oracle.synth_audio(30 + i, int((2.0 + 0.7 * i) * fs), fs) for i in range(3)]
+    eng = pre.SpecEngine(audio, fs, p)
+    rng = np.random.default_rng(11)
+    wl = p['window_length']
+    for n in (1, 2, 37, 512, 1023):
+        files = rng.integers(0, 3, size=n)
+        onsets = rng.uniform(0.0, 2.1, size=n)          # file 0 is 2.0 s long: some run off the end
+        onsets[0] = 0.0
+        t1, t2 = np.maximum(0.0, onsets - 0.05), onsets + wl + 0.05
+        if n > 9:
+            t2[9] = t1[9] + 0.004                       # shorter than nperseg -> zeros
+        tt = np.linspace(onsets, onsets + wl, 128, axis=-1).reshape(n, 128)
+        a32, a64 = eng.specs(files, t1, t2, tt, want_float64=True)
+        b32, b64 = eng.specs_linspace(files, t1, t2, onsets, onsets + wl, want_float64=True)
+        assert torch.equal(a32, b32) and torch.equal(a64, b64), n
+        # and the tables themselves
+        seg_start, seg_len, K, kmax, base = eng._segments(files, t1, t2)
+        t_idx, t_frac = pre.bracket(np.maximum(0.0, t1), base, K, tt)
+        dev = eng.device
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)       # noqa: E731
+        g0, Kd, bd, ts, te = d(np.maximum(0.0, t1)), d(K.astype(np.int32)), d(base), d(onsets), d(onsets + wl)
+        ti = torch.empty(n, 128, dtype=torch.int32, device=dev)
+        tf = torch.empty(n, 128, dtype=torch.float64, device=dev)
+        lib.call("ava_b200_window_time_tables", g0.data_ptr(), Kd.data_ptr(), bd.data_ptr(), kmax,
+                 ts.data_ptr(), te.data_ptr(), n, 128, ti.data_ptr(), tf.data_ptr(),
+                 torch.cuda.current_stream().cuda_stream)
+        np.testing.assert_array_equal(ti.cpu().numpy(), t_idx)
+        np.testing.assert_array_equal(tf.cpu().numpy(), t_frac)
+        if n == 512:
+            assert (t_idx < 0).any() and (t_idx >= 0).any()
+
+
 def test_fixed_window_dataset_bit_exact_sampling(win, tmp_path):
     from scipy.io import wavfile
     g = load_golden("sampler_cases")
