@@ -129,6 +129,7 @@ class SpecEngine:
         self.window_dev = torch.from_numpy(win).to(self.device)
         self._freq_cache = None
         self._base_cache = None
+        self._pin_rings = {}
 
     def _freq_tables(self, target_freqs):
         f = np.fft.rfftfreq(self.nperseg, 1 / self.fs)
@@ -201,6 +202,21 @@ class SpecEngine:
         return self._launch(seg_start, seg_len_d, n, t_idx_d, t_frac_d, n_t, target_freqs, kmax,
                             remove_dc_offset, out, want_float64)
 
+    def _pinned_slot(self, m):
+        """A pinned [5, m] int64 staging buffer from a ring of 4 per batch size; a slot is
+        reused only after the upload that last read it has completed."""
+        ring = self._pin_rings.setdefault(m, {"bufs": [], "events": [], "next": 0})
+        if len(ring["bufs"]) < 4:
+            ring["bufs"].append(torch.zeros(5, m, dtype=torch.int64).pin_memory())
+            ring["events"].append(None)
+            slot = len(ring["bufs"]) - 1
+        else:
+            slot = ring["next"]
+            ring["next"] = (slot + 1) % 4
+            if ring["events"][slot] is not None:
+                ring["events"][slot].synchronize()
+        return ring["bufs"][slot], ring, slot
+
     def specs_linspace(self, file_index, t1, t2, tstart, tstop, n_t=None, remove_dc_offset=True,
                        out=None, want_float64=False):
         """Same as ``specs`` with ``target_times[i] = np.linspace(tstart_i, tstop_i, n_t)`` (the
@@ -224,7 +240,8 @@ class SpecEngine:
         dev = self.device
         # one upload: rows [seg_start i64 | grid0 f64 | tstart f64 | tstop f64 | seg_len, K i32]
         m = n + (n & 1)
-        packed = np.zeros((5, m), dtype=np.int64)
+        pinned, slot_ring, slot = self._pinned_slot(m)
+        packed = pinned.numpy()
         packed[0, :n] = seg_start
         packed[1, :n] = np.maximum(0.0, t1).view(np.int64)
         packed[2, :n] = np.ascontiguousarray(tstart).view(np.int64)
@@ -232,7 +249,12 @@ class SpecEngine:
         tail = packed[4].view(np.int32)                          # 2m int32 slots
         tail[:n] = seg_len
         tail[m:m + n] = K
-        packed_d = torch.from_numpy(packed).to(dev)
+        # pinned staging + async copy: the host never waits behind the train step queued on
+        # this stream (a pageable upload of more than 64 KB would)
+        packed_d = pinned.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        slot_ring["events"][slot] = ev
         if self._base_cache is None or self._base_cache[0] < kmax:
             # frame times do not depend on the batch: element k of a longer table is the same
             # number, so a cached table of at least kmax entries serves every batch
