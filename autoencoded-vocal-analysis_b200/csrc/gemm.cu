@@ -7,6 +7,8 @@
 //
 // Reference call sites: ava/models/vae.py:225-232 (fc1..fc43), 258-261 (fc5..fc8) and
 // autograd's addmm backward for vae.py:352.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ava {
@@ -56,14 +58,38 @@ __device__ __forceinline__ float4 mask4(float4 v, float4 m) {
   return make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f);
 }
 
+// Tensor-core inner product for the same tiles (TERMS = 1: TF32; 3: error-compensated 3xTF32,
+// fp32-level accuracy), as in the conv kernels (conv.cu): hi = x rounded to nearest TF32,
+// lo = x - hi (exact); a_hi*b_hi per 8-deep step on a zero accumulator, a_lo*b_hi + a_hi*b_lo
+// chained separately, everything summed with round-to-nearest FADDs.
+__device__ __forceinline__ uint32_t gm_tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ void gm_mma_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ void gm_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // A_KCONTIG: A' contiguous along k (sak == 1) else along m (sam == 1)
 // B_NCONTIG: B' contiguous along n (sbn == 1) else along k (sbk == 1)
-template <bool A_KCONTIG, bool B_NCONTIG, bool MASK>
+// TERMS: 0 = fp32 FMA (4x4 register micro-tiles); 1 / 3 = tensor cores (mma.sync m16n8k8 TF32):
+//   warp w owns rows 16*(w&3).. and columns 32*(w>>2).. of the 64x64 tile (4 n8 tiles); the
+//   row pitch of the staged tiles is 72 floats (8 mod 32) so fragment loads are conflict-free.
+template <bool A_KCONTIG, bool B_NCONTIG, bool MASK, int TERMS>
 __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
-  __shared__ __align__(16) float As[2][BK][BM + 4];
-  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  constexpr int PAD = TERMS ? 8 : 4;
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
+  // tensor-core thread coordinates
+  const int lane = tid & 31, warp = tid >> 5;
+  const int fg = lane >> 2, ft = lane & 3;
+  const int wm0 = (warp & 3) * 16, wn0 = (warp >> 2) * 32;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int grp = blockIdx.z / P.splits, split = blockIdx.z % P.splits;
   const float* A = P.A + (size_t)grp * P.a_gs;
@@ -78,8 +104,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  float4 ra, rb;
-  auto gload = [&](int k0) {
+  // two register sets: chunk c+1 and c+2 are in flight while chunk c is being multiplied
+  float4 ra0, rb0, ra1, rb1;
+  auto gload = [&](int k0, float4& ra, float4& rb) {
     if (A_KCONTIG) {
       int m = m0 + (tid >> 2), k = k0 + (tid & 3) * 4;
       int valid = (m < P.M) ? (k_end - k) : 0;
@@ -103,7 +130,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
       rb = load4(B + (size_t)n * P.sbn + k, valid);
     }
   };
-  auto sstore = [&](int buf) {
+  auto sstore = [&](int buf, const float4& ra, const float4& rb) {
     if (A_KCONTIG) {
       int m = tid >> 2, k = (tid & 3) * 4;
       As[buf][k + 0][m] = ra.x;
@@ -127,54 +154,149 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
   };
 
   const int nk = (k_end - k_begin + BK - 1) / BK;
-  if (nk > 0) {
-    gload(k_begin);
-    sstore(0);
-  }
-  __syncthreads();
-  for (int it = 0; it < nk; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < nk) gload(k_begin + (it + 1) * BK);
+  auto compute = [&](int buf) {
+    if constexpr (TERMS == 0) {
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
+      for (int k = 0; k < BK; ++k) {
+        float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    } else {
+      // acc[nt][0..3] = C fragment of n8-tile nt: rows fg / fg+8, columns 2*ft / 2*ft+1.
+      // The tensor core adds into a non-zero accumulator with truncation, a coherent bias that
+      // BatchNorm backward amplifies (measured: whole-model gradients 5-9x further from float64
+      // when the hi*hi products of a 16-deep chunk are chained).  So every hi*hi product block
+      // starts from a zero accumulator and is added to the running sum with a round-to-nearest
+      // FADD; only the small cross terms (2^-12 of the magnitude) are chained, separately.
+      float cs[4][4];
+#pragma unroll
+      for (int ks = 0; ks < BK / 8; ++ks) {
+        const int k0 = ks * 8;
+        const float av[4] = {As[buf][k0 + ft][wm0 + fg], As[buf][k0 + ft][wm0 + fg + 8],
+                             As[buf][k0 + ft + 4][wm0 + fg], As[buf][k0 + ft + 4][wm0 + fg + 8]};
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ah[j] = (TERMS == 3) ? gm_tf32_hi(av[j]) : __float_as_uint(av[j]);
+          al[j] = (TERMS == 3) ? __float_as_uint(av[j] - __uint_as_float(ah[j])) : 0u;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float b0 = Bs[buf][k0 + ft][wn0 + nt * 8 + fg], b1 = Bs[buf][k0 + ft + 4][wn0 + nt * 8 + fg];
+          const uint32_t bh0 = (TERMS == 3) ? gm_tf32_hi(b0) : __float_as_uint(b0);
+          const uint32_t bh1 = (TERMS == 3) ? gm_tf32_hi(b1) : __float_as_uint(b1);
+          if constexpr (TERMS == 3) {
+            const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
+            const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
+            if (ks == 0) gm_mma_zero(cs[nt], al, bh0, bh1);
+            else gm_mma(cs[nt], al, bh0, bh1);
+            gm_mma(cs[nt], ah, bl0, bl1);
+          }
+          float cf[4];
+          gm_mma_zero(cf, ah, bh0, bh1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[nt][j] += cf[j];
+        }
+      }
+      if constexpr (TERMS == 3) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[nt][j] += cs[nt][j];
+      }
     }
-    if (it + 1 < nk) sstore(buf ^ 1);
+  };
+  if (nk > 0) {
+    gload(k_begin, ra0, rb0);
+    sstore(0, ra0, rb0);
+  }
+  if (nk > 1) gload(k_begin + BK, ra0, rb0);
+  if (nk > 2) gload(k_begin + 2 * BK, ra1, rb1);
+  __syncthreads();
+  for (int it = 0; it < nk; it += 2) {
+    // chunk `it` (buffer 0); chunk it+1 waits in register set 0
+    compute(0);
+    if (it + 1 < nk) sstore(1, ra0, rb0);
+    if (it + 3 < nk) gload(k_begin + (it + 3) * BK, ra0, rb0);
+    __syncthreads();
+    if (it + 1 >= nk) break;
+    // chunk it+1 (buffer 1); chunk it+2 waits in register set 1
+    compute(1);
+    if (it + 2 < nk) sstore(0, ra1, rb1);
+    if (it + 4 < nk) gload(k_begin + (it + 4) * BK, ra1, rb1);
     __syncthreads();
   }
 
+  // element (i, j) of this thread's 16 accumulators -> (row, column) of the tile
+  auto row_of = [&](int i, int j) { return TERMS ? wm0 + fg + 8 * (j >> 1) : ty * 4 + i; };
+  auto col_of = [&](int i, int j) { return TERMS ? wn0 + i * 8 + 2 * ft + (j & 1) : tx * 4 + j; };
   if (P.splits == 1) {
     float* C = P.C + (size_t)grp * P.c_gs;
     const float* bias = P.bias ? P.bias + (size_t)grp * P.bias_gs : nullptr;
+    if constexpr (TERMS == 0) {
+      // a thread's 4 consecutive columns go out as one 16-byte store when the row allows it
+      const int n = n0 + tx * 4;
+      const bool vec = (n + 3 < P.N) && ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int m = m0 + ty * 4 + i;
-      if (m >= P.M) continue;
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= P.M) continue;
+        float v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int n = n0 + tx * 4 + j;
-        if (n >= P.N) continue;
-        float v = acc[i][j] + (bias ? bias[n] : 0.f);
-        C[(size_t)m * P.ldc + n] = apply_act(v, P.act);
+        for (int j = 0; j < 4; ++j)
+          v[j] = apply_act(acc[i][j] + ((bias && n + j < P.N) ? bias[n + j] : 0.f), P.act);
+        if (vec) {
+          *reinterpret_cast<float4*>(&C[(size_t)m * P.ldc + n]) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < P.N) C[(size_t)m * P.ldc + n + j] = v[j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = m0 + row_of(i, j), n = n0 + col_of(i, j);
+          if (m >= P.M || n >= P.N) continue;
+          float v = acc[i][j] + (bias ? bias[n] : 0.f);
+          C[(size_t)m * P.ldc + n] = apply_act(v, P.act);
+        }
       }
     }
   } else {
     float* part = P.part + (size_t)blockIdx.z * P.M * P.N;
+    if constexpr (TERMS == 0) {
+      const int n = n0 + tx * 4;
+      const bool vec = (n + 3 < P.N) && ((P.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(part) & 15) == 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int m = m0 + ty * 4 + i;
-      if (m >= P.M) continue;
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= P.M) continue;
+        if (vec) {
+          *reinterpret_cast<float4*>(&part[(size_t)m * P.N + n]) =
+              make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int n = n0 + tx * 4 + j;
-        if (n < P.N) part[(size_t)m * P.N + n] = acc[i][j];
+          for (int j = 0; j < 4; ++j)
+            if (n + j < P.N) part[(size_t)m * P.N + n + j] = acc[i][j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = m0 + row_of(i, j), n = n0 + col_of(i, j);
+          if (m < P.M && n < P.N) part[(size_t)m * P.N + n] = acc[i][j];
+        }
       }
     }
   }
@@ -277,7 +399,7 @@ static long long ws_need(int M, int N, int K, int groups) {
 }
 
 static int run_gemm(GemmParams P, int a_kcontig, int b_ncontig, void* ws, long long ws_bytes,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, int terms = 0) {
   if (P.M <= 0 || P.N <= 0) return 0;
   P.splits = pick_splits(P.M, P.N, P.K, P.groups);
   if (P.splits > 1 && (ws == nullptr || ws_bytes < ws_need(P.M, P.N, P.K, P.groups))) P.splits = 1;
@@ -288,18 +410,28 @@ static int run_gemm(GemmParams P, int a_kcontig, int b_ncontig, void* ws, long l
   P.part = reinterpret_cast<float*>(ws);
   dim3 grid((P.N + BN - 1) / BN, (P.M + BM - 1) / BM, P.groups * P.splits);
   const bool mask = P.Amask != nullptr;
+#define AVA_GEMM_LAUNCH(AK, BNC, MK)                                                  \
+  do {                                                                                \
+    if (terms == 3)                                                                   \
+      sgemm_kernel<AK, BNC, MK, 3><<<grid, 256, 0, stream>>>(P);                      \
+    else if (terms == 1)                                                              \
+      sgemm_kernel<AK, BNC, MK, 1><<<grid, 256, 0, stream>>>(P);                      \
+    else                                                                              \
+      sgemm_kernel<AK, BNC, MK, 0><<<grid, 256, 0, stream>>>(P);                      \
+  } while (0)
 #define AVA_GEMM_CASE(AK, BNC)                                                        \
   if (a_kcontig == AK && b_ncontig == BNC) {                                          \
     if (mask)                                                                         \
-      sgemm_kernel<AK, BNC, true><<<grid, 256, 0, stream>>>(P);                       \
+      AVA_GEMM_LAUNCH(AK, BNC, true);                                                 \
     else                                                                              \
-      sgemm_kernel<AK, BNC, false><<<grid, 256, 0, stream>>>(P);                      \
+      AVA_GEMM_LAUNCH(AK, BNC, false);                                                \
   }
   AVA_GEMM_CASE(true, true)
   AVA_GEMM_CASE(true, false)
   AVA_GEMM_CASE(false, true)
   AVA_GEMM_CASE(false, false)
 #undef AVA_GEMM_CASE
+#undef AVA_GEMM_LAUNCH
   if (check_launch("sgemm")) return 1;
   if (P.splits > 1) {
     long long total = (long long)P.groups * P.M * P.N;
@@ -310,6 +442,28 @@ static int run_gemm(GemmParams P, int a_kcontig, int b_ncontig, void* ws, long l
     return check_launch("splitk_reduce");
   }
   return 0;
+}
+
+// Shapes the tcgen05 kernel does not tile (batch not a multiple of 128), layers large enough
+// for it to matter (>= 256 K weights): the same 64x64x16 kernel with its inner product on the
+// tensor cores (mma.sync) --
+//   precision 1 ('tf32'): single TF32 term;
+//   precision 2 ('tf32x3'/'auto'): stays on the exact fp32 FMA inner product.  The 3-term
+//   mma.sync variant passes the per-kernel bar (2e-5) but every mma.sync adds its 8 products
+//   with truncation, a coherent bias that grows with the number of MMAs per output (1024 for
+//   K = 8192) and that BatchNorm backward amplifies: whole-model gradients at batch 64 came out
+//   5-9x further from float64 than with the FMA kernel (scratch/b64_err.py).
+//   AVA_B200_GEMM_MMA3=1 forces it (diagnostics only).
+static int mma_terms(int precision, int groups, int M, int N, int K) {
+  (void)M;
+  if (precision < 1 || groups != 1 || (long long)N * K < (1 << 18)) return 0;
+  if (precision == 1) return 1;
+  static int force3 = -1;
+  if (force3 < 0) {
+    const char* e = getenv("AVA_B200_GEMM_MMA3");
+    force3 = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return force3 ? 3 : 0;
 }
 
 }  // namespace ava
@@ -342,7 +496,7 @@ extern "C" int ava_b200_linear_fwd(const float* x, int ldx, const float* w, cons
   P.C = y; P.ldc = ldy; P.bias = b;
   P.M = M; P.N = N; P.K = K; P.act = act;
   P.groups = groups; P.a_gs = x_gs; P.b_gs = w_gs; P.c_gs = y_gs; P.bias_gs = b_gs;
-  return run_gemm(P, 1, 0, ws, ws_bytes, (cudaStream_t)stream);
+  return run_gemm(P, 1, 0, ws, ws_bytes, (cudaStream_t)stream, mma_terms(precision, groups, M, N, K));
 }
 
 extern "C" int ava_b200_linear_bwd_data(const float* dy, int lddy, const float* ymask, const float* w, float* dx,
@@ -360,7 +514,7 @@ extern "C" int ava_b200_linear_bwd_data(const float* dy, int lddy, const float* 
   P.C = dx; P.ldc = lddx;
   P.M = M; P.N = K; P.K = N; P.act = 0;
   P.groups = groups; P.a_gs = dy_gs; P.b_gs = w_gs; P.c_gs = dx_gs;
-  return run_gemm(P, 1, 1, ws, ws_bytes, (cudaStream_t)stream);
+  return run_gemm(P, 1, 1, ws, ws_bytes, (cudaStream_t)stream, mma_terms(precision, groups, M, N, K));
 }
 
 extern "C" int ava_b200_linear_bwd_weight(const float* dy, int lddy, const float* ymask, const float* x, int ldx,
@@ -379,7 +533,7 @@ extern "C" int ava_b200_linear_bwd_weight(const float* dy, int lddy, const float
     P.C = dw; P.ldc = K;
     P.M = N; P.N = K; P.K = M; P.act = 0;
     P.groups = groups; P.a_gs = dy_gs; P.b_gs = x_gs; P.c_gs = dw_gs;
-    if (run_gemm(P, 0, 1, ws, ws_bytes, (cudaStream_t)stream)) return 1;
+    if (run_gemm(P, 0, 1, ws, ws_bytes, (cudaStream_t)stream, mma_terms(precision, groups, M, N, K))) return 1;
   }
   if (db) {
     for (int g = 0; g < groups; ++g) {

@@ -8,7 +8,7 @@
 //
 // Here: ONE pass over X builds the Gram matrix of (x - s) and the column sums, s being the mean
 // of the first rows (a shift close to the mean, so the N m m^T correction does not cancel); the
-// z x z symmetric eigenproblem is solved on the device by cyclic Jacobi rotations in shared
+// z x z symmetric eigenproblem is solved on the device by Jacobi rotations (round-robin order) in shared
 // memory; a second pass projects.  All fp64; every reduction has a fixed order (bitwise
 // reproducible).  Input rows may be fp64 or the fp32 latents exactly as the encoder wrote them.
 //
@@ -37,7 +37,7 @@ __global__ void pca_shift_kernel(const T* __restrict__ x, long long N, int D, do
 // A group of (DP/4)^2 threads covers the DP x DP outputs in 4x4 register blocks; the 256/(that)
 // groups of a CTA take alternate rows of a tile and are combined in a fixed order at the end.
 template <typename T, int DP>
-__global__ void __launch_bounds__(PCA_THREADS)
+__global__ void __launch_bounds__(PCA_THREADS, 2)
 pca_gram_kernel(const T* __restrict__ x, long long N, int D, const double* __restrict__ shift,
                 double* __restrict__ partial) {
   constexpr int NB = DP / 4;
@@ -57,18 +57,28 @@ pca_gram_kernel(const T* __restrict__ x, long long N, int D, const double* __res
   for (int p = 0; p < 4; ++p)
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
-  double csum = 0.0;
+  double csum[4] = {0.0, 0.0, 0.0, 0.0};   // column sums, kept by the diagonal-block threads
   const long long n_tiles = (N + PCA_ROWS - 1) / PCA_ROWS;
-  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  // the next tile's elements travel in registers while the current tile is multiplied
+  constexpr int EPT = PCA_ROWS * DP / PCA_THREADS;   // elements per thread per tile
+  double pre[EPT];
+  auto fetch = [&](long long t) {
     const long long row0 = t * PCA_ROWS;
-    __syncthreads();
-    for (int idx = tid; idx < PCA_ROWS * DP; idx += PCA_THREADS) {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int idx = tid + e * PCA_THREADS;
       const int r = idx / DP, c = idx - r * DP;
-      double v = 0.0;
-      if (c < D && row0 + r < N) v = (double)x[(row0 + r) * D + c] - sshift[c];
-      smem[idx] = v;
+      pre[e] = (c < D && row0 + r < N) ? (double)x[(row0 + r) * D + c] - sshift[c] : 0.0;
     }
+  };
+  __syncthreads();   // sshift
+  if ((long long)blockIdx.x < n_tiles) fetch(blockIdx.x);
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) smem[tid + e * PCA_THREADS] = pre[e];
+    __syncthreads();
+    if (t + gridDim.x < n_tiles) fetch(t + gridDim.x);
     for (int r = group; r < PCA_ROWS; r += NG) {
       const double* xr = smem + r * DP;
       const double2 a01 = *reinterpret_cast<const double2*>(xr + 4 * bi);
@@ -81,11 +91,10 @@ pca_gram_kernel(const T* __restrict__ x, long long N, int D, const double* __res
       for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
-    }
-    if (tid < DP) {
-      double s = 0.0;
-      for (int r = 0; r < PCA_ROWS; ++r) s += smem[r * DP + tid];
-      csum += s;
+      if (bi == bj) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) csum[p] += a[p];
+      }
     }
   }
   __syncthreads();
@@ -101,34 +110,47 @@ pca_gram_kernel(const T* __restrict__ x, long long N, int D, const double* __res
     for (int g = 0; g < NG; ++g) s += smem[g * DP * DP + idx];
     out[idx] = s;
   }
-  if (tid < DP) out[DP * DP + tid] = csum;
-}
-
-// Sum the per-CTA partials in CTA order; mean = shift + colsum/N;
-// cov = (G - colsum colsum^T / N) / (N - 1)   [D x D, row-major, unpadded]
-__global__ void pca_finalize_kernel(const double* __restrict__ partial, int n_parts, int DP, int D, long long N,
-                                    const double* __restrict__ shift, double* __restrict__ mean,
-                                    double* __restrict__ cov) {
-  __shared__ double cs[PCA_MAX_D];
-  const int tid = threadIdx.x;
-  const int stride = DP * DP + DP;
-  if (tid < D) {
-    double s = 0.0;
-    for (int k = 0; k < n_parts; ++k) s += partial[(size_t)k * stride + DP * DP + tid];
-    cs[tid] = s;
-    mean[tid] = shift[tid] + s / (double)N;
+  // column sums: group g's diagonal thread bi holds columns 4*bi..4*bi+3
+  __syncthreads();
+  if (bi == bj) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) smem[group * DP + 4 * bi + p] = csum[p];
   }
   __syncthreads();
+  if (tid < DP) {
+    double s = 0.0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) s += smem[g * DP + tid];
+    out[DP * DP + tid] = s;
+  }
+}
+
+// Sum the per-CTA partials in CTA order (one thread per entry, many CTAs): sums[DP*DP + DP]
+__global__ void __launch_bounds__(128)
+pca_reduce_kernel(const double* __restrict__ partial, int n_parts, int stride, double* __restrict__ sums) {
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= stride) return;
+  double s = 0.0;
+  for (int k = 0; k < n_parts; ++k) s += partial[(size_t)k * stride + e];
+  sums[e] = s;
+}
+
+// mean = shift + colsum/N;  cov = (G - colsum colsum^T / N) / (N - 1)   [D x D, row-major, unpadded]
+__global__ void pca_finalize_kernel(const double* __restrict__ sums, int DP, int D, long long N,
+                                    const double* __restrict__ shift, double* __restrict__ mean,
+                                    double* __restrict__ cov) {
+  const int tid = threadIdx.x;
+  const double* cs = sums + DP * DP;
+  if (tid < D) mean[tid] = shift[tid] + cs[tid] / (double)N;
   const double denom = N > 1 ? (double)(N - 1) : 1.0;
   for (int idx = tid; idx < D * D; idx += blockDim.x) {
     const int i = idx / D, j = idx - i * D;
-    double s = 0.0;
-    for (int k = 0; k < n_parts; ++k) s += partial[(size_t)k * stride + i * DP + j];
-    cov[idx] = (s - cs[i] * cs[j] / (double)N) / denom;
+    cov[idx] = (sums[i * DP + j] - cs[i] * cs[j] / (double)N) / denom;
   }
 }
 
-// Cyclic Jacobi eigen-solver for one symmetric D x D matrix (D <= 64) in shared memory.
+// Jacobi eigen-solver (parallel round-robin ordering) for one symmetric D x D matrix (D <= 64)
+// in shared memory.
 // evals: descending, clipped at 0; comps[k][:] = unit eigenvector k with its largest-magnitude
 // entry made positive (first such entry on ties), as sklearn's svd_flip on V^T.
 __global__ void __launch_bounds__(PCA_MAX_D)
@@ -140,6 +162,8 @@ pca_eigh_kernel(const double* __restrict__ cov, int D, double* __restrict__ eval
   __shared__ double red[PCA_MAX_D];
   __shared__ int order[PCA_MAX_D];
   __shared__ int converged;
+  __shared__ int rot_p[PCA_MAX_D / 2], rot_q[PCA_MAX_D / 2];
+  __shared__ double rot_c[PCA_MAX_D / 2], rot_s[PCA_MAX_D / 2];
   const int k = threadIdx.x;
   if (k < D)
     for (int j = 0; j < D; ++j) {
@@ -176,52 +200,81 @@ pca_eigh_kernel(const double* __restrict__ cov, int D, double* __restrict__ eval
     }
     __syncthreads();
     if (converged) break;
-    for (int p = 0; p < D - 1; ++p) {
-      for (int q = p + 1; q < D; ++q) {
-        const double apq = A[p * LD + q];
-        const double app = A[p * LD + p], aqq = A[q * LD + q];
-        double akp = 0.0, akq = 0.0, vkp = 0.0, vkq = 0.0;
-        if (k < D) {
-          akp = A[k * LD + p];
-          akq = A[k * LD + q];
-          vkp = V[k * LD + p];
-          vkq = V[k * LD + q];
+    // One sweep = n-1 rounds of a round-robin tournament over the columns: the D/2 pairs of a
+    // round are disjoint, so their rotations are computed from the current matrix and applied
+    // together -- columns (A <- A J, V <- V J; thread k owns row k), then rows (A <- J^T A;
+    // thread k owns column k), then the rotated 2x2 blocks are set from the closed form.
+    const int n = D + (D & 1);
+    for (int r = 0; r < n - 1; ++r) {
+      double t_rot = 0.0, app = 0.0, aqq = 0.0, apq = 0.0;
+      int p = 0, q = 0;
+      bool active = false;
+      if (k < n / 2) {
+        int u, v;
+        if (k == 0) {
+          u = r % (n - 1);
+          v = n - 1;
+        } else {
+          u = (r + k) % (n - 1);
+          v = (r - k + (n - 1)) % (n - 1);
         }
-        __syncthreads();
-        // a negligible off-diagonal entry is zeroed instead of rotated (after the first sweeps)
-        const double g100 = 100.0 * fabs(apq);
-        const bool tiny = sweep > 3 && (fabs(app) + g100 == fabs(app)) && (fabs(aqq) + g100 == fabs(aqq));
-        if (tiny) {
-          if (k == p) {
-            A[p * LD + q] = 0.0;
-            A[q * LD + p] = 0.0;
-          }
-        } else if (apq != 0.0) {   // uniform across the CTA
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          const double c = 1.0 / sqrt(1.0 + t * t);
-          const double s = t * c;
-          if (k < D) {
-            if (k == p) {
-              A[p * LD + p] = app - t * apq;
-              A[p * LD + q] = 0.0;
-            } else if (k == q) {
-              A[q * LD + q] = aqq + t * apq;
-              A[q * LD + p] = 0.0;
-            } else {
-              const double nkp = c * akp - s * akq;
-              const double nkq = s * akp + c * akq;
-              A[k * LD + p] = nkp;
-              A[p * LD + k] = nkp;
-              A[k * LD + q] = nkq;
-              A[q * LD + k] = nkq;
-            }
-            V[k * LD + p] = c * vkp - s * vkq;
-            V[k * LD + q] = s * vkp + c * vkq;
+        p = u < v ? u : v;
+        q = u < v ? v : u;
+        double c = 1.0, sn = 0.0;
+        if (q < D) {
+          apq = A[p * LD + q];
+          app = A[p * LD + p];
+          aqq = A[q * LD + q];
+          const double g100 = 100.0 * fabs(apq);
+          const bool tiny = sweep > 3 && (fabs(app) + g100 == fabs(app)) && (fabs(aqq) + g100 == fabs(aqq));
+          if (tiny) {
+            active = true;            // zero the entry, no rotation (t = 0)
+          } else if (apq != 0.0) {
+            const double tau = (aqq - app) / (2.0 * apq);
+            t_rot = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t_rot * t_rot);
+            sn = t_rot * c;
+            active = true;
           }
         }
-        __syncthreads();
+        rot_p[k] = p;
+        rot_q[k] = q < D ? q : -1;
+        rot_c[k] = c;
+        rot_s[k] = sn;
       }
+      __syncthreads();
+      if (k < D) {
+        for (int i = 0; i < n / 2; ++i) {
+          const int pi = rot_p[i], qi = rot_q[i];
+          const double c = rot_c[i], sn = rot_s[i];
+          if (qi < 0 || sn == 0.0) continue;
+          const double a = A[k * LD + pi], b2 = A[k * LD + qi];
+          A[k * LD + pi] = c * a - sn * b2;
+          A[k * LD + qi] = sn * a + c * b2;
+          const double va = V[k * LD + pi], vb = V[k * LD + qi];
+          V[k * LD + pi] = c * va - sn * vb;
+          V[k * LD + qi] = sn * va + c * vb;
+        }
+      }
+      __syncthreads();
+      if (k < D) {
+        for (int i = 0; i < n / 2; ++i) {
+          const int pi = rot_p[i], qi = rot_q[i];
+          const double c = rot_c[i], sn = rot_s[i];
+          if (qi < 0 || sn == 0.0) continue;
+          const double a = A[pi * LD + k], b2 = A[qi * LD + k];
+          A[pi * LD + k] = c * a - sn * b2;
+          A[qi * LD + k] = sn * a + c * b2;
+        }
+      }
+      __syncthreads();
+      if (active) {
+        A[p * LD + p] = app - t_rot * apq;
+        A[q * LD + q] = aqq + t_rot * apq;
+        A[p * LD + q] = 0.0;
+        A[q * LD + p] = 0.0;
+      }
+      __syncthreads();
     }
   }
   // order eigenvalues (descending; stable in the index on ties)
@@ -324,7 +377,7 @@ using namespace ava;
 extern "C" long long ava_b200_pca_ws_bytes(int D) {
   if (D < 1 || D > PCA_MAX_D) return -1;
   const int DP = padded_dim(D);
-  return (long long)sizeof(double) * ((long long)PCA_MAX_CTAS * (DP * DP + DP) + PCA_MAX_D);
+  return (long long)sizeof(double) * ((long long)(PCA_MAX_CTAS + 1) * (DP * DP + DP) + PCA_MAX_D);
 }
 
 extern "C" int ava_b200_pca_fit(const void* x, int is_f32, long long N, int D, double* mean, double* cov,
@@ -336,7 +389,9 @@ extern "C" int ava_b200_pca_fit(const void* x, int is_f32, long long N, int D, d
   cudaStream_t stream = (cudaStream_t)stream_;
   const int DP = padded_dim(D);
   double* shift = (double*)ws;
-  double* partial = shift + PCA_MAX_D;
+  const int stride = DP * DP + DP;
+  double* sums = shift + PCA_MAX_D;
+  double* partial = sums + stride;
   const int ctas = gram_ctas(N);
   if (is_f32) {
     pca_shift_kernel<float><<<1, PCA_MAX_D, 0, stream>>>((const float*)x, N, D, shift);
@@ -348,7 +403,9 @@ extern "C" int ava_b200_pca_fit(const void* x, int is_f32, long long N, int D, d
     launch_gram<double>((const double*)x, N, D, DP, shift, partial, ctas, stream);
   }
   if (check_launch("pca_gram")) return 1;
-  pca_finalize_kernel<<<1, 1024, 0, stream>>>(partial, ctas, DP, D, N, shift, mean, cov);
+  pca_reduce_kernel<<<(stride + 127) / 128, 128, 0, stream>>>(partial, ctas, stride, sums);
+  if (check_launch("pca_reduce")) return 1;
+  pca_finalize_kernel<<<1, 1024, 0, stream>>>(sums, DP, D, N, shift, mean, cov);
   if (check_launch("pca_finalize")) return 1;
   const size_t smem = sizeof(double) * 2 * (size_t)D * (D + 1);
   if (cudaFuncSetAttribute(pca_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

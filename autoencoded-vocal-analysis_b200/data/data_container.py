@@ -12,8 +12,9 @@ Its only calls into the VAE hot path are
 * ``_make_latent_mean_pca_projection`` (data_container.py:538-551): scikit-learn
   ``PCA(n_components=2, copy=False, random_state=42).fit_transform``.
 
-Here every syllable file is read once, the spectrograms stay resident in HBM, ``get_latent``
-runs on the device with a single download, and the PCA is three kernels (csrc/pca.cu).  The
+Here every syllable file is read once and uploaded whole (one file resident at a time, so a
+corpus larger than HBM streams through), ``get_latent`` runs on the device with a single
+download of the latent means, and the PCA is a handful of kernels (csrc/pca.cu).  The
 request / make / read / write protocol, field names, file naming and on-disk datasets are the
 reference's, so projections written here are read by the reference and vice versa.  The other
 field families (segments, MUPET / DeepSqueak / SAP feature tables, UMAP) never touch the VAE
@@ -246,8 +247,9 @@ class DataContainer():
                 os.makedirs(proj_dir)
             partition = get_syllable_partition([spec_dir], 1, shuffle=False)
             try:
+                # streaming: one file resident at a time, same batches as the resident loader
                 loader = get_syllable_data_loaders(partition, batch_size=self.latent_batch_size,
-                                                   shuffle=(False, False))['train']
+                                                   shuffle=(False, False), streaming=True)['train']
                 latent_means = model.get_latent(loader)
                 all_latent.append(latent_means)
                 spec_fns = get_hdf5s_from_dir(spec_dir)

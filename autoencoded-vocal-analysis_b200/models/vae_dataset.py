@@ -77,7 +77,11 @@ class DeviceSyllableLoader:
     Iteration order: a fresh ``torch.randperm`` per epoch when ``shuffle`` (the reference's
     DataLoader(shuffle=True) also draws a torch permutation), else dataset order."""
 
-    def __init__(self, dataset, batch_size=64, shuffle=False, device=None, rank=0, world_size=1):
+    def __init__(self, dataset, batch_size=64, shuffle=False, device=None, rank=0, world_size=1,
+                 streaming=False):
+        """`streaming` (addition; needs shuffle=False, one rank): do not keep the split
+        resident -- read one file at a time and yield the same batches (a batch may straddle
+        files), for corpora larger than HBM (`DataContainer` latent means)."""
         self.dataset = dataset
         self.batch_size = batch_size
         self.shuffle = shuffle
@@ -85,6 +89,11 @@ class DeviceSyllableLoader:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
         self.rank, self.world_size = rank, world_size
+        self.streaming = bool(streaming)
+        if self.streaming:
+            assert not shuffle and world_size == 1, "streaming loaders walk the files in order"
+            self.data = None
+            return
         chunks = [np.asarray(read_specs(fn), dtype=np.float32) for fn in dataset.filenames]
         for c in chunks:
             assert len(c) == dataset.sylls_per_file, "files must hold sylls_per_file syllables"
@@ -95,7 +104,26 @@ class DeviceSyllableLoader:
         n = len(self.dataset)
         return (n + self.batch_size - 1) // self.batch_size
 
+    def _iter_streaming(self):
+        carry = None
+        for fn in self.dataset.filenames:
+            chunk = torch.from_numpy(np.asarray(read_specs(fn), dtype=np.float32)).to(self.device)
+            assert len(chunk) == self.dataset.sylls_per_file, "files must hold sylls_per_file syllables"
+            if carry is not None:
+                chunk = torch.cat([carry, chunk])
+                carry = None
+            full = (len(chunk) // self.batch_size) * self.batch_size
+            for start in range(0, full, self.batch_size):
+                yield chunk[start:start + self.batch_size]
+            if full < len(chunk):
+                carry = chunk[full:]
+        if carry is not None:
+            yield carry
+
     def __iter__(self):
+        if self.streaming:
+            yield from self._iter_streaming()
+            return
         n = len(self.dataset)
         if self.shuffle:
             order = torch.randperm(n).to(self.device)
@@ -119,7 +147,7 @@ class DeviceSyllableLoader:
 
 
 def get_syllable_data_loaders(partition, batch_size=64, shuffle=(True, False), num_workers=4,
-                              device=None, rank=0, world_size=1):
+                              device=None, rank=0, world_size=1, streaming=False):
     """Return a pair of loaders given a test/train split
     (ava/models/vae_dataset.py:62-94).  `num_workers` is accepted for compatibility and
     ignored (no worker processes are needed)."""
@@ -127,13 +155,15 @@ def get_syllable_data_loaders(partition, batch_size=64, shuffle=(True, False), n
     train_dataset = SyllableDataset(filenames=partition['train'], transform=numpy_to_tensor,
                                     sylls_per_file=sylls_per_file)
     train_dataloader = DeviceSyllableLoader(train_dataset, batch_size=batch_size, shuffle=shuffle[0],
-                                            device=device, rank=rank, world_size=world_size)
+                                            device=device, rank=rank, world_size=world_size,
+                                            streaming=streaming)
     if not partition['test']:
         return {'train': train_dataloader, 'test': None}
     test_dataset = SyllableDataset(filenames=partition['test'], transform=numpy_to_tensor,
                                    sylls_per_file=sylls_per_file)
     test_dataloader = DeviceSyllableLoader(test_dataset, batch_size=batch_size, shuffle=shuffle[1],
-                                           device=device, rank=rank, world_size=world_size)
+                                           device=device, rank=rank, world_size=world_size,
+                                           streaming=streaming)
     return {'train': train_dataloader, 'test': test_dataloader}
 
 

@@ -256,3 +256,26 @@ def test_data_container_host_logic_and_no_cpu_fallback(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             dcm.LatentPCA(2).fit_transform(rng.standard_normal((50, 32)))
+
+
+def test_streaming_syllable_loader_matches_resident(tmp_path):
+    """The file-at-a-time loader used by DataContainer yields exactly the batches of the
+    resident loader (batches may straddle files; ragged last batch kept)."""
+    import importlib
+    import numpy as np
+    import torch
+    ds = importlib.import_module(PKG + ".models.vae_dataset")
+    rng = np.random.default_rng(1)
+    fns = []
+    for j in range(5):
+        fn = str(tmp_path / ("s%d.npy" % j))
+        np.save(fn, rng.random((7, 128, 128)))
+        fns.append(fn)
+    dataset = ds.SyllableDataset(fns, 7)
+    for bs in (1, 4, 7, 10, 64):
+        a = list(ds.DeviceSyllableLoader(dataset, batch_size=bs, device="cpu"))
+        loader = ds.DeviceSyllableLoader(dataset, batch_size=bs, device="cpu", streaming=True)
+        b = list(loader)
+        assert len(a) == len(b) == len(loader)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+        assert sum(len(x) for x in b) == len(dataset) == 35

@@ -354,10 +354,14 @@ def test_bn_bookkeeping(L):
 
 
 @pytest.mark.parametrize("precision,tol", [(2, 2e-5), (1, 3e-3)])
-@pytest.mark.parametrize("M,N,K", [(128, 1024, 8192), (256, 8192, 1024), (128, 128, 32)])
+@pytest.mark.parametrize("M,N,K", [(128, 1024, 8192), (256, 8192, 1024), (128, 128, 32),
+                                   (64, 1024, 8192), (64, 8192, 1024), (100, 256, 1024), (7, 1024, 256),
+                                   (130, 8192, 1024), (1, 1024, 8192)])
 def test_linear_tensor_core(L, precision, tol, M, N, K):
-    """fc1/fc8-shaped layers on the tcgen05 path: precision 2 = 3xTF32 (fp32-level parity,
-    tolerance 2e-5), precision 1 = single TF32 (stated tolerance 3e-3)."""
+    """fc1/fc8-shaped layers on the tensor cores: the tcgen05 path when the batch tiles by 128,
+    else the 64x64 tiled kernel with an mma.sync inner product (batch 64, ragged batches).
+    precision 2 = 3xTF32 (fp32-level parity, tolerance 2e-5), precision 1 = single TF32
+    (stated tolerance 3e-3)."""
     gen = torch.Generator().manual_seed(M + N + K + precision)
     x = (torch.randn(M, K, generator=gen, dtype=torch.float64) * 0.5).float().double()
     w = (torch.randn(N, K, generator=gen, dtype=torch.float64) / np.sqrt(K)).float().double()
