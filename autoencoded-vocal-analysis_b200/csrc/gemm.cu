@@ -95,8 +95,12 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
   const float* A = P.A + (size_t)grp * P.a_gs;
   const float* Am = MASK ? P.Amask + (size_t)grp * P.a_gs : nullptr;
   const float* B = P.B + (size_t)grp * P.b_gs;
-  const int k_begin = split * P.kchunk;
-  const int k_end = min(P.K, k_begin + P.kchunk);
+  // split-K by INTERLEAVED 16-deep chunks: split s takes chunks s, s+splits, s+2*splits, ...  The
+  // CTAs that share an output tile run concurrently and march through K together, so at any
+  // moment they read adjacent 64-byte pieces of the same weight rows (one DRAM page) instead of
+  // `splits` streams 1.7 KB apart per row (measured at batch 64: see DESIGN.md 3.3).
+  const int k_end = P.K;
+  auto chunk_k = [&](int j) { return (split + j * P.splits) * BK; };
 
   float acc[4][4];
 #pragma unroll
@@ -153,7 +157,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
     }
   };
 
-  const int nk = (k_end - k_begin + BK - 1) / BK;
+  const int total_chunks = (P.K + BK - 1) / BK;
+  const int nk = total_chunks > split ? (total_chunks - split + P.splits - 1) / P.splits : 0;
   auto compute = [&](int buf) {
     if constexpr (TERMS == 0) {
 #pragma unroll
@@ -169,11 +174,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
       }
     } else {
       // acc[nt][0..3] = C fragment of n8-tile nt: rows fg / fg+8, columns 2*ft / 2*ft+1.
-      // The tensor core adds into a non-zero accumulator with truncation, a coherent bias that
-      // BatchNorm backward amplifies (measured: whole-model gradients 5-9x further from float64
-      // when the hi*hi products of a 16-deep chunk are chained).  So every hi*hi product block
-      // starts from a zero accumulator and is added to the running sum with a round-to-nearest
-      // FADD; only the small cross terms (2^-12 of the magnitude) are chained, separately.
+      // The tensor core adds into a non-zero accumulator with truncation, so every hi*hi product
+      // block starts from a zero accumulator and is added to the running sum with a
+      // round-to-nearest FADD; only the small cross terms (2^-12 of the magnitude) are chained.
       float cs[4][4];
 #pragma unroll
       for (int ks = 0; ks < BK / 8; ++ks) {
@@ -213,23 +216,23 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
     }
   };
   if (nk > 0) {
-    gload(k_begin, ra0, rb0);
+    gload(chunk_k(0), ra0, rb0);
     sstore(0, ra0, rb0);
   }
-  if (nk > 1) gload(k_begin + BK, ra0, rb0);
-  if (nk > 2) gload(k_begin + 2 * BK, ra1, rb1);
+  if (nk > 1) gload(chunk_k(1), ra0, rb0);
+  if (nk > 2) gload(chunk_k(2), ra1, rb1);
   __syncthreads();
   for (int it = 0; it < nk; it += 2) {
     // chunk `it` (buffer 0); chunk it+1 waits in register set 0
     compute(0);
     if (it + 1 < nk) sstore(1, ra0, rb0);
-    if (it + 3 < nk) gload(k_begin + (it + 3) * BK, ra0, rb0);
+    if (it + 3 < nk) gload(chunk_k(it + 3), ra0, rb0);
     __syncthreads();
     if (it + 1 >= nk) break;
     // chunk it+1 (buffer 1); chunk it+2 waits in register set 1
     compute(1);
     if (it + 2 < nk) sstore(0, ra1, rb1);
-    if (it + 4 < nk) gload(k_begin + (it + 4) * BK, ra1, rb1);
+    if (it + 4 < nk) gload(chunk_k(it + 4), ra1, rb1);
     __syncthreads();
   }
 
@@ -448,12 +451,10 @@ static int run_gemm(GemmParams P, int a_kcontig, int b_ncontig, void* ws, long l
 // for it to matter (>= 256 K weights): the same 64x64x16 kernel with its inner product on the
 // tensor cores (mma.sync) --
 //   precision 1 ('tf32'): single TF32 term;
-//   precision 2 ('tf32x3'/'auto'): stays on the exact fp32 FMA inner product.  The 3-term
-//   mma.sync variant passes the per-kernel bar (2e-5) but every mma.sync adds its 8 products
-//   with truncation, a coherent bias that grows with the number of MMAs per output (1024 for
-//   K = 8192) and that BatchNorm backward amplifies: whole-model gradients at batch 64 came out
-//   5-9x further from float64 than with the FMA kernel (scratch/b64_err.py).
-//   AVA_B200_GEMM_MMA3=1 forces it (diagnostics only).
+//   precision 2 ('tf32x3'/'auto'): stays on the fp32 FMA inner product.  The 3-term mma.sync
+//   variant is as accurate (measured at the fc1 shape, batch 64: 4.6e-8 rms / no bias vs
+//   6.3e-8 for FMA) but no faster: at batch 64 these GEMMs are bound by the weight stream, not
+//   by the inner product.  AVA_B200_GEMM_MMA3=1 selects it (diagnostics).
 static int mma_terms(int precision, int groups, int M, int N, int K) {
   (void)M;
   if (precision < 1 || groups != 1 || (long long)N * K < (1 << 18)) return 0;

@@ -30,6 +30,32 @@ def grad_tol(g, key, floor=2e-3, k=3.0):
     return max(floor, k * float(g["err32:" + key]))
 
 
+KINK_TOL = 5e-2       # gradients of a run whose ReLU pattern differs from the float64 reference's
+MAX_FLIPS = 16        # units (of ~1.9 M per sample) allowed to sit on the other side of zero
+
+
+def relu_flips(bufs, seed, batch, eps_w, eps_d, prec, train):
+    """Number of ReLU units whose on/off state in the GPU forward differs from the float64
+    oracle's on the same inputs.  The network's gradient is discontinuous there: a unit whose
+    pre-activation is within rounding of zero (|v| ~ 1e-7) lands on either side depending on
+    summation order, and ONE such unit moves the BatchNorm-amplified gradients by ~1e-2
+    (measured over seeds 21-24 at batch 64, profiles/r01_b64_seeds.txt: whichever of the fp32
+    FMA / 3xTF32 paths has a flip is ~5e-3..1e-2 off, the other ~2e-5..2e-4)."""
+    P64 = {k: (v.double() if v.is_floating_point() else v) for k, v in vae_oracle.make_params(seed).items()}
+    acts = {}
+    x = vae_oracle.make_input(seed, batch).double()
+    vae_oracle.forward(P64, x, torch.from_numpy(eps_w).double(), torch.from_numpy(eps_d).double(), prec,
+                       train, {}, acts)
+    names = [n for n, _, _, _ in vae_oracle.ENC_CONVS] + [n for n, _, _, _ in vae_oracle.DEC_CONVTS]
+    pairs = [(acts[n], bufs.act[l]) for l, n in enumerate(names) if n != "convt7"]
+    pairs += [(acts["fc1"], bufs.h1), (acts["fc2"], bufs.h2), (acts["fc3"], bufs.h3), (acts["fc5"], bufs.t5),
+              (acts["fc6"], bufs.t6), (acts["fc7"], bufs.t7), (acts["fc8"], bufs.t8)]
+    flips = 0
+    for ref, got in pairs:
+        flips += int(((ref > 0) != (got.detach().cpu().reshape(ref.shape) > 0)).sum())
+    return flips
+
+
 @pytest.fixture(scope="module")
 def vae_mod():
     return importlib.import_module(PKG + ".models.vae")
@@ -64,11 +90,17 @@ def test_forward_backward_matches_reference_golden(vae_mod, name):
     check_against_golden(g, "", "x_rec", bufs.act[13].cpu().numpy().reshape(batch, 128, 128),
                          FWD_TOL)
     if train:
+        flips = relu_flips(bufs, seed, batch, g["eps_w"], g["eps_d"], prec, train)
+        assert flips <= MAX_FLIPS, "%d ReLU units differ from the float64 forward" % flips
         model._backward_native(bufs)
         torch.cuda.synchronize()
         grads = model.grad_dict()
         for k, v in grads.items():
-            check_against_golden(g, "grad:", k, v.cpu().numpy(), grad_tol(g, "grad:" + k))
+            # same ReLU pattern as the reference: the fp32 bar; a unit on the other side of the
+            # kink: the gradient legitimately differs by the kink's size (see relu_flips)
+            tol = grad_tol(g, "grad:" + k) if flips == 0 else max(KINK_TOL, grad_tol(g, "grad:" + k))
+            check_against_golden(g, "grad:", k, v.cpu().numpy(), tol)
+        print("%s: %d ReLU flips vs float64" % (name, flips))
     sd = model.state_dict()
     for k in g.files:
         if not k.startswith("buf:"):
