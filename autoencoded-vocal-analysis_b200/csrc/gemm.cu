@@ -34,6 +34,7 @@ struct GemmParams {
   int M, N, K;
   int act;
   int splits, kchunk;
+  int rotate;          // start each output tile's K walk at a different chunk (see sgemm_kernel)
   int groups;
   long long a_gs, b_gs, c_gs, bias_gs;
 };
@@ -100,7 +101,17 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
   // moment they read adjacent 64-byte pieces of the same weight rows (one DRAM page) instead of
   // `splits` streams 1.7 KB apart per row (measured at batch 64: see DESIGN.md 3.3).
   const int k_end = P.K;
-  auto chunk_k = [&](int j) { return (split + j * P.splits) * BK; };
+  const int total_chunks = (P.K + BK - 1) / BK;
+  const int nk = total_chunks > split ? (total_chunks - split + P.splits - 1) / P.splits : 0;
+  // P.rotate: tile (x, y) starts its walk over K at chunk 5x + 3y (mod nk), so CTAs running at the
+  // same time touch different offsets within the (power-of-two pitched) weight rows instead of
+  // all hammering the same few DRAM channels
+  const int rot = (P.rotate && nk > 0) ? (int)((blockIdx.x * 5u + blockIdx.y * 3u) % (unsigned)nk) : 0;
+  auto chunk_k = [&](int j) {
+    int jj = j + rot;
+    if (jj >= nk) jj -= nk;
+    return (split + jj * P.splits) * BK;
+  };
 
   float acc[4][4];
 #pragma unroll
@@ -157,8 +168,6 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
     }
   };
 
-  const int total_chunks = (P.K + BK - 1) / BK;
-  const int nk = total_chunks > split ? (total_chunks - split + P.splits - 1) / P.splits : 0;
   auto compute = [&](int buf) {
     if constexpr (TERMS == 0) {
 #pragma unroll
@@ -411,6 +420,14 @@ static int run_gemm(GemmParams P, int a_kcontig, int b_ncontig, void* ws, long l
   P.kchunk = kc;
   P.splits = (P.K + kc - 1) / kc;
   P.part = reinterpret_cast<float*>(ws);
+  {
+    static int rotate = -1;
+    if (rotate < 0) {
+      const char* e = getenv("AVA_B200_GEMM_ROTATE");
+      rotate = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    P.rotate = rotate;
+  }
   dim3 grid((P.N + BN - 1) / BN, (P.M + BM - 1) / BM, P.groups * P.splits);
   const bool mask = P.Amask != nullptr;
 #define AVA_GEMM_LAUNCH(AK, BNC, MK)                                                  \

@@ -34,7 +34,7 @@ for (N, K) in ((1024, 8192), (8192, 1024), (256, 1024)):
         L.call("ava_b200_linear_bwd_weight", dyd.data_ptr(), N, ymask.data_ptr(), xd.data_ptr(), K, gw.data_ptr(),
                gb.data_ptr(), M, N, K, 1, 0, 0, 0, 0, prec, ws.data_ptr(), ws_bytes, st())
         L.call("ava_b200_linear_bwd_data", dyd.data_ptr(), N, ymask.data_ptr(), wd.data_ptr(), gx.data_ptr(), K,
-               M, N, K, 1, 0, 0, 0, 0, 0, prec, ws.data_ptr(), ws_bytes, st())
+               M, N, K, 1, 0, 0, 0, 0, prec, ws.data_ptr(), ws_bytes, st())
         torch.cuda.synchronize()
         print("M=%d N=%d K=%d precision %d MMA3=%s" % (M, N, K, prec, os.environ.get("AVA_B200_GEMM_MMA3", "0")))
         stats("fwd", y.cpu().numpy(), y64.numpy())
