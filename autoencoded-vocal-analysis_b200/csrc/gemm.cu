@@ -81,7 +81,7 @@ __device__ __forceinline__ void gm_mma(float (&c)[4], const uint32_t (&a)[4], ui
 //   warp w owns rows 16*(w&3).. and columns 32*(w>>2).. of the 64x64 tile (4 n8 tiles); the
 //   row pitch of the staged tiles is 72 floats (8 mod 32) so fragment loads are conflict-free.
 template <bool A_KCONTIG, bool B_NCONTIG, bool MASK, int TERMS>
-__global__ void __launch_bounds__(256) sgemm_kernel(const GemmParams P) {
+__global__ void __launch_bounds__(256, TERMS == 3 ? 3 : 4) sgemm_kernel(const GemmParams P) {
   constexpr int PAD = TERMS ? 8 : 4;
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
@@ -392,15 +392,20 @@ void launch_splitk_reduce(const float* part, int splits, int M, int N, const flo
   check_launch("splitk_reduce");
 }
 
+// Split-K factor.  ncu of the fc1 forward at batch 64 (profiles/r01_ncu_sgemm_b64.txt): with 16 x 19 =
+// 304 CTAs the kernel is FMA-issue bound at 64 % issue activity with only 4 warps per scheduler,
+// and 304 CTAs over 148 SMs leave some SMs with 3 CTAs and most with 2 (the slowest SM sets the
+// time).  So: as many CTAs as are resident at once (4 per SM at <= 64 registers), never more.
 static int pick_splits(int M, int N, int K, int groups) {
   long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN) * groups;
   int splits = 1;
   if (tiles < 2 * kNumSMs) {
-    splits = (int)((2 * kNumSMs + tiles - 1) / tiles);
+    splits = (int)((4 * kNumSMs) / tiles);
+    if (splits < 1) splits = 1;
     int maxs = K / 128;  // at least 128 of K per split
     if (maxs < 1) maxs = 1;
     if (splits > maxs) splits = maxs;
-    if (splits > 32) splits = 32;
+    if (splits > 64) splits = 64;
   }
   return splits;
 }
