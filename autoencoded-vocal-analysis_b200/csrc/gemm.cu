@@ -34,7 +34,6 @@ struct GemmParams {
   int M, N, K;
   int act;
   int splits, kchunk;
-  int rotate;          // start each output tile's K walk at a different chunk (see sgemm_kernel)
   int groups;
   long long a_gs, b_gs, c_gs, bias_gs;
 };
@@ -103,15 +102,9 @@ __global__ void __launch_bounds__(256, TERMS == 3 ? 3 : 4) sgemm_kernel(const Ge
   const int k_end = P.K;
   const int total_chunks = (P.K + BK - 1) / BK;
   const int nk = total_chunks > split ? (total_chunks - split + P.splits - 1) / P.splits : 0;
-  // P.rotate: tile (x, y) starts its walk over K at chunk 5x + 3y (mod nk), so CTAs running at the
-  // same time touch different offsets within the (power-of-two pitched) weight rows instead of
-  // all hammering the same few DRAM channels
-  const int rot = (P.rotate && nk > 0) ? (int)((blockIdx.x * 5u + blockIdx.y * 3u) % (unsigned)nk) : 0;
-  auto chunk_k = [&](int j) {
-    int jj = j + rot;
-    if (jj >= nk) jj -= nk;
-    return (split + jj * P.splits) * BK;
-  };
+  // (starting each tile's walk at a different chunk, to spread concurrent CTAs over the DRAM
+  // channels, was measured too: no effect -- the kernel is issue bound, see pick_splits)
+  auto chunk_k = [&](int j) { return (split + j * P.splits) * BK; };
 
   float acc[4][4];
 #pragma unroll
@@ -425,14 +418,6 @@ static int run_gemm(GemmParams P, int a_kcontig, int b_ncontig, void* ws, long l
   P.kchunk = kc;
   P.splits = (P.K + kc - 1) / kc;
   P.part = reinterpret_cast<float*>(ws);
-  {
-    static int rotate = -1;
-    if (rotate < 0) {
-      const char* e = getenv("AVA_B200_GEMM_ROTATE");
-      rotate = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    P.rotate = rotate;
-  }
   dim3 grid((P.N + BN - 1) / BN, (P.M + BM - 1) / BM, P.groups * P.splits);
   const bool mask = P.Amask != nullptr;
 #define AVA_GEMM_LAUNCH(AK, BNC, MK)                                                  \
