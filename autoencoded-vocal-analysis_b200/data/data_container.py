@@ -31,7 +31,7 @@ import torch
 from .. import _lib
 from ..models.utils import (append_field, get_hdf5s_from_dir, read_field, stored_fields)
 from ..models.vae import VAE
-from ..models.vae_dataset import get_syllable_data_loaders, get_syllable_partition
+from ..models.vae_dataset import get_syllable_data_loaders, get_syllable_partition, shard_files
 
 AUDIO_FIELDS = ['audio']
 FILENAME_FIELDS = ['sap_time']
@@ -137,12 +137,16 @@ class DataContainer():
     goes through ``get_syllable_data_loaders``' default of 64) and ``latent_eval`` -- the
     reference never calls ``eval()`` before ``get_latent``, so BatchNorm runs on
     per-batch statistics; ``latent_eval=True`` uses the trained running statistics instead,
-    which makes the latent means independent of the batch size."""
+    which makes the latent means independent of the batch size.  ``rank`` / ``world_size``
+    (one process per GPU, ``torch.distributed`` initialised): every rank computes and writes the
+    latent means of its own contiguous block of syllable files (no collective on the data path,
+    one barrier before the files are read back); every rank returns the full arrays, rank 0
+    writes the PCA projection."""
 
     def __init__(self, audio_dirs=None, segment_dirs=None, spec_dirs=None,
                  feature_dirs=None, projection_dirs=None, plots_dir='',
                  model_filename=None, template_dir=None, verbose=True,
-                 latent_batch_size=64, latent_eval=False):
+                 latent_batch_size=64, latent_eval=False, rank=0, world_size=1):
         self.audio_dirs = audio_dirs
         self.segment_dirs = segment_dirs
         self.spec_dirs = spec_dirs
@@ -154,6 +158,8 @@ class DataContainer():
         self.verbose = verbose
         self.latent_batch_size = latent_batch_size
         self.latent_eval = latent_eval
+        self.rank, self.world_size = int(rank), int(world_size)
+        assert 0 <= self.rank < self.world_size
         self.sylls_per_file = None  # syllables in each file in spec_dirs
         self.fields = self._check_for_fields()
         if self.plots_dir not in [None, ''] and not os.path.exists(self.plots_dir):
@@ -244,22 +250,45 @@ class DataContainer():
         for i in range(len(self.spec_dirs)):
             spec_dir, proj_dir = self.spec_dirs[i], self.projection_dirs[i]
             if proj_dir != '' and not os.path.exists(proj_dir):
-                os.makedirs(proj_dir)
-            partition = get_syllable_partition([spec_dir], 1, shuffle=False)
+                os.makedirs(proj_dir, exist_ok=True)
+            if self.world_size == 1:
+                partition = get_syllable_partition([spec_dir], 1, shuffle=False)
+            else:
+                # this rank's contiguous block of the directory's files; batch-aligned when
+                # BatchNorm runs on per-batch statistics (the reference's train-mode quirk)
+                every = get_hdf5s_from_dir(spec_dir)
+                first, last = shard_files(len(every), self.rank, self.world_size, spf,
+                                          1 if self.latent_eval else self.latent_batch_size)
+                partition = {'train': every[first:last], 'test': []}
             try:
-                # streaming: one file resident at a time, same batches as the resident loader
-                loader = get_syllable_data_loaders(partition, batch_size=self.latent_batch_size,
-                                                   shuffle=(False, False), streaming=True)['train']
-                latent_means = model.get_latent(loader)
-                all_latent.append(latent_means)
-                spec_fns = get_hdf5s_from_dir(spec_dir)
-                assert len(latent_means) // len(spec_fns) == spf
-                for j in range(len(spec_fns)):
-                    filename = os.path.join(proj_dir, os.path.split(spec_fns[j])[-1])
-                    append_field(filename, 'latent_means', latent_means[j * spf:(j + 1) * spf])
+                assert len(partition['train']) > 0 or self.world_size > 1
+                if len(partition['train']) > 0:
+                    # streaming: one file resident at a time, same batches as a resident loader
+                    loader = get_syllable_data_loaders(partition, batch_size=self.latent_batch_size,
+                                                       shuffle=(False, False), streaming=True)['train']
+                    latent_means = model.get_latent(loader)
+                    spec_fns = partition['train'] if self.world_size > 1 else get_hdf5s_from_dir(spec_dir)
+                    assert len(latent_means) // len(spec_fns) == spf
+                    for j in range(len(spec_fns)):
+                        filename = os.path.join(proj_dir, os.path.split(spec_fns[j])[-1])
+                        append_field(filename, 'latent_means', latent_means[j * spf:(j + 1) * spf])
+                    if self.world_size == 1:
+                        all_latent.append(latent_means)
             except AssertionError:  # No specs in this directory
                 pass
+            if self.world_size > 1:
+                self._barrier()
+                parts = [read_field(os.path.join(proj_dir, os.path.split(fn)[-1]), 'latent_means')
+                         for fn in get_hdf5s_from_dir(spec_dir)]
+                if parts:
+                    all_latent.append(np.concatenate(parts))
         return np.concatenate(all_latent)
+
+    def _barrier(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("DataContainer(world_size > 1) needs torch.distributed to be initialised")
+        dist.barrier()
 
     def _make_latent_mean_pca_projection(self):
         """Project latent means to two dimensions with PCA (data_container.py:538-551)."""
@@ -271,7 +300,10 @@ class DataContainer():
         self.pca_ = transform
         if self.verbose:
             print("\tDone.")
-        self._write_projection("latent_mean_pca", embedding)
+        if self.rank == 0:
+            self._write_projection("latent_mean_pca", embedding)
+        if self.world_size > 1:
+            self._barrier()
         return embedding
 
     def _write_projection(self, key, data):

@@ -39,6 +39,31 @@ def get_syllable_partition(dirs, split, shuffle=True, max_num_files=None):
     return {'train': filenames[:index], 'test': filenames[index:]}
 
 
+def shard_files(n_files, rank, world_size, sylls_per_file=1, batch_size=1):
+    """Contiguous block ``[lo, hi)`` of the (sorted) syllable files for `rank` (SURVEY 8(e):
+    ``get_latent`` shards by contiguous index ranges with no collective).  Block boundaries are
+    moved to the nearest file boundary that is also a batch boundary
+    (``lo * sylls_per_file % batch_size == 0``) when there is one, so that every batch holds the
+    same syllables as in the unsharded run -- which matters because the reference leaves
+    BatchNorm in train mode during ``get_latent``."""
+    assert 0 <= rank < world_size
+    q = batch_size // np.gcd(batch_size, sylls_per_file)      # files per batch-aligned period
+
+    def boundary(r):
+        b = (n_files * r) // world_size
+        if q > 1 and 0 < r < world_size:
+            lo_al, hi_al = (b // q) * q, -(-b // q) * q
+            cands = [c for c in (lo_al, hi_al) if 0 <= c <= n_files]
+            if cands:
+                b = min(cands, key=lambda c: (abs(c - b), c))
+        return int(b)
+    bounds = [boundary(r) for r in range(world_size + 1)]
+    bounds[0], bounds[-1] = 0, n_files
+    for r in range(1, world_size + 1):                          # keep the blocks ordered
+        bounds[r] = max(bounds[r], bounds[r - 1])
+    return bounds[rank], bounds[rank + 1]
+
+
 class SyllableDataset(Dataset):
     """torch.utils.data.Dataset for animal vocalization syllables
     (ava/models/vae_dataset.py:98-145)."""

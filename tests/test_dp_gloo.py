@@ -86,3 +86,69 @@ def _worker(rank, world, port, tmp):
 def test_data_parallel_host_logic_world2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
+class _FakeModel:
+    """Stands in for the VAE in the DataContainer sharding test: 'latent means' that are a
+    deterministic function of each spectrogram AND of the batch it arrived in (like BatchNorm
+    on per-batch statistics), so misplaced rows or changed batch boundaries are both caught."""
+
+    def get_latent(self, loader):
+        out = []
+        for batch in loader:
+            b = batch.double()
+            out.append(torch.stack([b[:, 0, 0], b.mean(dim=(1, 2)), b[:, 5, 7] - b[:, 0, 0].mean()], 1))
+        return torch.cat(out).numpy()
+
+
+def _container_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import functools
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    dcm = importlib.import_module(PKG + ".data.data_container")
+    mu = importlib.import_module(PKG + ".models.utils")
+    dcm.get_syllable_data_loaders = functools.partial(dcm.get_syllable_data_loaders, device='cpu')
+    ext = ".npz" if not mu._have_h5py() else ".hdf5"
+    spf, batch = 4, 8
+    sdirs = [os.path.join(tmp, "s0"), os.path.join(tmp, "s1")]
+    pdirs = [os.path.join(tmp, "p0_w%d" % world), os.path.join(tmp, "p1_w%d" % world)]
+    if rank == 0 and not os.path.exists(sdirs[0]):
+        rng = np.random.default_rng(0)
+        for sd, nf in zip(sdirs, (5, 1)):
+            os.makedirs(sd)
+            for j in range(nf):
+                mu.append_field(os.path.join(sd, "syllables_%04d%s" % (j, ext)), 'specs',
+                                rng.random((spf, 128, 128)))
+    dist.barrier()
+    dc = dcm.DataContainer(spec_dirs=sdirs, projection_dirs=pdirs, model_filename="unused.tar",
+                           verbose=False, latent_batch_size=batch, rank=rank, world_size=world)
+    dc._load_model = lambda: _FakeModel()
+    latent = dc.request('latent_means')
+    # unsharded answer, directory by directory, batches of `batch` across file boundaries
+    want = []
+    for sd in sdirs:
+        specs = np.concatenate([mu.read_field(fn, 'specs') for fn in mu.get_hdf5s_from_dir(sd)])
+        chunks = [torch.from_numpy(specs[i:i + batch].astype(np.float32)) for i in range(0, len(specs), batch)]
+        want.append(_FakeModel().get_latent(chunks))
+    want = np.concatenate(want)
+    np.testing.assert_array_equal(latent, want)            # same rows, same batch boundaries
+    # every projection file written exactly once, by its owner
+    for sd, pd in zip(sdirs, pdirs):
+        assert sorted(os.listdir(pd)) == sorted(os.path.basename(f) for f in mu.get_hdf5s_from_dir(sd))
+    assert dc.sylls_per_file == spf and 'latent_means' in dc.fields
+    np.testing.assert_array_equal(dc.request('latent_means'), want)    # now read from the files
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_container_sharded_latent_means_world2(tmp_path):
+    """get_latent shards by contiguous blocks of syllable files with no data-path
+    collective; each rank writes its own projection files; all ranks return the full array."""
+    port = _free_port()
+    mp.spawn(_container_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    # and a world of one gives the same files through the unsharded code path
+    port = _free_port()
+    mp.spawn(_container_worker, args=(1, port, str(tmp_path)), nprocs=1, join=True)
