@@ -347,19 +347,32 @@ class WarpedWindowDataset(Dataset):
         slope = (x_knots[j + 1] - x_knots[j]) / (y_knots[j + 1] - y_knots[j])
         return x_knots[j] + slope * (y_vals - y_knots[j])
 
-    def sample(self, n, seed=None):
+    def _draw(self, n, seed=None):
+        """(file index, start quantile) of n items from numpy's global legacy stream, in the
+        reference's order -- ``randint`` then ``rand`` per item (window_vae_dataset.py:613-617)
+        -- and the [n, num_time_bins] un-warped target times (:618-624).  Only the two draws
+        per item are a Python loop; the linspace / inverse-warp arithmetic runs on whole arrays
+        with the same float64 operations per element."""
         np.random.seed(seed)
         files = np.empty(n, dtype=np.int64)
-        tts = np.empty((n, self.p['num_time_bins']), dtype=np.float64)
+        u = np.empty(n, dtype=np.float64)
+        n_files = len(self.audio)
         for i in range(n):
-            # window_vae_dataset.py:613-624: randint then rand, per item
-            files[i] = np.random.randint(len(self.audio))
-            start_t = self.start_q + np.random.rand() * \
-                (self.stop_q - self.start_q - self.window_frac)
-            stop_t = start_t + self.window_frac
-            t_vals = np.linspace(start_t, stop_t, self.p['num_time_bins'])
-            tts[i] = self._get_unwarped_times(t_vals, files[i]) * self.template_dur
+            files[i] = np.random.randint(n_files)
+            u[i] = np.random.rand()
         np.random.seed(None)
+        start_t = self.start_q + u * (self.stop_q - self.start_q - self.window_frac)
+        stop_t = start_t + self.window_frac
+        n_t = self.p['num_time_bins']
+        t_vals = np.linspace(start_t, stop_t, n_t, axis=-1).reshape(n, n_t)
+        tts = np.empty((n, n_t), dtype=np.float64)
+        for f in np.unique(files):
+            sel = np.nonzero(files == f)[0]
+            tts[sel] = self._get_unwarped_times(t_vals[sel], f) * self.template_dur
+        return files, tts
+
+    def sample(self, n, seed=None):
+        files, tts = self._draw(n, seed)
         t1 = np.zeros(n)
         t2 = np.full(n, self.template_dur)
         return self._engine.specs(files, t1, t2, tts), files

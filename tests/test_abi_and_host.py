@@ -335,3 +335,49 @@ def test_hdf5_code_path_with_stand_in_h5py(tmp_path, monkeypatch):
     assert len(part['train']) == 2 and mu._get_sylls_per_file(part) == 3
     item = ds.SyllableDataset(part['train'], 3, transform=mu.numpy_to_tensor)[4]
     assert tuple(item.shape) == (128, 128) and str(item.dtype) == "torch.float32"
+
+
+def test_warped_window_sampling_vectorised_equals_reference_loop(tmp_path):
+    """WarpedWindowDataset._draw (vectorised linspace / inverse warp) against the reference's
+    per-item loop (ava/models/window_vae_dataset.py:613-624) restated literally: same draws
+    from the legacy global stream, bit-identical target times -- null warp and saved knots."""
+    import importlib
+    import numpy as np
+    win = importlib.import_module(PKG + ".models.window_vae_dataset")
+    fs = 32000
+    p = {'fs': fs, 'nperseg': 512, 'noverlap': 256, 'num_time_bins': 128, 'num_freq_bins': 128,
+         'window_length': 0.12, 'min_freq': 400, 'max_freq': 10e3, 'spec_min_val': 2.0,
+         'spec_max_val': 6.5, 'mel': True, 'time_stretch': False, 'within_syll_normalize': False,
+         'max_dur': 1e9}
+    rng = np.random.default_rng(0)
+    audio = [np.zeros(int(fs * d), np.int16) for d in (0.9, 1.0, 1.1, 0.95)]
+    names = ["m%d.wav" % i for i in range(4)]
+    knots_fn = str(tmp_path / "knots.npy")
+    x_knots = np.sort(rng.uniform(0, 1, size=(4, 5)), axis=1)
+    y_knots = np.sort(rng.uniform(0, 1, size=(4, 5)), axis=1)
+    x_knots[:, 0] = y_knots[:, 0] = 0.0
+    x_knots[:, -1] = y_knots[:, -1] = 1.0
+    np.save(knots_fn, {'x_knots': x_knots, 'y_knots': y_knots, 'template_dur': 0.93,
+                       'audio_filenames': np.array(sorted(names))})
+    datasets = [win.WarpedWindowDataset(names, p, warp_type='null', audio=audio, fs=fs),
+                win.WarpedWindowDataset(names, p, load_warp=True, warp_fn=knots_fn, audio=audio, fs=fs)]
+
+    def reference_loop(ds, n, seed):
+        np.random.seed(seed)
+        files, tts = [], []
+        for _ in range(n):
+            file_index = np.random.randint(len(ds.audio))
+            start_t = ds.start_q + np.random.rand() * (ds.stop_q - ds.start_q - ds.window_frac)
+            stop_t = start_t + ds.window_frac
+            t_vals = np.linspace(start_t, stop_t, ds.p['num_time_bins'])
+            files.append(file_index)
+            tts.append(ds._get_unwarped_times(t_vals, file_index) * ds.template_dur)
+        np.random.seed(None)
+        return np.array(files), np.array(tts)
+
+    for ds in datasets:
+        for n, seed in ((1, 0), (7, 1), (300, 2)):
+            f_ref, t_ref = reference_loop(ds, n, seed)
+            f_new, t_new = ds._draw(n, seed)
+            assert np.array_equal(f_new, f_ref)
+            assert np.array_equal(t_new, t_ref)            # bit-identical
