@@ -381,3 +381,28 @@ def test_warped_window_sampling_vectorised_equals_reference_loop(tmp_path):
             f_new, t_new = ds._draw(n, seed)
             assert np.array_equal(f_new, f_ref)
             assert np.array_equal(t_new, t_ref)            # bit-identical
+
+
+def test_shard_files_partitions_and_aligns():
+    """vae_dataset.shard_files: the ranks' blocks tile [0, n_files) in order; interior boundaries
+    fall on batch boundaries whenever a file boundary that is also a batch boundary exists."""
+    import importlib
+    import numpy as np
+    ds = importlib.import_module(PKG + ".models.vae_dataset")
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        n = int(rng.integers(0, 200))
+        world = int(rng.integers(1, 9))
+        spf = int(rng.choice([1, 3, 4, 24, 100, 512]))
+        batch = int(rng.choice([1, 4, 64, 1024]))
+        blocks = [ds.shard_files(n, r, world, spf, batch) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(lo <= hi for lo, hi in blocks)
+        assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+        q = batch // np.gcd(batch, spf)
+        for lo, hi in blocks[1:]:
+            if lo not in (0, n):
+                assert (lo * spf) % batch == 0 or q > n, (n, world, spf, batch, blocks)
+    # batch size 1 (eval-mode BatchNorm: no alignment needed) splits evenly
+    assert [ds.shard_files(100, r, 8) for r in range(8)] == [(12 * r + (r * 4) // 8, 12 * (r + 1) + ((r + 1) * 4) // 8)
+                                                              for r in range(8)]
