@@ -205,6 +205,11 @@ class SpecEngine:
     def _pinned_slot(self, m):
         """A pinned [5, m] int64 staging buffer from a ring of 4 per batch size; a slot is
         reused only after the upload that last read it has completed."""
+        if m not in self._pin_rings and len(self._pin_rings) >= 8:
+            # many distinct batch sizes (silence-rejection retries): keep the staging rings of
+            # the 8 most recent sizes; torch's pinned-memory allocator defers the reuse of a
+            # dropped buffer until the copies reading it have completed
+            self._pin_rings.pop(next(iter(self._pin_rings)))
         ring = self._pin_rings.setdefault(m, {"bufs": [], "events": [], "next": 0})
         if len(ring["bufs"]) < 4:
             ring["bufs"].append(torch.zeros(5, m, dtype=torch.int64).pin_memory())
