@@ -339,13 +339,18 @@ class WarpedWindowDataset(Dataset):
         return self.dataset_length
 
     def _get_unwarped_times(self, y_vals, index):
-        """Template (warped) quantile times -> empirical quantile times: piecewise-linear
-        interpolation through the knots with linear extrapolation
-        (window_vae_dataset.py:461-477; scipy interp1d(fill_value='extrapolate'))."""
+        """Template (warped) quantile times -> empirical quantile times
+        (window_vae_dataset.py:461-477): ``scipy.interpolate.interp1d(y_knots, x_knots,
+        fill_value='extrapolate')``, i.e. piecewise-linear interpolation through the knots with
+        linear extrapolation, in the arithmetic of the installed SciPy (1.18:
+        ``_interpolate.py::interp1d._call_linear`` -- interval from ``searchsorted`` (left)
+        clipped to [1, n-1], value = ((t-lo)/(hi-lo))*x_hi + ((hi-t)/(hi-lo))*x_lo), so the
+        target times are bit-identical to the reference's."""
         x_knots, y_knots = self.x_knots[index], self.y_knots[index]
-        j = np.clip(np.searchsorted(y_knots, y_vals, side='right') - 1, 0, len(y_knots) - 2)
-        slope = (x_knots[j + 1] - x_knots[j]) / (y_knots[j + 1] - y_knots[j])
-        return x_knots[j] + slope * (y_vals - y_knots[j])
+        hi = np.clip(np.searchsorted(y_knots, y_vals), 1, len(y_knots) - 1)
+        lo = hi - 1
+        y_lo, y_hi = y_knots[lo], y_knots[hi]
+        return ((y_vals - y_lo) / (y_hi - y_lo)) * x_knots[hi] + ((y_hi - y_vals) / (y_hi - y_lo)) * x_knots[lo]
 
     def _draw(self, n, seed=None):
         """(file index, start quantile) of n items from numpy's global legacy stream, in the

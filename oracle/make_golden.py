@@ -541,11 +541,77 @@ def pca_case():
     np.savez_compressed(os.path.join(GOLDEN, "pca_cases.npz"), **out)
 
 
+
+# ---------------------------------------------------------------- SURVEY 8(f) N3
+WARP_DURS = (0.80, 0.93, 0.87, 1.02)        # seconds of the four synthetic "motifs"
+
+
+def write_warp_corpus(root):
+    """Four synthetic int16 wav files of different lengths + a saved 3-knot warp (the format
+    WarpedWindowDataset itself saves, window_vae_dataset.py:497-506); shared by the generator
+    and the test."""
+    from scipy.io import wavfile
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    adir = os.path.join(root, "motifs")
+    os.makedirs(adir, exist_ok=True)
+    names = []
+    for i, d in enumerate(WARP_DURS):
+        fn = os.path.join(adir, "motif_%d.wav" % i)
+        wavfile.write(fn, fs, spec_oracle.synth_audio(60 + i, int(d * fs), fs))
+        names.append(fn)
+    rng = np.random.default_rng(17)
+    x_knots = np.sort(rng.uniform(0.05, 0.95, size=(len(names), 5)), axis=1)
+    y_knots = np.sort(rng.uniform(0.05, 0.95, size=(len(names), 5)), axis=1)
+    x_knots[:, 0] = y_knots[:, 0] = 0.0
+    x_knots[:, -1] = y_knots[:, -1] = 1.0
+    warp_fn = os.path.join(root, "knots.npy")
+    np.save(warp_fn, {'x_knots': x_knots, 'y_knots': y_knots, 'template_dur': 0.79,
+                      'audio_filenames': sorted(names), 'warp_params': {}})
+    return names, warp_fn, p
+
+
+def warped_case(ref_win, ref_pre):
+    """The reference's WarpedWindowDataset run unmodified (window_vae_dataset.py:359-640) with
+    the null warp and with saved knots: template duration, and per seed the file each item was
+    drawn from and its un-warped target times (captured at the p['get_spec'] plugin boundary),
+    plus a few spectrograms from the reference's own get_spec."""
+    import tempfile
+    out = {"versions": np.array(versions())}
+    with tempfile.TemporaryDirectory() as root:
+        names, warp_fn, p = write_warp_corpus(root)
+        captured = []
+
+        def spy_get_spec(t1, t2, audio, p_, fs=32000, max_dur=None, target_times=None, **kw):
+            captured.append((t1, t2, len(audio), np.array(target_times)))
+            return ref_pre.get_spec(t1, t2, audio, p_, fs=fs, max_dur=max_dur, target_times=target_times)
+        p['get_spec'] = spy_get_spec
+        for tag, kw in (("null", dict(warp_type='null', save_warp=False)),
+                        ("knots", dict(load_warp=True, save_warp=False, warp_fn=warp_fn))):
+            ds = ref_win.WarpedWindowDataset(list(names), p, transform=None, **kw)
+            lens = [len(a) for a in ds.audio]
+            out[tag + ":template_dur"] = np.array(ds.template_dur)
+            out[tag + ":window_frac"] = np.array(ds.window_frac)
+            for seed, n in ((0, 6), (5, 40)):
+                del captured[:]
+                specs = ds.__getitem__(np.arange(n), seed=seed)
+                assert len(captured) == n
+                out["%s:seed%d_files" % (tag, seed)] = np.array([lens.index(c[2]) for c in captured])
+                out["%s:seed%d_times" % (tag, seed)] = np.stack([c[3] for c in captured])
+                assert all(c[0] == 0.0 and c[1] == ds.template_dur for c in captured)
+                if seed == 0:
+                    out[tag + ":seed0_specs"] = np.stack(specs[:2])
+            single = ds.__getitem__(0, seed=9)
+            out[tag + ":single_seed9"] = np.asarray(single)
+    np.savez_compressed(os.path.join(GOLDEN, "warped_cases.npz"), **out)
+    print("warped cases: template_dur", float(out["null:template_dur"]), float(out["knots:template_dur"]))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
     ref_vae, ref_pre, ref_win, ref_ds = _ref_import.import_reference()
-    which = sys.argv[1:] or ["vae", "adam", "spec", "sampler", "process", "mmd", "container", "pca"]
+    which = sys.argv[1:] or ["vae", "adam", "spec", "sampler", "process", "mmd", "container", "pca", "warped"]
     if "vae" in which:
         vae_case(ref_vae, "vae_train_b7", seed=0, batch=7, train=True)
         vae_case(ref_vae, "vae_eval_b7", seed=1, batch=7, train=False)
@@ -565,6 +631,8 @@ def main():
         container_case(ref_vae)
     if "pca" in which:
         pca_case()
+    if "warped" in which:
+        warped_case(ref_win, ref_pre)
 
 
 if __name__ == "__main__":

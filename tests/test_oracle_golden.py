@@ -153,3 +153,33 @@ def test_container_golden_is_self_consistent():
     np.testing.assert_array_equal(np.concatenate(parts), g["latent_means"])
     emb, _ = pca_oracle.pca_fit_transform(g["latent_means"], 2)
     assert np.abs(emb - g["latent_mean_pca"]).max() <= TOL64 * np.abs(g["latent_mean_pca"]).max()
+
+
+@pytest.mark.parametrize("tag", ["null", "knots"])
+def test_warped_window_sampling_matches_reference_golden(tag, tmp_path):
+    """the warped-window sampling path against the reference's own
+    WarpedWindowDataset (tests/golden/warped_cases.npz, generated by running it unmodified):
+    template duration, file draws and un-warped target times bit-exact; the oracle's get_spec
+    on those target times reproduces the reference's spectrograms."""
+    import importlib
+    from oracle import make_golden
+    win = importlib.import_module("autoencoded-vocal-analysis_b200.models.window_vae_dataset")
+    g = load_golden("warped_cases")
+    names, warp_fn, p = make_golden.write_warp_corpus(str(tmp_path))
+    kw = dict(warp_type='null') if tag == "null" else dict(load_warp=True, warp_fn=warp_fn)
+    ds = win.WarpedWindowDataset(list(names), p, **kw)
+    assert ds.template_dur == float(g[tag + ":template_dur"])
+    assert ds.window_frac == float(g[tag + ":window_frac"])
+    for seed, n in ((0, 6), (5, 40)):
+        files, tts = ds._draw(n, seed)
+        assert np.array_equal(files, g["%s:seed%d_files" % (tag, seed)])
+        assert np.array_equal(tts, g["%s:seed%d_times" % (tag, seed)])          # bit-exact
+    files, tts = ds._draw(6, 0)
+    fs = p['fs']
+    for i in range(2):
+        spec, _ = spec_oracle.get_spec(0.0, ds.template_dur, ds.audio[files[i]], p, fs=fs,
+                                       target_times=tts[i])
+        assert np.abs(spec - g[tag + ":seed0_specs"][i]).max() <= TOL64
+    files, tts = ds._draw(1, 9)
+    spec, _ = spec_oracle.get_spec(0.0, ds.template_dur, ds.audio[files[0]], p, fs=fs, target_times=tts[0])
+    assert np.abs(spec - g[tag + ":single_seed9"]).max() <= TOL64
