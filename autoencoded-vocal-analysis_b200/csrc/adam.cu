@@ -7,7 +7,13 @@ namespace ava {
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long n4, long long n, const float* step_count, double lr_d, double b1_d, double b2_d,
-            double eps_d, float gscale) {
+            double eps_d, float gscale, const double* __restrict__ hyper) {
+  if (hyper != nullptr) {   // hyper-parameters read from device memory (CUDA-graph replay safe)
+    lr_d = hyper[0];
+    b1_d = hyper[1];
+    b2_d = hyper[2];
+    eps_d = hyper[3];
+  }
   // Scalars exactly as torch.optim.Adam forms them (Python doubles, rounded to fp32 once):
   // step number of THIS update (torch increments `step` before using it)
   const double t = (double)step_count[0] + 1.0;
@@ -53,9 +59,9 @@ __global__ void adam_bump_step_kernel(float* step_count) { step_count[0] += 1.f;
 
 }  // namespace ava
 
-extern "C" int ava_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float* step_count,
-                                  double lr, double beta1, double beta2, double eps, float grad_scale,
-                                  void* stream_) {
+static int adam_launch(float* p, const float* g, float* m, float* v, long long n, float* step_count, double lr,
+                       double beta1, double beta2, double eps, float grad_scale, const double* hyper,
+                       void* stream_) {
   using namespace ava;
   if (n <= 0) return 0;
   AVA_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
@@ -65,8 +71,20 @@ extern "C" int ava_b200_adam_step(float* p, const float* g, float* m, float* v, 
   long long n4 = n / 4;
   long long want = (n4 + 255) / 256;
   int grid = (int)(want < 1 ? 1 : (want > 16 * kNumSMs ? 16 * kNumSMs : want));
-  adam_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n4, n, step_count, lr, beta1, beta2, eps, grad_scale);
+  adam_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n4, n, step_count, lr, beta1, beta2, eps, grad_scale, hyper);
   if (check_launch("adam")) return 1;
   adam_bump_step_kernel<<<1, 1, 0, stream>>>(step_count);
   return check_launch("adam_bump_step");
+}
+
+extern "C" int ava_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float* step_count,
+                                  double lr, double beta1, double beta2, double eps, float grad_scale,
+                                  void* stream_) {
+  return adam_launch(p, g, m, v, n, step_count, lr, beta1, beta2, eps, grad_scale, nullptr, stream_);
+}
+
+extern "C" int ava_b200_adam_step_dev(float* p, const float* g, float* m, float* v, long long n,
+                                      float* step_count, const double* hyper, float grad_scale, void* stream_) {
+  AVA_REQUIRE(hyper != nullptr, "adam_step_dev: hyper-parameter buffer required");
+  return adam_launch(p, g, m, v, n, step_count, 0.0, 0.0, 0.0, 0.0, grad_scale, hyper, stream_);
 }

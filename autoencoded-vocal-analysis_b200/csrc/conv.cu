@@ -19,7 +19,8 @@
 // Epilogue:
 //   EPI_FWD: + bias, ReLU, store, and per-channel sum / sum-of-squares of the output
 //            (the next BatchNorm's batch statistics) via warp shuffles -> smem -> fp64 atomics
-//   EPI_BWD: store, and per-channel sum g, sum g*(x-mean) (this BatchNorm's dbeta, dgamma)
+//   EPI_BWD: this layer's BatchNorm backward + the producing layer's ReLU backward applied to the
+//            accumulators (coefficients from the weight-gradient pass), store the next dz
 //
 // Thread mapping: a warp's lanes run along x (coalesced loads/stores, conflict-free
 // shared-memory reads), each thread owns 4 output rows x COT(<=8) output channels in
@@ -52,10 +53,17 @@ struct GconvParams {
   float* out;
   int relu_out;
   double* stats_out;
-  // EPI_BWD
+  // EPI_BWD: this layer's own BatchNorm (applied to x_self in the forward pass).  Its backward
+  // and the ReLU backward of the layer that produced x_self run in the epilogue:
+  //   out = [x_self > 0] * (p*(g - c1) + q*(x_self - mean))      (common.cuh: dz_coef / dz_apply)
+  // with the two BatchNorm-backward reductions dstats_in = (sum g, sum g*(x-mean)) supplied by
+  // the weight-gradient pass of the same layer (see bnconv_finalize_kernel): the gradient g
+  // w.r.t. the BatchNorm output never goes to memory.
   const float* x_self;
   const double* stats_self;
-  double* dstats;
+  const float* gamma_self;
+  const double* dstats_in;
+  int mask_in;
   double out_count;
   int B, H_in, W_in;
 };
@@ -234,8 +242,8 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
   float* s_c1 = s_c0 + 32;                          // AFFINE shift
   float* s_red = s_c1 + 32;                         // per-warp partial sums
   float* s_bias = s_red + C::RED_FLOATS;            // [CO]
-  double* s_meand = reinterpret_cast<double*>(s_bias + 32);  // [32] EPI_BWD: mean of own BN
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meand + 32);
+  double* s_dz = reinterpret_cast<double*>(s_bias + 32);  // [4][32] EPI_BWD: p | q | mean | c1 of own BN
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dz + 128);
 
   const int tid = threadIdx.x;
   // every instantiation serves exactly one layer, so the image size is a compile-time constant
@@ -409,9 +417,20 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
   }
   if (tid < CO) {
     s_bias[tid] = (EPI == EPI_FWD && P.bias) ? P.bias[tid] : 0.f;
-    if (EPI == EPI_BWD) s_meand[tid] = P.stats_self[tid] / P.out_count;
+    if (EPI == EPI_BWD) {
+      const DzCoef k = dz_coef(P.gamma_self, P.stats_self, P.dstats_in, tid, P.out_count);
+      s_dz[tid] = k.p;
+      s_dz[32 + tid] = k.q;
+      s_dz[64 + tid] = k.mean;
+      s_dz[96 + tid] = k.c1;
+    }
   }
   __syncthreads();
+  // EPI_BWD epilogue: BatchNorm backward (fp64 coefficient math, the two terms cancel) + ReLU mask
+  auto dzap = [&](int co, float g, float x) -> float {
+    const double d = s_dz[co] * ((double)g - s_dz[96 + co]) + s_dz[32 + co] * ((double)x - s_dz[64 + co]);
+    return (P.mask_in && !(x > 0.f)) ? 0.f : (float)d;
+  };
 
   if constexpr (C::MMA) {
     // ---------------------------------------------------------------- tensor-core path (K_S1, K_S2)
@@ -428,7 +447,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
     // every tile's warp-level partial sums are added to per-warp fp64 slots in shared memory
     // (fixed order: deterministic), so no fp32 rounding accumulates over the CTA's many tiles
     double* s_accd = reinterpret_cast<double*>(s_red) + warp * 64;
-    const bool want_stats = ((EPI == EPI_FWD) ? P.stats_out : P.dstats) != nullptr;
+    const bool want_stats = (EPI == EPI_FWD) && P.stats_out != nullptr;
     if (lane < 4) {
 #pragma unroll
       for (int i = 0; i < NTL; ++i)
@@ -712,8 +731,8 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
               float v0 = acc[2 * oa][i][j], v1 = acc[2 * oa + 1][i][j];
               if (EPI == EPI_BWD) {
                 const float2 xv = *reinterpret_cast<const float2*>(P.x_self + o);
-                st1[i][j & 1] += v0 + v1;
-                st2[i][j & 1] = fmaf(v0, xv.x, fmaf(v1, xv.y, st2[i][j & 1]));
+                v0 = dzap(co, v0, xv.x);
+                v1 = dzap(co, v1, xv.y);
               } else {
                 v0 += s_bias[co];
                 v1 += s_bias[co];
@@ -731,7 +750,6 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
         // c2 = (g+8, 2t), c3 = (g+8, 2t+1)
         const int oy0 = ty * G::TH + r0, ox0 = tx * TW + xh * 16 + g;
         if (EPI == EPI_BWD) {
-          // sum g and sum g*x per channel (centred with the exact mean at the very end)
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             float xs[NTL][4];
@@ -746,10 +764,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 #pragma unroll
             for (int i = 0; i < NTL; ++i)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                st1[i][j & 1] += acc[r][i][j];
-                st2[i][j & 1] = fmaf(acc[r][i][j], xs[i][j], st2[i][j & 1]);
-              }
+              for (int j = 0; j < 4; ++j) acc[r][i][j] = dzap(i * 8 + 2 * t + (j & 1), acc[r][i][j], xs[i][j]);
           }
         } else {
 #pragma unroll
@@ -799,7 +814,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
     }
 
     // ---- fixed-order sum over the warps, one fp64 atomic per channel per CTA
-    double* dst = (EPI == EPI_FWD) ? P.stats_out : P.dstats;
+    double* dst = (EPI == EPI_FWD) ? P.stats_out : nullptr;
     if (dst != nullptr) {
       __syncthreads();
       if (tid < CO) {
@@ -811,7 +826,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
           b += sd[w * 64 + 32 + tid];
         }
         atomicAdd(&dst[tid], a);
-        atomicAdd(&dst[32 + tid], (EPI == EPI_BWD) ? b - s_meand[tid] * a : b);
+        atomicAdd(&dst[32 + tid], b);
       }
     }
   } else {
@@ -929,8 +944,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 
     // ---- epilogue (the next tile group's loads are already in flight)
     if (EPI == EPI_BWD) {
-      // sum g and sum g*x per channel (centred with the exact mean at the very end); all
-      // NOUT*COT loads of x are issued before the first one is used
+      // all NOUT*COT loads of x are issued before the first one is used
       float xs[NOUT][COT];
 #pragma unroll
       for (int o = 0; o < NOUT; ++o) {
@@ -952,10 +966,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 #pragma unroll
       for (int o = 0; o < NOUT; ++o)
 #pragma unroll
-        for (int c = 0; c < COT; ++c) {
-          st1[c] += acc[o][c];
-          st2[c] = fmaf(acc[o][c], xs[o][c], st2[c]);
-        }
+        for (int c = 0; c < COT; ++c) acc[o][c] = dzap(cog * COT + c, acc[o][c], xs[o][c]);
     } else {
 #pragma unroll
       for (int o = 0; o < NOUT; ++o)
@@ -998,7 +1009,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 
   // ---- per-channel statistics: warp shuffle -> per-warp smem slots -> fixed-order sum ->
   // one fp64 atomic per channel per CTA (the in-CTA part is deterministic)
-  double* dst = (EPI == EPI_FWD) ? P.stats_out : P.dstats;
+  double* dst = (EPI == EPI_FWD) ? P.stats_out : nullptr;
   if (dst != nullptr) {
     const int warp = tid >> 5;
 #pragma unroll
@@ -1022,8 +1033,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
         }
       }
       atomicAdd(&dst[tid], (double)a);
-      // EPI_BWD: sum g*(x - mean) = sum g*x - mean * sum g, centred in fp64
-      atomicAdd(&dst[32 + tid], (EPI == EPI_BWD) ? (double)b - s_meand[tid] * (double)a : (double)b);
+      atomicAdd(&dst[32 + tid], (double)b);
     }
   }
   }
@@ -1059,7 +1069,7 @@ static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   using C = GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>;
   using G = typename C::G;
   const size_t smem = (size_t)(C::BUF_FLOATS + C::W_FLOATS + 64 + C::RED_FLOATS + 32) * sizeof(float) +
-                      32 * sizeof(double) + 16 + 128;
+                      128 * sizeof(double) + 16 + 128;
   if (P.H_in != HIN || P.W_in != HIN) {
     set_error("gconv: layer geometry mismatch");
     return 1;
@@ -1093,8 +1103,19 @@ static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
 
 // ------------------------------------------------------------------------------------
 // Weight gradient.  D[g][i][k] = sum_{n,y,x} Gt[n,g,y,x] * It[n,i,S*y+ky-1,S*x+kx-1]
-//   conv layers : Gt = dz (DZ loader),   It = bn(x) (AFFINE loader), D == dW[co][ci][3][3]
-//   convT layers: Gt = bn(x) (AFFINE),   It = dz (DZ),               D == dW[ci][co][3][3]
+//   conv layers : Gt = dz (DZ loader),    It = x - mean (zero padded), D ~ dW[co][ci][3][3]
+//   convT layers: Gt = x - mean,          It = dz (DZ),                D ~ dW[ci][co][3][3]
+// The kernels accumulate the CENTRED RAW product Rc = sum dz * (x - mean)_pad; the finalize pass
+// (bnconv_finalize_kernel) turns it into the weight gradient
+//   dW = gamma*invstd * Rc + beta * T_k        T_k[co] = sum of dz over the pixels whose tap-k
+//                                              partner lies inside the image
+// AND into this layer's two BatchNorm-backward reductions, which are linear in the same sums:
+//   sum_q g[ci,q]              = sum_{co,k} W[co,ci,k] * T_k[co]
+//   sum_q g[ci,q]*(x-mean)[q]  = sum_{co,k} W[co,ci,k] * Rc[co,ci,k]       (g = conv-transpose(dz, W))
+// so the backward-data kernel of the same layer can apply the BatchNorm backward in its
+// epilogue without a separate pass over g (measured equivalence: profiles/probes/
+// exp_algebraic_dstats.py -- the algebraic values agree with epilogue-accumulated ones to 1e-8
+// of the gradient's scale, and the whole-model gradients are unchanged at the 1e-6 level).
 // Each thread owns GT g-channels x one i-channel x 9 taps in registers and walks 4-pixel
 // strips of the tile; thread groups split the strips; partial sums live in registers
 // across the CTA's whole persistent loop and are reduced once at the end
@@ -1197,9 +1218,11 @@ __global__ void __launch_bounds__(256, 2)
     const int c = tid;
     constexpr int CA = CONVT ? CG : CI;  // channels of x
     if (c < CA) {
-      BnCoef k = bn_coef(P.stats, c, P.bn_count, P.gamma, P.beta, nullptr, nullptr, true);
-      s_aff[c] = k.scale;
-      s_aff[32 + c] = k.shift;
+      // centred raw input: x - mean (mean rounded to fp32; the finalize pass corrects for the
+      // rounding and applies gamma*invstd / beta, see bnconv_finalize_kernel)
+      BnCoef k = bn_coef(P.stats, c, P.bn_count, nullptr, nullptr, nullptr, nullptr, true);
+      s_aff[c] = 1.f;
+      s_aff[32 + c] = -k.mean;
     }
   }
   // per-thread transform work lists (identical for every tile)
@@ -1440,9 +1463,9 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
   if (tid < 32) {
     constexpr int CA = CONVT ? CG : CI;
     if (tid < CA) {
-      BnCoef k = bn_coef(P.stats, tid, P.bn_count, P.gamma, P.beta, nullptr, nullptr, true);
-      s_aff[tid] = k.scale;
-      s_aff[32 + tid] = k.shift;
+      BnCoef k = bn_coef(P.stats, tid, P.bn_count, nullptr, nullptr, nullptr, nullptr, true);
+      s_aff[tid] = 1.f;        // centred raw input, see wgrad_kernel
+      s_aff[32 + tid] = -k.mean;
     }
   }
 
@@ -1623,26 +1646,181 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
 
 constexpr int kWgradMaxCtas = 8 * kNumSMs;  // per-CTA partial slots in the workspace
 
-// second stage: out[j] = sum_p partial[p][j] for the weights (j < nw -> dw[j]) and the bias slots
-// (j >= nw -> db[j-nw]) in one launch; one warp per output element, lanes stride over the
-// partials and combine with a fixed-order shuffle tree (deterministic)
-__global__ void __launch_bounds__(256)
-reduce_partials_kernel(const float* __restrict__ partial, int nparts, int stride, int nw, int nb,
-                       float* __restrict__ dw, float* __restrict__ db) {
+// Border-trimmed sums of dz: T_k[c] = sum of dz[c] over the pixels whose tap-k partner lies inside
+// the image, from the 9 per-channel sums `ts` ([slot][32] doubles) that ava_b200_dz_border_sums (or a
+// producing kernel's epilogue) accumulated:
+//   mode 0 (conv layers, stride-1 conv-transpose): 0 total, 1 first row, 2 last row, 3 first column,
+//          4 last column, 5..8 corners (first/last row x first/last column)
+//   mode 1 (stride-2 conv-transpose; dz at 2x resolution, tap (ky,kx) reads dz[2p+k-1]):
+//          0..3 parity classes (row parity*2 + column parity), 4,5 last row by column parity,
+//          6,7 last column by row parity, 8 last corner
+__device__ __forceinline__ double trimmed_dz_sum(const double* ts, int c, int ky, int kx, int convt, int s2) {
+  if (convt && s2) {
+    const int ry = (ky != 1), rx = (kx != 1);
+    double v = ts[(ry * 2 + rx) * 32 + c];
+    if (ky == 0) v -= ts[(4 + rx) * 32 + c];
+    if (kx == 0) v -= ts[(6 + ry) * 32 + c];
+    if (ky == 0 && kx == 0) v += ts[8 * 32 + c];
+    return v;
+  }
+  int rex = -1, cex = -1;   // excluded row / column: 0 = first, 1 = last
+  if (!convt) {             // partner S*p + k - 1: tap 0 misses p = 0; tap 2 misses the last p (stride 1 only)
+    if (ky == 0) rex = 0; else if (ky == 2 && !s2) rex = 1;
+    if (kx == 0) cex = 0; else if (kx == 2 && !s2) cex = 1;
+  } else {                  // dz pixel p + k - 1: tap 0 never reaches the last row, tap 2 never the first
+    if (ky == 0) rex = 1; else if (ky == 2) rex = 0;
+    if (kx == 0) cex = 1; else if (kx == 2) cex = 0;
+  }
+  double v = ts[c];
+  if (rex >= 0) v -= ts[(1 + rex) * 32 + c];
+  if (cex >= 0) v -= ts[(3 + cex) * 32 + c];
+  if (rex >= 0 && cex >= 0) v += ts[(5 + rex * 2 + cex) * 32 + c];
+  return v;
+}
+
+struct FinalizeParams {
+  const float* partial;   // [nparts][stride] per-CTA partial sums of Rc (+ 32 unused slots)
+  int nparts, stride;
+  int Cx, Cz;             // channels of x (this layer's BatchNorm) and of dz
+  int convt, s2;
+  const float* w;         // same flat layout as dw
+  const float* gamma;
+  const float* beta;
+  const double* stats;    // sum x | sum x^2 of this layer's input
+  double count;
+  const double* tsums;    // [9][32], see trimmed_dz_sum
+  float* dw;
+  float* db;
+  double* dstats;         // out: sum g | sum g*(x-mean), accumulated (zeroed by the caller)
+};
+
+// Second stage of the weight gradient: one warp per weight element sums the per-CTA partials in
+// fp64 (lanes stride over the partials, fixed-order shuffle tree: deterministic), finishes dW, and
+// adds the element's contribution to this layer's BatchNorm-backward reductions.
+__global__ void __launch_bounds__(256) bnconv_finalize_kernel(const FinalizeParams P) {
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (j >= nw + nb) return;
-  float s = 0.f;
-  for (int p = lane; p < nparts; p += 32) s += partial[(size_t)p * stride + j];
-  s = warp_sum(s);
+  const int NW = P.Cx * P.Cz * 9;
+  if (j >= NW + P.Cz) return;
+  if (j >= NW) {
+    // bias gradient = sum of dz over all pixels
+    if (lane == 0) {
+      const int cz = j - NW;
+      double v;
+      if (P.convt && P.s2)
+        v = P.tsums[cz] + P.tsums[32 + cz] + P.tsums[64 + cz] + P.tsums[96 + cz];
+      else
+        v = P.tsums[cz];
+      P.db[cz] = (float)v;
+    }
+    return;
+  }
+  double r = 0.0;
+  for (int p = lane; p < P.nparts; p += 32) r += (double)P.partial[(size_t)p * P.stride + j];
+  r = warp_sum(r);
   if (lane == 0) {
-    if (j < nw) dw[j] = s;
-    else db[j - nw] = s;
+    const int k = j % 9;
+    int cx, cz;
+    if (!P.convt) {
+      cx = (j / 9) % P.Cx;
+      cz = j / (9 * P.Cx);
+    } else {
+      cz = (j / 9) % P.Cz;
+      cx = j / (9 * P.Cz);
+    }
+    const double T = trimmed_dz_sum(P.tsums, cz, k / 3, k % 3, P.convt, P.s2);
+    const double mean = P.stats[cx] / P.count;
+    double var = P.stats[32 + cx] / P.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double invstd = rsqrt(var + (double)kBnEps);
+    // the kernels centred with the fp32-rounded mean: sum dz*(x-mean) = sum dz*(x-mean32) + (mean32-mean)*T
+    const double rc = r + ((double)(float)mean - mean) * T;
+    const double wv = (double)P.w[j];
+    P.dw[j] = (float)((double)P.gamma[cx] * invstd * rc + (double)P.beta[cx] * T);
+    atomicAdd(&P.dstats[cx], wv * T);
+    atomicAdd(&P.dstats[32 + cx], wv * rc);
   }
 }
 
+// The nine per-channel sums of a dz tensor [B, C, H, W] that trimmed_dz_sum consumes.
+__global__ void __launch_bounds__(256)
+dz_border_sums_kernel(const float* __restrict__ dz, int B, int C, int H, int W, int mode, double* tsums) {
+  __shared__ double s_red[8][9];
+  const int c = blockIdx.y;
+  const int w4 = W >> 2, hw4 = (H * W) >> 2;
+  const long long total4 = (long long)B * hw4;
+  double a[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) a[i] = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / hw4;
+    const int q = (int)(i - n * hw4);
+    const int y = q / w4, x0 = (q - y * w4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(dz + ((size_t)n * C + c) * H * W) + q);
+    const bool first_row = (y == 0), last_row = (y == H - 1), first_col = (x0 == 0), last_col = (x0 + 4 == W);
+    if (mode == 0) {
+      const float s = (v.x + v.y) + (v.z + v.w);
+      a[0] += (double)s;
+      if (first_row) a[1] += (double)s;
+      if (last_row) a[2] += (double)s;
+      if (first_col) {
+        a[3] += (double)v.x;
+        if (first_row) a[5] += (double)v.x;
+        if (last_row) a[7] += (double)v.x;
+      }
+      if (last_col) {
+        a[4] += (double)v.w;
+        if (first_row) a[6] += (double)v.w;
+        if (last_row) a[8] += (double)v.w;
+      }
+    } else {
+      const int ry = y & 1;
+      const float e = v.x + v.z, o = v.y + v.w;
+      a[ry * 2] += (double)e;
+      a[ry * 2 + 1] += (double)o;
+      if (last_row) {
+        a[4] += (double)e;
+        a[5] += (double)o;
+      }
+      if (last_col) {
+        a[6 + ry] += (double)v.w;
+        if (last_row) a[8] += (double)v.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const double s = warp_sum(a[i]);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+    atomicAdd(&tsums[threadIdx.x * 32 + c], s);
+  }
+}
+
+// second stage, shared by both weight-gradient kernels
+template <int S, int CG, int CI, int CONVT>
+static int launch_finalize(const WgradParams& P, FinalizeParams F, int nparts, cudaStream_t stream) {
+  F.partial = P.partial;
+  F.nparts = nparts;
+  F.stride = CG * CI * 9 + 32;
+  F.Cx = CONVT ? CG : CI;
+  F.Cz = CONVT ? CI : CG;
+  F.convt = CONVT;
+  F.s2 = (S == 2);
+  F.stats = P.stats;
+  F.count = P.bn_count;
+  const int n = CG * CI * 9 + F.Cz;
+  bnconv_finalize_kernel<<<(n + 7) / 8, 256, 0, stream>>>(F);
+  return check_launch("bnconv_finalize");
+}
+
 template <int S, int CG, int CI, int TWG, int CONVT>
-static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStream_t stream) {
+static int launch_wgrad(WgradParams P, const FinalizeParams& F, void* ws, cudaStream_t stream) {
   using T = WTile<S, TWG>;
   constexpr int GW = (CI == 1) ? TWG + 4 : TWG, GROWS = (CI == 1) ? T::THG + 1 : T::THG;   // as in the kernel
   constexpr int G_PAD = (CG * GW * GROWS + 31) / 32 * 32;
@@ -1671,16 +1849,13 @@ static int launch_wgrad(WgradParams P, float* dw, float* db, void* ws, cudaStrea
   if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, GW, GROWS, CG)) return 1;
   if (make_act_map(&map_i, P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS, CI)) return 1;
   P.partial = reinterpret_cast<float*>(ws);
-  const int stride = CG * CI * 9 + 32;
   kern<<<grid, 256, smem, stream>>>(map_g, map_i, P);
   if (check_launch("wgrad")) return 1;
-  constexpr int NW = CG * CI * 9, NB = CONVT ? CI : CG;
-  reduce_partials_kernel<<<(NW + NB + 7) / 8, 256, 0, stream>>>(P.partial, grid, stride, NW, NB, dw, db);
-  return check_launch("wgrad_reduce");
+  return launch_finalize<S, CG, CI, CONVT>(P, F, grid, stream);
 }
 
 template <int S, int CG, int CI, int TWG, int CONVT, int TERMS>
-static int launch_wgrad_mma(WgradParams P, float* dw, float* db, void* ws, cudaStream_t stream) {
+static int launch_wgrad_mma(WgradParams P, const FinalizeParams& F, void* ws, cudaStream_t stream) {
   using T = WTileM<S, TWG>;
   constexpr int NPAIR = ((CG + 15) / 16) * (CI / 8);
   constexpr int NTHR = (NPAIR == 6) ? 192 : 256;
@@ -1710,19 +1885,16 @@ static int launch_wgrad_mma(WgradParams P, float* dw, float* db, void* ws, cudaS
   if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, T::G_W, T::G_ROWS_BOX, CG)) return 1;
   if (make_act_map(&map_i, P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS_BOX, CI)) return 1;
   P.partial = reinterpret_cast<float*>(ws);
-  const int stride = CG * CI * 9 + 32;
   kern<<<grid, NTHR, smem, stream>>>(map_g, map_i, P);
   if (check_launch("wgrad_mma")) return 1;
-  constexpr int NW = CG * CI * 9, NB = CONVT ? CI : CG;
-  reduce_partials_kernel<<<(NW + NB + 7) / 8, 256, 0, stream>>>(P.partial, grid, stride, NW, NB, dw, db);
-  return check_launch("wgrad_reduce");
+  return launch_finalize<S, CG, CI, CONVT>(P, F, grid, stream);
 }
 
 // tensor-core weight gradient (all layers with >= 8 channels on both sides), else the fp32 FMA kernel
 #define WGRAD_TC(S, CG, CI, TWG, CONVT)                                                              \
-  (g_conv_terms == 3   ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 3>(P, dw, db, ws, stream)          \
-   : g_conv_terms == 1 ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 1>(P, dw, db, ws, stream)          \
-                       : launch_wgrad<S, CG, CI, TWG, CONVT>(P, dw, db, ws, stream))
+  (g_conv_terms == 3   ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 3>(P, F, ws, stream)               \
+   : g_conv_terms == 1 ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 1>(P, F, ws, stream)               \
+                       : launch_wgrad<S, CG, CI, TWG, CONVT>(P, F, ws, stream))
 
 // ------------------------------------------------------------------------------------
 struct LayerGeom {
@@ -1820,8 +1992,10 @@ extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, c
 }
 
 extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const float* w, const float* x,
-                                        const double* stats_in, float* g_in, double* dstats, void* stream_) {
+                                        const float* gamma, const double* stats_in, const double* dstats,
+                                        int relu_mask, float* dz_prev, void* stream_) {
   AVA_REQUIRE(layer >= 0 && layer < 14, "bnconv_bwd_data: bad layer %d", layer);
+  AVA_REQUIRE(dz_prev != nullptr && x != nullptr, "bnconv_bwd_data: output and layer input required");
   if (B <= 0) return 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   const LayerGeom& L = kLayers[layer];
@@ -1829,10 +2003,12 @@ extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const
   GconvParams P = {};
   P.in = dz;
   P.w = w;
-  P.out = g_in;
+  P.out = dz_prev;
   P.x_self = x;
   P.stats_self = stats_in;
-  P.dstats = dstats;
+  P.gamma_self = gamma;
+  P.dstats_in = dstats;
+  P.mask_in = relu_mask;
   P.out_count = (double)B * L.h_in * L.h_in;
   P.B = B;
   P.H_in = P.W_in = ho;  // the gather reads the layer's OUTPUT-shaped gradient
@@ -1872,29 +2048,37 @@ extern "C" long long ava_b200_bnconv_bwd_weight_ws(int layer, int B) {
   return (long long)kWgradMaxCtas * (L.cin * L.cout * 9 + 32) * (long long)sizeof(float);
 }
 
-extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, const float* x, const float* gamma,
-                                          const float* beta, const double* stats_in, float* dw, float* db,
-                                          void* ws, void* stream_) {
+extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, const float* x, const float* w,
+                                          const float* gamma, const float* beta, const double* stats_in,
+                                          const double* tsums, float* dw, float* db, double* dstats, void* ws,
+                                          void* stream_) {
   AVA_REQUIRE(layer >= 0 && layer < 14, "bnconv_bwd_weight: bad layer %d", layer);
   AVA_REQUIRE(ws != nullptr, "bnconv_bwd_weight: workspace required");
+  AVA_REQUIRE(w != nullptr && tsums != nullptr && dstats != nullptr, "bnconv_bwd_weight: w, tsums, dstats required");
   if (B <= 0) return 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   const LayerGeom& L = kLayers[layer];
   const int ho = h_out_of(L);
   WgradParams P = {};
-  P.gamma = gamma;
-  P.beta = beta;
   P.stats = stats_in;
   P.bn_count = (double)B * L.h_in * L.h_in;
   P.B = B;
+  FinalizeParams F = {};
+  F.w = w;
+  F.gamma = gamma;
+  F.beta = beta;
+  F.tsums = tsums;
+  F.dw = dw;
+  F.db = db;
+  F.dstats = dstats;
   int rc = 1;
   if (!L.transposed) {
-    // G = dz (output resolution), I = bn(x) (input resolution)
+    // G = dz (output resolution), I = x - mean (input resolution)
     P.g_a = dz;
     P.i_a = x;
     P.Hg = P.Wg = ho;
     switch (layer) {
-      case 0: rc = launch_wgrad<1, 8, 1, 32, 0>(P, dw, db, ws, stream); break;
+      case 0: rc = launch_wgrad<1, 8, 1, 32, 0>(P, F, ws, stream); break;
       case 1: rc = WGRAD_TC(2, 8, 8, 32, 0); break;
       case 2: rc = WGRAD_TC(1, 16, 8, 32, 0); break;
       case 3: rc = WGRAD_TC(2, 16, 16, 32, 0); break;
@@ -1904,7 +2088,7 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, con
     }
     return rc;
   } else {
-    // G = bn(x) (input resolution), I = dz (output resolution)
+    // G = x - mean (input resolution), I = dz (output resolution)
     P.g_a = x;
     P.i_a = dz;
     P.Hg = P.Wg = L.h_in;
@@ -1914,9 +2098,23 @@ extern "C" int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, con
       case 9: rc = WGRAD_TC(1, 24, 16, 32, 1); break;
       case 10: rc = WGRAD_TC(2, 16, 16, 32, 1); break;
       case 11: rc = WGRAD_TC(1, 16, 8, 32, 1); break;
-      case 12: rc = launch_wgrad<2, 8, 8, 32, 1>(P, dw, db, ws, stream); break;  // HBM-bound: FMA kernel wins
-      case 13: rc = launch_wgrad<1, 8, 1, 32, 1>(P, dw, db, ws, stream); break;
+      case 12: rc = launch_wgrad<2, 8, 8, 32, 1>(P, F, ws, stream); break;  // HBM-bound: FMA kernel wins
+      case 13: rc = launch_wgrad<1, 8, 1, 32, 1>(P, F, ws, stream); break;
     }
     return rc;
   }
+}
+
+extern "C" int ava_b200_dz_border_sums(const float* dz, int B, int C, int H, int W, int mode, double* tsums,
+                                       void* stream) {
+  AVA_REQUIRE(C >= 1 && C <= 32 && W % 4 == 0 && H >= 2 && (mode == 0 || mode == 1),
+              "dz_border_sums: C=%d H=%d W=%d mode=%d", C, H, W, mode);
+  if (B <= 0) return 0;
+  const long long total4 = (long long)B * H * W / 4;
+  long long want = (total4 + 255) / 256;
+  int gx = (int)(want < 1 ? 1 : want);
+  const int cap = (8 * kNumSMs + C - 1) / C;
+  if (gx > cap) gx = cap;
+  dz_border_sums_kernel<<<dim3(gx, C), 256, 0, (cudaStream_t)stream>>>(dz, B, C, H, W, mode, tsums);
+  return check_launch("dz_border_sums");
 }

@@ -107,8 +107,38 @@ struct TcParams {
   int splits, kblocks_per_split;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (lane = row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+        "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+        "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+
+// The tensor core adds into its fp32 accumulator with truncation toward zero (measured on this
+// kernel, profiles/probes/tc_gemm_accuracy.py: a K = 8192 chain shrinks the large outputs by
+// 1.2e-5 -- ~8e-9 per accumulation -- where the fp32 FMA kernel is at 1e-9; at batch 1024 that
+// systematic shrink moved 1334 ReLU units across zero and the whole-model gradients by 5e-4).
+// The K loop is therefore cut into CHUNKS of TC_CHUNK k-blocks: each chunk is accumulated from
+// zero in one of two 128-column TMEM accumulators (ping-pong), and while the tensor core works
+// on the next chunk the epilogue warps drain the finished one and add it to running sums in
+// registers with ordinary round-to-nearest FADDs.  A chain is then at most
+// TC_CHUNK * 4 * TERMS accumulations long (48 in 3 terms: < 4e-7), and the drain is hidden
+// behind the MMAs of the other accumulator.
+constexpr int TC_CHUNK = 4;
+constexpr int TC_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+
 template <int TERMS, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                const TcParams P) {
@@ -118,9 +148,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   uint8_t* tiles = tc_smem;                                // [STAGES][A_hi, A_lo, B_hi, B_lo]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tc_smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_tr = reinterpret_cast<float*>(tmem_slot + 4);   // [4 warps][32][33] epilogue transpose
+  uint64_t* acc_full = empty_bar + STAGES;                 // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;                      // [2] epilogue -> MMA (8 warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  // epilogue transpose buffers [8 warps][32][33]: the operand ring is free by then
+  float* s_tr = reinterpret_cast<float*>(tiles);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
@@ -128,18 +160,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int kb0 = split * P.kblocks_per_split;
   const int total_kb = P.K / TC_BK;
   const int nkb = min(P.kblocks_per_split, total_kb - kb0);
+  const int nchunks = (nkb + TC_CHUNK - 1) / TC_CHUNK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(128));
+                 "n"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -164,58 +200,81 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   } else if (warp == 1 && lane == 0) {
     // ------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (i / STAGES) & 1;
-      mbar_wait(&full_bar[s], ph);
+    int i = 0;
+    for (int q = 0; q < nchunks; ++q) {
+      const int b = q & 1;
+      const uint32_t use = (uint32_t)(q >> 1);
+      mbar_wait(&acc_empty[b], (use & 1) ^ 1);   // the epilogue has drained this accumulator's last chunk
       tc_fence_after();
-      const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
-      const uint64_t a_hi = make_smem_desc(sa);
-      const uint64_t a_lo = make_smem_desc(sa + TC_TILE_BYTES);
-      const uint64_t b_hi = make_smem_desc(sa + NT_A * TC_TILE_BYTES);
-      const uint64_t b_lo = make_smem_desc(sa + (NT_A + 1) * TC_TILE_BYTES);
+      const uint32_t tacc = tmem_base + (uint32_t)(b * TC_BN);
+      const int iend = min(nkb, (q + 1) * TC_CHUNK);
+      bool fresh = true;
+      for (; i < iend; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
+        const uint64_t a_hi = make_smem_desc(sa);
+        const uint64_t a_lo = make_smem_desc(sa + TC_TILE_BYTES);
+        const uint64_t b_hi = make_smem_desc(sa + NT_A * TC_TILE_BYTES);
+        const uint64_t b_lo = make_smem_desc(sa + (NT_A + 1) * TC_TILE_BYTES);
 #pragma unroll
-      for (int k = 0; k < TC_BK / 8; ++k) {
-        const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K=8 step inside the atom
-        const uint32_t first = (i == 0 && k == 0) ? 0u : 1u;
-        umma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, first);
-        if (TERMS == 3) {
-          umma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
-          umma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, 1u);
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t koff = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K=8 step inside the atom
+          if (TERMS == 3) {
+            // small terms first, the full-magnitude product last
+            umma_tf32(tacc, a_hi + koff, b_lo + koff, idesc, fresh ? 0u : 1u);
+            umma_tf32(tacc, a_lo + koff, b_hi + koff, idesc, 1u);
+            umma_tf32(tacc, a_hi + koff, b_hi + koff, idesc, 1u);
+          } else {
+            umma_tf32(tacc, a_hi + koff, b_hi + koff, idesc, fresh ? 0u : 1u);
+          }
+          fresh = false;
         }
+        umma_commit(&empty_bar[s]);  // smem stage reusable once these MMAs have read it
       }
-      umma_commit(&empty_bar[s]);  // smem stage reusable once these MMAs have read it
+      umma_commit(&acc_full[b]);     // this chunk's accumulator is complete
     }
-    umma_commit(tmem_full_bar);    // accumulator complete
   } else if (warp >= 4) {
-    // ------------------------------ epilogue: TMEM -> registers -> smem transpose -> global
-    const int wq = warp - 4;  // TMEM lane quarter: rows 32*wq .. 32*wq+31 of the tile
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    float* tr = s_tr + wq * 32 * 33;
+    // ------------------------------ epilogue warps: drain chunks into running sums, then
+    // registers -> smem transpose -> global
+    const int wq = warp & 3;          // TMEM lane quarter: rows 32*wq .. 32*wq+31 of the tile
+    const int ch = (warp - 4) >> 2;   // column half: columns 64*ch .. 64*ch+63
+    float rs[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) rs[j] = 0.f;
+#pragma unroll 1
+    for (int q = 0; q < nchunks; ++q) {
+      const int b = q & 1;
+      mbar_wait(&acc_full[b], (uint32_t)((q >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b * TC_BN + ch * 64);
+      uint32_t v0[32], v1[32];
+      tmem_ld32(taddr, v0);
+      tmem_ld32(taddr + 32, v1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);   // the tensor core may overwrite this accumulator
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        rs[j] += __uint_as_float(v0[j]);
+        rs[32 + j] += __uint_as_float(v1[j]);
+      }
+    }
+    // all MMAs have completed (the last acc_full covers them): the operand ring is free
+    float* tr = s_tr + (warp - 4) * 32 * 33;
     float* dst = (P.splits > 1) ? P.part + (size_t)split * P.M * P.N : P.D;
     const int ldd = (P.splits > 1) ? P.N : P.ldd;
-#pragma unroll 1
-    for (int c = 0; c < TC_BN / 32; ++c) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
-            "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-            "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      // lane = row (32*wq + lane), v[j] = column c*32 + j  ->  smem [row][col]
 #pragma unroll
-      for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+    for (int c = 0; c < 2; ++c) {
+      // lane = row (32*wq + lane), rs[32c + j] = column 64*ch + 32*c + j  ->  smem [row][col]
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = rs[32 * c + j];
       __syncwarp();
       // read back with lanes along columns: coalesced 128-byte row segments
-      const int col = n0 + c * 32 + lane;
+      const int col = n0 + ch * 64 + c * 32 + lane;
       const float bv = (P.splits == 1 && P.bias) ? P.bias[col] : 0.f;
 #pragma unroll 4
       for (int r = 0; r < 32; ++r) {
@@ -228,12 +287,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
       __syncwarp();
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
   }
 }
 
@@ -392,25 +451,25 @@ int tc_gemm(const float* a, int lda, bool a_trans, const float* a_mask, const fl
   const int kb = K / TC_BK;
   P.kblocks_per_split = (kb + P.splits - 1) / P.splits;
   dim3 grid(N / TC_BN, M / TC_BM, P.splits);
-  constexpr int EXTRA = 1024;  // barriers + tmem slot, then the epilogue transpose buffers
+  constexpr int EXTRA = 1024;  // barriers + tmem slot (the epilogue transpose reuses the operand ring)
   if (x3) {
     constexpr int ST = 3;
-    const size_t smem = (size_t)ST * 4 * TC_TILE_BYTES + EXTRA + 4 * 32 * 33 * sizeof(float);
+    const size_t smem = (size_t)ST * 4 * TC_TILE_BYTES + EXTRA;
     static bool cfg = false;
     if (!cfg) {
       cudaFuncSetAttribute(tc_gemm_kernel<3, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cfg = true;
     }
-    tc_gemm_kernel<3, ST><<<grid, 256, smem, stream>>>(mA0, mA1, mB0, mB1, P);
+    tc_gemm_kernel<3, ST><<<grid, TC_THREADS, smem, stream>>>(mA0, mA1, mB0, mB1, P);
   } else {
     constexpr int ST = 6;
-    const size_t smem = (size_t)ST * 2 * TC_TILE_BYTES + EXTRA + 4 * 32 * 33 * sizeof(float);
+    const size_t smem = (size_t)ST * 2 * TC_TILE_BYTES + EXTRA;
     static bool cfg = false;
     if (!cfg) {
       cudaFuncSetAttribute(tc_gemm_kernel<1, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       cfg = true;
     }
-    tc_gemm_kernel<1, ST><<<grid, 256, smem, stream>>>(mA0, mA1, mB0, mB1, P);
+    tc_gemm_kernel<1, ST><<<grid, TC_THREADS, smem, stream>>>(mA0, mA1, mB0, mB1, P);
   }
   if (check_launch("tc_gemm")) return 1;
   if (P.splits > 1) launch_splitk_reduce(parts, P.splits, M, N, bias, d, ldd, act, stream);

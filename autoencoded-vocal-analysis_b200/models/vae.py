@@ -83,11 +83,12 @@ class _Buffers:
         self.t6 = torch.empty(B, 256, **f32)
         self.t7 = torch.empty(B, 1024, **f32)
         self.t8 = torch.empty(B, 8192, **f32)
-        # fp64 accumulators: stats[14][64] | dstats[14][64] | acc[4]
-        self.accum = torch.zeros(2 * 14 * 64 + 4, dtype=torch.float64, device=device)
+        # fp64 accumulators: stats[14][64] | dstats[14][64] | acc[4] | tsums[14][288]
+        self.accum = torch.zeros(2 * 14 * 64 + 4 + 14 * 288, dtype=torch.float64, device=device)
         self.stats = self.accum[:14 * 64]
         self.dstats = self.accum[14 * 64:2 * 14 * 64]
-        self.acc = self.accum[2 * 14 * 64:]
+        self.acc = self.accum[2 * 14 * 64:2 * 14 * 64 + 4]
+        self.tsums = self.accum[2 * 14 * 64 + 4:]
         self.loss = torch.zeros(1, **f32)
         # backward scratch (allocated lazily)
         self.g = None
@@ -305,6 +306,7 @@ class VAE(nn.Module):
         self._n_flat = (off + 3) // 4 * 4
         f32 = dict(dtype=torch.float32, device=dev)
         old_m = getattr(self, "_flat_m", None)
+        old_views_m = getattr(self, "_views_m", None)
         flat_p = torch.zeros(self._n_flat, **f32)
         flat_g = torch.zeros(self._n_flat, **f32)
         flat_m = torch.zeros(self._n_flat, **f32)
@@ -323,6 +325,15 @@ class VAE(nn.Module):
             self._views_v[k] = flat_v[o:o + n].view(p.shape)
             p.grad = None
         self._flat_p, self._flat_g, self._flat_m, self._flat_v = flat_p, flat_g, flat_m, flat_v
+        # optimizer state that aliased the previous flat moment buffers follows them (model.to(),
+        # .cuda(), .float() after training); the step count is kept, not re-adopted
+        opt = getattr(self, "optimizer", None)
+        if opt is not None and old_m is not None and old_m.numel() == self._n_flat:
+            for k in order:
+                st = opt.state.get(params[k])
+                if st is not None and 'exp_avg' in st and old_views_m is not None and \
+                        st['exp_avg'].data_ptr() == old_views_m[k].data_ptr():
+                    st['exp_avg'], st['exp_avg_sq'] = self._views_m[k], self._views_v[k]
         # BN running buffers: [rm_1 | rv_1 | rm_2 | rv_2 ...], 32 floats each
         run = torch.zeros(14 * 64, **f32)
         nbt = torch.zeros(14, dtype=torch.int64, device=dev)
@@ -339,6 +350,8 @@ class VAE(nn.Module):
             bn._buffers['num_batches_tracked'] = nbt[i]
         self._flat_run, self._nbt = run, nbt
         self._step_dev = torch.full((1,), float(self._step_host), **f32)
+        self._hyper_dev = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._hyper_host = None
         self._loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         self._bufs, self._scratch, self._graphs = {}, None, {}
         # host-side tables for the two BN bookkeeping kernels
@@ -381,18 +394,27 @@ class VAE(nn.Module):
                 "no CPU fallback" % self._flat_p.device)
         _lib.lib()
 
+    _MAX_BATCH_SIZES = 4
+
     def _buffers_for(self, B):
-        b = self._bufs.get(B)
+        """Activation workspace for batch size B.  The least recently used sizes are dropped
+        beyond _MAX_BATCH_SIZES (a default train_loop sees four: the regular batch, the ragged
+        train and test tails and visualize's 5).  A captured CUDA graph holds raw pointers into
+        its workspace, so a graph never outlives it: evicting a size drops its graph too."""
+        b = self._bufs.pop(B, None)
         if b is None:
-            # keep at most two batch sizes alive (the regular one and a ragged last batch)
-            while len(self._bufs) >= 2:
-                self._bufs.pop(next(iter(self._bufs)))
+            while len(self._bufs) >= self._MAX_BATCH_SIZES:
+                old = next(iter(self._bufs))
+                self._bufs.pop(old)
+                self._graphs.pop(old, None)
             b = _Buffers(B, self.z_dim, self._flat_p.device)
-            self._bufs[B] = b
+        self._bufs[B] = b          # most recently used last
         return b
 
     def _ws(self, nbytes):
         if self._scratch is None or self._scratch.numel() < nbytes:
+            # captured graphs point into the old scratch buffer: they go with it
+            self._graphs = {}
             self._scratch = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8,
                                         device=self._flat_p.device)
         return self._scratch
@@ -525,46 +547,46 @@ class VAE(nn.Module):
             cache[B] = self._scratch_bytes(B)
         return cache[B]
 
-    def _conv_bwd(self, l, bufs, g_out, y, x, g_in, has_next_bn):
-        """Backward of fused layer l.  (1) g_out -> dz IN PLACE: next BatchNorm's backward +
-        this layer's ReLU backward, one elementwise pass; (2) weight/bias gradients into the
-        flat gradient buffer; (3) data gradient (w.r.t. this layer's BN output) into g_in
-        and dstats[l] (this BN's dbeta / dgamma sums)."""
+    def _conv_bwd(self, l, bufs, dz, x, dz_prev):
+        """Backward of fused layer l given dz = the gradient w.r.t. its pre-activation output.
+        (1) the nine border sums of dz; (2) weight / bias gradients into the flat gradient
+        buffer AND this layer's BatchNorm-backward reductions dstats[l] (both from the same
+        centred raw product, see include/ava_b200.h); (3) the data gradient, pushed through this
+        layer's BatchNorm backward and the previous layer's ReLU in the kernel's epilogue, lands
+        in dz_prev as the previous layer's dz -- the gradient w.r.t. the BatchNorm output never
+        goes to memory."""
         B = bufs.B
-        name, _, co, _, _ = _LAYERS[l]
-        relu = 0 if l == 13 else 1
-        st, ds = bufs.stats.data_ptr(), bufs.dstats.data_ptr()
+        name, _, co, stride, _ = _LAYERS[l]
+        st, ds, ts = bufs.stats.data_ptr(), bufs.dstats.data_ptr(), bufs.tsums.data_ptr()
         s = _stream()
-        if relu or has_next_bn:
-            hw = _out_hw(l) ** 2
-            ng = self._p("bn%d.weight" % (l + 2)) if has_next_bn else None
-            call("ava_b200_bn_relu_bwd_apply", ptr(g_out), ptr(y), ng, st + 8 * 64 * (l + 1),
-                 ds + 8 * 64 * (l + 1), B, co, hw, relu, ptr(g_out), s)
+        ho = _out_hw(l)
+        mode = 1 if (l >= 7 and stride == 2) else 0
+        gamma, beta = self._p("bn%d.weight" % (l + 1)), self._p("bn%d.bias" % (l + 1))
+        call("ava_b200_dz_border_sums", ptr(dz), B, co, ho, ho, mode, ts + 8 * 288 * l, s)
         ws = self._ws(self._scratch_need)
         _set_conv_precision(self._tc)
-        call("ava_b200_bnconv_bwd_weight", l, B, ptr(g_out), ptr(x), self._p("bn%d.weight" % (l + 1)),
-             self._p("bn%d.bias" % (l + 1)), st + 8 * 64 * l, self._g(name + ".weight"),
-             self._g(name + ".bias"), ptr(ws), s)
-        call("ava_b200_bnconv_bwd_data", l, B, ptr(g_out), self._p(name + ".weight"), ptr(x),
-             st + 8 * 64 * l, ptr(g_in), ds + 8 * 64 * l, s)
+        call("ava_b200_bnconv_bwd_weight", l, B, ptr(dz), ptr(x), self._p(name + ".weight"), gamma, beta,
+             st + 8 * 64 * l, ts + 8 * 288 * l, self._g(name + ".weight"), self._g(name + ".bias"),
+             ds + 8 * 64 * l, ptr(ws), s)
+        if dz_prev is not None:
+            call("ava_b200_bnconv_bwd_data", l, B, ptr(dz), self._p(name + ".weight"), ptr(x), gamma,
+                 st + 8 * 64 * l, ds + 8 * 64 * l, 1, ptr(dz_prev), s)
 
-    def _backward_native(self, bufs, after_decoder=None):
+    def _backward_native(self, bufs, after_decoder=None, after_dense=None):
         """Backward of the whole loss; leaves every parameter gradient in the flat
         gradient buffer (overwritten, not accumulated).  Replaces loss.backward(),
         ava/models/vae.py:352."""
         B, Z, s = bufs.B, self.z_dim, _stream()
         bufs.alloc_backward(Z)
         x = bufs.x
-        g_cur, g_nxt = bufs.g[0], bufs.g[1]
-        # ---- decoder conv stack, layers 13..7
+        g_cur, g_nxt = bufs.g[0], bufs.g[1]      # g[0] holds dL/dx_rec = convt7's dz (recon kernel)
+        # ---- decoder conv stack, layers 13..7; layer 7 writes the gradient w.r.t. fc8's
+        # pre-activation output (bn8 backward + fc8's ReLU) straight into dt8
         for l in range(13, 6, -1):
             xin = bufs.act[l - 1] if l > 7 else bufs.t8
-            self._conv_bwd(l, bufs, g_cur, bufs.act[l], xin, g_nxt, has_next_bn=(l < 13))
+            out = g_nxt if l > 7 else bufs.dt8
+            self._conv_bwd(l, bufs, g_cur, xin, out)
             g_cur, g_nxt = g_nxt, g_cur
-        # ---- bn8 backward + fc8's ReLU
-        st, ds = bufs.stats.data_ptr(), bufs.dstats.data_ptr()
-        call("ava_b200_bn_relu_bwd_apply", ptr(g_cur), ptr(bufs.t8), self._p("bn8.weight"),
-             st + 8 * 64 * 7, ds + 8 * 64 * 7, B, 32, 256, 1, ptr(bufs.dt8), s)
         # ---- decoder dense layers
         self._linear_bwd(bufs.dt8, 8192, None, bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.dt7, 1024,
                          B, 8192, 1024, tc=self._tc)
@@ -589,24 +611,43 @@ class VAE(nn.Module):
                          1024, B, 256, 1024, tc=self._tc)
         self._linear_bwd(bufs.dh1, 1024, bufs.h1, bufs.act[6], 8192, "fc1.weight", "fc1.bias",
                          bufs.da6, 8192, B, 1024, 8192, tc=self._tc)
-        # ---- encoder conv stack, layers 6..0
+        if after_dense is not None:
+            # fc1..fc43 gradients are final (fc1.weight is half of all parameters)
+            after_dense()
+        # ---- conv7's ReLU on the gradient arriving from fc1 (no BatchNorm at this seam)
+        call("ava_b200_bn_relu_bwd_apply", ptr(bufs.da6), ptr(bufs.act[6]), None, None, None, B, 32, 256,
+             1, ptr(bufs.da6), s)
+        # ---- encoder conv stack, layers 6..0 (layer 0 needs no data gradient)
         g_cur = bufs.da6
         free = [bufs.g[0], bufs.g[1]]
         for l in range(6, -1, -1):
             xin = bufs.act[l - 1] if l > 0 else x
-            g_in = free[0] if l > 0 else None   # layer 0: only bn1's dgamma/dbeta are needed
-            self._conv_bwd(l, bufs, g_cur, bufs.act[l], xin, g_in, has_next_bn=(l < 6))
-            g_cur, free = g_in, [free[1], free[0]]
+            out = free[0] if l > 0 else None
+            self._conv_bwd(l, bufs, g_cur, xin, out)
+            g_cur, free = out, [free[1], free[0]]
         # ---- BatchNorm affine parameter gradients for all 14 layers
+        st, ds = bufs.stats.data_ptr(), bufs.dstats.data_ptr()
         counts = [B * _LAYERS[l][4] ** 2 for l in range(14)]
         h_counts = (ctypes.c_longlong * 14)(*counts)
         call("ava_b200_bn_param_grads", st, ds, self._h_channels, h_counts, ptr(self._flat_g),
              self._h_dg_off, self._h_db_off, s)
 
+    def _sync_hyper(self):
+        """lr / betas / eps as torch.optim.Adam holds them (optimizer.param_groups[0]: what
+        load_state restores from a checkpoint, ava/models/vae.py:470, and what LR schedulers
+        change), mirrored into a device buffer the Adam kernel reads -- so a captured CUDA graph
+        of the step follows them too."""
+        grp = self.optimizer.param_groups[0]
+        if grp.get('weight_decay', 0) != 0 or grp.get('amsgrad', False) or grp.get('maximize', False):
+            raise NotImplementedError("ava_b200: Adam with weight_decay/amsgrad/maximize is not implemented")
+        hyper = (float(grp['lr']), float(grp['betas'][0]), float(grp['betas'][1]), float(grp['eps']))
+        if hyper != self._hyper_host:
+            self._hyper_dev.copy_(torch.tensor(hyper, dtype=torch.float64))
+            self._hyper_host = hyper
+
     def _adam_native(self):
-        call("ava_b200_adam_step", ptr(self._flat_p), ptr(self._flat_g), ptr(self._flat_m),
-             ptr(self._flat_v), self._n_flat, ptr(self._step_dev), float(self.lr), 0.9, 0.999, 1e-8,
-             1.0, _stream())
+        call("ava_b200_adam_step_dev", ptr(self._flat_p), ptr(self._flat_g), ptr(self._flat_m),
+             ptr(self._flat_v), self._n_flat, ptr(self._step_dev), ptr(self._hyper_dev), 1.0, _stream())
         self._step_host += 1
 
     def _as_input(self, x):
@@ -764,10 +805,14 @@ class VAE(nn.Module):
                     loss = self._train_step_eager(st["x"], (st["ew"], st["ed"]))
                 self._step_host = host_step      # capture records, it does not execute
                 st["graph"], st["loss"] = g, loss
+                # the graph owns references to everything it points into
+                st["bufs"], st["scratch"] = self._bufs[B], self._scratch
             except Exception:
                 self.cuda_graphs = False
                 torch.cuda.synchronize()
                 return self._train_step_eager(st["x"], (st["ew"], st["ed"]))
+        self._buffers_for(B)             # keep this size most recently used
+        self._cur = st["bufs"]
         st["graph"].replay()
         self._step_host += 1
         return st["loss"]
@@ -779,10 +824,28 @@ class VAE(nn.Module):
         shard and the gradient all-reduce overlaps the encoder half of the backward."""
         self._ensure_optimizer_state()
         self._require_cuda()
+        self._sync_hyper()
         x = self._as_input(x)
+        if x.shape[0] == 0:
+            return self._train_step_empty()
         if self._graph_wanted(x.shape[0]):
             return self._train_step_graph(x, noise)
         return self._train_step_eager(x, noise)
+
+    def _train_step_empty(self):
+        """This rank's shard of the global batch is empty (a ragged last batch smaller than the
+        world size): contribute zero gradients to the same all-reduces as the other ranks and
+        apply the same update.  The per-batch loss constants are booked as on every other rank
+        (_epoch_loss counts them once per global batch)."""
+        if self._dp_world <= 1:
+            raise ValueError("train_step: empty batch")
+        self._flat_g.zero_()
+        early, late = self._grad_buckets()
+        for w in self._allreduce(early, async_op=True) + self._allreduce(late, async_op=True):
+            w.wait()
+        self._adam_native()
+        self._loss_sum += self.loss_constant()
+        return torch.full((), self.loss_constant(), dtype=torch.float32, device=self._flat_p.device)
 
     def _train_step_eager(self, x, noise):
         bufs = self._forward_native(x, noise, True, want_grad_seed=True)
@@ -827,7 +890,10 @@ class VAE(nn.Module):
         n_steps = 0
         with torch.no_grad():
             for i, data in enumerate(prefetch_to_device(test_loader, self._flat_p.device)):
-                self._forward_native(data, None, False, want_grad_seed=False)
+                if len(data) == 0 and self._dp_world > 1:    # empty shard of a small last batch
+                    self._loss_sum += self.loss_constant()
+                else:
+                    self._forward_native(data, None, False, want_grad_seed=False)
                 n_steps += 1
         test_loss = self._epoch_loss(n_steps)
         test_loss /= len(test_loader.dataset)
@@ -872,21 +938,27 @@ class VAE(nn.Module):
         params = dict(self.named_parameters())
         first = next(iter(params.values()))
         st = self.optimizer.state.get(first)
-        if st is not None and st['exp_avg'].data_ptr() == self._views_m[next(iter(params))].data_ptr():
+        if st is not None and 'exp_avg' in st and \
+                st['exp_avg'].data_ptr() == self._views_m[next(iter(params))].data_ptr():
             return
         adopted_step = None
         for k, p in params.items():
             st = self.optimizer.state.get(p)
-            if st is not None and 'exp_avg' in st:
-                # state created by torch (load_state_dict or a user-driven optimizer.step())
+            if st is not None and 'exp_avg' in st and \
+                    st['exp_avg'].data_ptr() != self._views_m[k].data_ptr():
+                # state created by torch (load_state_dict or a user-driven optimizer.step()):
+                # its moments and step count win.  State that already aliases the flat buffers
+                # is ours: its `step` entry is only published at save_state (the live count is
+                # self._step_host / self._step_dev) and must not be re-adopted.
                 self._views_m[k].copy_(st['exp_avg'])
                 self._views_v[k].copy_(st['exp_avg_sq'])
                 adopted_step = float(st['step'])
-            self.optimizer.state[p] = {'step': torch.tensor(0.0), 'exp_avg': self._views_m[k],
-                                       'exp_avg_sq': self._views_v[k]}
+            self.optimizer.state[p] = {'step': torch.tensor(float(self._step_host)),
+                                       'exp_avg': self._views_m[k], 'exp_avg_sq': self._views_v[k]}
         if adopted_step is not None:
             self._step_host = int(adopted_step)
             self._step_dev.fill_(float(self._step_host))
+            self._publish_optimizer_steps()
 
     def _publish_optimizer_steps(self):
         for p in self.parameters():
@@ -973,6 +1045,8 @@ class VAE(nn.Module):
             for data in prefetch_to_device(loader, self._flat_p.device):
                 x = self._as_input(data)
                 B = x.shape[0]
+                if B == 0:
+                    continue
                 bufs = self._buffers_for(B)
                 self._cur = bufs
                 self._scratch_need = self._scratch_need_for(B)

@@ -100,10 +100,18 @@ class DeviceSyllableLoader:
     """All syllables of a split resident on the device; batches are device-side gathers.
 
     Iteration order: a fresh ``torch.randperm`` per epoch when ``shuffle`` (the reference's
-    DataLoader(shuffle=True) also draws a torch permutation), else dataset order."""
+    DataLoader(shuffle=True) also draws a torch permutation), else dataset order.
+
+    Data parallel (``world_size`` > 1): every rank walks the SAME global batches and takes its
+    slice of each, so the union over the ranks is exactly the single-process batch.  The
+    permutation is therefore drawn from a generator seeded with (``seed``, epoch number) --
+    identical on every rank without communication -- instead of each process's global RNG; and
+    every rank takes the same number of steps: a rank whose slice of a small ragged last batch
+    is empty still yields a ``[0,128,128]`` batch (``VAE.train_step`` then contributes zero
+    gradients to the all-reduce), so the collectives of the ranks always match."""
 
     def __init__(self, dataset, batch_size=64, shuffle=False, device=None, rank=0, world_size=1,
-                 streaming=False):
+                 streaming=False, seed=0):
         """`streaming` (addition; needs shuffle=False, one rank): do not keep the split
         resident -- read one file at a time and yield the same batches (a batch may straddle
         files), for corpora larger than HBM (`DataContainer` latent means)."""
@@ -114,6 +122,7 @@ class DeviceSyllableLoader:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
         self.rank, self.world_size = rank, world_size
+        self.seed, self._epoch = int(seed), 0
         self.streaming = bool(streaming)
         if self.streaming:
             assert not shuffle and world_size == 1, "streaming loaders walk the files in order"
@@ -150,10 +159,15 @@ class DeviceSyllableLoader:
             yield from self._iter_streaming()
             return
         n = len(self.dataset)
-        if self.shuffle:
+        if self.shuffle and self.world_size > 1:
+            gen = torch.Generator()
+            gen.manual_seed(1000003 * self.seed + self._epoch)
+            order = torch.randperm(n, generator=gen).to(self.device)
+        elif self.shuffle:
             order = torch.randperm(n).to(self.device)
         else:
             order = None
+        self._epoch += 1
         # data-parallel: every rank walks the same global batches and takes its slice
         for start in range(0, n, self.batch_size):
             stop = min(n, start + self.batch_size)
@@ -164,7 +178,9 @@ class DeviceSyllableLoader:
             else:
                 lo, hi = start, stop
             if hi <= lo:
-                continue
+                if self.world_size == 1:
+                    continue
+                lo = hi = min(lo, stop)      # empty shard of a small last batch: still a step
             if order is None:
                 yield self.data[lo:hi]
             else:
@@ -172,7 +188,7 @@ class DeviceSyllableLoader:
 
 
 def get_syllable_data_loaders(partition, batch_size=64, shuffle=(True, False), num_workers=4,
-                              device=None, rank=0, world_size=1, streaming=False):
+                              device=None, rank=0, world_size=1, streaming=False, seed=0):
     """Return a pair of loaders given a test/train split
     (ava/models/vae_dataset.py:62-94).  `num_workers` is accepted for compatibility and
     ignored (no worker processes are needed)."""
@@ -181,14 +197,14 @@ def get_syllable_data_loaders(partition, batch_size=64, shuffle=(True, False), n
                                     sylls_per_file=sylls_per_file)
     train_dataloader = DeviceSyllableLoader(train_dataset, batch_size=batch_size, shuffle=shuffle[0],
                                             device=device, rank=rank, world_size=world_size,
-                                            streaming=streaming)
+                                            streaming=streaming, seed=seed)
     if not partition['test']:
         return {'train': train_dataloader, 'test': None}
     test_dataset = SyllableDataset(filenames=partition['test'], transform=numpy_to_tensor,
                                    sylls_per_file=sylls_per_file)
     test_dataloader = DeviceSyllableLoader(test_dataset, batch_size=batch_size, shuffle=shuffle[1],
                                            device=device, rank=rank, world_size=world_size,
-                                           streaming=streaming)
+                                           streaming=streaming, seed=seed)
     return {'train': train_dataloader, 'test': test_dataloader}
 
 

@@ -61,9 +61,8 @@ def algorithmic(key, args, B):
         if name.endswith("fwd"):
             return 4.0 * B * (n_in + n_out), 2.0 * B * macs
         if name.endswith("bwd_data"):
-            # reads dz (out-shaped), x (in-shaped, for dgamma); writes g_in
-            w = 0 if l == 0 else n_in
-            return 4.0 * B * (n_out + n_in + w), 2.0 * B * macs
+            # reads dz (out-shaped) and x (in-shaped: BN backward + ReLU mask); writes the next dz
+            return 4.0 * B * (n_out + 2 * n_in), 2.0 * B * macs
         return 4.0 * B * (n_out + n_in), 2.0 * B * macs   # reads dz, x
     if name == "ava_b200_linear_fwd":
         M, N, K, groups = args[6], args[7], args[8], args[10]
@@ -83,6 +82,9 @@ def algorithmic(key, args, B):
     if name == "ava_b200_channel_stats":
         Bn, C, HW = args[1], args[2], args[3]
         return 4.0 * Bn * C * HW, 3.0 * Bn * C * HW
+    if name == "ava_b200_dz_border_sums":
+        Bn, C, H, W = args[1], args[2], args[3], args[4]
+        return 4.0 * Bn * C * H * W, 2.0 * Bn * C * H * W
     if name == "ava_b200_bn_relu_bwd_apply":
         Bn, C, HW = args[5], args[6], args[7]
         return 4.0 * 3 * Bn * C * HW, 8.0 * Bn * C * HW

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AVA_B200_ABI_VERSION 1
+#define AVA_B200_ABI_VERSION 2
 #define AVA_NUM_BN_LAYERS 14
 #define AVA_STATS_STRIDE 64 /* doubles per layer in a stats block: [0..31]=sum, [32..63]=sum of squares */
 
@@ -82,26 +82,41 @@ int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float*
 int ava_b200_set_conv_precision(int mode);
 int ava_b200_get_conv_precision(void);
 
-/* Backward of layer `layer`.  `dz` is the gradient w.r.t. this layer's PRE-activation
- * conv output: the gradient arriving from the next layer already pushed through the next
- * BatchNorm's backward and this layer's ReLU by ava_b200_bn_relu_bwd_apply (in place is
- * fine).  For layer 13 (no ReLU, nothing after it) dz is the loss gradient itself.
+/* Backward of layer `layer`.  `dz` is the gradient w.r.t. this layer's PRE-activation conv output
+ * (for layer 13 -- no ReLU, nothing after it -- the loss gradient itself).  Order per layer:
  *
- * Backward-data: g_in = gradient w.r.t. THIS layer's BN output (same shape as x) and dstats
- * (this BN's dbeta = sum g_in, sum g_in*(x-mean) = dgamma/invstd) accumulated in the
- * epilogue.  g_in may be NULL (layer 0: only the bn1 parameter gradients are needed).
- * Replaces autograd's cudnn_convolution_backward(input) + the statistics half of
- * native_batch_norm_backward for ava/models/vae.py:352. */
-int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const float* w, const float* x,
-                             const double* stats_in, float* g_in, double* dstats, void* stream);
+ *   1. ava_b200_dz_border_sums(dz)  -> tsums: nine per-channel sums of dz (total / first and last
+ *      row and column / corners; for the stride-2 conv-transpose layers 8, 10, 12 the four
+ *      row-parity x column-parity classes and the last row / column), from which the sum of dz over
+ *      the pixels whose tap-k partner lies inside the image follows for each of the 9 taps.
+ *   2. ava_b200_bnconv_bwd_weight   -> dw, db (OVERWRITTEN) and this layer's two BatchNorm-backward
+ *      reductions dstats = (sum g, sum g*(x-mean)), ACCUMULATED (zero them first).  g is the gradient
+ *      w.r.t. the BatchNorm output; it is never materialised: both reductions are linear in the
+ *      centred raw product Rc = sum dz*(x-mean)_pad the kernel accumulates anyway,
+ *         dw = gamma*invstd*Rc + beta*T_k,  sum g = <w, T_k>,  sum g*(x-mean) = <w, Rc>.
+ *   3. ava_b200_bnconv_bwd_data     -> dz_prev = [x > 0] * BN-backward(g) with g formed tile by tile
+ *      on chip: the gradient w.r.t. the PREVIOUS layer's pre-activation output (same shape as x;
+ *      relu_mask = 0 skips the [x > 0] factor).  Not needed for layer 0.
+ *
+ * Replaces autograd's cudnn_convolution_backward (input + weight), native_batch_norm_backward and
+ * threshold_backward for ava/models/vae.py:217-223,263-269 (called from vae.py:352).
+ * mode: 1 for the stride-2 conv-transpose layers (8, 10, 12), else 0.  tsums: [9][32] doubles,
+ * ACCUMULATED (zero them first). */
+#define AVA_TSUM_STRIDE 288 /* doubles per layer in a tsums block: [slot 0..8][channel 0..31] */
+int ava_b200_dz_border_sums(const float* dz, int B, int C, int H, int W, int mode, double* tsums, void* stream);
 
-/* Backward-weight of layer `layer`: dw (same layout as w) and db, OVERWRITTEN (not
- * accumulated).  x/gamma/beta/stats_in give bn(x) (recomputed on load).
+/* x/stats_in: this layer's input and its batch statistics; w/gamma/beta: this layer's parameters.
  * ws: scratch of ava_b200_bnconv_bwd_weight_ws(layer,B) bytes. */
-int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, const float* x, const float* gamma,
-                               const float* beta, const double* stats_in, float* dw, float* db, void* ws,
+int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, const float* x, const float* w,
+                               const float* gamma, const float* beta, const double* stats_in,
+                               const double* tsums, float* dw, float* db, double* dstats, void* ws,
                                void* stream);
 long long ava_b200_bnconv_bwd_weight_ws(int layer, int B);
+
+/* gamma == NULL: no BatchNorm backward (dz_prev = [x > 0] * g). */
+int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const float* w, const float* x,
+                             const float* gamma, const double* stats_in, const double* dstats, int relu_mask,
+                             float* dz_prev, void* stream);
 
 /* BN backward finalisation: dgamma[c] = invstd*dstats[32+c], dbeta[c] = dstats[c]
  * for all 14 layers (dstats[32+c] holds sum g*(x-mean)). */
@@ -112,8 +127,9 @@ int ava_b200_bn_param_grads(const double* stats, const double* dstats, const int
 /* out = [a>0] * (p*(g - c1) + q*(a - mean)), per channel c = (i / HW) % C: the backward of
  * the BatchNorm that consumes `a` (train mode; fp64 coefficient math) followed by the ReLU
  * backward of the layer that produced `a`, as one elementwise pass; out may alias g.
- * gamma == NULL: no BatchNorm, only the ReLU mask.  relu == 0: no mask.  Produces the `dz`
- * the conv backward kernels and the dense backward (fc8 -> bn8 seam) consume. */
+ * gamma == NULL: no BatchNorm, only the ReLU mask.  relu == 0: no mask.  The conv layers apply
+ * this inside ava_b200_bnconv_bwd_data; the stand-alone pass serves the fc1 -> conv7 seam (ReLU
+ * mask of conv7's output on the gradient arriving from fc1). */
 int ava_b200_bn_relu_bwd_apply(const float* g, const float* a, const float* gamma, const double* stats,
                                const double* dstats, int B, int C, int HW, int relu, float* out, void* stream);
 
@@ -169,6 +185,12 @@ int ava_b200_elbo_finalize(const double* acc, int Z, int xdim, float precision, 
  * per-tensor `step` state).  lr/betas/eps are doubles, as torch holds them. grad_scale multiplies g on load (1.0 normally). */
 int ava_b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float* step_count, double lr,
                        double beta1, double beta2, double eps, float grad_scale, void* stream);
+
+/* Same update with the hyper-parameters read from DEVICE memory: hyper = {lr, beta1, beta2, eps}
+ * (doubles), so that a captured CUDA graph of the step follows optimizer.param_groups (learning-
+ * rate schedules, the lr a checkpoint restores: ava/models/vae.py:470) without re-capture. */
+int ava_b200_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float* step_count,
+                           const double* hyper, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------- get_spec
  * Batched spectrogram front end: ava/preprocessing/utils.py:18-110 (get_spec) with

@@ -64,3 +64,42 @@ def check_against_golden(g, prefix, name, value, tol, kink_factor=10.0):
     ok = err <= tol or (err2 <= tol and err <= kink_factor * tol)
     assert ok, "%s: max-norm rel err %.3e, L2 rel err %.3e > %.1e" % (key, err, err2, tol)
     return err
+
+
+# ---------------------------------------------------------------- mask-forced gradient oracle
+ACT_NAMES = ["conv%d" % i for i in range(1, 8)] + ["convt%d" % i for i in range(1, 8)]
+
+
+def gpu_relu_masks(bufs):
+    """ReLU on/off pattern of a GPU forward pass (name -> bool CPU tensor), read from the
+    activation buffers of autoencoded-vocal-analysis_b200.models.vae._Buffers."""
+    masks = {}
+    for l, n in enumerate(ACT_NAMES):
+        if n != "convt7":          # the last decoder layer has no ReLU (ava/models/vae.py:269)
+            masks[n] = (bufs.act[l] > 0).cpu()
+    for n, t in (("fc1", bufs.h1), ("fc2", bufs.h2), ("fc3", bufs.h3), ("fc5", bufs.t5),
+                 ("fc6", bufs.t6), ("fc7", bufs.t7), ("fc8", bufs.t8)):
+        masks[n] = (t > 0).cpu()
+    return masks
+
+
+def relu_flips(masks, acts64):
+    """Units whose on/off state differs from the float64 oracle's own forward."""
+    return sum(int((masks[n] != (acts64[n].reshape(masks[n].shape) > 0)).sum()) for n in masks)
+
+
+def masked_oracle_grads(P, x, eps_w, eps_d, prec, masks):
+    """float64 loss terms and gradients of the oracle with the ReLU pattern forced to `masks`,
+    its own unforced float64 activations, and the max-norm error of the SAME forced computation
+    done in float32 (the reference arithmetic's own rounding noise on that pattern)."""
+    import torch
+    from oracle import vae_oracle
+    P64 = {k: (v.double() if v.is_floating_point() else v) for k, v in P.items()}
+    acts = {}
+    with torch.no_grad():
+        vae_oracle.forward(P64, x.double(), eps_w.double(), eps_d.double(), prec, True, {}, acts)
+    out64, g64, bufs64 = vae_oracle.loss_and_grads(P64, x.double(), eps_w.double(), eps_d.double(), prec,
+                                                   True, masks=masks)
+    _, g32, _ = vae_oracle.loss_and_grads(P, x.float(), eps_w.float(), eps_d.float(), prec, True, masks=masks)
+    err32 = {k: rel_err(g32[k].numpy(), g64[k].numpy()) for k in g64}
+    return out64, g64, bufs64, acts, err32

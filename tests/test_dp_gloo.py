@@ -76,6 +76,27 @@ def _worker(rank, world, port, tmp):
         firsts += gathered[0][step] + gathered[1][step]
     want_first = [float(np.float32(r * 128 * 128 + 1e6 * f)) for f in range(2) for r in range(5)]
     assert firsts == want_first
+    # shuffle=True with a 1-sample tail (round-1 advisor finding): both ranks walk the SAME
+    # permutation, take the same number of steps (the rank with an empty shard still yields a
+    # [0,128,128] batch), and their shards tile each global batch exactly
+    sh = ds_mod.get_syllable_data_loaders({'train': files, 'test': []}, batch_size=3,
+                                          shuffle=(True, False), device='cpu', rank=rank,
+                                          world_size=world, seed=7)['train']
+    for epoch in range(2):
+        mine = [b[:, 0, 0].tolist() for b in sh]
+        assert len(mine) == 4 and [len(b) for b in mine] == ([2, 2, 2, 1] if rank == 0 else [1, 1, 1, 0])
+        both = [None, None]
+        dist.all_gather_object(both, mine)
+        seen = [v for step in range(4) for r in range(2) for v in both[r][step]]
+        assert sorted(seen) == sorted(want_first)                 # every syllable exactly once
+        if epoch == 0:
+            first_epoch = seen
+        else:
+            assert seen != first_epoch                            # a fresh permutation per epoch
+        gen = torch.Generator()
+        gen.manual_seed(1000003 * 7 + epoch)
+        perm = torch.randperm(10, generator=gen).tolist()
+        assert seen == [want_first[i] for i in perm]              # == the single-process batches
     # only rank 0 writes checkpoints
     model.save_state("dp.tar")
     dist.barrier()

@@ -74,106 +74,142 @@ def make_layer_inputs(l, B, seed):
     return [t.float().double() for t in (x, w, b, gamma, beta, rm, rv)]
 
 
+# batch sizes of the per-layer tests: 3 (a handful of tiles), 64 and 130 (several waves of tiles per
+# CTA, ragged tile counts, many per-CTA partials in the fp64 statistics / weight-gradient reductions);
+# the reduced-precision mode is exercised at the small size only
+def _batches(mode):
+    return (3,) if mode == 1 else (3, 64, 130)
+
+
 @pytest.mark.parametrize("l", range(14))
 @pytest.mark.parametrize("train", [True, False])
 def test_bnconv_fwd(L, l, train, conv_mode):
-    B = 3
     mode, tol = conv_mode
     name, ci, co, s, h, tr = LAYERS[l]
-    x, w, b, gamma, beta, rm, rv = make_layer_inputs(l, B, 100 + l)
-    _, y_ref = layer_ref(l, x, w, b, gamma, beta, train, rm, rv)
-    dx, dw, db, dg, dbeta, drm, drv = [dev(t) for t in (x, w, b, gamma, beta, rm, rv)]
-    stats = torch.zeros(2 * 64, dtype=torch.float64, device="cuda")
-    L.call("ava_b200_channel_stats", dx.data_ptr(), B, ci, h * h, stats.data_ptr(), stream())
-    ho = y_ref.shape[-1]
-    y = torch.empty(B, co, ho, ho, device="cuda")
-    L.call("ava_b200_bnconv_fwd", l, B, dx.data_ptr(), y.data_ptr(), dw.data_ptr(), db.data_ptr(),
-           dg.data_ptr(), dbeta.data_ptr(), stats.data_ptr(), drm.data_ptr(), drv.data_ptr(),
-           1 if train else 0, stats.data_ptr() + 8 * 64, stream())
-    torch.cuda.synchronize()
-    assert rel_err(y.cpu().numpy(), y_ref.numpy()) <= tol
-    st = stats.cpu().numpy()
-    # input statistics kernel
-    assert rel_err(st[:ci], x.sum(dim=(0, 2, 3)).numpy()) <= 1e-5
-    assert rel_err(st[32:32 + ci], (x * x).sum(dim=(0, 2, 3)).numpy()) <= 1e-5
-    # epilogue statistics of the output (the next BN's batch statistics)
-    assert rel_err(st[64:64 + co], y_ref.sum(dim=(0, 2, 3)).numpy()) <= tol
-    assert rel_err(st[96:96 + co], (y_ref * y_ref).sum(dim=(0, 2, 3)).numpy()) <= tol
+    for B in _batches(mode):
+        if B != 3 and not train:
+            continue
+        x, w, b, gamma, beta, rm, rv = make_layer_inputs(l, B, 100 + l)
+        _, y_ref = layer_ref(l, x, w, b, gamma, beta, train, rm, rv)
+        dx, dw, db, dg, dbeta, drm, drv = [dev(t) for t in (x, w, b, gamma, beta, rm, rv)]
+        stats = torch.zeros(2 * 64, dtype=torch.float64, device="cuda")
+        L.call("ava_b200_channel_stats", dx.data_ptr(), B, ci, h * h, stats.data_ptr(), stream())
+        ho = y_ref.shape[-1]
+        y = torch.empty(B, co, ho, ho, device="cuda")
+        L.call("ava_b200_bnconv_fwd", l, B, dx.data_ptr(), y.data_ptr(), dw.data_ptr(), db.data_ptr(),
+               dg.data_ptr(), dbeta.data_ptr(), stats.data_ptr(), drm.data_ptr(), drv.data_ptr(),
+               1 if train else 0, stats.data_ptr() + 8 * 64, stream())
+        torch.cuda.synchronize()
+        assert rel_err(y.cpu().numpy(), y_ref.numpy()) <= tol, B
+        st = stats.cpu().numpy()
+        # input statistics kernel
+        assert rel_err(st[:ci], x.sum(dim=(0, 2, 3)).numpy()) <= 1e-5
+        assert rel_err(st[32:32 + ci], (x * x).sum(dim=(0, 2, 3)).numpy()) <= 1e-5
+        # epilogue statistics of the output (the next BN's batch statistics)
+        assert rel_err(st[64:64 + co], y_ref.sum(dim=(0, 2, 3)).numpy()) <= tol, B
+        assert rel_err(st[96:96 + co], (y_ref * y_ref).sum(dim=(0, 2, 3)).numpy()) <= tol, B
+
+
+def _trimmed_sums_ref(l, dz, h_in):
+    """T[co,3,3]: sum of dz over the pixels whose tap partner lies inside the image = the
+    weight gradient of the layer w.r.t. an all-ones single input channel (float64)."""
+    name, ci, co, s, h, tr = LAYERS[l]
+    ones = torch.ones(dz.shape[0], 1, h_in, h_in, dtype=torch.float64)
+    if not tr:
+        w0 = torch.zeros(co, 1, 3, 3, dtype=torch.float64, requires_grad=True)
+        y = F.conv2d(ones, w0, stride=s, padding=1)
+    else:
+        w0 = torch.zeros(1, co, 3, 3, dtype=torch.float64, requires_grad=True)
+        y = F.conv_transpose2d(ones, w0, stride=s, padding=1, output_padding=s - 1)
+    (y * dz).sum().backward()
+    return w0.grad.reshape(co, 3, 3)
 
 
 @pytest.mark.parametrize("l", range(14))
-@pytest.mark.parametrize("next_bn", [True, False])
-def test_bnconv_bwd(L, l, next_bn, conv_mode):
-    B = 3
+def test_bnconv_bwd(L, l, conv_mode):
+    """Backward of one fused layer through the C ABI in its three steps (include/ava_b200.h):
+    border sums of dz -> weight / bias gradients + the layer's BatchNorm-backward reductions
+    (algebraically, from the same centred raw product) -> data gradient with the BatchNorm
+    backward and the previous layer's ReLU mask applied in the epilogue.  Reference: float64
+    autograd through bn(x) -> conv for the same dz."""
     mode, tol = conv_mode
     name, ci, co, s, h, tr = LAYERS[l]
-    x, w, b, gamma, beta, rm, rv = make_layer_inputs(l, B, 200 + l)
-    x.requires_grad_(True)
-    w.requires_grad_(True)
-    b.requires_grad_(True)
-    gen = torch.Generator().manual_seed(300 + l)
-    xn, y = layer_ref(l, x, w, b, gamma, beta, True, rm, rv)
-    xn.retain_grad()
-    y.retain_grad()
-    g2 = (torch.rand(co, generator=gen, dtype=torch.float64) + 0.5).float().double()
-    if next_bn:
-        out = F.batch_norm(y, None, None, g2, None, training=True, eps=1e-5)
-    else:
-        out = y
-    R = torch.randn(out.shape, generator=gen, dtype=torch.float64).float().double()
-    (out * R).sum().backward()
-    # what the next layer's backward-data epilogue would have accumulated
-    ho = y.shape[-1]
-    yd = y.detach()
-    mean_y = yd.mean(dim=(0, 2, 3), keepdim=True)
-    nstats = torch.zeros(64, dtype=torch.float64)
-    nstats[:co] = yd.sum(dim=(0, 2, 3))
-    nstats[32:32 + co] = (yd * yd).sum(dim=(0, 2, 3))
-    ndstats = torch.zeros(64, dtype=torch.float64)
-    ndstats[:co] = R.sum(dim=(0, 2, 3))
-    ndstats[32:32 + co] = (R * (yd - mean_y)).sum(dim=(0, 2, 3))
-    x = x.detach()
-    stats = torch.zeros(64, dtype=torch.float64)
-    stats[:ci] = x.sum(dim=(0, 2, 3))
-    stats[32:32 + ci] = (x * x).sum(dim=(0, 2, 3))
-    d = lambda t: dev(t)          # noqa: E731
-    d64 = lambda t: t.cuda()      # noqa: E731
-    dx, dw_, dg, dbeta, dR, dy, dg2 = d(x), d(w.detach()), d(gamma), d(beta), d(R), d(yd), d(g2)
-    dstats, dnstats, dndstats = d64(stats), d64(nstats), d64(ndstats)
-    ng = dg2.data_ptr() if next_bn else None
-    ns = dnstats.data_ptr() if next_bn else None
-    nd = dndstats.data_ptr() if next_bn else None
-    # --- dz: next BN's backward + this layer's ReLU backward, in place over the gradient
-    relu = 0 if l == 13 else 1
-    L.call("ava_b200_bn_relu_bwd_apply", dR.data_ptr(), dy.data_ptr(), ng, ns, nd, B, co, ho * ho, relu,
-           dR.data_ptr(), stream())
-    # --- weight gradient
-    ws_bytes = L.lib().ava_b200_bnconv_bwd_weight_ws(l, B)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
-    gw = torch.full(w.shape, 7.0, device="cuda")
-    gb = torch.full((co,), 7.0, device="cuda")
-    L.call("ava_b200_bnconv_bwd_weight", l, B, dR.data_ptr(), dx.data_ptr(), dg.data_ptr(),
-           dbeta.data_ptr(), dstats.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), stream())
-    # --- data gradient
-    gin = torch.empty(B, ci, h, h, device="cuda")
-    dst = torch.zeros(64, dtype=torch.float64, device="cuda")
-    L.call("ava_b200_bnconv_bwd_data", l, B, dR.data_ptr(), dw_.data_ptr(), dx.data_ptr(),
-           dstats.data_ptr(), gin.data_ptr(), dst.data_ptr(), stream())
-    torch.cuda.synchronize()
-    assert rel_err(gw.cpu().numpy(), w.grad.numpy()) <= tol, "dw"
-    # a bias in front of a BatchNorm has (nearly) zero gradient: absolute tolerance scaled by
-    # the magnitude of the terms that cancel
-    dz_scale = np.abs(y.grad.numpy()).sum() / co
-    assert np.abs(gb.cpu().numpy() - b.grad.numpy()).max() <= 1e-5 * dz_scale, "db"
-    assert rel_err(gin.cpu().numpy(), xn.grad.numpy()) <= tol, "g_in"
-    mean_x = x.mean(dim=(0, 2, 3), keepdim=True)
-    dbeta_ref = xn.grad.sum(dim=(0, 2, 3)).numpy()
-    dgc_ref = (xn.grad * (x - mean_x)).sum(dim=(0, 2, 3)).numpy()
-    got = dst.cpu().numpy()
-    scale = max(np.abs(xn.grad.numpy()).sum() / ci, 1e-30)   # cancellation-aware scale
-    stol = 1e-5 if mode != 1 else 1e-3
-    assert np.abs(got[:ci] - dbeta_ref).max() <= stol * scale, "dbeta"
-    assert np.abs(got[32:32 + ci] - dgc_ref).max() <= stol * scale, "dgamma"
+    for B in _batches(mode):
+        x, w, b, gamma, beta, rm, rv = make_layer_inputs(l, B, 200 + l)
+        x.requires_grad_(True)
+        w.requires_grad_(True)
+        b.requires_grad_(True)
+        gen = torch.Generator().manual_seed(300 + l)
+        xn = F.batch_norm(x, None, None, gamma, beta, training=True, eps=1e-5)
+        xn.retain_grad()
+        if tr:
+            z = F.conv_transpose2d(xn, w, b, stride=s, padding=1, output_padding=s - 1)
+        else:
+            z = F.conv2d(xn, w, b, stride=s, padding=1)
+        ho = z.shape[-1]
+        dz = (torch.randn(z.shape, generator=gen, dtype=torch.float64) + 0.1).float().double()
+        z.backward(dz)
+        g = xn.grad                                   # gradient w.r.t. the BatchNorm output
+        xd = x.detach()
+        mean_x = xd.mean(dim=(0, 2, 3), keepdim=True)
+        stats = torch.zeros(64, dtype=torch.float64)
+        stats[:ci] = xd.sum(dim=(0, 2, 3))
+        stats[32:32 + ci] = (xd * xd).sum(dim=(0, 2, 3))
+        d = lambda t: dev(t)          # noqa: E731
+        dx, dw_, dg, dbeta, ddz = d(xd), d(w.detach()), d(gamma), d(beta), d(dz)
+        dstats_in = stats.cuda()
+        tsums = torch.zeros(288, dtype=torch.float64, device="cuda")
+        tmode = 1 if (tr and s == 2) else 0
+        L.call("ava_b200_dz_border_sums", ddz.data_ptr(), B, co, ho, ho, tmode, tsums.data_ptr(), stream())
+        ws_bytes = L.lib().ava_b200_bnconv_bwd_weight_ws(l, B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        gw = torch.full(w.shape, 7.0, device="cuda")
+        gb = torch.full((co,), 7.0, device="cuda")
+        dst = torch.zeros(64, dtype=torch.float64, device="cuda")
+        L.call("ava_b200_bnconv_bwd_weight", l, B, ddz.data_ptr(), dx.data_ptr(), dw_.data_ptr(), dg.data_ptr(),
+               dbeta.data_ptr(), dstats_in.data_ptr(), tsums.data_ptr(), gw.data_ptr(), gb.data_ptr(),
+               dst.data_ptr(), ws.data_ptr(), stream())
+        gin = torch.empty(B, ci, h, h, device="cuda")
+        L.call("ava_b200_bnconv_bwd_data", l, B, ddz.data_ptr(), dw_.data_ptr(), dx.data_ptr(), dg.data_ptr(),
+               dstats_in.data_ptr(), dst.data_ptr(), 1, gin.data_ptr(), stream())
+        gin_nomask = torch.empty(B, ci, h, h, device="cuda")
+        L.call("ava_b200_bnconv_bwd_data", l, B, ddz.data_ptr(), dw_.data_ptr(), dx.data_ptr(), dg.data_ptr(),
+               dstats_in.data_ptr(), dst.data_ptr(), 0, gin_nomask.data_ptr(), stream())
+        torch.cuda.synchronize()
+        # trimmed sums (float64 accumulation of fp32 values: near exact)
+        T = _trimmed_sums_ref(l, dz, h)
+        ts = tsums.cpu().reshape(9, 32)
+        if tmode == 0:
+            assert rel_err(ts[0, :co].numpy(), dz.sum(dim=(0, 2, 3)).numpy()) <= 1e-9
+            assert rel_err(ts[1, :co].numpy(), dz[:, :, 0, :].sum(dim=(0, 2)).numpy()) <= 1e-9
+            assert rel_err(ts[4, :co].numpy(), dz[:, :, :, -1].sum(dim=(0, 2)).numpy()) <= 1e-9
+            assert rel_err(ts[8, :co].numpy(), dz[:, :, -1, -1].sum(dim=0).numpy()) <= 1e-9
+        else:
+            assert rel_err(ts[1, :co].numpy(), dz[:, :, 0::2, 1::2].sum(dim=(0, 2, 3)).numpy()) <= 1e-9
+        assert rel_err(gw.cpu().numpy(), w.grad.numpy()) <= tol, ("dw", B)
+        # a bias in front of a BatchNorm has (nearly) zero gradient in the full network: absolute
+        # tolerance scaled by the magnitude of the terms that cancel
+        dz_scale = np.abs(dz.numpy()).sum() / co
+        assert np.abs(gb.cpu().numpy() - b.grad.numpy()).max() <= 1e-6 * dz_scale, ("db", B)
+        # the layer's BatchNorm-backward reductions, obtained algebraically
+        dbeta_ref = g.sum(dim=(0, 2, 3)).numpy()
+        dgc_ref = (g * (xd - mean_x)).sum(dim=(0, 2, 3)).numpy()
+        got = dst.cpu().numpy()
+        scale = max(np.abs(g.numpy()).sum() / ci, 1e-30)   # cancellation-aware scale
+        stol = 1e-5 if mode != 1 else 1e-3
+        assert np.abs(got[:ci] - dbeta_ref).max() <= stol * scale, ("dbeta", B)
+        assert np.abs(got[32:32 + ci] - dgc_ref).max() <= stol * scale, ("dgamma", B)
+        # data gradient through the BatchNorm backward, with and without the ReLU mask of the
+        # producing layer ([x > 0]: x has both signs here)
+        assert rel_err(gin_nomask.cpu().numpy(), x.grad.numpy()) <= tol, ("dx", B)
+        assert rel_err(gin.cpu().numpy(), (x.grad * (xd > 0)).numpy()) <= tol, ("dx masked", B)
+        # consistency of the algebra with the reference's own T (all nine taps)
+        Wd = w.detach()
+        if not tr:
+            sum_g = torch.einsum("oikl,okl->i", Wd, T)
+        else:
+            sum_g = torch.einsum("iokl,okl->i", Wd, T)
+        assert np.abs(sum_g.numpy() - dbeta_ref).max() <= 1e-9 * scale
 
 
 @pytest.mark.parametrize("M,N,K,act,groups", [(64, 1024, 8192, 1, 1), (7, 256, 1024, 1, 1),

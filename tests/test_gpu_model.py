@@ -17,43 +17,44 @@ PKG = "autoencoded-vocal-analysis_b200"
 FWD_TOL = 1e-4        # forward quantities, fp32 kernels vs float64 reference (rtol 1e-4)
 
 
-def grad_tol(g, key, floor=2e-3, k=3.0):
-    """Whole-model gradient tolerance.  Per-kernel arithmetic is held to rtol 1e-4 in
-    tests/test_gpu_kernels.py (well-conditioned single layers vs float64).  End to end the
-    gradient of this network is chaotic at the 1e-3 level in ANY fp32 implementation: every
-    BatchNorm backward cancels the dominant gradient component (amplifying rounding noise
-    ~1000x) and a forward rounding difference of 1e-7 can flip a ReLU mask (measured: one
-    flipped unit of 917,504 in convt6 moves the conv-stack gradients by 1e-3; the
-    reference's own fp32 CPU path is up to 2.5e-3 away from its float64 path at B=64, see
-    err32:* in the goldens).  So: within 2e-3 of the float64 reference, or within 3x the
-    reference's own fp32 error on that tensor, whichever is larger."""
-    return max(floor, k * float(g["err32:" + key]))
-
-
-KINK_TOL = 5e-2       # gradients of a run whose ReLU pattern differs from the float64 reference's
+GRAD_TOL = 1e-4       # parameter gradients vs the float64 oracle ON THE SAME ReLU PATTERN (rtol 1e-4)
 MAX_FLIPS = 16        # units (of ~1.9 M per sample) allowed to sit on the other side of zero
 
 
-def relu_flips(bufs, seed, batch, eps_w, eps_d, prec, train):
-    """Number of ReLU units whose on/off state in the GPU forward differs from the float64
-    oracle's on the same inputs.  The network's gradient is discontinuous there: a unit whose
-    pre-activation is within rounding of zero (|v| ~ 1e-7) lands on either side depending on
-    summation order, and ONE such unit moves the BatchNorm-amplified gradients by ~1e-2
-    (measured over seeds 21-24 at batch 64, profiles/r01_b64_seeds.txt: whichever of the fp32
-    FMA / 3xTF32 paths has a flip is ~5e-3..1e-2 off, the other ~2e-5..2e-4)."""
-    P64 = {k: (v.double() if v.is_floating_point() else v) for k, v in vae_oracle.make_params(seed).items()}
-    acts = {}
-    x = vae_oracle.make_input(seed, batch).double()
-    vae_oracle.forward(P64, x, torch.from_numpy(eps_w).double(), torch.from_numpy(eps_d).double(), prec,
-                       train, {}, acts)
-    names = [n for n, _, _, _ in vae_oracle.ENC_CONVS] + [n for n, _, _, _ in vae_oracle.DEC_CONVTS]
-    pairs = [(acts[n], bufs.act[l]) for l, n in enumerate(names) if n != "convt7"]
-    pairs += [(acts["fc1"], bufs.h1), (acts["fc2"], bufs.h2), (acts["fc3"], bufs.h3), (acts["fc5"], bufs.t5),
-              (acts["fc6"], bufs.t6), (acts["fc7"], bufs.t7), (acts["fc8"], bufs.t8)]
-    flips = 0
-    for ref, got in pairs:
-        flips += int(((ref > 0) != (got.detach().cpu().reshape(ref.shape) > 0)).sum())
-    return flips
+def assert_grads_match(model, bufs, P, x, eps_w, eps_d, prec, tag, floor=GRAD_TOL):
+    """Whole-model gradient parity, north_star's rtol 1e-4, with no allowance for kinks.
+
+    The gradient of a ReLU network is discontinuous where a pre-activation crosses zero, and a
+    unit within rounding (1e-7) of zero can land on either side depending on summation order.
+    Instead of widening the tolerance for such runs, the float64 oracle is evaluated with the
+    ReLU on/off pattern FORCED to the one the GPU forward produced (oracle/vae_oracle._relu):
+    that is the exact gradient of the function the GPU differentiated.  Every parameter
+    gradient must then be within max(1e-4, 3 x the float32 oracle's own error on the same
+    pattern) in the max-norm.  The number of units whose state differs from the float64
+    oracle's own forward is asserted separately (the forward outputs are compared elsewhere)."""
+    from tests.helpers import gpu_relu_masks, masked_oracle_grads, relu_flips
+    masks = gpu_relu_masks(bufs)
+    out64, g64, _, acts64, err32 = masked_oracle_grads(P, x, eps_w, eps_d, prec, masks)
+    flips = relu_flips(masks, acts64)
+    rows = []
+    for k, v in model.grad_dict().items():
+        err = rel_err(v.detach().cpu().numpy(), g64[k].numpy())
+        rows.append((k, err, max(floor, 3.0 * err32[k]), err32[k]))
+    worst = sorted(rows, key=lambda r: -r[1] / r[2])[:6]
+    report = "%s: %d ReLU flips vs float64; worst gradients (err / tol / oracle-fp32 err): %s" % (
+        tag, flips, ", ".join("%s %.1e/%.1e/%.1e" % r for r in worst))
+    print(report)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "grad_parity.txt"), "a") as f:
+            f.write(report + "\n")
+    except OSError:
+        pass
+    bad = [r for r in rows if not r[1] <= r[2]]
+    assert not bad, report
+    assert flips <= MAX_FLIPS, report
+    return out64, flips
 
 
 @pytest.fixture(scope="module")
@@ -67,13 +68,18 @@ def build(vae_mod, seed, prec=10.0, **kw):
     return model
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("name", ["vae_train_b7", "vae_eval_b7", "vae_train_b1",
                                   "vae_train_b64"])
-def test_forward_backward_matches_reference_golden(vae_mod, name):
+def test_forward_backward_matches_reference_golden(vae_mod, name, precision):
+    """Forward quantities against the goldens written by the reference's own code (rtol 1e-4);
+    parameter gradients against the float64 oracle on the GPU's ReLU pattern (rtol 1e-4, see
+    assert_grads_match) -- and, when that pattern equals the reference's (no unit on the other
+    side of a kink), against the reference's golden gradients at the same tolerance."""
     g = load_golden(name)
     seed, batch, train = int(g["seed"]), int(g["batch"]), bool(g["train"])
     prec = float(g["model_precision"])
-    model = build(vae_mod, seed, prec)
+    model = build(vae_mod, seed, prec, precision=precision)
     model.train(train)
     x = vae_oracle.make_input(seed, batch).cuda()
     noise = (torch.from_numpy(g["eps_w"]).cuda(), torch.from_numpy(g["eps_d"]).cuda())
@@ -90,17 +96,14 @@ def test_forward_backward_matches_reference_golden(vae_mod, name):
     check_against_golden(g, "", "x_rec", bufs.act[13].cpu().numpy().reshape(batch, 128, 128),
                          FWD_TOL)
     if train:
-        flips = relu_flips(bufs, seed, batch, g["eps_w"], g["eps_d"], prec, train)
-        assert flips <= MAX_FLIPS, "%d ReLU units differ from the float64 forward" % flips
         model._backward_native(bufs)
         torch.cuda.synchronize()
-        grads = model.grad_dict()
-        for k, v in grads.items():
-            # same ReLU pattern as the reference: the fp32 bar; a unit on the other side of the
-            # kink: the gradient legitimately differs by the kink's size (see relu_flips)
-            tol = grad_tol(g, "grad:" + k) if flips == 0 else max(KINK_TOL, grad_tol(g, "grad:" + k))
-            check_against_golden(g, "grad:", k, v.cpu().numpy(), tol)
-        print("%s: %d ReLU flips vs float64" % (name, flips))
+        _, flips = assert_grads_match(model, bufs, vae_oracle.make_params(seed), x.cpu(),
+                                      torch.from_numpy(g["eps_w"]), torch.from_numpy(g["eps_d"]), prec,
+                                      "%s[%s]" % (name, precision))
+        if flips == 0:
+            for k, v in model.grad_dict().items():
+                check_against_golden(g, "grad:", k, v.cpu().numpy(), GRAD_TOL, kink_factor=1.0)
     sd = model.state_dict()
     for k in g.files:
         if not k.startswith("buf:"):
@@ -112,17 +115,17 @@ def test_forward_backward_matches_reference_golden(vae_mod, name):
             assert rel_err(sd[kk].cpu().numpy(), g[k]) <= FWD_TOL, kk
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32"])
-def test_precision_modes(vae_mod, precision):
-    """precision='fp32' (FMA only) and 'tf32x3' (error-compensated tensor-core products, the
-    'auto' default) both hold the fp32 parity bar; 'tf32' is the opt-in reduced-precision mode
-    (what torch/cuDNN do by default for the reference's convs on a GPU) with its own
-    stated tolerance: forward 1e-2, gradients within 25% in the L2 sense (BatchNorm backward
-    amplifies a 5e-4 operand rounding by ~1000x, see grad_tol)."""
-    from tests.helpers import l2_err
+def test_reduced_precision_mode_tf32(vae_mod):
+    """'tf32' is the opt-in reduced-precision mode (what torch/cuDNN do by default for the
+    reference's convs on a GPU) with its own stated tolerance: forward 1e-2,
+    gradients within 25% in the L2 sense of the float64 oracle on the same ReLU pattern
+    (BatchNorm backward amplifies the 5e-4 operand rounding).  'fp32' and 'tf32x3' hold the
+    fp32 bar and are covered by test_forward_backward_matches_reference_golden."""
+    from tests.helpers import gpu_relu_masks, l2_err, masked_oracle_grads
     g = load_golden("vae_train_b7")
     seed, batch = int(g["seed"]), int(g["batch"])
-    model = build(vae_mod, seed, float(g["model_precision"]), precision=precision)
+    prec = float(g["model_precision"])
+    model = build(vae_mod, seed, prec, precision="tf32")
     model.train(True)
     x = vae_oracle.make_input(seed, batch).cuda()
     noise = (torch.from_numpy(g["eps_w"]).cuda(), torch.from_numpy(g["eps_d"]).cuda())
@@ -130,18 +133,15 @@ def test_precision_modes(vae_mod, precision):
     model._backward_native(bufs)
     torch.cuda.synchronize()
     lib = importlib.import_module(PKG + "._lib").lib()
-    assert lib.ava_b200_get_conv_precision() == {"fp32": 0, "tf32x3": 2, "tf32": 1}[precision]
-    ftol = 1e-2 if precision == "tf32" else FWD_TOL
+    assert lib.ava_b200_get_conv_precision() == 1
+    ftol = 1e-2
     assert abs(float(bufs.loss.item()) - float(g["loss"])) <= ftol * abs(float(g["loss"]))
     assert rel_err(bufs.heads.cpu().numpy()[:, :32], g["mu"]) <= ftol
     check_against_golden(g, "", "x_rec", bufs.act[13].cpu().numpy().reshape(batch, 128, 128), ftol)
+    _, g64, _, _, _ = masked_oracle_grads(vae_oracle.make_params(seed), x.cpu(), torch.from_numpy(g["eps_w"]),
+                                          torch.from_numpy(g["eps_d"]), prec, gpu_relu_masks(bufs))
     for k, v in model.grad_dict().items():
-        if precision == "tf32":
-            key = "grad:" + k
-            if key in g.files:
-                assert l2_err(v.cpu().numpy().reshape(g[key].shape), g[key]) <= 0.25, k
-        else:
-            check_against_golden(g, "grad:", k, v.cpu().numpy(), grad_tol(g, "grad:" + k))
+        assert l2_err(v.cpu().numpy(), g64[k].numpy()) <= 0.25, k
 
 
 def test_public_api_encode_decode_forward(vae_mod):
@@ -189,7 +189,10 @@ def test_autograd_backward_and_torch_seeded_noise(vae_mod):
     torch.cuda.synchronize()
     for k, p in model.named_parameters():
         assert p.grad is not None, k
-        check_against_golden(g, "grad:", k, p.grad.cpu().numpy(), grad_tol(g, "grad:" + k))
+        # .grad is the native backward's flat gradient buffer (scaled by grad_loss = 1)
+        assert torch.equal(p.grad, model.grad_dict()[k]), k
+    assert_grads_match(model, model._cur, vae_oracle.make_params(seed), x.cpu(), torch.from_numpy(g["eps_w"]),
+                       torch.from_numpy(g["eps_d"]), float(g["model_precision"]), "autograd_b7")
     # torch-seeded draws: eps_W [B,1] first, then eps_D [B,32]
     torch.manual_seed(123)
     ew = torch.randn(batch, 1, device="cuda")
@@ -228,11 +231,29 @@ def test_train_steps_match_reference_adam_trajectory(vae_mod):
     assert int(sd["bn1.num_batches_tracked"]) == 3 + steps
 
 
+class _DS:
+    """Dataset stand-in with the reference SyllableDataset's indexing contract
+    (ava/models/vae_dataset.py:121-145): an int gives one item, an iterable a LIST of items."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def __len__(self):
+        return len(self.t)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            return self.t[idx]
+        if np.ndim(idx) == 0:
+            return self.t[int(idx)]
+        return [self.t[int(i)] for i in idx]
+
+
 class _ListLoader:
     """Minimal stand-in for a DataLoader: iterable of CPU batches with a .dataset."""
 
     def __init__(self, data, batch_size):
-        self.dataset = data
+        self.dataset = data if isinstance(data, _DS) else _DS(data)
         self.batch_size = batch_size
 
     def __iter__(self):
@@ -247,7 +268,7 @@ def test_epoch_loops_get_latent_and_checkpoint(vae_mod, tmp_path):
     model = vae_mod.VAE(save_dir=str(tmp_path), device_name='cuda')
     model.load_flat_state(vae_oracle.make_params(seed))
     torch.manual_seed(0)
-    l0 = model.train_epoch(loader)
+    l0 = model.train_epoch(loader)       # (values: test_train_epoch_and_test_epoch_losses_match_oracle)
     assert model.epoch == 1 and np.isfinite(l0)
     lt = model.test_epoch(loader)
     assert np.isfinite(lt)
@@ -293,6 +314,159 @@ def test_epoch_loops_get_latent_and_checkpoint(vae_mod, tmp_path):
         mu, _, _ = vae_oracle.encode(P, data[:8], train=True)
     lat2 = model.get_latent(_ListLoader(data[:8], 8))
     assert rel_err(lat2, mu.numpy()) <= 1e-3   # running stats moved between the two calls only
+
+
+def _replay_noise(seed, sizes):
+    """The (eps_W, eps_D) pairs the eager path draws for batches of these sizes after
+    torch.manual_seed(seed): torch.randn [b,1] then [b,32] per batch (VAE._draw_noise, the
+    reference's rsample order)."""
+    torch.manual_seed(seed)
+    return [(torch.randn(b, 1, device="cuda").cpu(), torch.randn(b, 32, device="cuda").cpu()) for b in sizes]
+
+
+def test_train_epoch_and_test_epoch_losses_match_oracle(vae_mod, tmp_path):
+    """train_epoch / test_epoch (ava/models/vae.py:330-385) return the reference's numbers: the
+    epoch's summed per-batch losses over len(dataset), with a ragged last batch, Adam between
+    the batches, and eval-mode BatchNorm (running buffers as updated by the training epoch) in
+    test_epoch.  Oracle: the float64 restatement stepped through the same batches and noise."""
+    seed = 6
+    data = vae_oracle.make_input(seed, 20)          # batches of 8, 8, 4
+    loader = _ListLoader(data, 8)
+    model = vae_mod.VAE(save_dir=str(tmp_path), device_name='cuda', cuda_graphs=False)
+    model.load_flat_state(vae_oracle.make_params(seed))
+    torch.manual_seed(11)
+    l_train = model.train_epoch(loader)
+    torch.manual_seed(12)
+    l_test = model.test_epoch(loader)
+    assert model.epoch == 1
+    P = {k: (v.double() if v.is_floating_point() else v) for k, v in vae_oracle.make_params(seed).items()}
+    keys = [k for k, _ in vae_oracle.param_order()]
+    st = {"step": 0, "m": {k: torch.zeros_like(P[k]) for k in keys},
+          "v": {k: torch.zeros_like(P[k]) for k in keys}}
+    want = 0.0
+    for i, (ew, ed) in enumerate(_replay_noise(11, (8, 8, 4))):
+        want += float(vae_oracle.train_step_cpu(P, st, data[8 * i:8 * i + 8].double(), ew.double(), ed.double()))
+    want /= 20
+    # Adam's first steps are sign-like, which amplifies fp32 noise in tiny gradients: the
+    # reference's own fp32 run is 2e-4 off its float64 run after 3 steps (err32:losses in
+    # tests/golden/adam_b5_s3.npz); same bar as test_train_steps_match_reference_adam_trajectory
+    tol = max(1e-4, 3 * abs(float(load_golden("adam_b5_s3")["err32:losses"])))
+    assert abs(l_train - want) <= tol * abs(want), (l_train, want)
+    want_t = 0.0
+    with torch.no_grad():
+        for i, (ew, ed) in enumerate(_replay_noise(12, (8, 8, 4))):
+            want_t += float(vae_oracle.forward(P, data[8 * i:8 * i + 8].double(), ew.double(), ed.double(),
+                                               10.0, train=False)["loss"])
+    want_t /= 20
+    assert abs(l_test - want_t) <= tol * abs(want_t), (l_test, want_t)
+
+
+def test_train_loop_runs_reference_schedule(vae_mod, tmp_path, capsys):
+    """train_loop (ava/models/vae.py:388-430): epochs range(self.epoch, self.epoch+epochs), test
+    every test_freq, checkpoint_{epoch:03d}.tar when epoch % save_freq == 0 and epoch > 0,
+    visualize every vis_freq; the loss dictionary is keyed by epoch.  Four batch sizes pass
+    through the model per epoch (8, ragged 4, test 8 / ragged 2, visualize 5) with the CUDA-graph
+    path on: the result must equal the eager path's (graphs whose buffers were evicted would
+    read freed memory -- round-1 advisor finding)."""
+    seed = 4
+    train = vae_oracle.make_input(seed, 20)
+    test = vae_oracle.make_input(seed + 1, 10)
+    results = {}
+    for graphs in (True, False):
+        d = tmp_path / ("g%d" % graphs)
+        model = vae_mod.VAE(save_dir=str(d), device_name='cuda', cuda_graphs=graphs)
+        model.load_flat_state(vae_oracle.make_params(seed))
+        loaders = {'train': _ListLoader(train, 8), 'test': _ListLoader(test, 8)}
+        torch.manual_seed(5)
+        np.random.seed(5)
+        model.train_loop(loaders, epochs=5, test_freq=2, save_freq=2, vis_freq=1)
+        assert model.epoch == 5
+        assert sorted(model.loss['train']) == [0, 1, 2, 3, 4]
+        assert sorted(model.loss['test']) == [0, 2, 4]
+        assert sorted(os.listdir(str(d))) == ['checkpoint_002.tar', 'checkpoint_004.tar'] or \
+            sorted(f for f in os.listdir(str(d)) if f.endswith('.tar')) == ['checkpoint_002.tar', 'checkpoint_004.tar']
+        ck = torch.load(os.path.join(str(d), 'checkpoint_004.tar'), map_location='cpu')
+        assert ck['epoch'] == 5 and sorted(ck['loss']['train']) == [0, 1, 2, 3, 4]
+        results[graphs] = (dict(model.loss['train']), dict(model.loss['test']),
+                           {k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+    out = capsys.readouterr().out
+    assert "Training: epochs 0 to 4" in out and "Training set: 20" in out and "Test set: 10" in out
+    assert "Epoch: 4 Average loss:" in out and "Test loss:" in out
+    # graph replay and eager launches run the same kernels on the same data: same trajectory
+    # (up to the fp64-atomic ordering of the BN statistics and Adam's sign-like early steps)
+    from tests.helpers import l2_err
+    for e in range(5):
+        a, b = results[True][0][e], results[False][0][e]
+        assert abs(a - b) <= 2e-4 * abs(b), (e, a, b)
+    for e in (0, 2, 4):
+        a, b = results[True][1][e], results[False][1][e]
+        assert abs(a - b) <= 2e-4 * abs(b), (e, a, b)
+    for k, v in results[True][2].items():
+        if v.is_floating_point():
+            assert l2_err(v.double().numpy(), results[False][2][k].double().numpy()) <= 2e-2, k
+
+
+def test_visualize_returns_specs_and_reconstructions(vae_mod, tmp_path):
+    """visualize (ava/models/vae.py:475-516): np.random.choice of num_specs indices without
+    replacement, dataset indexed with the index ARRAY, forward(..., return_latent_rec=True),
+    returns (specs, rec_specs) as [num_specs,128,128] arrays (the pdf needs matplotlib)."""
+    seed = 4
+    data = vae_oracle.make_input(seed, 12)
+    loader = _ListLoader(data, 4)
+    model = vae_mod.VAE(save_dir=str(tmp_path), device_name='cuda')
+    model.load_flat_state(vae_oracle.make_params(seed))
+    model.eval()
+    np.random.seed(3)
+    specs, rec = model.visualize(loader, num_specs=5)
+    np.random.seed(3)
+    idx = np.random.choice(np.arange(12), size=5, replace=False)
+    assert specs.shape == (5, 128, 128) and rec.shape == (5, 128, 128)
+    assert np.array_equal(specs, data[idx].numpy())
+    # the reconstruction is the decoder mean of a SAMPLE z: same encoder outputs as encode()
+    with torch.no_grad():
+        mu, _, _ = model.encode(data[idx].cuda())
+        rec_mu = model.decode(mu).cpu().numpy().reshape(5, 128, 128)
+    assert np.isfinite(rec).all() and rel_err(rec, rec_mu) < 0.5
+    with pytest.raises(AssertionError):
+        model.visualize(loader, num_specs=13)
+
+
+def test_full_batch_1024_train_mode_matches_float64_oracle(vae_mod):
+    """The benchmarked configuration itself (batch 1024, train-mode BatchNorm, precision
+    'auto') against the float64 oracle: loss, mu, z, x_rec and the BN running buffers at rtol
+    1e-4; every parameter gradient at rtol 1e-4 on the GPU's ReLU pattern.  At this size the
+    persistent tile loops make many trips, the grids span several waves and the cross-CTA fp64
+    statistics atomics see 1000+ contributions."""
+    seed, B, prec = 9, 1024, 10.0
+    P = vae_oracle.make_params(seed)
+    model = build(vae_mod, seed, prec)
+    model.train()
+    x = vae_oracle.make_input(seed, B)
+    ew, ed = vae_oracle.make_noise(seed, B)
+    bufs = model._forward_native(x.cuda(), (ew.cuda(), ed.cuda()), True, want_grad_seed=True)
+    model._backward_native(bufs)
+    torch.cuda.synchronize()
+    out64, flips = assert_grads_match(model, bufs, P, x, ew, ed, prec, "train_b1024[auto]")
+    if flips == 0:
+        # identical ReLU pattern: the forced oracle IS the reference forward
+        assert abs(float(bufs.loss.item()) - float(out64["loss"])) <= FWD_TOL * abs(float(out64["loss"]))
+    P64 = {k: (v.double() if v.is_floating_point() else v) for k, v in P.items()}
+    nb = {}
+    with torch.no_grad():
+        ref = vae_oracle.forward(P64, x.double(), ew.double(), ed.double(), prec, True, nb)
+    assert abs(float(bufs.loss.item()) - float(ref["loss"])) <= FWD_TOL * abs(float(ref["loss"]))
+    heads = bufs.heads.cpu().numpy()
+    assert rel_err(heads[:, :32], ref["mu"].numpy()) <= FWD_TOL
+    assert rel_err(heads[:, 32:64], ref["u"][:, :, 0].numpy()) <= FWD_TOL
+    assert rel_err(bufs.d.cpu().numpy(), ref["d"].numpy()) <= FWD_TOL
+    assert rel_err(bufs.z.cpu().numpy(), ref["z"].numpy()) <= FWD_TOL
+    assert rel_err(bufs.act[13].cpu().numpy().reshape(B, -1), ref["x_rec"].numpy()) <= FWD_TOL
+    sd = model.state_dict()
+    for k, v in nb.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            assert rel_err(sd[k].cpu().numpy(), v.numpy()) <= FWD_TOL, k
 
 
 def test_full_size_batch_properties(vae_mod):
