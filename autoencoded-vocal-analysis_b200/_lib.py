@@ -20,7 +20,7 @@ SIGNATURES = {
     "ava_b200_bn_update_running": (P, P, P, P, P, P, P, F, P),
     "ava_b200_bnconv_fwd": (I, I, P, P, P, P, P, P, P, P, P, I, P, P),
     "ava_b200_dz_border_sums": (P, I, I, I, I, I, P, P),
-    "ava_b200_bnconv_bwd_data": (I, I, P, P, P, P, P, P, I, P, P),
+    "ava_b200_bnconv_bwd_data": (I, I, P, P, P, P, P, P, I, P, P, P),
     "ava_b200_bnconv_bwd_weight": (I, I, P, P, P, P, P, P, P, P, P, P, P, P),
     "ava_b200_bnconv_bwd_weight_ws": (I, I),
     "ava_b200_set_conv_precision": (I,),
@@ -38,6 +38,7 @@ SIGNATURES = {
     "ava_b200_adam_step": (P, P, P, P, LL, P, D, D, D, D, F, P),
     "ava_b200_adam_step_dev": (P, P, P, P, LL, P, P, F, P),
     "ava_b200_get_spec_batch": (P, I, P, P, I, I, I, I, P, D, P, P, I, P, P, I, I, D, D, P, P, P),
+    "ava_b200_quantile_normalize": (P, P, I, I, D, P),
     "ava_b200_window_time_tables": (P, P, P, I, P, P, I, I, P, P, P),
     "ava_b200_mmd_block_sums": (P, I, I, P, I, D, P, P),
     "ava_b200_pair_kernel": (P, I, P, P, LL, D, I, P, P),

@@ -64,6 +64,11 @@ struct GconvParams {
   const float* gamma_self;
   const double* dstats_in;
   int mask_in;
+  // EPI_BWD, optional: the nine per-channel border sums of the dz written here (what
+  // ava_b200_dz_border_sums would compute in a separate pass; mode 0 / 1 as there), accumulated
+  // in the epilogue -- the consumer layer's weight-gradient finalisation needs them
+  double* tsums_out;
+  int tsum_mode;
   double out_count;
   int B, H_in, W_in;
 };
@@ -242,8 +247,11 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
   float* s_c1 = s_c0 + 32;                          // AFFINE shift
   float* s_red = s_c1 + 32;                         // per-warp partial sums
   float* s_bias = s_red + C::RED_FLOATS;            // [CO]
-  double* s_dz = reinterpret_cast<double*>(s_bias + 32);  // [4][32] EPI_BWD: p | q | mean | c1 of own BN
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dz + 128);
+  double* s_dz = reinterpret_cast<double*>(s_bias + 32);  // EPI_BWD coefficients of own BN, as
+  float* s_dzf = reinterpret_cast<float*>(s_dz);          // floats [2: hi | lo][4: p | q | mean | c1][32]
+  double* s_ts = s_dz + 128;                               // [9][32] EPI_BWD: border sums of the output
+  double* s_tsw = s_ts + 288;                              // [warps][4][32] EPI_BWD: per-warp totals / classes
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tsw + (EPI == EPI_BWD ? (NT / 32) * 128 : 0));
 
   const int tid = threadIdx.x;
   // every instantiation serves exactly one layer, so the image size is a compile-time constant
@@ -418,19 +426,38 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
   if (tid < CO) {
     s_bias[tid] = (EPI == EPI_FWD && P.bias) ? P.bias[tid] : 0.f;
     if (EPI == EPI_BWD) {
+      // fp64 coefficients, stored as fp32 hi + lo pairs: p | q | mean | c1
       const DzCoef k = dz_coef(P.gamma_self, P.stats_self, P.dstats_in, tid, P.out_count);
-      s_dz[tid] = k.p;
-      s_dz[32 + tid] = k.q;
-      s_dz[64 + tid] = k.mean;
-      s_dz[96 + tid] = k.c1;
+      const double v[4] = {k.p, k.q, k.mean, k.c1};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float hi = (float)v[j];
+        s_dzf[j * 32 + tid] = hi;
+        s_dzf[128 + j * 32 + tid] = (float)(v[j] - (double)hi);
+      }
     }
   }
   __syncthreads();
-  // EPI_BWD epilogue: BatchNorm backward (fp64 coefficient math, the two terms cancel) + ReLU mask
+  // EPI_BWD epilogue: BatchNorm backward + ReLU mask,  out = [x > 0] * (p*(g - c1) + q*(x - mean)).
+  // The coefficients are exact to fp64 (hi + lo), the element arithmetic is fp32: both differences
+  // are formed against the hi part first (no rounding of the coefficient enters), and the
+  // expression is well conditioned -- measured over the network (profiles/probes/
+  // exp_algebraic_dstats.py): |mean g| <= 0.2 std g and |q (x-mean)| <= 0.5 |p (g-c1)| in every
+  // layer, so nothing cancels.  (A float64 evaluation costs three F2F conversions per element on
+  // a 16-lane pipe: +0.75 ms per step at batch 1024 when it ran in this epilogue.)
   auto dzap = [&](int co, float g, float x) -> float {
-    const double d = s_dz[co] * ((double)g - s_dz[96 + co]) + s_dz[32 + co] * ((double)x - s_dz[64 + co]);
-    return (P.mask_in && !(x > 0.f)) ? 0.f : (float)d;
+    const float a = (g - s_dzf[96 + co]) - s_dzf[128 + 96 + co];
+    const float b = (x - s_dzf[64 + co]) - s_dzf[128 + 64 + co];
+    const float d = fmaf(s_dzf[co], a, fmaf(s_dzf[32 + co], b, fmaf(s_dzf[128 + co], a, s_dzf[128 + 32 + co] * b)));
+    return (P.mask_in && !(x > 0.f)) ? 0.f : d;
   };
+  const bool want_ts = (EPI == EPI_BWD) && P.tsums_out != nullptr;
+  if (want_ts) {
+    for (int i = tid; i < 288; i += NT) s_ts[i] = 0.0;
+    for (int i = tid; i < (NT / 32) * 128; i += NT) s_tsw[i] = 0.0;
+    __syncthreads();
+  }
+  auto ts_add = [&](int slot, int co, float v) { atomicAdd(&s_ts[slot * 32 + co], (double)v); };
 
   if constexpr (C::MMA) {
     // ---------------------------------------------------------------- tensor-core path (K_S1, K_S2)
@@ -744,7 +771,77 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
                 st2[i][j & 1] = fmaf(v0, v0, fmaf(v1, v1, st2[i][j & 1]));
               }
               if (P.out) *reinterpret_cast<float2*>(P.out + o) = make_float2(v0, v1);
+              acc[2 * oa][i][j] = v0;
+              acc[2 * oa + 1][i][j] = v1;
             }
+        if (want_ts) {
+          // border sums of the written dz (mode 0; the stride-2-up kernels never feed a stride-2
+          // conv-transpose layer): output (2a+oa, 2x+ob), x = x_in (+8 for j >= 2), channel
+          // i*8 + 2t + (j&1).  Totals: shuffle over g, then lanes g == 0 add to this warp's own fp64
+          // slots (no atomics).  Border rows / columns / corners are rare: the per-channel values are
+          // moved so that lane L holds channel L and ONE shared atomic per lane follows.
+          double* tw = s_tsw + warp * 128;
+          auto spread = [&](float (&v)[NTL][2], int src_base, int slot) {
+            float mine = 0.f;
+#pragma unroll
+            for (int i = 0; i < NTL; ++i)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const float tmp = __shfl_sync(0xffffffffu, v[i][c], src_base + ((lane & 7) >> 1));
+                if ((lane >> 3) == i && (lane & 1) == c) mine = tmp;
+              }
+            if (lane < CO) ts_add(slot, lane, mine);
+          };
+          const bool tile_c0 = (tx == 0) && (xh == 0);
+          const bool tile_cl = (tx == tiles_x - 1) && (TW == 16 || xh == 1);
+          float tot[NTL][2], cf[NTL][2], cl[NTL][2];
+#pragma unroll
+          for (int i = 0; i < NTL; ++i) tot[i][0] = tot[i][1] = cf[i][0] = cf[i][1] = cl[i][0] = cl[i][1] = 0.f;
+#pragma unroll
+          for (int oa = 0; oa < 2; ++oa) {
+            const int oy = 2 * a_in + oa;
+            const bool rb = (oy == 0) || (oy == H_out - 1);      // warp-uniform
+            float rw[NTL][2], c0v[NTL][2], clv[NTL][2];
+#pragma unroll
+            for (int i = 0; i < NTL; ++i)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                rw[i][c] = (acc[2 * oa][i][c] + acc[2 * oa + 1][i][c]) + (acc[2 * oa][i][2 + c] + acc[2 * oa + 1][i][2 + c]);
+                tot[i][c] += rw[i][c];
+                c0v[i][c] = acc[2 * oa][i][c];            // output column 0: x = 0 (j < 2), ob = 0, lanes g == 0
+                clv[i][c] = acc[2 * oa + 1][i][2 + c];    // last output column: x = W_in-1 (j >= 2), ob = 1, lanes g == 7
+                cf[i][c] += c0v[i][c];
+                cl[i][c] += clv[i][c];
+              }
+            if (rb) {
+#pragma unroll
+              for (int i = 0; i < NTL; ++i)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  float a = rw[i][c];
+                  a += __shfl_xor_sync(0xffffffffu, a, 4);
+                  a += __shfl_xor_sync(0xffffffffu, a, 8);
+                  a += __shfl_xor_sync(0xffffffffu, a, 16);
+                  rw[i][c] = a;
+                }
+              spread(rw, 0, (oy == 0) ? 1 : 2);
+              if (tile_c0) spread(c0v, 0, (oy == 0) ? 5 : 7);
+              if (tile_cl) spread(clv, 28, (oy == 0) ? 6 : 8);
+            }
+          }
+          if (tile_c0) spread(cf, 0, 3);
+          if (tile_cl) spread(cl, 28, 4);
+#pragma unroll
+          for (int i = 0; i < NTL; ++i)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float a = tot[i][c];
+              a += __shfl_xor_sync(0xffffffffu, a, 4);
+              a += __shfl_xor_sync(0xffffffffu, a, 8);
+              a += __shfl_xor_sync(0xffffffffu, a, 16);
+              if (g == 0) tw[i * 8 + 2 * t + c] += (double)a;
+            }
+        }
       } else {
         // ---- epilogue on the accumulator fragments: c0 = (pixel g, channel 2t), c1 = (g, 2t+1),
         // c2 = (g+8, 2t), c3 = (g+8, 2t+1)
@@ -791,6 +888,126 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
                 P.out[(((size_t)n * CO + co) * H_out + oy0 + r) * W_out + ox0 + 8 * (j >> 1)] = acc[r][i][j];
               }
         }
+        if (want_ts) {
+          // border sums of the written dz: element (row oy0+r, column ox0 + 8*(j>>1), channel
+          // i*8 + 2t + (j&1)).  Totals / parity classes: fp32 within the tile, then this warp's own
+          // fp64 slots (no atomics).  Border rows / columns / corners are rare: values are moved so
+          // that lane L holds channel L, then one shared atomic per lane.
+          double* tw = s_tsw + warp * 128;
+          auto spread = [&](float (&v)[NTL][2], int src_base, int slot) {
+            float mine = 0.f;
+#pragma unroll
+            for (int i = 0; i < NTL; ++i)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const float tmp = __shfl_sync(0xffffffffu, v[i][c], src_base + ((lane & 7) >> 1));
+                if ((lane >> 3) == i && (lane & 1) == c) mine = tmp;
+              }
+            if (lane < CO) ts_add(slot, lane, mine);
+          };
+          const bool tile_c0 = (tx == 0) && (xh == 0);
+          const bool tile_cl = (tx == tiles_x - 1) && (TW == 16 || xh == 1);
+          if (P.tsum_mode == 0) {
+            float tot[NTL][2], cf[NTL][2], cl[NTL][2];
+#pragma unroll
+            for (int i = 0; i < NTL; ++i) tot[i][0] = tot[i][1] = cf[i][0] = cf[i][1] = cl[i][0] = cl[i][1] = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const int oy = oy0 + r;
+              const bool rb = (oy == 0) || (oy == H_out - 1);    // warp-uniform
+              float rw[NTL][2], c0v[NTL][2], clv[NTL][2];
+#pragma unroll
+              for (int i = 0; i < NTL; ++i)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  rw[i][c] = acc[r][i][c] + acc[r][i][2 + c];
+                  tot[i][c] += rw[i][c];
+                  c0v[i][c] = acc[r][i][c];         // column 0 lives in lanes g == 0 (j < 2)
+                  clv[i][c] = acc[r][i][2 + c];     // the last column in lanes g == 7 (j >= 2)
+                  cf[i][c] += c0v[i][c];
+                  cl[i][c] += clv[i][c];
+                }
+              if (rb) {
+#pragma unroll
+                for (int i = 0; i < NTL; ++i)
+#pragma unroll
+                  for (int c = 0; c < 2; ++c) {
+                    float a = rw[i][c];
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    a += __shfl_xor_sync(0xffffffffu, a, 16);
+                    rw[i][c] = a;
+                  }
+                spread(rw, 0, (oy == 0) ? 1 : 2);
+                if (tile_c0) spread(c0v, 0, (oy == 0) ? 5 : 7);
+                if (tile_cl) spread(clv, 28, (oy == 0) ? 6 : 8);
+              }
+            }
+            if (tile_c0) spread(cf, 0, 3);
+            if (tile_cl) spread(cl, 28, 4);
+#pragma unroll
+            for (int i = 0; i < NTL; ++i)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                float a = tot[i][c];
+                a += __shfl_xor_sync(0xffffffffu, a, 4);
+                a += __shfl_xor_sync(0xffffffffu, a, 8);
+                a += __shfl_xor_sync(0xffffffffu, a, 16);
+                if (g == 0) tw[i * 8 + 2 * t + c] += (double)a;
+              }
+          } else {
+            // mode 1: row-parity x column-parity classes (the column parity of this lane's pixels
+            // is g & 1: tile origins and the +8 step are even; oy0 is even, so row parity = r & 1),
+            // last row by column parity, last column by row parity, last corner
+            float cls[2][NTL][2], lc[2][NTL][2];
+#pragma unroll
+            for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+              for (int i = 0; i < NTL; ++i) cls[rp][i][0] = cls[rp][i][1] = lc[rp][i][0] = lc[rp][i][1] = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              float rw[NTL][2], clv[NTL][2];
+#pragma unroll
+              for (int i = 0; i < NTL; ++i)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  rw[i][c] = acc[r][i][c] + acc[r][i][2 + c];
+                  clv[i][c] = acc[r][i][2 + c];
+                  cls[r & 1][i][c] += rw[i][c];
+                  lc[r & 1][i][c] += clv[i][c];
+                }
+              if (oy0 + r == H_out - 1) {                       // warp-uniform
+#pragma unroll
+                for (int i = 0; i < NTL; ++i)
+#pragma unroll
+                  for (int c = 0; c < 2; ++c) {
+                    float a = rw[i][c];
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    a += __shfl_xor_sync(0xffffffffu, a, 16);
+                    rw[i][c] = a;                               // lanes g = 0 / 1: even / odd columns
+                  }
+                spread(rw, 0, 4);
+                spread(rw, 4, 5);
+                if (tile_cl) spread(clv, 28, 8);
+              }
+            }
+            if (tile_cl) {
+              spread(lc[0], 28, 6);
+              spread(lc[1], 28, 7);
+            }
+#pragma unroll
+            for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+              for (int i = 0; i < NTL; ++i)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  float a = cls[rp][i][c];
+                  a += __shfl_xor_sync(0xffffffffu, a, 8);
+                  a += __shfl_xor_sync(0xffffffffu, a, 16);
+                  if (g < 2) tw[(rp * 2 + g) * 32 + i * 8 + 2 * t + c] += (double)a;
+                }
+          }
+        }
       }
       // this tile's statistics: lanes sharing t hold the same channels -> xor-shuffle over g, then
       // lanes 0..3 add to the warp's fp64 slots
@@ -828,6 +1045,20 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
         atomicAdd(&dst[tid], a);
         atomicAdd(&dst[32 + tid], b);
       }
+    }
+    if (want_ts) {
+      // per-warp totals / classes -> s_ts (fixed order), then one fp64 atomic per value per CTA
+      __syncthreads();
+      const int nhot = (P.tsum_mode == 0) ? 32 : 128;
+      for (int i = tid; i < nhot; i += NT) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) a += s_tsw[w * 128 + i];
+        s_ts[i] = a;
+      }
+      __syncthreads();
+      for (int i = tid; i < 288; i += NT)
+        if ((i & 31) < CO && s_ts[i] != 0.0) atomicAdd(&P.tsums_out[i], s_ts[i]);
     }
   } else {
     // ---------------------------------------------------------------- fp32 SIMT path
@@ -1005,6 +1236,137 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
         }
       }
     }
+    if (want_ts) {
+      // border sums of the written dz.  Lanes of a row group run along x (lx); a row group is a
+      // whole warp (TW == 32) or a half warp (TW == 16).  Totals / parity classes: xor-shuffle
+      // reduction over the WARP (the butterfly leaves the sum in every lane), then lane k adds
+      // value k to this warp's own fp64 slot k (no atomics, one add per lane).  Border rows /
+      // columns / corners are rare: one shared atomic per lane after the same kind of spreading.
+      const int lane = tid & 31;
+      const int warp = tid >> 5;
+      const unsigned gmask = (TW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
+      double* tw = s_tsw + warp * 128;
+      // v[c] valid in lane `src` of every row group -> channel c to lane c of that group -> atomic
+      auto spread_from = [&](float (&v)[COT], int src, int slot, bool on) {
+        float mine = 0.f;
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+          const float tmp = __shfl_sync(0xffffffffu, v[c], (lane & ~(TW - 1) & 31) + src);
+          if (lx == c) mine = tmp;
+        }
+        if (on && lx < COT) ts_add(slot, cog * COT + lx, mine);
+      };
+      const bool tile_c0 = (tx == 0), tile_cl = (tx == tiles_x - 1);
+      if (P.tsum_mode == 0) {
+        float tot[COT], cfv[COT], clv[COT];
+#pragma unroll
+        for (int c = 0; c < COT; ++c) tot[c] = cfv[c] = clv[c] = 0.f;
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+          int oy;
+          bool is_c0, is_cl;     // does this element sit in the first / last output column (owner lanes only)
+          if (KIND == K_UP) {
+            oy = 2 * (ty * G::TH + 2 * rg + (o >> 2)) + ((o >> 1) & 1);
+            is_c0 = (o & 1) == 0;      // column 2*lx + ob: first for lx == 0, ob == 0
+            is_cl = (o & 1) == 1;      // last for lx == TW-1, ob == 1
+          } else {
+            oy = ty * G::TH + 4 * rg + o;
+            is_c0 = is_cl = true;
+          }
+          const bool rb = (oy == 0) || (oy == H_out - 1);      // uniform over the row group
+          float rv[COT];
+#pragma unroll
+          for (int c = 0; c < COT; ++c) {
+            rv[c] = acc[o][c];
+            tot[c] += rv[c];
+            if (is_c0) cfv[c] += rv[c];
+            if (is_cl) clv[c] += rv[c];
+          }
+          // (TW == 16: the two half warps may differ in rb; shuffles run warp-wide, the atomic is predicated)
+          const bool any_rb = __any_sync(0xffffffffu, rb);
+          if (any_rb) {
+            if (tile_c0 && is_c0) spread_from(rv, 0, (oy == 0) ? 5 : 7, rb);
+            if (tile_cl && is_cl) spread_from(rv, TW - 1, (oy == 0) ? 6 : 8, rb);
+#pragma unroll
+            for (int c = 0; c < COT; ++c) {
+#pragma unroll
+              for (int sh = 1; sh < TW; sh <<= 1) rv[c] += __shfl_xor_sync(0xffffffffu, rv[c], sh);
+            }
+            spread_from(rv, 0, (oy == 0) ? 1 : 2, rb);
+          }
+        }
+        if (tile_c0) spread_from(cfv, 0, 3, true);
+        if (tile_cl) spread_from(clv, TW - 1, 4, true);
+        float mine = 0.f;
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+          float a = tot[c];
+#pragma unroll
+          for (int sh = 1; sh < 32; sh <<= 1) a += __shfl_xor_sync(0xffffffffu, a, sh);
+          if (lane == c) mine = a;
+        }
+        if (lane < COT) tw[cog * COT + lane] += (double)mine;
+      } else if (KIND != K_UP) {
+        // mode 1: parity classes (row parity = o & 1, column parity = lx & 1: tile origins are even)
+        float cls[2][COT], lcv[2][COT];
+#pragma unroll
+        for (int c = 0; c < COT; ++c) cls[0][c] = cls[1][c] = lcv[0][c] = lcv[1][c] = 0.f;
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+          const int oy = ty * G::TH + 4 * rg + o;
+          const bool last_row = (oy == H_out - 1);              // uniform over the row group
+          float rv[COT];
+#pragma unroll
+          for (int c = 0; c < COT; ++c) {
+            rv[c] = acc[o][c];
+            cls[o & 1][c] += rv[c];
+            lcv[o & 1][c] += rv[c];
+          }
+          if (__any_sync(0xffffffffu, last_row)) {
+            if (tile_cl) spread_from(rv, TW - 1, 8, last_row);
+#pragma unroll
+            for (int c = 0; c < COT; ++c) {
+#pragma unroll
+              for (int sh = 2; sh < TW; sh <<= 1) rv[c] += __shfl_xor_sync(0xffffffffu, rv[c], sh);
+            }
+            spread_from(rv, 0, 4, last_row);      // lane 0 of the group: even columns
+            spread_from(rv, 1, 5, last_row);      // lane 1: odd columns
+          }
+        }
+        if (tile_cl) {
+          spread_from(lcv[0], TW - 1, 6, true);
+          spread_from(lcv[1], TW - 1, 7, true);
+        }
+        // classes: lane l takes (row parity, channel) = l >> 1 with its own column parity l & 1
+        float mine = 0.f;
+#pragma unroll
+        for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+          for (int c = 0; c < COT; ++c) {
+            float a = cls[rp][c];
+#pragma unroll
+            for (int sh = 2; sh < 32; sh <<= 1) a += __shfl_xor_sync(0xffffffffu, a, sh);
+            if ((lane >> 1) == rp * COT + c) mine = a;
+          }
+        if ((lane >> 1) < 2 * COT) {
+          const int rp = (lane >> 1) / COT, c = (lane >> 1) % COT;
+          tw[(rp * 2 + (lane & 1)) * 32 + cog * COT + c] += (double)mine;
+        }
+      }
+    }
+  }
+  if (want_ts) {
+    __syncthreads();
+    const int nhot = (P.tsum_mode == 0) ? 32 : 128;
+    for (int i = tid; i < nhot; i += NT) {
+      double a = 0.0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) a += s_tsw[w * 128 + i];
+      s_ts[i] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < 288; i += NT)
+      if ((i & 31) < CO && s_ts[i] != 0.0) atomicAdd(&P.tsums_out[i], s_ts[i]);
   }
 
   // ---- per-channel statistics: warp shuffle -> per-warp smem slots -> fixed-order sum ->
@@ -1069,7 +1431,7 @@ static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   using C = GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>;
   using G = typename C::G;
   const size_t smem = (size_t)(C::BUF_FLOATS + C::W_FLOATS + 64 + C::RED_FLOATS + 32) * sizeof(float) +
-                      128 * sizeof(double) + 16 + 128;
+                      (128 + 288 + (EPI == EPI_BWD ? (C::NT / 32) * 128 : 0)) * sizeof(double) + 16 + 128;
   if (P.H_in != HIN || P.W_in != HIN) {
     set_error("gconv: layer geometry mismatch");
     return 1;
@@ -1993,7 +2355,7 @@ extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, c
 
 extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const float* w, const float* x,
                                         const float* gamma, const double* stats_in, const double* dstats,
-                                        int relu_mask, float* dz_prev, void* stream_) {
+                                        int relu_mask, float* dz_prev, double* tsums_prev, void* stream_) {
   AVA_REQUIRE(layer >= 0 && layer < 14, "bnconv_bwd_data: bad layer %d", layer);
   AVA_REQUIRE(dz_prev != nullptr && x != nullptr, "bnconv_bwd_data: output and layer input required");
   if (B <= 0) return 0;
@@ -2009,6 +2371,9 @@ extern "C" int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const
   P.gamma_self = gamma;
   P.dstats_in = dstats;
   P.mask_in = relu_mask;
+  P.tsums_out = tsums_prev;
+  // the dz written here belongs to layer-1: parity classes if that is a stride-2 conv-transpose
+  P.tsum_mode = (layer >= 1 && kLayers[layer - 1].transposed && kLayers[layer - 1].stride == 2) ? 1 : 0;
   P.out_count = (double)B * L.h_in * L.h_in;
   P.B = B;
   P.H_in = P.W_in = ho;  // the gather reads the layer's OUTPUT-shaped gradient

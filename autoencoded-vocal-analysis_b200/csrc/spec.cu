@@ -34,8 +34,11 @@ struct SpecParams {
   double* out64;
 };
 
+// audio sample type: 0 int16, 1 float32, 2 float64 (the reference's stft runs in complex128 on
+// int16 / float64 audio; everything here is fp64)
 __device__ __forceinline__ double load_sample(const SpecParams& P, long long i) {
-  if (P.is_f32) return (double)reinterpret_cast<const float*>(P.audio)[i];
+  if (P.is_f32 == 2) return reinterpret_cast<const double*>(P.audio)[i];
+  if (P.is_f32 == 1) return (double)reinterpret_cast<const float*>(P.audio)[i];
   return (double)reinterpret_cast<const short*>(P.audio)[i];
 }
 
@@ -159,6 +162,110 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P) {
 }
 
 }  // namespace ava
+
+// ------------------------------------------------------------------ within_syll_normalize
+// ava/preprocessing/utils.py:106-109, per spectrogram (one CTA each, the m = n_f*n_t values in
+// shared memory):   spec -= np.quantile(spec, q); spec[spec < 0] = 0; spec /= spec.max() + 1e-12
+// np.quantile (method 'linear'): the two order statistics bracketing q*(m-1), found exactly by a
+// radix select over the bit patterns (the values are clipped to [0,1], so the IEEE-754 patterns
+// of the doubles are ordered like the values), combined with numpy's own lerp formula.
+namespace ava {
+__device__ double radix_select(const double* v, int m, int k, unsigned int* hist, unsigned long long* s_state) {
+  // returns the k-th smallest (0-based) of v[0..m); all threads of the CTA call this together
+  unsigned long long prefix = 0ull;   // high bits decided so far
+  int rank = k;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    const unsigned long long mask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const unsigned long long b = (unsigned long long)__double_as_longlong(v[i]);
+      if ((b & mask) == prefix) atomicAdd(&hist[(unsigned)((b >> shift) & 0xffull)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int r = rank, bin = 0;
+      for (; bin < 255; ++bin) {
+        if (r < (int)hist[bin]) break;
+        r -= (int)hist[bin];
+      }
+      s_state[0] = prefix | ((unsigned long long)bin << shift);
+      s_state[1] = (unsigned long long)r;
+    }
+    __syncthreads();
+    prefix = s_state[0];
+    rank = (int)s_state[1];
+    __syncthreads();
+  }
+  return __longlong_as_double((long long)prefix);
+}
+
+__global__ void __launch_bounds__(1024)
+quantile_normalize_kernel(double* __restrict__ spec64, float* __restrict__ spec32, int m, double q) {
+  extern __shared__ __align__(16) double qs[];
+  double* v = qs;                                                   // [m]
+  unsigned long long* s_state = reinterpret_cast<unsigned long long*>(v + m);   // [2]
+  double* s_max = reinterpret_cast<double*>(s_state + 2);           // [32]
+  unsigned int* hist = reinterpret_cast<unsigned int*>(s_max + 32);  // [256]
+  double* g64 = spec64 + (size_t)blockIdx.x * m;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    double x = g64[i];
+    v[i] = (x == 0.0) ? 0.0 : x;      // -0.0 -> +0.0 (bit-pattern order)
+  }
+  __syncthreads();
+  // numpy: virtual index q*(m-1), previous = floor, next = previous + 1 (clipped), gamma = fraction
+  const double pos = q * (double)(m - 1);
+  int lo = (int)floor(pos);
+  lo = lo < 0 ? 0 : (lo > m - 1 ? m - 1 : lo);
+  const int hi = (lo + 1 > m - 1) ? m - 1 : lo + 1;
+  const double t = pos - (double)lo;
+  const double a = radix_select(v, m, lo, hist, s_state);
+  const double b = radix_select(v, m, hi, hist, s_state);
+  // numpy.lib._function_base_impl._lerp: a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
+  const double diff = b - a;
+  double qv = (t >= 0.5) ? b - diff * (1.0 - t) : a + diff * t;
+  if (t == 0.0) qv = a;
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    double x = v[i] - qv;
+    if (x < 0.0) x = 0.0;
+    v[i] = x;
+    mx = fmax(mx, x);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, s_max[w]);
+  const double den = mx + 1e-12;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const double x = v[i] / den;
+    g64[i] = x;
+    if (spec32) spec32[(size_t)blockIdx.x * m + i] = (float)x;
+  }
+}
+}  // namespace ava
+
+extern "C" int ava_b200_quantile_normalize(double* spec64, float* spec32, int n, int m, double q, void* stream) {
+  using namespace ava;
+  AVA_REQUIRE(spec64 != nullptr && m >= 2 && m <= 24576, "quantile_normalize: m=%d (2..24576 values per spectrogram)", m);
+  AVA_REQUIRE(q >= 0.0 && q <= 1.0, "quantile_normalize: quantile %f outside [0,1]", q);
+  if (n <= 0) return 0;
+  const size_t smem = (size_t)m * 8 + 16 + 32 * 8 + 256 * 4;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(quantile_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess) {
+      cudaGetLastError();
+      set_error("quantile_normalize: %zu bytes of shared memory unavailable", smem);
+      return 1;
+    }
+    configured = smem;
+  }
+  quantile_normalize_kernel<<<n, 1024, smem, (cudaStream_t)stream>>>(spec64, spec32, m, q);
+  return check_launch("quantile_normalize");
+}
 
 // Target-time tables of a batch of fixed-duration windows, on the device.  Bit-for-bit the
 // float64 arithmetic of the host path (preprocessing/utils.py::bracket), which follows

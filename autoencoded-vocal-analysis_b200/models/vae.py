@@ -43,6 +43,9 @@ _CONVT = [("convt1", 32, 24, 1, 16), ("convt2", 24, 24, 2, 16), ("convt3", 24, 1
           ("convt7", 8, 1, 1, 128)]
 _LAYERS = _CONV + _CONVT           # layer id 0..13 of the C ABI
 _BN_MOMENTUM = 0.1
+# the backward-data kernels accumulate the border sums of the dz they write in their epilogue
+# (AVA_B200_FUSED_TSUMS=0: a separate ava_b200_dz_border_sums pass per layer instead)
+_FUSED_TSUMS = os.environ.get("AVA_B200_FUSED_TSUMS", "1") != "0"
 
 
 def _out_hw(layer):
@@ -413,8 +416,9 @@ class VAE(nn.Module):
 
     def _ws(self, nbytes):
         if self._scratch is None or self._scratch.numel() < nbytes:
-            # captured graphs point into the old scratch buffer: they go with it
-            self._graphs = {}
+            if self._scratch is not None:
+                # captured graphs point into the old scratch buffer: they go with it
+                self._graphs = {}
             self._scratch = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8,
                                         device=self._flat_p.device)
         return self._scratch
@@ -547,14 +551,15 @@ class VAE(nn.Module):
             cache[B] = self._scratch_bytes(B)
         return cache[B]
 
-    def _conv_bwd(self, l, bufs, dz, x, dz_prev):
+    def _conv_bwd(self, l, bufs, dz, x, dz_prev, have_tsums=False):
         """Backward of fused layer l given dz = the gradient w.r.t. its pre-activation output.
         (1) the nine border sums of dz; (2) weight / bias gradients into the flat gradient
         buffer AND this layer's BatchNorm-backward reductions dstats[l] (both from the same
         centred raw product, see include/ava_b200.h); (3) the data gradient, pushed through this
         layer's BatchNorm backward and the previous layer's ReLU in the kernel's epilogue, lands
         in dz_prev as the previous layer's dz -- the gradient w.r.t. the BatchNorm output never
-        goes to memory."""
+        goes to memory.  `have_tsums`: the kernel that wrote dz already accumulated its border
+        sums (step 1 is then skipped); returns whether that holds for dz_prev."""
         B = bufs.B
         name, _, co, stride, _ = _LAYERS[l]
         st, ds, ts = bufs.stats.data_ptr(), bufs.dstats.data_ptr(), bufs.tsums.data_ptr()
@@ -562,15 +567,21 @@ class VAE(nn.Module):
         ho = _out_hw(l)
         mode = 1 if (l >= 7 and stride == 2) else 0
         gamma, beta = self._p("bn%d.weight" % (l + 1)), self._p("bn%d.bias" % (l + 1))
-        call("ava_b200_dz_border_sums", ptr(dz), B, co, ho, ho, mode, ts + 8 * 288 * l, s)
+        if not have_tsums:
+            call("ava_b200_dz_border_sums", ptr(dz), B, co, ho, ho, mode, ts + 8 * 288 * l, s)
         ws = self._ws(self._scratch_need)
         _set_conv_precision(self._tc)
         call("ava_b200_bnconv_bwd_weight", l, B, ptr(dz), ptr(x), self._p(name + ".weight"), gamma, beta,
              st + 8 * 64 * l, ts + 8 * 288 * l, self._g(name + ".weight"), self._g(name + ".bias"),
              ds + 8 * 64 * l, ptr(ws), s)
         if dz_prev is not None:
+            # the epilogue also accumulates the border sums of the dz it writes (layer l-1's)
+            fuse = _FUSED_TSUMS and l >= 1 and l != 7
             call("ava_b200_bnconv_bwd_data", l, B, ptr(dz), self._p(name + ".weight"), ptr(x), gamma,
-                 st + 8 * 64 * l, ds + 8 * 64 * l, 1, ptr(dz_prev), s)
+                 st + 8 * 64 * l, ds + 8 * 64 * l, 1, ptr(dz_prev),
+                 (ts + 8 * 288 * (l - 1)) if fuse else None, s)
+            return fuse
+        return False
 
     def _backward_native(self, bufs, after_decoder=None, after_dense=None):
         """Backward of the whole loss; leaves every parameter gradient in the flat
@@ -582,10 +593,11 @@ class VAE(nn.Module):
         g_cur, g_nxt = bufs.g[0], bufs.g[1]      # g[0] holds dL/dx_rec = convt7's dz (recon kernel)
         # ---- decoder conv stack, layers 13..7; layer 7 writes the gradient w.r.t. fc8's
         # pre-activation output (bn8 backward + fc8's ReLU) straight into dt8
+        have = False
         for l in range(13, 6, -1):
             xin = bufs.act[l - 1] if l > 7 else bufs.t8
             out = g_nxt if l > 7 else bufs.dt8
-            self._conv_bwd(l, bufs, g_cur, xin, out)
+            have = self._conv_bwd(l, bufs, g_cur, xin, out, have)
             g_cur, g_nxt = g_nxt, g_cur
         # ---- decoder dense layers
         self._linear_bwd(bufs.dt8, 8192, None, bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.dt7, 1024,
@@ -620,10 +632,11 @@ class VAE(nn.Module):
         # ---- encoder conv stack, layers 6..0 (layer 0 needs no data gradient)
         g_cur = bufs.da6
         free = [bufs.g[0], bufs.g[1]]
+        have = False
         for l in range(6, -1, -1):
             xin = bufs.act[l - 1] if l > 0 else x
             out = free[0] if l > 0 else None
-            self._conv_bwd(l, bufs, g_cur, xin, out)
+            have = self._conv_bwd(l, bufs, g_cur, xin, out, have)
             g_cur, free = out, [free[1], free[0]]
         # ---- BatchNorm affine parameter gradients for all 14 layers
         st, ds = bufs.stats.data_ptr(), bufs.dstats.data_ptr()
@@ -740,12 +753,16 @@ class VAE(nn.Module):
         return self
 
     def _grad_buckets(self):
-        """(early, late) slices of the flat gradient buffer.  `early` = fc5..convt7 (the
-        decoder, ~36 MB incl. fc8.weight) is complete after the decoder half of the
-        backward pass, so its all-reduce overlaps the encoder backward; `late` = the rest."""
-        a0 = self._off["fc5.weight"]
-        a1 = self._off["bn1.weight"]
-        return [(a0, a1)], [(0, a0), (a1, self._n_flat)]
+        """(early, mid, late) slices of the flat gradient buffer, in the order the backward pass
+        completes them:
+        `early` = fc5..fc8 + convt1..7 (36 MB incl. fc8.weight), final after the decoder half;
+        `mid`   = fc1..fc43 (34 MB incl. fc1.weight), final after the encoder's dense layers --
+                  its all-reduce overlaps the encoder conv backward (a third of the backward);
+        `late`  = conv1..7 and the 14 BatchNorm affine pairs (0.1 MB), final at the very end."""
+        a0 = self._off["fc1.weight"]
+        a1 = self._off["fc5.weight"]
+        a2 = self._off["bn1.weight"]
+        return [(a1, a2)], [(a0, a1)], [(0, a0), (a2, self._n_flat)]
 
     def _allreduce(self, slices, async_op):
         import torch.distributed as dist
@@ -766,8 +783,10 @@ class VAE(nn.Module):
             0.5 * X_DIM * math.log(2 * math.pi / self.model_precision)
 
     def _graph_wanted(self, B):
-        if self._dp_world > 1 or self._flat_p.device.type != "cuda":
+        if self._flat_p.device.type != "cuda":
             return False
+        if self._dp_world > 1 and os.environ.get("AVA_B200_DP_GRAPHS", "1") == "0":
+            return False    # (NCCL collectives are captured with the step; opt-out switch)
         if self.cuda_graphs == 'auto':
             return True     # measured: 1.41 vs 1.68 ms at batch 64, 8.13 vs 8.46 ms at batch 1024
         return bool(self.cuda_graphs)
@@ -840,8 +859,8 @@ class VAE(nn.Module):
         if self._dp_world <= 1:
             raise ValueError("train_step: empty batch")
         self._flat_g.zero_()
-        early, late = self._grad_buckets()
-        for w in self._allreduce(early, async_op=True) + self._allreduce(late, async_op=True):
+        early, mid, late = self._grad_buckets()
+        for w in self._allreduce(early + mid + late, async_op=True):
             w.wait()
         self._adam_native()
         self._loss_sum += self.loss_constant()
@@ -850,10 +869,11 @@ class VAE(nn.Module):
     def _train_step_eager(self, x, noise):
         bufs = self._forward_native(x, noise, True, want_grad_seed=True)
         if self._dp_world > 1:
-            early, late = self._grad_buckets()
+            early, mid, late = self._grad_buckets()
             works = []
-            self._backward_native(bufs, after_decoder=lambda: works.extend(
-                self._allreduce(early, async_op=True)))
+            self._backward_native(
+                bufs, after_decoder=lambda: works.extend(self._allreduce(early, async_op=True)),
+                after_dense=lambda: works.extend(self._allreduce(mid, async_op=True)))
             works += self._allreduce(late, async_op=True)
             for w in works:
                 w.wait()

@@ -20,6 +20,7 @@ import torch
 from torch.utils.data import Dataset
 
 from ..preprocessing.utils import SpecEngine
+from ..preprocessing.utils import get_spec as _builtin_get_spec
 from .utils import _get_wavs_from_dir, _require_h5py, numpy_to_tensor  # noqa: F401
 
 DEFAULT_WARP_PARAMS = {
@@ -31,6 +32,18 @@ DEFAULT_WARP_PARAMS = {
 """Default time-warping parameters sent to affinewarp"""
 
 EPSILON = 1e-9
+
+
+def _foreign_get_spec(p):
+    """The user's spectrogram function if ``p['get_spec']`` (the reference's plugin point,
+    ava/models/window_vae_dataset.py:233-235,629-631) is anything other than this package's or
+    the reference's own ``get_spec``; None if the batched GPU engine computes the same thing."""
+    fn = p.get('get_spec', None) if isinstance(p, dict) else None
+    if fn is None or fn is _builtin_get_spec:
+        return None
+    if getattr(fn, "__module__", "") == "ava.preprocessing.utils" and getattr(fn, "__name__", "") == "get_spec":
+        return None
+    return fn
 
 
 def _read_wav(fn):
@@ -180,6 +193,20 @@ class FixedWindowDataset(Dataset):
     def _specs(self, files, onsets, shoulder):
         wl = self.p['window_length']
         offsets = onsets + wl
+        plugin = _foreign_get_spec(self.p)
+        if plugin is not None:
+            # a user-supplied spectrogram function: call it exactly as the reference does, one
+            # window at a time on the host (window_vae_dataset.py:229-235); windows it flags as
+            # invalid come back as NaN rows and are dropped by `sample`
+            specs = []
+            for f, on, off in zip(files, onsets, offsets):
+                tt = np.linspace(on, off, self.p['num_time_bins'])
+                spec, flag = plugin(max(0.0, on - shoulder), off + shoulder, self.audio[f], self.p,
+                                    fs=self.fs, target_times=tt)
+                spec = np.asarray(spec, dtype=np.float32)
+                specs.append(spec if flag else np.full_like(spec, np.nan))
+            dev = self._device if self._device is not None else torch.device("cuda", torch.cuda.current_device())
+            return torch.from_numpy(np.stack(specs)).to(dev)
         # target_times = np.linspace(onset, offset, num_time_bins), built on the device
         return self._engine.specs_linspace(files, np.maximum(0.0, onsets - shoulder), offsets + shoulder,
                                            onsets, offsets)
@@ -198,8 +225,13 @@ class FixedWindowDataset(Dataset):
         while need > 0:
             files, onsets = self._draw(need)
             specs = self._specs(files, onsets, shoulder)
+            keep = None
+            if _foreign_get_spec(self.p) is not None:
+                keep = ~torch.isnan(specs[:, 0, 0])           # the plugin's `flag` (:236-237)
             if self.min_spec_val is not None:
-                keep = (specs.amax(dim=(1, 2)) >= self.min_spec_val)
+                loud = specs.amax(dim=(1, 2)) >= self.min_spec_val
+                keep = loud if keep is None else (keep & loud)
+            if keep is not None:
                 keep_h = keep.cpu().numpy()
                 if not keep_h.all():
                     specs, files, onsets = specs[keep], files[keep_h], onsets[keep_h]
@@ -378,6 +410,14 @@ class WarpedWindowDataset(Dataset):
 
     def sample(self, n, seed=None):
         files, tts = self._draw(n, seed)
+        plugin = _foreign_get_spec(self.p)
+        if plugin is not None:
+            # user-supplied spectrogram function, called as the reference does (:629-631)
+            specs = [np.asarray(plugin(0.0, self.template_dur, self.audio[f], self.p, fs=self.fs,
+                                       max_dur=None, target_times=tt)[0], dtype=np.float32)
+                     for f, tt in zip(files, tts)]
+            dev = self._device if self._device is not None else torch.device("cuda", torch.cuda.current_device())
+            return torch.from_numpy(np.stack(specs)).to(dev), files
         t1 = np.zeros(n)
         t2 = np.full(n, self.template_dur)
         return self._engine.specs(files, t1, t2, tts), files

@@ -153,25 +153,12 @@ def _syll_specs_batched(onsets, offsets, audio, fs, p, target_freqs):
     audio = np.asarray(audio)
     if audio.ndim > 1:
         raise ValueError("mono audio expected (the reference slices a 1-D array)")
-    if audio.dtype != np.int16:
-        audio = audio.astype(np.float32)
     eng = SpecEngine([audio], fs, p)
+    # (within_syll_normalize, when set, is applied on the device by the engine)
     _, spec64 = eng.specs(np.zeros(n, dtype=np.int64), onsets, offsets, target_times,
                           target_freqs=target_freqs, want_float64=True)
     out = spec64.cpu().numpy()
-    specs = []
-    for i in range(n):
-        spec = out[i]
-        if p['within_syll_normalize']:
-            # a 16,384-element quantile per spectrogram on an already downloaded result; every
-            # shipped configuration disables it
-            nonzero = spec.any()
-            if nonzero:
-                spec = spec - np.quantile(spec, p['normalize_quantile'])
-                spec[spec < 0.0] = 0.0
-                spec /= np.max(spec) + EPSILON
-        specs.append(spec)
-    return specs, list(range(n))
+    return [out[i] for i in range(n)], list(range(n))
 
 
 def get_audio_seg_filenames(audio_dir, segment_dir, p):

@@ -11,6 +11,9 @@ indices -- with the same numpy expressions, so in/out-of-range decisions are bit
 ``SpecEngine`` is the batched form used by the datasets: audio stays resident in HBM and a
 whole batch of windows is one kernel launch writing ``[n, 128, 128]`` fp32 in place.
 
+``within_syll_normalize`` (the per-spectrogram quantile normalisation) also runs on the device
+(``ava_b200_quantile_normalize``), in the single-segment and the batched path alike.
+
 No CPU fallback: without a CUDA device / the native library these functions raise.
 """
 import warnings
@@ -113,9 +116,16 @@ class SpecEngine:
             torch.device("cuda", torch.cuda.current_device())
         self.fs = fs
         self.p = p
-        kinds = {np.asarray(a).dtype.kind for a in audio}
-        self.is_f32 = not (kinds <= {'i'} and all(np.asarray(a).dtype == np.int16 for a in audio))
-        dt = np.float32 if self.is_f32 else np.int16
+        # sample type on the device: int16 as is; float32 as is; anything else (float64, wider
+        # integers) as float64 -- the reference's scipy stft runs in complex128 on all of these
+        # and in complex64 only on float32 audio (the kernel computes in fp64 throughout)
+        dtypes = {np.asarray(a).dtype for a in audio}
+        if dtypes <= {np.dtype(np.int16)}:
+            self.is_f32, dt = 0, np.int16
+        elif dtypes <= {np.dtype(np.float32)}:
+            self.is_f32, dt = 1, np.float32
+        else:
+            self.is_f32, dt = 2, np.float64
         self.lengths = np.array([len(a) for a in audio], dtype=np.int64)
         self.offsets = np.concatenate([[0], np.cumsum(self.lengths)[:-1]]).astype(np.int64)
         flat = np.concatenate([np.asarray(a).astype(dt, copy=False) for a in audio]) if len(audio) \
@@ -171,14 +181,26 @@ class SpecEngine:
         if out is None:
             out = torch.empty(n, n_f, n_t, dtype=torch.float32, device=dev)
         out64 = torch.empty(n, n_f, n_t, dtype=torch.float64, device=dev) if want_float64 else None
-        call("ava_b200_get_spec_batch", self.audio_dev.data_ptr(), 1 if self.is_f32 else 0,
+        normalize = bool(p.get('within_syll_normalize', False))
+        if normalize and out64 is None:
+            out64 = torch.empty(n, n_f, n_t, dtype=torch.float64, device=dev)
+        call("ava_b200_get_spec_batch", self.audio_dev.data_ptr(), int(self.is_f32),
              seg_start.data_ptr(), seg_len_d.data_ptr(), n, self.nperseg, self.noverlap,
              1 if remove_dc_offset else 0, self.window_dev.data_ptr(), self.scale,
              t_idx_d.data_ptr(), t_frac_d.data_ptr(), n_t, f_idx_dev.data_ptr(),
              f_frac_dev.data_ptr(), n_f, kmax + 1, float(p['spec_min_val']), float(p['spec_max_val']),
              out.data_ptr(), out64.data_ptr() if out64 is not None else None,
              torch.cuda.current_stream().cuda_stream)
+        if normalize:
+            self._normalize(out64, out)
         return (out, out64) if want_float64 else out
+
+    def _normalize(self, out64, out32):
+        """within_syll_normalize (ava/preprocessing/utils.py:106-109) on the device, in float64."""
+        n = out64.shape[0]
+        call("ava_b200_quantile_normalize", out64.data_ptr(), out32.data_ptr() if out32 is not None else None,
+             n, int(out64.shape[1] * out64.shape[2]), float(self.p['normalize_quantile']),
+             torch.cuda.current_stream().cuda_stream)
 
     def specs(self, file_index, t1, t2, target_times, target_freqs=None, remove_dc_offset=True,
               out=None, want_float64=False):
@@ -314,26 +336,18 @@ def get_spec(t1, t2, audio, p, fs=32000, target_freqs=None, target_times=None,
     # upload only the segment (indices shifted so that the segment starts at sample 0)
     lo, hi = max(0, s1), min(len(audio), s2)
     seg = audio[lo:hi]
-    if seg.dtype != np.int16:
-        seg = seg.astype(np.float32)
     eng = SpecEngine([seg], fs, p)
-    spec32, spec64 = eng._specs_shifted(t1, t2, lo, hi - lo, target_times, target_freqs,
-                                        remove_dc_offset)
-    spec = spec64[0].cpu().numpy()
+    fv = None
     if fill_value != -1 / EPSILON:
-        # non-default fill value: patch the out-of-range rows/columns on the host
-        fv = np.clip((fill_value - p['spec_min_val']) / (p['spec_max_val'] - p['spec_min_val']),
-                     0.0, 1.0)
-        spec[:, eng._last_bad_t] = fv
-        spec[eng._last_bad_f, :] = fv
-    if p['within_syll_normalize']:
-        spec -= np.quantile(spec, p['normalize_quantile'])
-        spec[spec < 0.0] = 0.0
-        spec /= np.max(spec) + EPSILON
-    return spec, True
+        # non-default fill value: out-of-range rows / columns take its normalised, clipped value
+        fv = float(np.clip((fill_value - p['spec_min_val']) / (p['spec_max_val'] - p['spec_min_val']),
+                           0.0, 1.0))
+    spec32, spec64 = eng._specs_shifted(t1, t2, lo, hi - lo, target_times, target_freqs,
+                                        remove_dc_offset, fill=fv)
+    return spec64[0].cpu().numpy(), True
 
 
-def _specs_shifted(self, t1, t2, seg_lo, seg_len, target_times, target_freqs, remove_dc_offset):
+def _specs_shifted(self, t1, t2, seg_lo, seg_len, target_times, target_freqs, remove_dc_offset, fill=None):
     """One segment whose samples [seg_lo, seg_lo+seg_len) of the original file were uploaded
     as samples [0, seg_len): same tables as `specs`, indices relative to the upload."""
     p, fs = self.p, self.fs
@@ -354,12 +368,20 @@ def _specs_shifted(self, t1, t2, seg_lo, seg_len, target_times, target_freqs, re
     t_frac_d = torch.from_numpy(np.ascontiguousarray(t_frac)).to(dev)
     out = torch.empty(1, n_f, n_t, dtype=torch.float32, device=dev)
     out64 = torch.empty(1, n_f, n_t, dtype=torch.float64, device=dev)
-    call("ava_b200_get_spec_batch", self.audio_dev.data_ptr(), 1 if self.is_f32 else 0,
+    call("ava_b200_get_spec_batch", self.audio_dev.data_ptr(), int(self.is_f32),
          seg_start.data_ptr(), seg_len_d.data_ptr(), 1, self.nperseg, self.noverlap,
          1 if remove_dc_offset else 0, self.window_dev.data_ptr(), self.scale, t_idx_d.data_ptr(),
          t_frac_d.data_ptr(), n_t, f_idx_dev.data_ptr(), f_frac_dev.data_ptr(), n_f, kmax + 1,
          float(p['spec_min_val']), float(p['spec_max_val']), out.data_ptr(), out64.data_ptr(),
          torch.cuda.current_stream().cuda_stream)
+    if fill is not None:
+        bad_t = torch.from_numpy(self._last_bad_t).to(dev)
+        bad_f = torch.from_numpy(self._last_bad_f).to(dev)
+        for o in (out, out64):
+            o[0][:, bad_t] = fill
+            o[0][bad_f, :] = fill
+    if p.get('within_syll_normalize', False):
+        self._normalize(out64, out)
     torch.cuda.current_stream().synchronize()
     return out, out64
 

@@ -200,10 +200,13 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_train_samples_per_sec(batch, steps, warmup, seed=0):
-    """The oracle's restatement of the reference train step on the host CPU."""
+def cpu_train_samples_per_sec(batch, steps, warmup, seed=0, threads=None):
+    """The oracle's restatement of the reference train step on the host CPU, on `threads`
+    host threads (default: all cores -- torchrun exports OMP_NUM_THREADS=1, which is overridden
+    here so that the figure is the box's, not one core's)."""
     import torch
     from oracle import vae_oracle
+    torch.set_num_threads(threads if threads else (os.cpu_count() or 1))
     torch.manual_seed(seed)
     P = vae_oracle.make_params(seed)
     keys = [k for k, _ in vae_oracle.param_order()]
@@ -233,23 +236,214 @@ def make_config(B, world, precision, graphs=None):
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's train step (its arithmetic restated in
+    oracle/vae_oracle.py; the reference itself needs h5py/affinewarp/matplotlib at import and is
+    not installable here) on the host CPU with all cores, on the SAME workload as our arm: one
+    step = one optimizer step on a batch of `--batch` spectrograms.  If the box is too slow for
+    K+W such steps to finish in ~4 minutes, the per-step batch is halved until they do and the
+    line says so (`config.reference_sample_batch`); samples/s on the CPU is flat in the batch
+    size, so the figure stays comparable."""
     if rank != 0:
         return
-    sample_batch = 64
-    v, ms, cores = cpu_train_samples_per_sec(sample_batch, args.steps, args.warmup)
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = args.batch
+    budget_s = 240.0
+    v1, ms1, cores = cpu_train_samples_per_sec(64, 1, 1)      # probe: one batch-64 step
+    est = (ms1 * 1e-3) * (sample / 64.0) * (args.steps + args.warmup)
+    while est > budget_s and sample > 64:
+        sample //= 2
+        est /= 2
+    v, ms, cores = cpu_train_samples_per_sec(sample, args.steps, args.warmup)
+    cfg = make_config(args.batch, max(world, 1), args.precision)
+    cfg["reference_sample_batch"] = sample
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": make_config(args.batch, max(world, 1), args.precision),
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d train steps of a %d-spectrogram sample of the batch (the "
-                                   "reference's arithmetic restated in oracle/vae_oracle.py, torch CPU, "
-                                   "%d threads); samples/s does not depend on the batch size on CPU"
-                                   % (args.steps, sample_batch, cores)},
+                         "sample": "%d timed train steps (after %d warm-up) of batch %d%s: the reference's "
+                                   "arithmetic restated in oracle/vae_oracle.py, torch CPU, %d threads"
+                                   % (args.steps, args.warmup, sample,
+                                      "" if sample == args.batch else " (a sample of the %d-batch; the full "
+                                      "batch would not finish in the time budget)" % args.batch, cores)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def dp_check(model, vae_mod, dist, world, rank):
+    """Numerical equivalence of the data-parallel step ON THE GPUS, before anything is timed
+    (SURVEY section 4 test 9).  (a) every rank runs the same batch and noise: the all-reduced flat
+    gradient must equal world x the local one.  (b) distinct shards: the all-reduced gradient and
+    loss must equal what rank 0 gets by pushing every rank's shard through the model itself and
+    summing (local-BatchNorm semantics: each rank == the reference on its shard; the loss is a
+    batch SUM, so gradients add).  Parameters are untouched (no optimizer step); the BatchNorm
+    running buffers are restored afterwards."""
+    import torch
+    Bc = 64
+    keep_run, keep_nbt = model._flat_run.clone(), model._nbt.clone()
+    gen = torch.Generator(device="cuda")
+    res = {}
+
+    def fwd_bwd(x, ew, ed, reduce):
+        bufs = model._forward_native(x, (ew, ed), True, want_grad_seed=True)
+        model._backward_native(bufs)
+        if reduce:
+            early, mid, late = model._grad_buckets()
+            for w in model._allreduce(early + mid + late, async_op=True):
+                w.wait()
+        return bufs.loss.clone()
+
+    def draw(seed):
+        gen.manual_seed(seed)
+        return (torch.rand(Bc, 128, 128, device="cuda", generator=gen),
+                torch.randn(Bc, 1, device="cuda", generator=gen),
+                torch.randn(Bc, 32, device="cuda", generator=gen))
+    # (a) same batch everywhere
+    x, ew, ed = draw(777)
+    fwd_bwd(x, ew, ed, False)
+    g_local = model._flat_g.clone()
+    fwd_bwd(x, ew, ed, True)
+    den = float(g_local.abs().max()) * world
+    res["same_batch_max_rel_err"] = float((model._flat_g - world * g_local).abs().max()) / den
+    # (b) distinct shards vs rank 0's own recomputation of every shard
+    x, ew, ed = draw(1000 + rank)
+    loss = fwd_bwd(x, ew, ed, True)
+    g_dp = model._flat_g.clone()
+    dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+    shards = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(shards, x)
+    g_sum = torch.zeros_like(g_dp, dtype=torch.float64)
+    loss_sum = 0.0
+    for r in range(world):
+        xr, ewr, edr = draw(1000 + r)
+        assert torch.equal(xr, shards[r]), "dp_check: rank %d's shard differs from its seed" % r
+        loss_sum += float(fwd_bwd(xr, ewr, edr, False))
+        g_sum += model._flat_g.double()
+    den = float(g_sum.abs().max())
+    res["sharded_grad_max_rel_err"] = float((g_dp.double() - g_sum).abs().max()) / den
+    res["sharded_loss_rel_err"] = abs(float(loss) - loss_sum) / abs(loss_sum)
+    res["ok"] = bool(res["same_batch_max_rel_err"] < 1e-5 and res["sharded_grad_max_rel_err"] < 1e-5 and
+                     res["sharded_loss_rel_err"] < 1e-6)
+    res["what"] = ("batch %d per rank; (a) same batch on every rank: all-reduced gradient vs world x local; "
+                   "(b) distinct shards: all-reduced gradient / loss vs this rank's recomputation of all %d "
+                   "shards summed" % (Bc, world))
+    model._flat_run.copy_(keep_run)
+    model._nbt.copy_(keep_nbt)
+    return res
+
+
+FINCH_P = {  # examples/finch_window_mwe.py:29-49 (the shotgun VAE's preprocessing parameters)
+    'fs': 32000, 'num_freq_bins': 128, 'num_time_bins': 128, 'nperseg': 512, 'noverlap': 256,
+    'max_dur': 1e9, 'window_length': 0.12, 'min_freq': 400, 'max_freq': 10e3, 'spec_min_val': 2.0,
+    'spec_max_val': 6.5, 'mel': True, 'time_stretch': False, 'within_syll_normalize': False,
+}
+
+
+def extra_get_latent(model, torch, dist, world, rank, n_total, B, peak):
+    """BASELINE configs[4] / SURVEY 8(d) config 5: get_latent-style projection of `n_total`
+    synthetic spectrograms sharded over the ranks in contiguous blocks, no collective on the data
+    path.  Chunks are generated ON THE DEVICE inside the timed region (torch.rand, generator seeded
+    per chunk: the corpus is never materialised -- 10 M specs would be 655 GB), encoded with
+    eval-mode BatchNorm (stated; the reference's train-mode quirk F8 is covered by the parity
+    tests), the latent means stay on the device and are downloaded once per rank, widened to
+    float64 and gathered on rank 0's host as [n_total, 32]."""
+    import numpy as np
+    lo = (n_total * rank) // world
+    hi = (n_total * (rank + 1)) // world
+    n_mine = hi - lo
+    model.eval()
+    gen = torch.Generator(device="cuda")
+    xbuf = torch.empty(B, 128, 128, device="cuda")
+    lat = torch.empty(n_mine, model.z_dim, device="cuda")
+
+    def run(n):
+        done = 0
+        with torch.no_grad():
+            while done < n:
+                b = min(B, n - done)
+                gen.manual_seed(lo + done)
+                xb = xbuf[:b]
+                xb.uniform_(generator=gen)
+                bufs = model._buffers_for(b)
+                model._cur = bufs
+                model._scratch_need = model._scratch_need_for(b)
+                model._encode_native(xb, bufs, False)
+                lat[done:done + b].copy_(bufs.heads[:, :model.z_dim])
+                done += b
+    run(min(n_mine, 4 * B))                        # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(n_mine)
+    e1.record()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    host = lat.cpu().numpy().astype(np.float64)
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(host, gathered, dst=0)
+        if rank == 0:
+            host = np.concatenate(gathered)
+    t_gather = time.perf_counter() - t0
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    model.train()
+    if rank != 0:
+        return None
+    assert host.shape == (n_total, model.z_dim) and np.isfinite(host).all()
+    sps = n_total / (ms * 1e-3)
+    return {"workload": "get_latent: %d synthetic specs generated on device in chunks of %d, sharded in "
+                        "contiguous blocks over %d GPU(s), eval-mode BatchNorm, no collective on the data "
+                        "path" % (n_total, B, world),
+            "specs_per_s": sps, "device_ms": ms, "n_gpus": world,
+            "hbm_frac_layer_granular": round(2.36e6 * sps / world / 1e9 / peak, 4),
+            "algorithmic_bytes_per_spec": 2.36e6,
+            "host_gather_s": round(t_gather, 3), "output": "float64 [%d, %d] on rank 0's host" % host.shape}
+
+
+def extra_shotgun(model, torch, vae_mod, steps):
+    """BASELINE configs[3] / SURVEY 8(d) config 4: synthetic corpus of 16 files x 600 s int16 audio
+    @ 32 kHz, 2 ROIs per file, finch parameters; windows are sampled on the host with numpy's
+    legacy RNG (bit-exact indices) and turned into 128x128 spectrograms by ONE launch of the GPU
+    get_spec kernel per batch, feeding the train step.  "Training never waits" <=> the rate with
+    on-the-fly windows equals the rate of the same step on a resident batch."""
+    import numpy as np
+    win_mod = importlib.import_module(PKG + ".models.window_vae_dataset")
+    rng = np.random.default_rng(0)
+    fs, n_files, dur = FINCH_P['fs'], 16, 600.0
+    audio = [(3000 * rng.standard_normal(int(dur * fs), dtype=np.float32)).astype(np.int16)
+             for _ in range(n_files)]
+    rois = [np.array([[1.0, 250.0], [300.0, 598.0]]) for _ in range(n_files)]
+    ds = win_mod.FixedWindowDataset(["f%02d.wav" % k for k in range(n_files)], None, dict(FINCH_P),
+                                    audio=audio, fs=fs, rois=rois)
+    out = {"workload": "shotgun VAE: random 0.12 s windows of 16 x 600 s synthetic int16 audio, finch "
+                       "parameters, GPU get_spec on the fly"}
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / iters
+    for nb in (128, 1024):
+        x = ds.sample_batch(nb)
+        t_res = timed(lambda: model.train_step(x), steps)
+        t_fly = timed(lambda: model.train_step(ds.sample_batch(nb)), steps)
+        t_win = timed(lambda: ds.sample_batch(nb), steps)
+        out["batch_%d" % nb] = {"train_samples_per_s_on_the_fly": nb / t_fly,
+                                "train_samples_per_s_resident_batch": nb / t_res,
+                                "ratio": t_res / t_fly, "windows_per_s_sampler_plus_get_spec": nb / t_win}
+    return out
 
 
 def main():
@@ -263,6 +457,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--all-kernels", action="store_true", help="list every native call, not the top 12")
+    ap.add_argument("--no-extra", action="store_true", help="skip the get_latent / shotgun blocks")
+    ap.add_argument("--latent-specs", type=int, default=10_000_000,
+                    help="corpus size of the get_latent block (BASELINE configs[4]: 10 M)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -290,8 +487,11 @@ def main():
     # the public default (the whole step replayed as a CUDA graph when not data parallel) for the
     # `value` and `e2e` loops; eager launches for the per-call event profile
     model = vae_mod.VAE(save_dir='', device_name='cuda', precision=args.precision)
+    dp = None
     if world > 1:
         model.enable_data_parallel()
+        model.train()
+        dp = dp_check(model, vae_mod, dist, world, rank)
     model.train()
     # two resident synthetic batches (alternated) + pinned host copies for the e2e leg
     xs = [torch.rand(B, 128, 128, device="cuda") for _ in range(2)]
@@ -380,6 +580,20 @@ def main():
 
     sampler.stop_flag = True      # sampled through both timed regions (device-resident and e2e)
     sampler.join(timeout=2)
+    # ---------------------------------------------------------------- the other BASELINE configs
+    extra = {}
+    if not args.no_extra:
+        peak_x, _ = measured_peaks()
+        lat_model = vae_mod.VAE(save_dir='', device_name='cuda', precision=args.precision)
+        r = extra_get_latent(lat_model, torch, dist, world, rank, args.latent_specs, 1024, peak_x)
+        if r is not None:
+            extra["get_latent"] = r
+        del lat_model
+        if world == 1:
+            sg_model = vae_mod.VAE(save_dir='', device_name='cuda', precision=args.precision)
+            sg_model.train()
+            extra["shotgun"] = extra_shotgun(sg_model, torch, vae_mod, 10)
+            del sg_model
     if rank == 0:
         peak, peak_src = measured_peaks()
         roof, kernels, families = None, [], []
@@ -426,10 +640,14 @@ def main():
                     "share_of_step": round(d["ms"] / tot, 4)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, ms, cores = cpu_train_samples_per_sec(64, 3, 1)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "3 train steps of batch 64 after 1 warm-up (oracle/vae_oracle.py, "
-                             "torch CPU, %d threads)" % cores}
+            # batch 64, >= 3 warm-up and >= 10 timed steps on all host cores,
+            # plus a 1-thread figure (about 15 s of CPU work in total)
+            v, ms, cores = cpu_train_samples_per_sec(64, 10, 3)
+            v1, _, _ = cpu_train_samples_per_sec(64, 3, 1, threads=1)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "value_1_thread": v1,
+                   "sample": "10 train steps of batch 64 after 3 warm-up (the reference's arithmetic "
+                             "restated in oracle/vae_oracle.py, torch CPU, %d threads); value_1_thread: 3 "
+                             "steps after 1 warm-up on one thread" % cores}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "profiled_ms_per_step": ms_prof,
@@ -449,6 +667,8 @@ def main():
             "kernel_families": families,
             "kernels": kernels,
             "cpu_baseline": cpu,
+            "dp_check": dp,
+            "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:

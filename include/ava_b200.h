@@ -113,10 +113,12 @@ int ava_b200_bnconv_bwd_weight(int layer, int B, const float* dz, const float* x
                                void* stream);
 long long ava_b200_bnconv_bwd_weight_ws(int layer, int B);
 
-/* gamma == NULL: no BatchNorm backward (dz_prev = [x > 0] * g). */
+/* gamma == NULL: no BatchNorm backward (dz_prev = [x > 0] * g).
+ * tsums_prev (optional): the nine border sums of dz_prev -- layer-1's tsums block -- are accumulated
+ * in the epilogue, which saves step 1 (a full read of dz_prev) for layer-1. */
 int ava_b200_bnconv_bwd_data(int layer, int B, const float* dz, const float* w, const float* x,
                              const float* gamma, const double* stats_in, const double* dstats, int relu_mask,
-                             float* dz_prev, void* stream);
+                             float* dz_prev, double* tsums_prev, void* stream);
 
 /* BN backward finalisation: dgamma[c] = invstd*dstats[32+c], dbeta[c] = dstats[c]
  * for all 14 layers (dstats[32+c] holds sum g*(x-mean)). */
@@ -196,7 +198,7 @@ int ava_b200_adam_step_dev(float* p, const float* g, float* m, float* v, long lo
  * Batched spectrogram front end: ava/preprocessing/utils.py:18-110 (get_spec) with
  * scipy.signal.stft semantics (periodic Hann, zero boundary extension, zero padding to a
  * hop multiple, scale 1/sum(win)).  One CTA per window; computed in fp64.
- *   audio:      concatenated audio of all files on device, int16 (is_f32=0) or fp32
+ *   audio:      concatenated audio of all files on device: int16 (is_f32 = 0), fp32 (1) or fp64 (2)
  *   seg_start:  [n] first sample of each segment in `audio`
  *   seg_len:    [n] number of samples (0 => output zeros, the reference's
  *               "too short" branch, ava/preprocessing/utils.py:69-71)
@@ -213,6 +215,12 @@ int ava_b200_get_spec_batch(const void* audio, int is_f32, const long long* seg_
                             const int* t_idx, const double* t_frac, int n_t, const int* f_idx,
                             const double* f_frac, int n_f, int max_frames, double spec_min, double spec_max,
                             float* out, double* out64, void* stream);
+
+/* within_syll_normalize (ava/preprocessing/utils.py:106-109), per spectrogram of m = n_f*n_t values:
+ *   spec -= np.quantile(spec, q); spec[spec < 0] = 0; spec /= spec.max() + 1e-12
+ * in float64 on spec64 [n, m] in place (the quantile by an exact radix select + numpy's linear
+ * interpolation); spec32 (optional) receives the float32 copy. */
+int ava_b200_quantile_normalize(double* spec64, float* spec32, int n, int m, double q, void* stream);
 
 /* Target-time tables of a batch of fixed-duration windows computed on the device (the
  * shotgun path, ava/models/window_vae_dataset.py:231-235: target_times = linspace(onset,

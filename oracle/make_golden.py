@@ -607,11 +607,77 @@ def warped_case(ref_win, ref_pre):
     print("warped cases: template_dur", float(out["null:template_dur"]), float(out["knots:template_dur"]))
 
 
+def round2_cases(ref_win, ref_pre):
+    """Round-2 additions: float64 audio (the reference's complex128
+    STFT path), within_syll_normalize, and the silence-rejection loop with REAL rejections."""
+    from scipy.io import wavfile
+    out = {"versions": np.array(versions())}
+    # --- float64 audio, finch and mouse parameters
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    a64 = spec_oracle.synth_audio(21, int(2.0 * fs), fs, dtype=np.float64) / 7.0 + 0.123456789
+    assert a64.dtype == np.float64
+    for name, onset in [("f64_a", 0.7131), ("f64_b", 0.02)]:
+        tt = np.linspace(onset, onset + p['window_length'], 128)
+        spec, _ = ref_pre.get_spec(max(0.0, onset - 0.05), onset + p['window_length'] + 0.05, a64, p,
+                                   fs=fs, target_times=tt)
+        out[name] = spec
+        out[name + "_t"] = np.array([onset])
+    # --- within_syll_normalize (preprocessing/utils.py:106-109)
+    for q in (0.5, 0.87):
+        pn = dict(spec_oracle.MOUSE_P)
+        pn.update(within_syll_normalize=True, normalize_quantile=q)
+        fsm = pn['fs']
+        am = spec_oracle.synth_audio(11, int(0.6 * fsm), fsm)
+        spec, _ = ref_pre.get_spec(0.100, 0.180, am, pn, fs=fsm)
+        out["norm_q%02d" % int(100 * q)] = spec
+    pn = dict(spec_oracle.FINCH_P)
+    pn.update(within_syll_normalize=True, normalize_quantile=0.5)
+    a2 = spec_oracle.synth_audio(12, int(4.0 * fs), fs)
+    tt = np.linspace(1.2345, 1.2345 + pn['window_length'], 128)
+    spec, _ = ref_pre.get_spec(1.2345 - 0.05, 1.2345 + pn['window_length'] + 0.05, a2, pn, fs=fs,
+                               target_times=tt)
+    out["norm_finch"] = spec
+    # --- FixedWindowDataset with real rejections
+    calls = []
+    real = ref_pre.get_spec
+
+    def spy(*a, **k):
+        calls.append(1)
+        return real(*a, **k)
+    p = dict(spec_oracle.FINCH_P)
+    p['get_spec'] = spy
+    with tempfile.TemporaryDirectory() as tmp:
+        adir, rdir = os.path.join(tmp, "audio"), os.path.join(tmp, "rois")
+        os.mkdir(adir)
+        os.mkdir(rdir)
+        for i, nm in enumerate(["x_song", "y_song", "z_song"]):
+            wavfile.write(os.path.join(adir, nm + ".wav"), fs, spec_oracle.silent_half_audio(200 + i, fs))
+            np.savetxt(os.path.join(rdir, nm + ".txt"), np.array([[0.2, 2.8]]))
+        part = ref_win.get_window_partition([adir], [rdir], split=1.0)
+        ds = ref_win.FixedWindowDataset(part['train']['audio'], part['train']['rois'], p,
+                                        transform=None, min_spec_val=0.3)
+        for seed in (0, 3):
+            calls.clear()
+            specs, fidx, onsets, offsets = ds.__getitem__(np.arange(16), seed=seed, return_seg_info=True)
+            out["rej_seed%d_files" % seed] = np.array(fidx, dtype=np.int64)
+            out["rej_seed%d_onsets" % seed] = np.array(onsets, dtype=np.float64)
+            out["rej_seed%d_candidates" % seed] = np.array(len(calls))
+            assert len(calls) > 16, "no rejection happened"
+            assert all(np.max(sp) >= 0.3 for sp in specs)
+            if seed == 0:
+                out["rej_seed0_specs"] = np.stack(specs[:2]).astype(np.float64)
+        out["rej_audio_order"] = np.array([os.path.basename(f) for f in part['train']['audio']])
+    np.savez_compressed(os.path.join(GOLDEN, "round2_cases.npz"), **out)
+    print("round-2 cases: candidates", int(out["rej_seed0_candidates"]), int(out["rej_seed3_candidates"]))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
     ref_vae, ref_pre, ref_win, ref_ds = _ref_import.import_reference()
-    which = sys.argv[1:] or ["vae", "adam", "spec", "sampler", "process", "mmd", "container", "pca", "warped"]
+    which = sys.argv[1:] or ["vae", "adam", "spec", "sampler", "process", "mmd", "container", "pca", "warped",
+                             "round2"]
     if "vae" in which:
         vae_case(ref_vae, "vae_train_b7", seed=0, batch=7, train=True)
         vae_case(ref_vae, "vae_eval_b7", seed=1, batch=7, train=False)
@@ -633,6 +699,8 @@ def main():
         pca_case()
     if "warped" in which:
         warped_case(ref_win, ref_pre)
+    if "round2" in which:
+        round2_cases(ref_win, ref_pre)
 
 
 if __name__ == "__main__":

@@ -102,4 +102,10 @@ def masked_oracle_grads(P, x, eps_w, eps_d, prec, masks):
                                                    True, masks=masks)
     _, g32, _ = vae_oracle.loss_and_grads(P, x.float(), eps_w.float(), eps_d.float(), prec, True, masks=masks)
     err32 = {k: rel_err(g32[k].numpy(), g64[k].numpy()) for k in g64}
+    # how many units the float32 ORACLE's own (unforced) forward puts on the other side of a
+    # kink than the float64 one: the yardstick for the GPU's flip count
+    acts32 = {}
+    with torch.no_grad():
+        vae_oracle.forward(P, x.float(), eps_w.float(), eps_d.float(), prec, True, {}, acts32)
+    err32["__flips32__"] = sum(int(((acts32[n] > 0) != (acts[n] > 0)).sum()) for n in acts if n != "convt7")
     return out64, g64, bufs64, acts, err32

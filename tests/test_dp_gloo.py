@@ -36,13 +36,18 @@ def _worker(rank, world, port, tmp):
     dist.all_gather(ref, model._flat_p)
     assert torch.equal(ref[0], ref[1])
     # gradient buckets: SUM over ranks, every element reduced exactly once
-    early, late = model._grad_buckets()
+    early, mid, late = model._grad_buckets()
     covered = torch.zeros(model._n_flat, dtype=torch.int32)
-    for lo, hi in early + late:
+    for lo, hi in early + mid + late:
         covered[lo:hi] += 1
+    # each bucket holds exactly the parameters its point of the backward pass has completed
+    off = model._off
+    assert early == [(off["fc5.weight"], off["bn1.weight"])] and mid == [(off["fc1.weight"], off["fc5.weight"])]
+    assert off["fc43.bias"] < off["fc5.weight"] and off["conv7.bias"] < off["fc1.weight"]
     assert bool((covered == 1).all())
     model._flat_g.copy_(torch.arange(model._n_flat, dtype=torch.float32) % 97 + rank)
-    works = model._allreduce(early, async_op=True) + model._allreduce(late, async_op=True)
+    works = model._allreduce(early, async_op=True) + model._allreduce(mid, async_op=True) + \
+        model._allreduce(late, async_op=True)
     for w in works:
         w.wait()
     want = 2 * (torch.arange(model._n_flat, dtype=torch.float32) % 97) + 1

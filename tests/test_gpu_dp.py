@@ -1,0 +1,85 @@
+"""Data parallelism on real GPUs (needs >= 2 devices: `gpurun --gpus 2 -- python -m pytest
+tests/test_gpu_dp.py -m gpu`; skipped on a single-GPU box, where bench.py's `dp_check` -- the same
+routine, run by the driver before every multi-GPU timing -- is the evidence)."""
+import importlib
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+PKG = "autoencoded-vocal-analysis_b200"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import bench
+    from oracle import vae_oracle
+    vae_mod = importlib.import_module(PKG + ".models.vae")
+    torch.manual_seed(50 + rank)
+    model = vae_mod.VAE(save_dir='', device_name='cuda')
+    model.enable_data_parallel()
+    model.train()
+    # (1) summed rank gradients == the gradients of the shards pushed through one model
+    res = bench.dp_check(model, vae_mod, dist, world, rank)
+    assert res["ok"], res
+    # (2) the captured-graph step (NCCL all-reduces inside the graph) follows the eager step
+    losses = {}
+    for graphs in (True, False):
+        m = vae_mod.VAE(save_dir='', device_name='cuda', cuda_graphs=graphs)
+        m.load_flat_state(vae_oracle.make_params(3))
+        m.enable_data_parallel()
+        m.train()
+        out = []
+        for step in range(6):
+            x = vae_oracle.make_input(100 * rank + step, 16).cuda()
+            noise = tuple(t.cuda() for t in vae_oracle.make_noise(100 * rank + step, 16))
+            out.append(float(m.train_step(x, noise=noise)))
+        losses[graphs] = out
+        if graphs:
+            assert m._graphs[16]["graph"] is not None, "the data-parallel step was not captured"
+    for a, b in zip(losses[True], losses[False]):
+        assert abs(a - b) <= 2e-4 * abs(b), (losses[True], losses[False])
+    # (3) a rank with an empty shard still takes the step (zero gradients into the all-reduce)
+    m = vae_mod.VAE(save_dir='', device_name='cuda')
+    m.load_flat_state(vae_oracle.make_params(3))
+    m.enable_data_parallel()
+    m.train()
+    x = vae_oracle.make_input(7, 4).cuda()
+    noise = tuple(t.cuda() for t in vae_oracle.make_noise(7, 4))
+    if rank == 0:
+        m.train_step(x, noise=noise)
+    else:
+        m.train_step(x[:0])
+    ref = vae_mod.VAE(save_dir='', device_name='cuda')       # not data parallel: the whole batch on one GPU
+    ref.load_flat_state(vae_oracle.make_params(3))
+    ref.train()
+    ref.train_step(x, noise=noise)
+    torch.cuda.synchronize()
+    d = (m._flat_p - ref._flat_p).abs().max().item()
+    assert d <= 2.5e-3, d        # Adam's first step is sign-like: at most lr-sized flips of ~0 gradients
+    assert (m._flat_p - ref._flat_p).abs().mean().item() <= 1e-6
+    dist.destroy_process_group()
+
+
+def test_data_parallel_equivalence_on_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)

@@ -18,7 +18,8 @@ FWD_TOL = 1e-4        # forward quantities, fp32 kernels vs float64 reference (r
 
 
 GRAD_TOL = 1e-4       # parameter gradients vs the float64 oracle ON THE SAME ReLU PATTERN (rtol 1e-4)
-MAX_FLIPS = 16        # units (of ~1.9 M per sample) allowed to sit on the other side of zero
+MAX_FLIPS = 16        # units (of ~1.9 M per sample) allowed to sit on the other side of zero, or
+FLIP_FACTOR = 4       # this many times the float32 oracle's own count, whichever is larger
 
 
 def assert_grads_match(model, bufs, P, x, eps_w, eps_d, prec, tag, floor=GRAD_TOL):
@@ -31,18 +32,22 @@ def assert_grads_match(model, bufs, P, x, eps_w, eps_d, prec, tag, floor=GRAD_TO
     that is the exact gradient of the function the GPU differentiated.  Every parameter
     gradient must then be within max(1e-4, 3 x the float32 oracle's own error on the same
     pattern) in the max-norm.  The number of units whose state differs from the float64
-    oracle's own forward is asserted separately (the forward outputs are compared elsewhere)."""
+    oracle's own forward is asserted separately: at most 16, or 4x the number the reference's
+    own float32 arithmetic (the float32 oracle) flips on the same inputs -- at batch 1024 there
+    are 1.9e9 units, a few hundred of which sit within float32 rounding of zero (the forward
+    outputs themselves are compared elsewhere at rtol 1e-4)."""
     from tests.helpers import gpu_relu_masks, masked_oracle_grads, relu_flips
     masks = gpu_relu_masks(bufs)
     out64, g64, _, acts64, err32 = masked_oracle_grads(P, x, eps_w, eps_d, prec, masks)
     flips = relu_flips(masks, acts64)
+    flips32 = err32.pop("__flips32__")
     rows = []
     for k, v in model.grad_dict().items():
         err = rel_err(v.detach().cpu().numpy(), g64[k].numpy())
         rows.append((k, err, max(floor, 3.0 * err32[k]), err32[k]))
     worst = sorted(rows, key=lambda r: -r[1] / r[2])[:6]
-    report = "%s: %d ReLU flips vs float64; worst gradients (err / tol / oracle-fp32 err): %s" % (
-        tag, flips, ", ".join("%s %.1e/%.1e/%.1e" % r for r in worst))
+    report = "%s: %d ReLU flips vs float64 (float32 oracle: %d); worst gradients (err / tol / oracle-fp32 err): %s" % (
+        tag, flips, flips32, ", ".join("%s %.1e/%.1e/%.1e" % r for r in worst))
     print(report)
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     try:
@@ -53,7 +58,7 @@ def assert_grads_match(model, bufs, P, x, eps_w, eps_d, prec, tag, floor=GRAD_TO
         pass
     bad = [r for r in rows if not r[1] <= r[2]]
     assert not bad, report
-    assert flips <= MAX_FLIPS, report
+    assert flips <= max(MAX_FLIPS, FLIP_FACTOR * flips32), report
     return out64, flips
 
 

@@ -101,6 +101,41 @@ def test_get_spec_oracle_matches_reference_golden():
     assert np.abs(spec - g["f32_a"]).max() <= 1e-5
 
 
+def test_round2_goldens_float64_audio_normalize_and_rejection():
+    """tests/golden/round2_cases.npz (oracle/make_golden.py round2_cases, the reference run
+    unmodified): float64 audio (complex128 STFT), within_syll_normalize, and the silence-rejection
+    loop with real rejections -- accepted (file, onset) pairs bit-exact, candidate count equal."""
+    g = load_golden("round2_cases")
+    p = dict(spec_oracle.FINCH_P)
+    fs = p['fs']
+    a64 = spec_oracle.synth_audio(21, int(2.0 * fs), fs, dtype=np.float64) / 7.0 + 0.123456789
+    for name in ("f64_a", "f64_b"):
+        onset = float(g[name + "_t"][0])
+        tt = np.linspace(onset, onset + p['window_length'], 128)
+        spec, _ = spec_oracle.get_spec(max(0.0, onset - 0.05), onset + p['window_length'] + 0.05, a64, p,
+                                       fs=fs, target_times=tt)
+        assert np.abs(spec - g[name]).max() <= 1e-9, name
+    for q in (0.5, 0.87):
+        pn = dict(spec_oracle.MOUSE_P)
+        pn.update(within_syll_normalize=True, normalize_quantile=q)
+        am = spec_oracle.synth_audio(11, int(0.6 * pn['fs']), pn['fs'])
+        spec, _ = spec_oracle.get_spec(0.100, 0.180, am, pn, fs=pn['fs'])
+        assert np.abs(spec - g["norm_q%02d" % int(100 * q)]).max() <= 1e-9, q
+    audio = [spec_oracle.silent_half_audio(200 + i, fs) for i in range(3)]
+    assert list(g["rej_audio_order"]) == ["x_song.wav", "y_song.wav", "z_song.wav"]
+    rois = [np.array([[0.2, 2.8]])] * 3
+    fw = np.full(3, 1.0 / 3.0)
+    rw = [np.array([1.0])] * 3
+    for seed in (0, 3):
+        files, onsets, specs, n_cand = spec_oracle.sample_windows_rejecting(
+            16, seed, audio, fs, p, rois, fw, rw, 0.3)
+        assert np.array_equal(files, g["rej_seed%d_files" % seed])
+        assert np.array_equal(onsets, g["rej_seed%d_onsets" % seed])
+        assert n_cand == int(g["rej_seed%d_candidates" % seed]) and n_cand > 16
+        if seed == 0:
+            assert np.abs(np.stack(specs[:2]) - g["rej_seed0_specs"]).max() <= 1e-9
+
+
 def test_mmd_oracle_matches_reference_golden():
     """oracle/mmd_oracle.py (numpy restatement of ava/plotting/mmd_plots.py:255-312,450-476)
     against outputs of the reference itself."""
