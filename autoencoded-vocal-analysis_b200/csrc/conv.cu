@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
   float* s_red = s_c1 + 32;                         // per-warp partial sums
   float* s_bias = s_red + C::RED_FLOATS;            // [CO]
   double* s_dz = reinterpret_cast<double*>(s_bias + 32);  // EPI_BWD coefficients of own BN, as
-  float* s_dzf = reinterpret_cast<float*>(s_dz);          // floats [2: hi | lo][4: p | q | mean | c1][32]
+  float* s_dzf = reinterpret_cast<float*>(s_dz);          // floats [3: p | q | k][32]
   double* s_ts = s_dz + 128;                               // [9][32] EPI_BWD: border sums of the output
   double* s_tsw = s_ts + 288;                              // [warps][4][32] EPI_BWD: per-warp totals / classes
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tsw + (EPI == EPI_BWD ? (NT / 32) * 128 : 0));
@@ -426,29 +426,25 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
   if (tid < CO) {
     s_bias[tid] = (EPI == EPI_FWD && P.bias) ? P.bias[tid] : 0.f;
     if (EPI == EPI_BWD) {
-      // fp64 coefficients, stored as fp32 hi + lo pairs: p | q | mean | c1
+      // out = p*(g - c1) + q*(x - mean) = p*g + q*x + k: p, q rounded to fp32 (a relative error of
+      // 6e-8 on a whole channel's gradient), k = -(p*c1 + q*mean) formed in fp64 from the ROUNDED
+      // p, q, then rounded once (a constant shift of <= 6e-8 |k| for the whole channel)
       const DzCoef k = dz_coef(P.gamma_self, P.stats_self, P.dstats_in, tid, P.out_count);
-      const double v[4] = {k.p, k.q, k.mean, k.c1};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float hi = (float)v[j];
-        s_dzf[j * 32 + tid] = hi;
-        s_dzf[128 + j * 32 + tid] = (float)(v[j] - (double)hi);
-      }
+      const float pf = (float)k.p, qf = (float)k.q;
+      s_dzf[tid] = pf;
+      s_dzf[32 + tid] = qf;
+      s_dzf[64 + tid] = (float)(-((double)pf * k.c1 + (double)qf * k.mean));
     }
   }
   __syncthreads();
-  // EPI_BWD epilogue: BatchNorm backward + ReLU mask,  out = [x > 0] * (p*(g - c1) + q*(x - mean)).
-  // The coefficients are exact to fp64 (hi + lo), the element arithmetic is fp32: both differences
-  // are formed against the hi part first (no rounding of the coefficient enters), and the
-  // expression is well conditioned -- measured over the network (profiles/probes/
-  // exp_algebraic_dstats.py): |mean g| <= 0.2 std g and |q (x-mean)| <= 0.5 |p (g-c1)| in every
-  // layer, so nothing cancels.  (A float64 evaluation costs three F2F conversions per element on
-  // a 16-lane pipe: +0.75 ms per step at batch 1024 when it ran in this epilogue.)
+  // EPI_BWD epilogue: BatchNorm backward + ReLU mask,  out = [x > 0] * (p*(g - c1) + q*(x - mean)),
+  // in fp32 against fp64-exact constants.  The expression is well conditioned -- measured over
+  // the network (profiles/probes/exp_algebraic_dstats.py): |mean g| <= 0.2 std g and
+  // |q (x-mean)| <= 0.5 |p (g-c1)| in every layer, so nothing cancels.  (A float64 evaluation
+  // costs three F2F conversions per element on a 16-lane pipe: +0.75 ms per step at batch 1024
+  // when it ran in this epilogue.)
   auto dzap = [&](int co, float g, float x) -> float {
-    const float a = (g - s_dzf[96 + co]) - s_dzf[128 + 96 + co];
-    const float b = (x - s_dzf[64 + co]) - s_dzf[128 + 64 + co];
-    const float d = fmaf(s_dzf[co], a, fmaf(s_dzf[32 + co], b, fmaf(s_dzf[128 + co], a, s_dzf[128 + 32 + co] * b)));
+    const float d = fmaf(s_dzf[co], g, fmaf(s_dzf[32 + co], x, s_dzf[64 + co]));
     return (P.mask_in && !(x > 0.f)) ? 0.f : d;
   };
   const bool want_ts = (EPI == EPI_BWD) && P.tsums_out != nullptr;
@@ -481,6 +477,16 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 #pragma unroll
         for (int j = 0; j < 2; ++j) s_accd[i * 8 + 2 * t + j] = s_accd[32 + i * 8 + 2 * t + j] = 0.0;
     }
+
+    // EPI_BWD border sums: totals (mode 0) / parity classes (mode 1) of the written dz, summed in
+    // fp32 per thread over ALL of this CTA's tiles and reduced once at the end (each partial is a
+    // few hundred values; the rounding errors of the ~1e5 independent partials of a layer are
+    // random and average out)
+    float ts_hot[2][NTL][2];
+#pragma unroll
+    for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+      for (int i = 0; i < NTL; ++i) ts_hot[rp][i][0] = ts_hot[rp][i][1] = 0.f;
 
     uint32_t phase = 0;
     int it = 0;
@@ -748,7 +754,19 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
         // (+8 for j >= 2), channel i*8 + 2t + (j&1); the two column parities form one float2
         const int a_in = ty * G::TH + r0, x_in = tx * TW + xh * 16 + g;
 #pragma unroll
-        for (int oa = 0; oa < 2; ++oa)
+        for (int oa = 0; oa < 2; ++oa) {
+          // EPI_BWD: all loads of x for this output row are issued before the first one is used
+          float2 xv[NTL][4];
+          if (EPI == EPI_BWD) {
+#pragma unroll
+            for (int i = 0; i < NTL; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int co = i * 8 + 2 * t + (j & 1);
+                const float* px = P.x_self + (((size_t)n * CO + co) * H_out + 2 * a_in + oa) * W_out + 2 * (x_in + 8 * (j >> 1));
+                asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(xv[i][j].x), "=f"(xv[i][j].y) : "l"(px));
+              }
+          }
 #pragma unroll
           for (int i = 0; i < NTL; ++i)
 #pragma unroll
@@ -757,9 +775,8 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
               const size_t o = (((size_t)n * CO + co) * H_out + 2 * a_in + oa) * W_out + 2 * (x_in + 8 * (j >> 1));
               float v0 = acc[2 * oa][i][j], v1 = acc[2 * oa + 1][i][j];
               if (EPI == EPI_BWD) {
-                const float2 xv = *reinterpret_cast<const float2*>(P.x_self + o);
-                v0 = dzap(co, v0, xv.x);
-                v1 = dzap(co, v1, xv.y);
+                v0 = dzap(co, v0, xv[i][j].x);
+                v1 = dzap(co, v1, xv[i][j].y);
               } else {
                 v0 += s_bias[co];
                 v1 += s_bias[co];
@@ -774,13 +791,13 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
               acc[2 * oa][i][j] = v0;
               acc[2 * oa + 1][i][j] = v1;
             }
+        }
         if (want_ts) {
           // border sums of the written dz (mode 0; the stride-2-up kernels never feed a stride-2
           // conv-transpose layer): output (2a+oa, 2x+ob), x = x_in (+8 for j >= 2), channel
-          // i*8 + 2t + (j&1).  Totals: shuffle over g, then lanes g == 0 add to this warp's own fp64
-          // slots (no atomics).  Border rows / columns / corners are rare: the per-channel values are
-          // moved so that lane L holds channel L and ONE shared atomic per lane follows.
-          double* tw = s_tsw + warp * 128;
+          // i*8 + 2t + (j&1).  Totals go to ts_hot (reduced after the tile loop).  Border rows /
+          // columns / corners are rare: the per-channel values are moved so that lane L holds
+          // channel L and ONE shared atomic per lane follows.
           auto spread = [&](float (&v)[NTL][2], int src_base, int slot) {
             float mine = 0.f;
 #pragma unroll
@@ -794,9 +811,9 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
           };
           const bool tile_c0 = (tx == 0) && (xh == 0);
           const bool tile_cl = (tx == tiles_x - 1) && (TW == 16 || xh == 1);
-          float tot[NTL][2], cf[NTL][2], cl[NTL][2];
+          float cf[NTL][2], cl[NTL][2];
 #pragma unroll
-          for (int i = 0; i < NTL; ++i) tot[i][0] = tot[i][1] = cf[i][0] = cf[i][1] = cl[i][0] = cl[i][1] = 0.f;
+          for (int i = 0; i < NTL; ++i) cf[i][0] = cf[i][1] = cl[i][0] = cl[i][1] = 0.f;
 #pragma unroll
           for (int oa = 0; oa < 2; ++oa) {
             const int oy = 2 * a_in + oa;
@@ -807,7 +824,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 #pragma unroll
               for (int c = 0; c < 2; ++c) {
                 rw[i][c] = (acc[2 * oa][i][c] + acc[2 * oa + 1][i][c]) + (acc[2 * oa][i][2 + c] + acc[2 * oa + 1][i][2 + c]);
-                tot[i][c] += rw[i][c];
+                ts_hot[0][i][c] += rw[i][c];
                 c0v[i][c] = acc[2 * oa][i][c];            // output column 0: x = 0 (j < 2), ob = 0, lanes g == 0
                 clv[i][c] = acc[2 * oa + 1][i][2 + c];    // last output column: x = W_in-1 (j >= 2), ob = 1, lanes g == 7
                 cf[i][c] += c0v[i][c];
@@ -831,16 +848,6 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
           }
           if (tile_c0) spread(cf, 0, 3);
           if (tile_cl) spread(cl, 28, 4);
-#pragma unroll
-          for (int i = 0; i < NTL; ++i)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              float a = tot[i][c];
-              a += __shfl_xor_sync(0xffffffffu, a, 4);
-              a += __shfl_xor_sync(0xffffffffu, a, 8);
-              a += __shfl_xor_sync(0xffffffffu, a, 16);
-              if (g == 0) tw[i * 8 + 2 * t + c] += (double)a;
-            }
         }
       } else {
         // ---- epilogue on the accumulator fragments: c0 = (pixel g, channel 2t), c1 = (g, 2t+1),
@@ -890,10 +897,9 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
         }
         if (want_ts) {
           // border sums of the written dz: element (row oy0+r, column ox0 + 8*(j>>1), channel
-          // i*8 + 2t + (j&1)).  Totals / parity classes: fp32 within the tile, then this warp's own
-          // fp64 slots (no atomics).  Border rows / columns / corners are rare: values are moved so
-          // that lane L holds channel L, then one shared atomic per lane.
-          double* tw = s_tsw + warp * 128;
+          // i*8 + 2t + (j&1)).  Totals / parity classes go to ts_hot (reduced after the tile loop).
+          // Border rows / columns / corners are rare: values are moved so that lane L holds
+          // channel L, then one shared atomic per lane.
           auto spread = [&](float (&v)[NTL][2], int src_base, int slot) {
             float mine = 0.f;
 #pragma unroll
@@ -908,9 +914,9 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
           const bool tile_c0 = (tx == 0) && (xh == 0);
           const bool tile_cl = (tx == tiles_x - 1) && (TW == 16 || xh == 1);
           if (P.tsum_mode == 0) {
-            float tot[NTL][2], cf[NTL][2], cl[NTL][2];
+            float cf[NTL][2], cl[NTL][2];
 #pragma unroll
-            for (int i = 0; i < NTL; ++i) tot[i][0] = tot[i][1] = cf[i][0] = cf[i][1] = cl[i][0] = cl[i][1] = 0.f;
+            for (int i = 0; i < NTL; ++i) cf[i][0] = cf[i][1] = cl[i][0] = cl[i][1] = 0.f;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
               const int oy = oy0 + r;
@@ -921,7 +927,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                   rw[i][c] = acc[r][i][c] + acc[r][i][2 + c];
-                  tot[i][c] += rw[i][c];
+                  ts_hot[0][i][c] += rw[i][c];
                   c0v[i][c] = acc[r][i][c];         // column 0 lives in lanes g == 0 (j < 2)
                   clv[i][c] = acc[r][i][2 + c];     // the last column in lanes g == 7 (j >= 2)
                   cf[i][c] += c0v[i][c];
@@ -945,25 +951,15 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
             }
             if (tile_c0) spread(cf, 0, 3);
             if (tile_cl) spread(cl, 28, 4);
-#pragma unroll
-            for (int i = 0; i < NTL; ++i)
-#pragma unroll
-              for (int c = 0; c < 2; ++c) {
-                float a = tot[i][c];
-                a += __shfl_xor_sync(0xffffffffu, a, 4);
-                a += __shfl_xor_sync(0xffffffffu, a, 8);
-                a += __shfl_xor_sync(0xffffffffu, a, 16);
-                if (g == 0) tw[i * 8 + 2 * t + c] += (double)a;
-              }
           } else {
             // mode 1: row-parity x column-parity classes (the column parity of this lane's pixels
             // is g & 1: tile origins and the +8 step are even; oy0 is even, so row parity = r & 1),
             // last row by column parity, last column by row parity, last corner
-            float cls[2][NTL][2], lc[2][NTL][2];
+            float lc[2][NTL][2];
 #pragma unroll
             for (int rp = 0; rp < 2; ++rp)
 #pragma unroll
-              for (int i = 0; i < NTL; ++i) cls[rp][i][0] = cls[rp][i][1] = lc[rp][i][0] = lc[rp][i][1] = 0.f;
+              for (int i = 0; i < NTL; ++i) lc[rp][i][0] = lc[rp][i][1] = 0.f;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
               float rw[NTL][2], clv[NTL][2];
@@ -973,7 +969,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
                 for (int c = 0; c < 2; ++c) {
                   rw[i][c] = acc[r][i][c] + acc[r][i][2 + c];
                   clv[i][c] = acc[r][i][2 + c];
-                  cls[r & 1][i][c] += rw[i][c];
+                  ts_hot[r & 1][i][c] += rw[i][c];
                   lc[r & 1][i][c] += clv[i][c];
                 }
               if (oy0 + r == H_out - 1) {                       // warp-uniform
@@ -995,17 +991,6 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
               spread(lc[0], 28, 6);
               spread(lc[1], 28, 7);
             }
-#pragma unroll
-            for (int rp = 0; rp < 2; ++rp)
-#pragma unroll
-              for (int i = 0; i < NTL; ++i)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                  float a = cls[rp][i][c];
-                  a += __shfl_xor_sync(0xffffffffu, a, 8);
-                  a += __shfl_xor_sync(0xffffffffu, a, 16);
-                  if (g < 2) tw[(rp * 2 + g) * 32 + i * 8 + 2 * t + c] += (double)a;
-                }
           }
         }
       }
@@ -1047,7 +1032,26 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       }
     }
     if (want_ts) {
-      // per-warp totals / classes -> s_ts (fixed order), then one fp64 atomic per value per CTA
+      // this warp's totals / classes: shuffle over g (mode 1: over the lanes of equal column
+      // parity g & 1), one add per lane into the warp's own fp64 slots; then the warps are summed
+      // in a fixed order and every value goes out as one fp64 atomic per CTA
+      double* tw = s_tsw + warp * 128;
+#pragma unroll
+      for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+        for (int i = 0; i < NTL; ++i)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float a = ts_hot[rp][i][c];
+            if (P.tsum_mode == 0) a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+            if (P.tsum_mode == 0) {
+              if (rp == 0 && g == 0) tw[i * 8 + 2 * t + c] = (double)a;
+            } else if (g < 2) {
+              tw[(rp * 2 + g) * 32 + i * 8 + 2 * t + c] = (double)a;
+            }
+          }
       __syncthreads();
       const int nhot = (P.tsum_mode == 0) ? 32 : 128;
       for (int i = tid; i < nhot; i += NT) {
@@ -1072,6 +1076,10 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
   float st1[COT], st2[COT];
 #pragma unroll
   for (int c = 0; c < COT; ++c) st1[c] = st2[c] = 0.f;
+  // EPI_BWD border sums: totals / parity classes of the written dz (see the tensor-core path)
+  float ts_hot[2][COT];
+#pragma unroll
+  for (int c = 0; c < COT; ++c) ts_hot[0][c] = ts_hot[1][c] = 0.f;
 
   uint32_t phase = 0;
   int it = 0;
@@ -1243,9 +1251,6 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       // value k to this warp's own fp64 slot k (no atomics, one add per lane).  Border rows /
       // columns / corners are rare: one shared atomic per lane after the same kind of spreading.
       const int lane = tid & 31;
-      const int warp = tid >> 5;
-      const unsigned gmask = (TW == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
-      double* tw = s_tsw + warp * 128;
       // v[c] valid in lane `src` of every row group -> channel c to lane c of that group -> atomic
       auto spread_from = [&](float (&v)[COT], int src, int slot, bool on) {
         float mine = 0.f;
@@ -1258,9 +1263,9 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       };
       const bool tile_c0 = (tx == 0), tile_cl = (tx == tiles_x - 1);
       if (P.tsum_mode == 0) {
-        float tot[COT], cfv[COT], clv[COT];
+        float cfv[COT], clv[COT];
 #pragma unroll
-        for (int c = 0; c < COT; ++c) tot[c] = cfv[c] = clv[c] = 0.f;
+        for (int c = 0; c < COT; ++c) cfv[c] = clv[c] = 0.f;
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) {
           int oy;
@@ -1278,9 +1283,15 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 #pragma unroll
           for (int c = 0; c < COT; ++c) {
             rv[c] = acc[o][c];
-            tot[c] += rv[c];
-            if (is_c0) cfv[c] += rv[c];
-            if (is_cl) clv[c] += rv[c];
+            ts_hot[0][c] += rv[c];
+          }
+          if (tile_c0 && is_c0) {
+#pragma unroll
+            for (int c = 0; c < COT; ++c) cfv[c] += rv[c];
+          }
+          if (tile_cl && is_cl) {
+#pragma unroll
+            for (int c = 0; c < COT; ++c) clv[c] += rv[c];
           }
           // (TW == 16: the two half warps may differ in rb; shuffles run warp-wide, the atomic is predicated)
           const bool any_rb = __any_sync(0xffffffffu, rb);
@@ -1297,20 +1308,11 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
         }
         if (tile_c0) spread_from(cfv, 0, 3, true);
         if (tile_cl) spread_from(clv, TW - 1, 4, true);
-        float mine = 0.f;
-#pragma unroll
-        for (int c = 0; c < COT; ++c) {
-          float a = tot[c];
-#pragma unroll
-          for (int sh = 1; sh < 32; sh <<= 1) a += __shfl_xor_sync(0xffffffffu, a, sh);
-          if (lane == c) mine = a;
-        }
-        if (lane < COT) tw[cog * COT + lane] += (double)mine;
       } else if (KIND != K_UP) {
         // mode 1: parity classes (row parity = o & 1, column parity = lx & 1: tile origins are even)
-        float cls[2][COT], lcv[2][COT];
+        float lcv[2][COT];
 #pragma unroll
-        for (int c = 0; c < COT; ++c) cls[0][c] = cls[1][c] = lcv[0][c] = lcv[1][c] = 0.f;
+        for (int c = 0; c < COT; ++c) lcv[0][c] = lcv[1][c] = 0.f;
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) {
           const int oy = ty * G::TH + 4 * rg + o;
@@ -1319,8 +1321,11 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 #pragma unroll
           for (int c = 0; c < COT; ++c) {
             rv[c] = acc[o][c];
-            cls[o & 1][c] += rv[c];
-            lcv[o & 1][c] += rv[c];
+            ts_hot[o & 1][c] += rv[c];
+          }
+          if (tile_cl) {
+#pragma unroll
+            for (int c = 0; c < COT; ++c) lcv[o & 1][c] += rv[c];
           }
           if (__any_sync(0xffffffffu, last_row)) {
             if (tile_cl) spread_from(rv, TW - 1, 8, last_row);
@@ -1337,25 +1342,31 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
           spread_from(lcv[0], TW - 1, 6, true);
           spread_from(lcv[1], TW - 1, 7, true);
         }
-        // classes: lane l takes (row parity, channel) = l >> 1 with its own column parity l & 1
-        float mine = 0.f;
-#pragma unroll
-        for (int rp = 0; rp < 2; ++rp)
-#pragma unroll
-          for (int c = 0; c < COT; ++c) {
-            float a = cls[rp][c];
-#pragma unroll
-            for (int sh = 2; sh < 32; sh <<= 1) a += __shfl_xor_sync(0xffffffffu, a, sh);
-            if ((lane >> 1) == rp * COT + c) mine = a;
-          }
-        if ((lane >> 1) < 2 * COT) {
-          const int rp = (lane >> 1) / COT, c = (lane >> 1) % COT;
-          tw[(rp * 2 + (lane & 1)) * 32 + cog * COT + c] += (double)mine;
-        }
       }
     }
   }
   if (want_ts) {
+    // this warp's totals / classes: butterfly over the warp (mode 1: over the lanes of equal
+    // column parity), lane k writes value k to the warp's own fp64 slots; then as above
+    const int lane = tid & 31;
+    double* tw = s_tsw + (tid >> 5) * 128;
+    float mine = 0.f;
+#pragma unroll
+    for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+      for (int c = 0; c < COT; ++c) {
+        float a = ts_hot[rp][c];
+        if (P.tsum_mode == 0) a += __shfl_xor_sync(0xffffffffu, a, 1);
+#pragma unroll
+        for (int sh = 2; sh < 32; sh <<= 1) a += __shfl_xor_sync(0xffffffffu, a, sh);
+        if (P.tsum_mode == 0 ? (rp == 0 && lane == c) : ((lane >> 1) == rp * COT + c)) mine = a;
+      }
+    if (P.tsum_mode == 0) {
+      if (lane < COT) tw[cog * COT + lane] = (double)mine;
+    } else if ((lane >> 1) < 2 * COT) {
+      const int rp = (lane >> 1) / COT, c = (lane >> 1) % COT;
+      tw[(rp * 2 + (lane & 1)) * 32 + cog * COT + c] = (double)mine;
+    }
     __syncthreads();
     const int nhot = (P.tsum_mode == 0) ? 32 : 128;
     for (int i = tid; i < nhot; i += NT) {

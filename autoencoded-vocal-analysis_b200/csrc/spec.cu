@@ -1,15 +1,13 @@
 // Batched GPU `get_spec`: STFT -> log magnitude -> bilinear resampling onto the
-// 128x128 (freq x time) grid -> normalise/clip.  One CTA per window, fp64 throughout
-// (B200 runs fp64 at half the fp32 rate; the path is bound by the 64 KiB/window output
-// write, not by arithmetic), so parity with the reference's float64 scipy path is ~1e-12.
+// 128x128 (freq x time) grid -> normalise/clip.  One CTA per window, fp64 throughout, so parity
+// with the reference's float64 scipy path is ~1e-12.  The kernel is bound by fp64 arithmetic and
+// shared-memory latency (FFT butterflies, log / hypot), not by its HBM traffic (14 KB in, 64 KB
+// out per finch window): see profiles/ for the measured rate against the HBM roofline.
 //
 // Reference: ava/preprocessing/utils.py:59-104 and scipy.signal.stft (_spectral_helper):
 // zero boundary extension by nperseg/2, zero padding to a hop multiple, no detrend,
 // window multiply, one-sided FFT, scale 1/sum(window).
 //
-// Frames are streamed: after frame k's log-spectrum is in the 2-deep ring buffer, every
-// target time whose lower frame is k-1 is interpolated and written, so shared memory
-// holds two spectra, not the whole spectrogram.  Frames no target touches are skipped.
 #include "common.cuh"
 
 namespace ava {
@@ -42,51 +40,65 @@ __device__ __forceinline__ double load_sample(const SpecParams& P, long long i) 
   return (double)reinterpret_cast<const short*>(P.audio)[i];
 }
 
-__global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P) {
+// Kernel anatomy (one CTA of 256 threads per window):
+//  * only the STFT frames some target time touches are computed ("needed" frames: two per target);
+//  * the frames are real, so TWO of them share one complex FFT (frame a in the real part, frame b
+//    in the imaginary part; X_a[k] = (Z[k] + conj Z[N-k]) / 2, X_b[k] = (Z[k] - conj Z[N-k]) / 2i),
+//    and G such packed transforms run side by side in shared memory, so every radix-2 stage (one
+//    __syncthreads) moves G*N/2 butterflies -- G per thread at nperseg 512 -- instead of one;
+//  * the log-magnitude spectra of a whole run of needed frames stay in shared memory (CF slots);
+//    the output pass then walks the [n_f, n_t] grid row-major, so a warp writes 128 consecutive
+//    floats of one frequency row, and every output is written exactly once (no zero-fill pass).
+//    Windows with more needed frames than slots are handled in overlapping runs of slots.
+struct SpecSmem {
+  int G, CF, NBP;   // packed transforms per batch, log-spectrum slots, slot pitch (doubles)
+};
+
+__global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const SpecSmem S) {
   extern __shared__ __align__(16) double sm[];
-  const int N = P.nperseg, NB = N / 2 + 1;
-  double2* s_x = reinterpret_cast<double2*>(sm);        // [N] FFT buffer
-  double2* s_tw = s_x + N;                               // [N/2] twiddles
-  double* s_log = reinterpret_cast<double*>(s_tw + N / 2);  // [2][NB] ring of log spectra
-  double* s_red = s_log + 2 * NB;                        // [8]
-  int* s_list = reinterpret_cast<int*>(s_red + 8);       // [n_t]
-  int* s_cnt = s_list + P.n_t;                           // [1]
-  unsigned char* s_need = reinterpret_cast<unsigned char*>(s_cnt + 1);  // [max_frames+1]
+  const int N = P.nperseg, NB = N / 2 + 1, half = N / 2;
+  double2* s_x = reinterpret_cast<double2*>(sm);                  // [G][N] packed FFT buffers
+  double2* s_tw = s_x + (size_t)S.G * N;                          // [N/2] twiddles
+  double* s_log = reinterpret_cast<double*>(s_tw + N / 2);        // [CF][NBP] log spectra
+  double* s_red = s_log + (size_t)S.CF * S.NBP;                   // [8]
+  int* s_list = reinterpret_cast<int*>(s_red + 8);                // [max_frames+1] needed frames, ascending
+  int* s_slot = s_list + (P.max_frames + 1);                      // [max_frames+1] frame -> slot in the current run
+  int* s_cnt = s_slot + (P.max_frames + 1);                       // [1]
 
   const int tid = threadIdx.x;
   const int w = blockIdx.x;
   const int len = P.seg_len[w];
   const size_t out_base = (size_t)w * P.n_f * P.n_t;
   const int n_out = P.n_f * P.n_t;
-
-  // every output starts at 0 (fill value / too-short segment / out-of-range targets)
-  for (int i = tid; i < n_out; i += 256) {
-    if (P.out) P.out[out_base + i] = 0.f;
-    if (P.out64) P.out64[out_base + i] = 0.0;
+  if (len <= 0) {
+    // too-short segment (the reference returns zeros, ava/preprocessing/utils.py:69-71)
+    for (int i = tid; i < n_out; i += 256) {
+      if (P.out) P.out[out_base + i] = 0.f;
+      if (P.out64) P.out64[out_base + i] = 0.0;
+    }
+    return;
   }
-  if (len <= 0) return;
   const long long start = P.seg_start[w];
-  const int half = N / 2;
   const int L = len + 2 * half;
   const int nadd = ((P.hop - (L - N) % P.hop) % P.hop) % N;
-  const int K = (L + nadd - N) / P.hop + 1;
+  int K = (L + nadd - N) / P.hop + 1;
+  if (K > P.max_frames) K = P.max_frames;
 
-  // twiddles exp(-2 pi i j / N)
+  // twiddles exp(-2 pi i j / N); frame -> "needed" flags (in s_slot for now)
   for (int j = tid; j < N / 2; j += 256) {
-    double s, c;
-    sincospi(-2.0 * (double)j / (double)N, &s, &c);
-    s_tw[j] = make_double2(c, s);
+    double sn, cs;
+    sincospi(-2.0 * (double)j / (double)N, &sn, &cs);
+    s_tw[j] = make_double2(cs, sn);
   }
-  // which frames are referenced by a target time
-  for (int k = tid; k <= K && k <= P.max_frames; k += 256) s_need[k] = 0;
+  for (int k = tid; k <= K; k += 256) s_slot[k] = 0;
   __syncthreads();
   const int* tix = P.t_idx + (size_t)w * P.n_t;
   const double* tfr = P.t_frac + (size_t)w * P.n_t;
   for (int j = tid; j < P.n_t; j += 256) {
-    int i = tix[j];
+    const int i = tix[j];
     if (i >= 0 && i + 1 < K) {
-      s_need[i] = 1;
-      s_need[i + 1] = 1;
+      s_slot[i] = 1;
+      s_slot[i + 1] = 1;
     }
   }
   // mean (np.mean: exact for int16 in fp64)
@@ -101,63 +113,108 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P) {
     mean /= (double)len;
   }
   __syncthreads();
+  if (tid == 0) {
+    int n = 0;
+    for (int k = 0; k < K; ++k)
+      if (s_slot[k]) s_list[n++] = k;
+    *s_cnt = n;
+  }
+  __syncthreads();
+  const int nneed = *s_cnt;
 
-  for (int k = 0; k < K; ++k) {
-    if (!s_need[k]) continue;  // uniform across the CTA
-    // ---- windowed frame, bit-reversed order
-    for (int j = tid; j < N; j += 256) {
-      int idx = k * P.hop + j - half;
+  // runs of needed frames: [a, a + CF) of the list; consecutive runs overlap by one entry so that
+  // both frames of every target's bracketing pair fall into one run
+  bool first_run = true;
+  for (int a = 0; first_run || a + 1 < nneed; a += S.CF - 1) {
+    const int nrun = min(S.CF, nneed - a);
+    __syncthreads();                                    // previous run's output pass is done with s_log / s_slot
+    for (int k = tid; k <= K; k += 256) s_slot[k] = -1;
+    __syncthreads();
+    for (int j = tid; j < nrun; j += 256) s_slot[s_list[a + j]] = j;
+    // ---- packed FFTs of this run, G at a time
+    for (int p0 = 0; p0 < nrun; p0 += 2 * S.G) {
+      const int npair = min(S.G, (nrun - p0 + 1) / 2);
+      __syncthreads();
+      // windowed frames, bit-reversed order: real part = entry p0+2g, imaginary = entry p0+2g+1
+      for (int idx = tid; idx < npair * N; idx += 256) {
+        const int g = idx / N, j = idx - g * N;
+        const int fa = s_list[a + p0 + 2 * g];
+        const int eb = p0 + 2 * g + 1;
+        const double wj = P.window[j];
+        double va = 0.0, vb = 0.0;
+        int ia = fa * P.hop + j - half;
+        if (ia >= 0 && ia < len) va = (load_sample(P, start + ia) - mean) * wj;
+        if (eb < nrun) {
+          const int ib = s_list[a + eb] * P.hop + j - half;
+          if (ib >= 0 && ib < len) vb = (load_sample(P, start + ib) - mean) * wj;
+        }
+        const int r = (int)(__brev((unsigned)j) >> (32 - P.log2n));
+        s_x[(size_t)g * N + r] = make_double2(va, vb);
+      }
+      __syncthreads();
+      // radix-2 DIT over all npair transforms
+      for (int st = 1; st <= P.log2n; ++st) {
+        const int mh = 1 << (st - 1);
+        const int tstep = N >> st;
+        for (int b = tid; b < npair * half; b += 256) {
+          const int g = b / half, bb = b - g * half;
+          const int grp = bb >> (st - 1), pos = bb & (mh - 1);
+          const int i0 = (grp << st) + pos, i1 = i0 + mh;
+          double2* x = s_x + (size_t)g * N;
+          const double2 wv = s_tw[pos * tstep];
+          const double2 u = x[i0], c = x[i1];
+          const double tr = wv.x * c.x - wv.y * c.y, ti = wv.x * c.y + wv.y * c.x;
+          x[i0] = make_double2(u.x + tr, u.y + ti);
+          x[i1] = make_double2(u.x - tr, u.y - ti);
+        }
+        __syncthreads();
+      }
+      // unpack the two real spectra and take log magnitudes (ava/preprocessing/utils.py:79)
+      for (int idx = tid; idx < npair * NB; idx += 256) {
+        const int g = idx / NB, k = idx - g * NB;
+        const double2* x = s_x + (size_t)g * N;
+        const double2 z = x[k], zc = x[(N - k) & (N - 1)];
+        // X_a = (Z[k] + conj Z[N-k]) / 2 ; X_b = (Z[k] - conj Z[N-k]) / (2i)
+        const double ar = 0.5 * (z.x + zc.x), ai = 0.5 * (z.y - zc.y);
+        const double br = 0.5 * (z.y + zc.y), bi = -0.5 * (z.x - zc.x);
+        const int ea = p0 + 2 * g;
+        s_log[(size_t)ea * S.NBP + k] = log(hypot(ar * P.scale, ai * P.scale) + 1e-12);
+        if (ea + 1 < nrun) s_log[(size_t)(ea + 1) * S.NBP + k] = log(hypot(br * P.scale, bi * P.scale) + 1e-12);
+      }
+    }
+    __syncthreads();
+    // ---- output pass, row-major over [n_f, n_t]: the targets whose bracketing frames are the
+    // entries (j, j+1) of this run with j + 1 < nrun; on the first run also everything that is
+    // out of range (fill value -> 0 after normalise + clip)
+    for (int i = tid; i < n_out; i += 256) {
+      const int f = i / P.n_t, t = i - f * P.n_t;
+      const int ti = tix[t];
+      const int fi = P.f_idx[f];
+      const bool valid = (ti >= 0) && (ti + 1 < K) && (fi >= 0);
       double v = 0.0;
-      if (idx >= 0 && idx < len) v = (load_sample(P, start + idx) - mean) * P.window[j];
-      int r = (int)(__brev((unsigned)j) >> (32 - P.log2n));
-      s_x[r] = make_double2(v, 0.0);
-    }
-    __syncthreads();
-    // ---- radix-2 DIT
-    for (int s = 1; s <= P.log2n; ++s) {
-      const int mh = 1 << (s - 1);
-      const int tstep = N >> s;
-      for (int b = tid; b < N / 2; b += 256) {
-        int grp = b >> (s - 1), pos = b & (mh - 1);
-        int i0 = (grp << s) + pos, i1 = i0 + mh;
-        double2 wv = s_tw[pos * tstep];
-        double2 a = s_x[i0], c = s_x[i1];
-        double tr = wv.x * c.x - wv.y * c.y, ti = wv.x * c.y + wv.y * c.x;
-        s_x[i0] = make_double2(a.x + tr, a.y + ti);
-        s_x[i1] = make_double2(a.x - tr, a.y - ti);
+      bool write = false;
+      if (!valid) {
+        write = first_run;
+      } else {
+        const int j = s_slot[ti];
+        if (j >= 0 && j + 1 < nrun) {      // (a run's last entry is the next run's first: handled there)
+          const double* lo = s_log + (size_t)j * S.NBP;
+          const double* hi = lo + S.NBP;
+          const double wy = P.f_frac[f], wx = tfr[t];
+          const double s00 = lo[fi], s01 = hi[fi], s10 = lo[fi + 1], s11 = hi[fi + 1];
+          v = (1.0 - wy) * ((1.0 - wx) * s00 + wx * s01) + wy * ((1.0 - wx) * s10 + wx * s11);
+          v = (v - P.spec_min) * P.inv_range;
+          v = fmin(fmax(v, 0.0), 1.0);
+          write = true;
+        }
       }
-      __syncthreads();
-    }
-    // ---- log magnitude (ava/preprocessing/utils.py:79)
-    double* lg = s_log + (k & 1) * NB;
-    for (int j = tid; j < NB; j += 256) {
-      double2 z = s_x[j];
-      lg[j] = log(hypot(z.x * P.scale, z.y * P.scale) + 1e-12);
-    }
-    if (tid == 0) *s_cnt = 0;
-    __syncthreads();
-    // ---- targets whose lower frame is k-1 can now be written
-    if (k >= 1) {
-      for (int j = tid; j < P.n_t; j += 256)
-        if (tix[j] == k - 1) s_list[atomicAdd(s_cnt, 1)] = j;
-      __syncthreads();
-      const int cnt = *s_cnt;
-      const double* lo = s_log + ((k - 1) & 1) * NB;
-      const double* hi = lg;
-      for (int i = tid; i < cnt * P.n_f; i += 256) {
-        int f = i / cnt, t = s_list[i - f * cnt];
-        int fi = P.f_idx[f];
-        if (fi < 0) continue;
-        double wy = P.f_frac[f], wx = tfr[t];
-        double s00 = lo[fi], s01 = hi[fi], s10 = lo[fi + 1], s11 = hi[fi + 1];
-        double v = (1.0 - wy) * ((1.0 - wx) * s00 + wx * s01) + wy * ((1.0 - wx) * s10 + wx * s11);
-        v = (v - P.spec_min) * P.inv_range;
-        v = fmin(fmax(v, 0.0), 1.0);
-        if (P.out) P.out[out_base + (size_t)f * P.n_t + t] = (float)v;
-        if (P.out64) P.out64[out_base + (size_t)f * P.n_t + t] = v;
+      if (write) {
+        if (P.out) P.out[out_base + i] = (float)v;
+        if (P.out64) P.out64[out_base + i] = v;
       }
     }
-    __syncthreads();
+    first_run = false;
+    if (nneed == 0) break;
   }
 }
 
@@ -355,19 +412,24 @@ extern "C" int ava_b200_get_spec_batch(const void* audio, int is_f32, const long
   P.inv_range = 1.0 / (spec_max - spec_min);
   P.out = out;
   P.out64 = out64;
-  size_t smem = (size_t)nperseg * 16 + (size_t)(nperseg / 2) * 16 + (size_t)2 * (nperseg / 2 + 1) * 8 + 64 +
-                (size_t)n_t * 4 + 4 + (size_t)max_frames + 16;
+  // shared memory: G packed transforms (G*N ~ 2048 points), twiddles, CF log-spectrum slots within
+  // ~96 KB (two CTAs per SM), frame lists
+  SpecSmem S;
+  S.G = 2048 / nperseg;
+  if (S.G < 1) S.G = 1;
+  if (S.G > 8) S.G = 8;
+  S.NBP = nperseg / 2 + 2;
+  const size_t fixed = (size_t)S.G * nperseg * 16 + (size_t)(nperseg / 2) * 16 + 64 +
+                       (size_t)2 * (max_frames + 1) * 4 + 16;
+  const size_t budget = (size_t)96 * 1024;
+  long long cf = fixed < budget ? (long long)((budget - fixed) / ((size_t)S.NBP * 8)) : 0;
+  if (cf < 4) cf = 4;
+  if (cf > max_frames + 1) cf = max_frames + 1;
+  if (cf < 2) cf = 2;
+  S.CF = (int)cf;
+  size_t smem = fixed + (size_t)S.CF * S.NBP * 8;
   smem = (smem + 15) / 16 * 16;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(get_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess) {
-      cudaGetLastError();
-      set_error("get_spec: %zu bytes of shared memory unavailable", smem);
-      return 1;
-    }
-    configured = smem;
-  }
-  get_spec_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(P);
+  AVA_REQUIRE(smem <= 227 * 1024, "get_spec: %zu bytes of shared memory needed (nperseg %d)", smem, nperseg);
+  get_spec_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(P, S);
   return check_launch("get_spec");
 }

@@ -583,23 +583,20 @@ class VAE(nn.Module):
             return fuse
         return False
 
-    def _backward_native(self, bufs, after_decoder=None, after_dense=None):
-        """Backward of the whole loss; leaves every parameter gradient in the flat
-        gradient buffer (overwritten, not accumulated).  Replaces loss.backward(),
-        ava/models/vae.py:352."""
-        B, Z, s = bufs.B, self.z_dim, _stream()
+    def _bwd_decoder(self, bufs):
+        """Backward segment 1: decoder conv stack (layers 13..7) and fc8..fc5.  Afterwards the
+        gradients of fc5..fc8 and convt1..7 are final."""
+        B, Z = bufs.B, self.z_dim
         bufs.alloc_backward(Z)
-        x = bufs.x
         g_cur, g_nxt = bufs.g[0], bufs.g[1]      # g[0] holds dL/dx_rec = convt7's dz (recon kernel)
-        # ---- decoder conv stack, layers 13..7; layer 7 writes the gradient w.r.t. fc8's
-        # pre-activation output (bn8 backward + fc8's ReLU) straight into dt8
+        # layer 7 writes the gradient w.r.t. fc8's pre-activation output (bn8 backward + fc8's
+        # ReLU) straight into dt8
         have = False
         for l in range(13, 6, -1):
             xin = bufs.act[l - 1] if l > 7 else bufs.t8
             out = g_nxt if l > 7 else bufs.dt8
             have = self._conv_bwd(l, bufs, g_cur, xin, out, have)
             g_cur, g_nxt = g_nxt, g_cur
-        # ---- decoder dense layers
         self._linear_bwd(bufs.dt8, 8192, None, bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.dt7, 1024,
                          B, 8192, 1024, tc=self._tc)
         self._linear_bwd(bufs.dt7, 1024, bufs.t7, bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.dt6, 256,
@@ -608,13 +605,14 @@ class VAE(nn.Module):
                          B, 256, 64)
         self._linear_bwd(bufs.dt5, 64, bufs.t5, bufs.z, Z, "fc5.weight", "fc5.bias", bufs.gz, Z,
                          B, 64, Z)
-        if after_decoder is not None:
-            # decoder parameter gradients (fc5..fc8, convt1..7) are final: start reducing them
-            after_decoder()
-        # ---- latent: analytic gradients of sample + prior + entropy
+
+    def _bwd_dense_encoder(self, bufs):
+        """Backward segment 2: latent (analytic gradients of sample + prior + entropy) and the
+        encoder's dense layers.  Afterwards the gradients of fc1..fc43 are final (fc1.weight is
+        half of all parameters)."""
+        B, Z, s = bufs.B, self.z_dim, _stream()
         call("ava_b200_latent_bwd", ptr(bufs.heads), ptr(bufs.eps_w), ptr(bufs.eps_d), ptr(bufs.z),
              ptr(bufs.gz), B, Z, ptr(bufs.gheads), s)
-        # ---- encoder dense layers
         self._linear_bwd(bufs.gheads, 3 * Z, None, bufs.h3, 192, "fc41.weight", "fc41.bias", bufs.dh3,
                          192, B, Z, 64, groups=3, dy_gs=Z, x_gs=64, w_gs=Z * 64, b_gs=Z, dx_gs=64)
         self._linear_bwd(bufs.dh3, 192, bufs.h3, bufs.h2, 256, "fc31.weight", "fc31.bias", bufs.dh2,
@@ -623,27 +621,39 @@ class VAE(nn.Module):
                          1024, B, 256, 1024, tc=self._tc)
         self._linear_bwd(bufs.dh1, 1024, bufs.h1, bufs.act[6], 8192, "fc1.weight", "fc1.bias",
                          bufs.da6, 8192, B, 1024, 8192, tc=self._tc)
-        if after_dense is not None:
-            # fc1..fc43 gradients are final (fc1.weight is half of all parameters)
-            after_dense()
-        # ---- conv7's ReLU on the gradient arriving from fc1 (no BatchNorm at this seam)
+
+    def _bwd_conv_encoder(self, bufs):
+        """Backward segment 3: encoder conv stack (layers 6..0) and the BatchNorm affine
+        parameter gradients of all 14 layers."""
+        B, s = bufs.B, _stream()
+        # conv7's ReLU on the gradient arriving from fc1 (no BatchNorm at this seam)
         call("ava_b200_bn_relu_bwd_apply", ptr(bufs.da6), ptr(bufs.act[6]), None, None, None, B, 32, 256,
              1, ptr(bufs.da6), s)
-        # ---- encoder conv stack, layers 6..0 (layer 0 needs no data gradient)
         g_cur = bufs.da6
         free = [bufs.g[0], bufs.g[1]]
         have = False
-        for l in range(6, -1, -1):
-            xin = bufs.act[l - 1] if l > 0 else x
+        for l in range(6, -1, -1):          # (layer 0 needs no data gradient)
+            xin = bufs.act[l - 1] if l > 0 else bufs.x
             out = free[0] if l > 0 else None
             have = self._conv_bwd(l, bufs, g_cur, xin, out, have)
             g_cur, free = out, [free[1], free[0]]
-        # ---- BatchNorm affine parameter gradients for all 14 layers
         st, ds = bufs.stats.data_ptr(), bufs.dstats.data_ptr()
         counts = [B * _LAYERS[l][4] ** 2 for l in range(14)]
         h_counts = (ctypes.c_longlong * 14)(*counts)
         call("ava_b200_bn_param_grads", st, ds, self._h_channels, h_counts, ptr(self._flat_g),
              self._h_dg_off, self._h_db_off, s)
+
+    def _backward_native(self, bufs, after_decoder=None, after_dense=None):
+        """Backward of the whole loss; leaves every parameter gradient in the flat
+        gradient buffer (overwritten, not accumulated).  Replaces loss.backward(),
+        ava/models/vae.py:352.  The two callbacks fire where a gradient bucket becomes final."""
+        self._bwd_decoder(bufs)
+        if after_decoder is not None:
+            after_decoder()
+        self._bwd_dense_encoder(bufs)
+        if after_dense is not None:
+            after_dense()
+        self._bwd_conv_encoder(bufs)
 
     def _sync_hyper(self):
         """lr / betas / eps as torch.optim.Adam holds them (optimizer.param_groups[0]: what
@@ -786,13 +796,14 @@ class VAE(nn.Module):
         if self._flat_p.device.type != "cuda":
             return False
         if self._dp_world > 1 and os.environ.get("AVA_B200_DP_GRAPHS", "1") == "0":
-            return False    # (NCCL collectives are captured with the step; opt-out switch)
+            return False    # (opt-out switch for the segmented data-parallel graphs)
         if self.cuda_graphs == 'auto':
             return True     # measured: 1.41 vs 1.68 ms at batch 64, 8.13 vs 8.46 ms at batch 1024
         return bool(self.cuda_graphs)
 
     def _train_step_graph(self, x, noise):
-        """The whole step (~190 launches) replayed as one CUDA graph per batch size: at
+        """The whole step (~160 launches) replayed as one CUDA graph per batch size (data
+        parallel: four graphs with the collectives between them, _capture_dp_segments): at
         batch 64 the step is otherwise bound by host launch overhead, and even at batch 1024
         the launch gaps between the many small kernels cost 4 %.  The first two steps
         at a new batch size run eagerly (they also warm up lazy initialisation), the third
@@ -818,23 +829,62 @@ class VAE(nn.Module):
             if st["count"] <= 2:
                 return self._train_step_eager(st["x"], (st["ew"], st["ed"]))
             try:
-                g = torch.cuda.CUDAGraph()
                 host_step = self._step_host
-                with torch.cuda.graph(g):
-                    loss = self._train_step_eager(st["x"], (st["ew"], st["ed"]))
+                if self._dp_world > 1:
+                    st["graph"] = self._capture_dp_segments(st)
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        st["loss"] = self._train_step_eager(st["x"], (st["ew"], st["ed"]))
+                    st["graph"] = [g]
                 self._step_host = host_step      # capture records, it does not execute
-                st["graph"], st["loss"] = g, loss
                 # the graph owns references to everything it points into
                 st["bufs"], st["scratch"] = self._bufs[B], self._scratch
             except Exception:
                 self.cuda_graphs = False
+                st["graph"] = None
                 torch.cuda.synchronize()
                 return self._train_step_eager(st["x"], (st["ew"], st["ed"]))
         self._buffers_for(B)             # keep this size most recently used
         self._cur = st["bufs"]
-        st["graph"].replay()
+        graphs = st["graph"]
+        if len(graphs) == 1:
+            graphs[0].replay()
+        else:
+            # data parallel: the collectives stay OUTSIDE the graphs (NCCL kernels captured into a
+            # graph ran slower than eager ones here and the process hung at teardown); each is
+            # launched right after the segment that completes its bucket and overlaps the next
+            early, mid, late = self._grad_buckets()
+            graphs[0].replay()
+            works = self._allreduce(early, async_op=True)
+            graphs[1].replay()
+            works += self._allreduce(mid, async_op=True)
+            graphs[2].replay()
+            works += self._allreduce(late, async_op=True)
+            for w in works:
+                w.wait()
+            graphs[3].replay()
         self._step_host += 1
         return st["loss"]
+
+    def _capture_dp_segments(self, st):
+        """The data-parallel step as four CUDA graphs -- forward + decoder backward | dense encoder
+        backward | encoder conv backward | Adam -- with the three gradient all-reduces between
+        them.  All four share one memory pool (they run strictly in this order)."""
+        x, noise = st["x"], (st["ew"], st["ed"])
+        graphs = [torch.cuda.CUDAGraph() for _ in range(4)]
+        pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(graphs[0], pool=pool):
+            bufs = self._forward_native(x, noise, True, want_grad_seed=True)
+            self._bwd_decoder(bufs)
+        with torch.cuda.graph(graphs[1], pool=pool):
+            self._bwd_dense_encoder(bufs)
+        with torch.cuda.graph(graphs[2], pool=pool):
+            self._bwd_conv_encoder(bufs)
+        with torch.cuda.graph(graphs[3], pool=pool):
+            self._adam_native()
+        st["loss"] = bufs.loss[0]
+        return graphs
 
     def train_step(self, x, noise=None):
         """zero_grad + forward + backward + Adam for one batch, entirely native

@@ -383,12 +383,19 @@ def extra_get_latent(model, torch, dist, world, rank, n_total, B, peak):
     e1.record()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    host = lat.cpu().numpy().astype(np.float64)
     if world > 1:
-        gathered = [None] * world if rank == 0 else None
-        dist.gather_object(host, gathered, dst=0)
+        # results only: one gather of the fp32 latent means to rank 0 (blocks padded to equal size)
+        n_max = (n_total + world - 1) // world
+        pad = torch.zeros(n_max, model.z_dim, device="cuda")
+        pad[:n_mine].copy_(lat)
+        parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, parts, dst=0)
+        host = None
         if rank == 0:
-            host = np.concatenate(gathered)
+            sizes = [(n_total * (r + 1)) // world - (n_total * r) // world for r in range(world)]
+            host = np.concatenate([p[:n].cpu().numpy() for p, n in zip(parts, sizes)]).astype(np.float64)
+    else:
+        host = lat.cpu().numpy().astype(np.float64)
     t_gather = time.perf_counter() - t0
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -672,6 +679,8 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -513,3 +513,50 @@ def test_full_size_batch_properties(vae_mod):
         if p.is_floating_point():
             d = (p.double() - q.double()).abs().max().item()
             assert d <= 2.5e-3, k      # Adam's first step is sign-like: lr-sized flips of ~0 gradients only
+
+
+def test_optimizer_hyperparameters_follow_param_groups_and_state_survives_reflatten(vae_mod, tmp_path):
+    """Round-1 advisor findings.  (1) Adam's lr / betas / eps come from optimizer.param_groups
+    (what load_state restores from a checkpoint, ava/models/vae.py:470, and what LR schedulers
+    change), also under CUDA-graph replay: with lr set to 0 a replayed step must leave the
+    parameters untouched.  (2) Re-flattening the model after training (.cuda() / .to()) keeps the
+    Adam step count and moments instead of re-adopting step 0."""
+    seed = 8
+    model = build(vae_mod, seed, cuda_graphs=True)
+    model.train()
+    x = vae_oracle.make_input(seed, 8).cuda()
+    noise = tuple(t.cuda() for t in vae_oracle.make_noise(seed, 8))
+    for _ in range(4):                                  # steps 1, 2 eager, 3 captured, 4 replayed
+        model.train_step(x, noise=noise)
+    assert model._graphs[8]["graph"] is not None
+    before = model._flat_p.clone()
+    model.optimizer.param_groups[0]['lr'] = 0.0
+    model.train_step(x, noise=noise)                    # replay of the same graph
+    torch.cuda.synchronize()
+    assert torch.equal(model._flat_p, before)
+    model.optimizer.param_groups[0]['lr'] = 5e-4
+    model.train_step(x, noise=noise)
+    torch.cuda.synchronize()
+    step = (model._flat_p - before).abs().max().item()
+    assert 0 < step <= 5.1e-4 * 10                      # an Adam step of the new size (|m|/sqrt(v) is O(1))
+    assert model._step_host == 6 and float(model._step_dev.item()) == 6.0
+    # (2) re-flatten: step count, moments and the optimizer's aliases survive
+    m_before = model._flat_m.clone()
+    model.cuda()
+    assert model._step_host == 6 and float(model._step_dev.item()) == 6.0
+    assert torch.equal(model._flat_m, m_before)
+    st0 = model.optimizer.state[next(iter(model.parameters()))]
+    assert st0['exp_avg'].data_ptr() == model._views_m[next(iter(dict(model.named_parameters())))].data_ptr()
+    model.train_step(x, noise=noise)
+    assert model._step_host == 7 and float(model._step_dev.item()) == 7.0
+    # load_state restores the checkpoint's lr into param_groups and the native step uses it
+    model.save_state(str(tmp_path / "lr.tar"))
+    other = vae_mod.VAE(save_dir='', device_name='cuda', lr=1e-3)
+    other.load_state(str(tmp_path / "lr.tar"))
+    assert other.optimizer.param_groups[0]['lr'] == 5e-4 and other._step_host == 7
+    other.train()
+    other.train_step(x, noise=noise)
+    assert other._hyper_host[0] == 5e-4
+    with pytest.raises(NotImplementedError):
+        other.optimizer.param_groups[0]['weight_decay'] = 0.1
+        other.train_step(x, noise=noise)
