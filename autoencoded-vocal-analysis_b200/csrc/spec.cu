@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
   extern __shared__ __align__(16) double sm[];
   const int N = P.nperseg, NB = N / 2 + 1, half = N / 2;
   double2* s_x = reinterpret_cast<double2*>(sm);                  // [G][N] packed FFT buffers
-  double2* s_tw = s_x + (size_t)S.G * N;                          // [N/2] twiddles
-  double* s_log = reinterpret_cast<double*>(s_tw + N / 2);        // [CF][NBP] log spectra
+  double2* s_tw = s_x + (size_t)S.G * N;                          // [N] per-stage twiddle tables (N-1 used)
+  double* s_log = reinterpret_cast<double*>(s_tw + N);            // [CF][NBP] log spectra
   double* s_red = s_log + (size_t)S.CF * S.NBP;                   // [8]
   int* s_list = reinterpret_cast<int*>(s_red + 8);                // [max_frames+1] needed frames, ascending
   int* s_slot = s_list + (P.max_frames + 1);                      // [max_frames+1] frame -> slot in the current run
@@ -84,11 +84,17 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
   int K = (L + nadd - N) / P.hop + 1;
   if (K > P.max_frames) K = P.max_frames;
 
-  // twiddles exp(-2 pi i j / N); frame -> "needed" flags (in s_slot for now)
-  for (int j = tid; j < N / 2; j += 256) {
+  // twiddles, one contiguous table per radix-2 stage (stage st, mh = 2^(st-1) butterflies per group:
+  // entries [mh-1, 2mh-1) = exp(-2 pi i pos / (2 mh)) -- lanes then read consecutive entries instead
+  // of a strided walk through one table, which put 16 of them on the same banks in the middle
+  // stages); frame -> "needed" flags (in s_slot for now)
+  for (int e = tid; e < N - 1; e += 256) {
+    const int st = 31 - __clz(e + 1);                 // e + 1 in [mh, 2mh)
+    const int mh = 1 << st;
+    const int pos = e + 1 - mh;
     double sn, cs;
-    sincospi(-2.0 * (double)j / (double)N, &sn, &cs);
-    s_tw[j] = make_double2(cs, sn);
+    sincospi(-(double)pos / (double)mh, &sn, &cs);    // -2 pi pos / (2 mh)
+    s_tw[e] = make_double2(cs, sn);
   }
   for (int k = tid; k <= K; k += 256) s_slot[k] = 0;
   __syncthreads();
@@ -137,7 +143,10 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
       __syncthreads();
       // windowed frames, bit-reversed order: real part = entry p0+2g, imaginary = entry p0+2g+1
       for (int idx = tid; idx < npair * N; idx += 256) {
-        const int g = idx / N, j = idx - g * N;
+        // destination index r runs with the lanes (conflict-free stores); the source sample index
+        // j = bitrev(r) scatters over the 2*N bytes of a frame, which sit in L1
+        const int g = idx / N, r = idx - g * N;
+        const int j = (int)(__brev((unsigned)r) >> (32 - P.log2n));
         const int fa = s_list[a + p0 + 2 * g];
         const int eb = p0 + 2 * g + 1;
         const double wj = P.window[j];
@@ -148,20 +157,19 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
           const int ib = s_list[a + eb] * P.hop + j - half;
           if (ib >= 0 && ib < len) vb = (load_sample(P, start + ib) - mean) * wj;
         }
-        const int r = (int)(__brev((unsigned)j) >> (32 - P.log2n));
         s_x[(size_t)g * N + r] = make_double2(va, vb);
       }
       __syncthreads();
       // radix-2 DIT over all npair transforms
       for (int st = 1; st <= P.log2n; ++st) {
         const int mh = 1 << (st - 1);
-        const int tstep = N >> st;
+        const double2* twst = s_tw + (mh - 1);
         for (int b = tid; b < npair * half; b += 256) {
           const int g = b / half, bb = b - g * half;
           const int grp = bb >> (st - 1), pos = bb & (mh - 1);
           const int i0 = (grp << st) + pos, i1 = i0 + mh;
           double2* x = s_x + (size_t)g * N;
-          const double2 wv = s_tw[pos * tstep];
+          const double2 wv = twst[pos];
           const double2 u = x[i0], c = x[i1];
           const double tr = wv.x * c.x - wv.y * c.y, ti = wv.x * c.y + wv.y * c.x;
           x[i0] = make_double2(u.x + tr, u.y + ti);
@@ -178,39 +186,47 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
         const double ar = 0.5 * (z.x + zc.x), ai = 0.5 * (z.y - zc.y);
         const double br = 0.5 * (z.y + zc.y), bi = -0.5 * (z.x - zc.x);
         const int ea = p0 + 2 * g;
-        s_log[(size_t)ea * S.NBP + k] = log(hypot(ar * P.scale, ai * P.scale) + 1e-12);
-        if (ea + 1 < nrun) s_log[(size_t)(ea + 1) * S.NBP + k] = log(hypot(br * P.scale, bi * P.scale) + 1e-12);
+        // |X| * scale: audio-scale magnitudes cannot overflow or underflow the squares, so a plain
+        // sqrt of the sum of squares stands in for hypot (<= 1 ulp apart)
+        s_log[(size_t)ea * S.NBP + k] = log(sqrt(ar * ar + ai * ai) * P.scale + 1e-12);
+        if (ea + 1 < nrun) s_log[(size_t)(ea + 1) * S.NBP + k] = log(sqrt(br * br + bi * bi) * P.scale + 1e-12);
       }
     }
     __syncthreads();
     // ---- output pass, row-major over [n_f, n_t]: the targets whose bracketing frames are the
     // entries (j, j+1) of this run with j + 1 < nrun; on the first run also everything that is
     // out of range (fill value -> 0 after normalise + clip)
-    for (int i = tid; i < n_out; i += 256) {
-      const int f = i / P.n_t, t = i - f * P.n_t;
-      const int ti = tix[t];
-      const int fi = P.f_idx[f];
-      const bool valid = (ti >= 0) && (ti + 1 < K) && (fi >= 0);
-      double v = 0.0;
-      bool write = false;
-      if (!valid) {
-        write = first_run;
-      } else {
-        const int j = s_slot[ti];
-        if (j >= 0 && j + 1 < nrun) {      // (a run's last entry is the next run's first: handled there)
-          const double* lo = s_log + (size_t)j * S.NBP;
-          const double* hi = lo + S.NBP;
-          const double wy = P.f_frac[f], wx = tfr[t];
+    // (a thread keeps its target times: slot and weight are looked up once per run, then it walks the
+    // frequency rows; a warp's lanes are consecutive t of one row -> 128-byte coalesced stores)
+    for (int t0 = 0; t0 < P.n_t; t0 += 128) {
+      const int t = t0 + (tid & 127);
+      const bool t_in = t < P.n_t;
+      const int ti = t_in ? tix[t] : -1;
+      const bool t_valid = (ti >= 0) && (ti + 1 < K);
+      const int j = t_valid ? s_slot[ti] : -1;
+      const bool here = (j >= 0) && (j + 1 < nrun);   // (a run's last entry is the next run's first: handled there)
+      const double wx = here ? tfr[t] : 0.0;
+      const double* lo = s_log + (size_t)(here ? j : 0) * S.NBP;
+      const double* hi = lo + S.NBP;
+      for (int f = tid >> 7; f < P.n_f; f += 2) {
+        const int fi = P.f_idx[f];
+        double v = 0.0;
+        bool write = false;
+        if (!t_valid || fi < 0) {
+          write = first_run;                            // out of range: fill value -> 0 after normalise + clip
+        } else if (here) {
+          const double wy = P.f_frac[f];
           const double s00 = lo[fi], s01 = hi[fi], s10 = lo[fi + 1], s11 = hi[fi + 1];
           v = (1.0 - wy) * ((1.0 - wx) * s00 + wx * s01) + wy * ((1.0 - wx) * s10 + wx * s11);
           v = (v - P.spec_min) * P.inv_range;
           v = fmin(fmax(v, 0.0), 1.0);
           write = true;
         }
-      }
-      if (write) {
-        if (P.out) P.out[out_base + i] = (float)v;
-        if (P.out64) P.out64[out_base + i] = v;
+        if (write && t_in) {
+          const size_t o = out_base + (size_t)f * P.n_t + t;
+          if (P.out) P.out[o] = (float)v;
+          if (P.out64) P.out64[o] = v;
+        }
       }
     }
     first_run = false;
@@ -419,7 +435,7 @@ extern "C" int ava_b200_get_spec_batch(const void* audio, int is_f32, const long
   if (S.G < 1) S.G = 1;
   if (S.G > 8) S.G = 8;
   S.NBP = nperseg / 2 + 2;
-  const size_t fixed = (size_t)S.G * nperseg * 16 + (size_t)(nperseg / 2) * 16 + 64 +
+  const size_t fixed = (size_t)S.G * nperseg * 16 + (size_t)nperseg * 16 + 64 +
                        (size_t)2 * (max_frames + 1) * 4 + 16;
   const size_t budget = (size_t)96 * 1024;
   long long cf = fixed < budget ? (long long)((budget - fixed) / ((size_t)S.NBP * 8)) : 0;
@@ -430,6 +446,16 @@ extern "C" int ava_b200_get_spec_batch(const void* audio, int is_f32, const long
   size_t smem = fixed + (size_t)S.CF * S.NBP * 8;
   smem = (smem + 15) / 16 * 16;
   AVA_REQUIRE(smem <= 227 * 1024, "get_spec: %zu bytes of shared memory needed (nperseg %d)", smem, nperseg);
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(get_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess) {
+      cudaGetLastError();
+      set_error("get_spec: %zu bytes of shared memory unavailable", smem);
+      return 1;
+    }
+    configured = smem;
+  }
   get_spec_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(P, S);
   return check_launch("get_spec");
 }

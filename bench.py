@@ -590,17 +590,26 @@ def main():
     # ---------------------------------------------------------------- the other BASELINE configs
     extra = {}
     if not args.no_extra:
+        # (secondary workloads never take the headline line down with them: a failure is reported)
         peak_x, _ = measured_peaks()
-        lat_model = vae_mod.VAE(save_dir='', device_name='cuda', precision=args.precision)
-        r = extra_get_latent(lat_model, torch, dist, world, rank, args.latent_specs, 1024, peak_x)
-        if r is not None:
-            extra["get_latent"] = r
-        del lat_model
+        try:
+            lat_model = vae_mod.VAE(save_dir='', device_name='cuda', precision=args.precision)
+            r = extra_get_latent(lat_model, torch, dist, world, rank, args.latent_specs, 1024, peak_x)
+            if r is not None:
+                extra["get_latent"] = r
+            del lat_model
+        except Exception as e:      # noqa: BLE001
+            if world > 1:
+                raise               # ranks must not diverge around a collective
+            extra["get_latent"] = {"error": repr(e)}
         if world == 1:
-            sg_model = vae_mod.VAE(save_dir='', device_name='cuda', precision=args.precision)
-            sg_model.train()
-            extra["shotgun"] = extra_shotgun(sg_model, torch, vae_mod, 10)
-            del sg_model
+            try:
+                sg_model = vae_mod.VAE(save_dir='', device_name='cuda', precision=args.precision)
+                sg_model.train()
+                extra["shotgun"] = extra_shotgun(sg_model, torch, vae_mod, 10)
+                del sg_model
+            except Exception as e:  # noqa: BLE001
+                extra["shotgun"] = {"error": repr(e)}
     if rank == 0:
         peak, peak_src = measured_peaks()
         roof, kernels, families = None, [], []
