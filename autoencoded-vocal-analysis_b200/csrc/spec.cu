@@ -54,16 +54,21 @@ struct SpecSmem {
   int G, CF, NBP;   // packed transforms per batch, log-spectrum slots, slot pitch (doubles)
 };
 
+// LOG2N = log2(nperseg) is a template parameter: every index split in the hot loops is then a shift
+// (the first version of this kernel spent 25 % of its instructions in IMAD / software division).
+template <int LOG2N>
 __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const SpecSmem S) {
   extern __shared__ __align__(16) double sm[];
-  const int N = P.nperseg, NB = N / 2 + 1, half = N / 2;
+  constexpr int N = 1 << LOG2N, half = N / 2;
   double2* s_x = reinterpret_cast<double2*>(sm);                  // [G][N] packed FFT buffers
   double2* s_tw = s_x + (size_t)S.G * N;                          // [N] per-stage twiddle tables (N-1 used)
   double* s_log = reinterpret_cast<double*>(s_tw + N);            // [CF][NBP] log spectra
   double* s_red = s_log + (size_t)S.CF * S.NBP;                   // [8]
   int* s_list = reinterpret_cast<int*>(s_red + 8);                // [max_frames+1] needed frames, ascending
   int* s_slot = s_list + (P.max_frames + 1);                      // [max_frames+1] frame -> slot in the current run
-  int* s_cnt = s_slot + (P.max_frames + 1);                       // [1]
+  int* s_cnt = s_slot + (P.max_frames + 1);                       // [2]
+  int* s_fi = s_cnt + 2;                                          // [n_f] frequency bracket index
+  double* s_wy = reinterpret_cast<double*>(s_fi + ((P.n_f + 1) & ~1));   // [n_f] and weight
 
   const int tid = threadIdx.x;
   const int w = blockIdx.x;
@@ -97,6 +102,10 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
     s_tw[e] = make_double2(cs, sn);
   }
   for (int k = tid; k <= K; k += 256) s_slot[k] = 0;
+  for (int f = tid; f < P.n_f; f += 256) {
+    s_fi[f] = P.f_idx[f];
+    s_wy[f] = P.f_frac[f];
+  }
   __syncthreads();
   const int* tix = P.t_idx + (size_t)w * P.n_t;
   const double* tfr = P.t_frac + (size_t)w * P.n_t;
@@ -145,8 +154,8 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
       for (int idx = tid; idx < npair * N; idx += 256) {
         // destination index r runs with the lanes (conflict-free stores); the source sample index
         // j = bitrev(r) scatters over the 2*N bytes of a frame, which sit in L1
-        const int g = idx / N, r = idx - g * N;
-        const int j = (int)(__brev((unsigned)r) >> (32 - P.log2n));
+        const int g = idx >> LOG2N, r = idx & (N - 1);
+        const int j = (int)(__brev((unsigned)r) >> (32 - LOG2N));
         const int fa = s_list[a + p0 + 2 * g];
         const int eb = p0 + 2 * g + 1;
         const double wj = P.window[j];
@@ -161,11 +170,12 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
       }
       __syncthreads();
       // radix-2 DIT over all npair transforms
-      for (int st = 1; st <= P.log2n; ++st) {
+#pragma unroll 1
+      for (int st = 1; st <= LOG2N; ++st) {
         const int mh = 1 << (st - 1);
         const double2* twst = s_tw + (mh - 1);
         for (int b = tid; b < npair * half; b += 256) {
-          const int g = b / half, bb = b - g * half;
+          const int g = b >> (LOG2N - 1), bb = b & (half - 1);
           const int grp = bb >> (st - 1), pos = bb & (mh - 1);
           const int i0 = (grp << st) + pos, i1 = i0 + mh;
           double2* x = s_x + (size_t)g * N;
@@ -178,18 +188,28 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
         __syncthreads();
       }
       // unpack the two real spectra and take log magnitudes (ava/preprocessing/utils.py:79)
-      for (int idx = tid; idx < npair * NB; idx += 256) {
-        const int g = idx / NB, k = idx - g * NB;
+      auto logmag = [&](double re, double im) {
+        // |X| * scale: audio-scale magnitudes cannot overflow or underflow the squares, so a plain
+        // sqrt of the sum of squares stands in for hypot (<= 1 ulp apart)
+        return log(sqrt(re * re + im * im) * P.scale + 1e-12);
+      };
+      for (int idx = tid; idx < npair * half; idx += 256) {
+        const int g = idx >> (LOG2N - 1), k = idx & (half - 1);
         const double2* x = s_x + (size_t)g * N;
         const double2 z = x[k], zc = x[(N - k) & (N - 1)];
         // X_a = (Z[k] + conj Z[N-k]) / 2 ; X_b = (Z[k] - conj Z[N-k]) / (2i)
         const double ar = 0.5 * (z.x + zc.x), ai = 0.5 * (z.y - zc.y);
         const double br = 0.5 * (z.y + zc.y), bi = -0.5 * (z.x - zc.x);
         const int ea = p0 + 2 * g;
-        // |X| * scale: audio-scale magnitudes cannot overflow or underflow the squares, so a plain
-        // sqrt of the sum of squares stands in for hypot (<= 1 ulp apart)
-        s_log[(size_t)ea * S.NBP + k] = log(sqrt(ar * ar + ai * ai) * P.scale + 1e-12);
-        if (ea + 1 < nrun) s_log[(size_t)(ea + 1) * S.NBP + k] = log(sqrt(br * br + bi * bi) * P.scale + 1e-12);
+        s_log[(size_t)ea * S.NBP + k] = logmag(ar, ai);
+        if (ea + 1 < nrun) s_log[(size_t)(ea + 1) * S.NBP + k] = logmag(br, bi);
+      }
+      if (tid < npair) {
+        // Nyquist bin k = N/2: Z[N/2] pairs with itself -> X_a = Re Z, X_b = Im Z
+        const double2 z = s_x[(size_t)tid * N + half];
+        const int ea = p0 + 2 * tid;
+        s_log[(size_t)ea * S.NBP + half] = logmag(z.x, 0.0);
+        if (ea + 1 < nrun) s_log[(size_t)(ea + 1) * S.NBP + half] = logmag(z.y, 0.0);
       }
     }
     __syncthreads();
@@ -208,14 +228,15 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
       const double wx = here ? tfr[t] : 0.0;
       const double* lo = s_log + (size_t)(here ? j : 0) * S.NBP;
       const double* hi = lo + S.NBP;
-      for (int f = tid >> 7; f < P.n_f; f += 2) {
-        const int fi = P.f_idx[f];
+      size_t o = out_base + (size_t)(tid >> 7) * P.n_t + t;
+      for (int f = tid >> 7; f < P.n_f; f += 2, o += 2 * (size_t)P.n_t) {
+        const int fi = s_fi[f];
         double v = 0.0;
         bool write = false;
         if (!t_valid || fi < 0) {
           write = first_run;                            // out of range: fill value -> 0 after normalise + clip
         } else if (here) {
-          const double wy = P.f_frac[f];
+          const double wy = s_wy[f];
           const double s00 = lo[fi], s01 = hi[fi], s10 = lo[fi + 1], s11 = hi[fi + 1];
           v = (1.0 - wy) * ((1.0 - wx) * s00 + wx * s01) + wy * ((1.0 - wx) * s10 + wx * s11);
           v = (v - P.spec_min) * P.inv_range;
@@ -223,7 +244,6 @@ __global__ void __launch_bounds__(256) get_spec_kernel(const SpecParams P, const
           write = true;
         }
         if (write && t_in) {
-          const size_t o = out_base + (size_t)f * P.n_t + t;
           if (P.out) P.out[o] = (float)v;
           if (P.out64) P.out64[o] = v;
         }
@@ -436,7 +456,7 @@ extern "C" int ava_b200_get_spec_batch(const void* audio, int is_f32, const long
   if (S.G > 8) S.G = 8;
   S.NBP = nperseg / 2 + 2;
   const size_t fixed = (size_t)S.G * nperseg * 16 + (size_t)nperseg * 16 + 64 +
-                       (size_t)2 * (max_frames + 1) * 4 + 16;
+                       (size_t)2 * (max_frames + 1) * 4 + 16 + (size_t)(n_f + 2) * 12 + 16;
   const size_t budget = (size_t)96 * 1024;
   long long cf = fixed < budget ? (long long)((budget - fixed) / ((size_t)S.NBP * 8)) : 0;
   if (cf < 4) cf = 4;
@@ -446,16 +466,21 @@ extern "C" int ava_b200_get_spec_batch(const void* audio, int is_f32, const long
   size_t smem = fixed + (size_t)S.CF * S.NBP * 8;
   smem = (smem + 15) / 16 * 16;
   AVA_REQUIRE(smem <= 227 * 1024, "get_spec: %zu bytes of shared memory needed (nperseg %d)", smem, nperseg);
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(get_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess) {
+  // one instantiation per power-of-two nperseg
+  using Kern = void (*)(const SpecParams, const SpecSmem);
+  static const Kern kerns[13] = {nullptr, nullptr, nullptr, nullptr, get_spec_kernel<4>, get_spec_kernel<5>,
+                                 get_spec_kernel<6>, get_spec_kernel<7>, get_spec_kernel<8>, get_spec_kernel<9>,
+                                 get_spec_kernel<10>, get_spec_kernel<11>, get_spec_kernel<12>};
+  static size_t configured[13] = {0};
+  Kern kern = kerns[P.log2n];
+  if (smem > configured[P.log2n]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
       set_error("get_spec: %zu bytes of shared memory unavailable", smem);
       return 1;
     }
-    configured = smem;
+    configured[P.log2n] = smem;
   }
-  get_spec_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(P, S);
+  kern<<<n, 256, smem, (cudaStream_t)stream>>>(P, S);
   return check_launch("get_spec");
 }

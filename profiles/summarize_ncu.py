@@ -99,7 +99,10 @@ WANT = OrderedDict([
 
 
 def full(path, traffic_path=None):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):      # already exported on the GPU box: ncu -i X.ncu-rep --page raw --csv
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     start = raw.find('"ID"')
     rd = csv.reader(io.StringIO(raw[start:]))
     header = next(rd)
