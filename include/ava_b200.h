@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AVA_B200_ABI_VERSION 2
+#define AVA_B200_ABI_VERSION 3
 #define AVA_NUM_BN_LAYERS 14
 #define AVA_STATS_STRIDE 64 /* doubles per layer in a stats block: [0..31]=sum, [32..63]=sum of squares */
 
@@ -193,6 +193,33 @@ int ava_b200_adam_step(float* p, const float* g, float* m, float* v, long long n
  * rate schedules, the lr a checkpoint restores: ava/models/vae.py:470) without re-capture. */
 int ava_b200_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float* step_count,
                            const double* hyper, float grad_scale, void* stream);
+
+/* Data-parallel optimizer step fused with its collectives over NVLink / NVSwitch peer memory
+ * (csrc/dp.cu): the data-parallel form of optimizer.step(), ava/models/vae.py:353 -- replaces
+ * "NCCL all-reduce(SUM) of the flat gradient, then Adam on every rank".  Rank r sums the
+ * world gradient copies of ITS 1/world slice (peer loads, or one multimem.ld_reduce through the
+ * switch when multicast pointers are given), applies Adam to that slice only (moments are sharded)
+ * and stores the new parameters into every rank's parameter buffer; two flag barriers order it
+ * against the ranks' backward / next forward passes.
+ *   h_peers: HOST struct of DEVICE pointers: every rank's flat gradient buffer, flat parameter
+ *            buffer and flag block (2*AVA_DP_MAX_WORLD uint32, zero-initialised once), all in
+ *            symmetric (peer-mapped) memory; index = rank; grad_mc/param_mc = multicast views or NULL
+ *   m, v:    this rank's LOCAL moment buffers (only its slice is read and written)
+ *   local:   LOCAL device uint32[4], zero-initialised once: [0] step sequence number,
+ *            [1] CTA counter, [2] set to 1 if a peer did not arrive within 20 s (the kernel
+ *            then carries on instead of hanging; the caller checks it)
+ * Every rank must make the same sequence of calls.  n % 4 == 0; world <= AVA_DP_MAX_WORLD. */
+#define AVA_DP_MAX_WORLD 8
+typedef struct {
+  const float* grad[AVA_DP_MAX_WORLD];
+  float* param[AVA_DP_MAX_WORLD];
+  unsigned int* flags[AVA_DP_MAX_WORLD];
+  const float* grad_mc;
+  float* param_mc;
+} ava_b200_dp_peers;
+int ava_b200_adam_step_dp(const ava_b200_dp_peers* h_peers, int rank, int world, float* m, float* v,
+                          long long n, float* step_count, const double* hyper, float grad_scale,
+                          unsigned int* local, void* stream);
 
 /* ------------------------------------------------------------------- get_spec
  * Batched spectrogram front end: ava/preprocessing/utils.py:18-110 (get_spec) with
