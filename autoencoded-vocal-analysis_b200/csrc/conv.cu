@@ -190,6 +190,28 @@ __device__ __forceinline__ void cv_mma_tf32(float (&c)[4], const uint32_t (&a)[4
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// TERMS == 2: the error-compensated product with its two correction terms at half the tensor-core
+// cost.  x = x_hi + x_lo as above; a*b = a_hi*b_hi + a_lo*b + a*b_lo - a_lo*b_lo.  The main term
+// stays on mma.m16n8k8 TF32; the corrections are 2^-11 of it, so their factors only need 8
+// significant bits: a_lo*b and a*b_lo run as BF16 mma.m16n8k16, which covers TWO k-chunks per
+// instruction at the TF32 instruction's issue cost (probe: profiles/probes/hmma_kinds.cu, 8.9
+// cycles per SMSP for either shape).  4 tensor-core instructions per pair of k-chunks instead of
+// 6; per-product error <= 2^-11 * 2 * 2^-8 = 2^-18 relative, unbiased (round-to-nearest
+// everywhere), i.e. ~1e-6 of the result's scale after the random-sign sum.
+// A pair of k-chunks (c0, c1) maps onto the k16 fragment as k16 = {2t: c0[t], 2t+1: c1[t],
+// 2t+8: c0[t+4], 2t+9: c1[t+4]} for BOTH operands, so every lane packs only its own registers.
+__device__ __forceinline__ uint32_t cv_pack_bf16(float lo_half, float hi_half) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+  return r;
+}
+__device__ __forceinline__ void cv_mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __device__ __forceinline__ uint32_t cv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cv_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cv_smem_u32(bar)), "r"(count));
@@ -1436,6 +1458,9 @@ static int make_act_map(CUtensorMap* map, const float* base, long long nc, int H
 
 // 0: fp32 SIMT; 1: TF32 tensor cores; 3: error-compensated 3xTF32 (layers the tensor-core path covers)
 static int g_conv_terms = 0;
+// 3-term layers: correction terms as half-rate BF16 k16 instructions (cv_pack_bf16) where a kernel
+// has that variant (mode 3 of ava_b200_set_conv_precision); mode 2 keeps all three terms in TF32
+static int g_conv_bf16corr = 0;
 
 template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN, int TERMS = 0>
 static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
@@ -1911,12 +1936,74 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
     const float* gbase = s_g + (mt * 16 + g) * T::G_PLANE + t;
     const float* ibase = s_i + (nt * 8 + g) * T::I_PLANE + 3 + S * t;
     float tq[9][4];
-    if (TERMS == 3) {
+    if (TERMS >= 2) {
 #pragma unroll
       for (int k = 0; k < 9; ++k)
 #pragma unroll
         for (int q = 0; q < 4; ++q) tq[k][q] = 0.f;
     }
+    if constexpr (TERMS == 2) {
+      // two k-steps (8 pixels each) per iteration: TF32 main terms separately, the two correction
+      // terms of both steps as one BF16 k16 instruction each (see cv_pack_bf16)
+      static_assert((KSTEPS / KS) % 2 == 0, "k-steps per warp must pair up");
+#pragma unroll 1
+      for (int j = ks; j < KSTEPS; j += 2 * KS) {
+        const int j1 = j + KS;
+        const int y0 = j / (TWG / 8), x00 = (j % (TWG / 8)) * 8;
+        const int y1 = j1 / (TWG / 8), x01 = (j1 % (TWG / 8)) * 8;
+        const float* gp0 = gbase + y0 * T::G_W + x00;
+        const float* gp1 = gbase + y1 * T::G_W + x01;
+        float av0[4], av1[4];
+        av0[0] = gp0[0];
+        av0[2] = gp0[4];
+        av0[1] = hi_rows ? gp0[8 * T::G_PLANE] : 0.f;
+        av0[3] = hi_rows ? gp0[8 * T::G_PLANE + 4] : 0.f;
+        av1[0] = gp1[0];
+        av1[2] = gp1[4];
+        av1[1] = hi_rows ? gp1[8 * T::G_PLANE] : 0.f;
+        av1[3] = hi_rows ? gp1[8 * T::G_PLANE + 4] : 0.f;
+        if (!CONVT && nt == 0) {
+          bs0 += (av0[0] + av0[2]) + (av1[0] + av1[2]);
+          bs1 += (av0[1] + av0[3]) + (av1[1] + av1[3]);
+        }
+        uint32_t ah0[4], ah1[4], alp[4], ap[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ah0[q] = cv_tf32_hi(av0[q]);
+          ah1[q] = cv_tf32_hi(av1[q]);
+          alp[q] = cv_pack_bf16(av0[q] - __uint_as_float(ah0[q]), av1[q] - __uint_as_float(ah1[q]));
+          ap[q] = cv_pack_bf16(av0[q], av1[q]);
+        }
+        const float* ip0 = ibase + (S * y0) * T::I_PITCH + S * x00;
+        const float* ip1 = ibase + (S * y1) * T::I_PITCH + S * x01;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          uint32_t bh0[3][2], bh1[3][2], bp[3][2], blp[3][2];
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float b0 = ip0[ky * T::I_PITCH + kx + 4 * S * q];
+              const float b1 = ip1[ky * T::I_PITCH + kx + 4 * S * q];
+              if (CONVT && mt == 0) {
+                if (S == 1 ? (ky == 1 && kx == 1) : (ky >= 1 && kx >= 1)) bs0 += b0 + b1;
+              }
+              bh0[kx][q] = cv_tf32_hi(b0);
+              bh1[kx][q] = cv_tf32_hi(b1);
+              blp[kx][q] = cv_pack_bf16(b0 - __uint_as_float(bh0[kx][q]), b1 - __uint_as_float(bh1[kx][q]));
+              bp[kx][q] = cv_pack_bf16(b0, b1);
+            }
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) cv_mma_bf16(tq[ky * 3 + kx], alp, bp[kx][0], bp[kx][1]);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) cv_mma_bf16(tq[ky * 3 + kx], ap, blp[kx][0], blp[kx][1]);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32(tq[ky * 3 + kx], ah0, bh0[kx][0], bh0[kx][1]);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) cv_mma_tf32(tq[ky * 3 + kx], ah1, bh1[kx][0], bh1[kx][1]);
+        }
+      }
+    } else {
 #pragma unroll 2
     for (int j = ks; j < KSTEPS; j += KS) {
       const int y = j / (TWG / 8), x0 = (j % (TWG / 8)) * 8;
@@ -1976,7 +2063,8 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
         }
       }
     }
-    if (TERMS == 3) {
+    }
+    if (TERMS >= 2) {
 #pragma unroll
       for (int k = 0; k < 9; ++k)
 #pragma unroll
@@ -2265,7 +2353,8 @@ static int launch_wgrad_mma(WgradParams P, const FinalizeParams& F, void* ws, cu
 
 // tensor-core weight gradient (all layers with >= 8 channels on both sides), else the fp32 FMA kernel
 #define WGRAD_TC(S, CG, CI, TWG, CONVT)                                                              \
-  (g_conv_terms == 3   ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 3>(P, F, ws, stream)               \
+  (g_conv_terms == 3   ? (g_conv_bf16corr ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 2>(P, F, ws, stream)  \
+                                          : launch_wgrad_mma<S, CG, CI, TWG, CONVT, 3>(P, F, ws, stream)) \
    : g_conv_terms == 1 ? launch_wgrad_mma<S, CG, CI, TWG, CONVT, 1>(P, F, ws, stream)               \
                        : launch_wgrad<S, CG, CI, TWG, CONVT>(P, F, ws, stream))
 
@@ -2305,11 +2394,13 @@ using namespace ava;
                      : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 0>(P, stream))
 
 extern "C" int ava_b200_set_conv_precision(int mode) {
-  AVA_REQUIRE(mode == 0 || mode == 1 || mode == 2, "set_conv_precision: mode %d (0 fp32, 1 tf32, 2 tf32x3)", mode);
-  g_conv_terms = (mode == 2) ? 3 : mode;
+  AVA_REQUIRE(mode >= 0 && mode <= 3, "set_conv_precision: mode %d (0 fp32, 1 tf32, 2 tf32x3, 3 tf32 + bf16 corrections)",
+              mode);
+  g_conv_terms = (mode >= 2) ? 3 : mode;
+  g_conv_bf16corr = (mode == 3) ? 1 : 0;
   return 0;
 }
-extern "C" int ava_b200_get_conv_precision(void) { return g_conv_terms == 3 ? 2 : g_conv_terms; }
+extern "C" int ava_b200_get_conv_precision(void) { return g_conv_terms == 3 ? (g_conv_bf16corr ? 3 : 2) : g_conv_terms; }
 
 extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float* w, const float* b,
                                    const float* gamma, const float* beta, const double* stats_in,

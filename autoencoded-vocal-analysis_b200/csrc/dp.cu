@@ -117,42 +117,76 @@ adam_dp_kernel(const DpPeers P, const int rank, const int world, float* __restri
   const float b1 = (float)b1_d, b2 = (float)b2_d, eps = (float)eps_d;
   const float omb1 = (float)(1.0 - b1_d), omb2 = (float)(1.0 - b2_d);
 
-  // ---- phase 1: this rank's slice (float4 units)
+  // ---- phase 1: this rank's slice (float4 units), U float4 per thread and trip with every
+  // gradient load of the trip issued before the first is used (an NVLink / NVSwitch round trip is
+  // several microseconds: the kernel lives on memory-level parallelism)
+  constexpr int U = 4;
   const long long lo = n4 * rank / world, hi = n4 * (rank + 1) / world;
   float* p_own = P.param[rank];
-  for (long long i = lo + (long long)blockIdx.x * blockDim.x + tid; i < hi; i += (long long)gridDim.x * blockDim.x) {
-    float4 gv;
-    if (MC) {
-      gv = dp_ld_reduce_mc(P.grad_mc + 4 * i);
-    } else {
-      // fixed order 0..world-1: the sum does not depend on which rank owns the slice
-      gv = dp_ld_peer(P.grad[0] + 4 * i);
-      for (int r = 1; r < world; ++r) {
-        const float4 a = dp_ld_peer(P.grad[r] + 4 * i);
-        gv.x += a.x;
-        gv.y += a.y;
-        gv.z += a.z;
-        gv.w += a.w;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + tid; i0 < hi; i0 += U * stride) {
+    float4 gv[U], pv[U], mv[U], vv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) {
+        if (MC) {
+          gv[u] = dp_ld_reduce_mc(P.grad_mc + 4 * i);
+        } else {
+          gv[u] = dp_ld_peer(P.grad[0] + 4 * i);
+        }
       }
     }
-    float4 pv = reinterpret_cast<const float4*>(p_own)[i];
-    float4 mv = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-#define AVA_ADAM_DP1(c)                                      \
-  {                                                          \
-    float gg = gv.c * gscale;                                \
-    mv.c = b1 * mv.c + omb1 * gg;                            \
-    vv.c = b2 * vv.c + omb2 * gg * gg;                       \
-    float denom = sqrtf(vv.c) * inv_sqrt_bc2 + eps;          \
-    pv.c = pv.c - step_size * (mv.c / denom);                \
+    if (!MC) {
+      // fixed order 0..world-1: the sum does not depend on which rank owns the slice
+      for (int r = 1; r < world; ++r) {
+        float4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < hi) a[u] = dp_ld_peer(P.grad[r] + 4 * i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < hi) {
+            gv[u].x += a[u].x;
+            gv[u].y += a[u].y;
+            gv[u].z += a[u].z;
+            gv[u].w += a[u].w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) {
+        pv[u] = reinterpret_cast<const float4*>(p_own)[i];
+        mv[u] = reinterpret_cast<float4*>(m)[i];
+        vv[u] = reinterpret_cast<float4*>(v)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= hi) continue;
+#define AVA_ADAM_DP1(c)                                            \
+  {                                                                \
+    float gg = gv[u].c * gscale;                                   \
+    mv[u].c = b1 * mv[u].c + omb1 * gg;                            \
+    vv[u].c = b2 * vv[u].c + omb2 * gg * gg;                       \
+    float denom = sqrtf(vv[u].c) * inv_sqrt_bc2 + eps;             \
+    pv[u].c = pv[u].c - step_size * (mv[u].c / denom);             \
   }
-    AVA_ADAM_DP1(x) AVA_ADAM_DP1(y) AVA_ADAM_DP1(z) AVA_ADAM_DP1(w)
-    reinterpret_cast<float4*>(m)[i] = mv;
-    reinterpret_cast<float4*>(v)[i] = vv;
-    if (MC) {
-      dp_st_mc(P.param_mc + 4 * i, pv);
-    } else {
-      for (int r = 0; r < world; ++r) dp_st_peer(P.param[r] + 4 * i, pv);
+      AVA_ADAM_DP1(x) AVA_ADAM_DP1(y) AVA_ADAM_DP1(z) AVA_ADAM_DP1(w)
+      reinterpret_cast<float4*>(m)[i] = mv[u];
+      reinterpret_cast<float4*>(v)[i] = vv[u];
+      if (MC) {
+        dp_st_mc(P.param_mc + 4 * i, pv[u]);
+      } else {
+        for (int r = 0; r < world; ++r) dp_st_peer(P.param[r] + 4 * i, pv[u]);
+      }
     }
   }
 
@@ -208,7 +242,7 @@ extern "C" int ava_b200_adam_step_dp(const ava_b200_dp_peers* h_peers, int rank,
   cudaStream_t stream = (cudaStream_t)stream_;
   const long long n4 = n / 4;
   // (no co-residency requirement: whichever CTA finishes last does the phase-2 handshake)
-  long long want = (n4 / world + 255) / 256;
+  long long want = (n4 / world + 4 * 256 - 1) / (4 * 256);
   int grid = (int)(want < 1 ? 1 : (want > 4 * kNumSMs ? 4 * kNumSMs : want));
   if (mc)
     adam_dp_kernel<true><<<grid, 256, 0, stream>>>(P, rank, world, m, v, n4, step_count, hyper, grad_scale, local);

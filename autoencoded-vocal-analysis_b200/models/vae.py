@@ -20,6 +20,7 @@ behaviour): ``precision=`` constructor argument, ``train_step``, ``compute_loss`
 import ctypes
 import math
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -43,6 +44,16 @@ _CONVT = [("convt1", 32, 24, 1, 16), ("convt2", 24, 24, 2, 16), ("convt3", 24, 1
           ("convt7", 8, 1, 1, 128)]
 _LAYERS = _CONV + _CONVT           # layer id 0..13 of the C ABI
 _BN_MOMENTUM = 0.1
+# what precision='auto' means for the conv layers (2: 3xTF32; 3: TF32 + BF16 corrections)
+_AUTO_CONV_MODE = int(os.environ.get("AVA_B200_AUTO_CONV_MODE", "3"))
+_DP_MAX_WORLD = 8          # AVA_DP_MAX_WORLD, include/ava_b200.h
+
+
+class _DpPeers(ctypes.Structure):
+    """ava_b200_dp_peers (include/ava_b200.h): per-rank device pointers into symmetric memory."""
+    _fields_ = [("grad", ctypes.c_void_p * _DP_MAX_WORLD), ("param", ctypes.c_void_p * _DP_MAX_WORLD),
+                ("flags", ctypes.c_void_p * _DP_MAX_WORLD), ("grad_mc", ctypes.c_void_p),
+                ("param_mc", ctypes.c_void_p)]
 # the backward-data kernels accumulate the border sums of the dz they write in their epilogue
 # (AVA_B200_FUSED_TSUMS=0: a separate ava_b200_dz_border_sums pass per layer instead)
 _FUSED_TSUMS = os.environ.get("AVA_B200_FUSED_TSUMS", "1") != "0"
@@ -215,9 +226,12 @@ class VAE(nn.Module):
         self.device = torch.device(device_name)
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        assert precision in ('auto', 'fp32', 'tf32x3', 'tf32')
+        assert precision in ('auto', 'fp32', 'tf32x3', 'tf32x3b', 'tf32')
         self.precision = precision
-        self._tc = {'auto': 2, 'fp32': 0, 'tf32x3': 2, 'tf32': 1}[precision]
+        # dense layers: 0 fp32 FMA, 1 TF32, 2 3xTF32; conv layers additionally 3 = 3-term product
+        # with the two correction terms as half-rate BF16 instructions (csrc/conv.cu, cv_pack_bf16)
+        self._tc = {'auto': 2, 'fp32': 0, 'tf32x3': 2, 'tf32x3b': 2, 'tf32': 1}[precision]
+        self._tc_conv = {'auto': _AUTO_CONV_MODE, 'tf32x3b': 3}.get(precision, self._tc)
         # CUDA graphs for the train step: 'auto' = when the step is host-bound (batch <= 256)
         assert cuda_graphs in ('auto', True, False)
         self.cuda_graphs = cuda_graphs
@@ -328,6 +342,7 @@ class VAE(nn.Module):
             self._views_v[k] = flat_v[o:o + n].view(p.shape)
             p.grad = None
         self._flat_p, self._flat_g, self._flat_m, self._flat_v = flat_p, flat_g, flat_m, flat_v
+        self._dp_fused = None      # (a re-flatten leaves the symmetric-memory buffers of the fused DP path)
         # optimizer state that aliased the previous flat moment buffers follows them (model.to(),
         # .cuda(), .float() after training); the step count is kept, not re-adopted
         opt = getattr(self, "optimizer", None)
@@ -454,7 +469,7 @@ class VAE(nn.Module):
     def _conv_fwd(self, l, B, x, y, bufs, train, want_stats_out):
         name = _LAYERS[l][0]
         st = bufs.stats.data_ptr()
-        _set_conv_precision(self._tc)
+        _set_conv_precision(self._tc_conv)
         call("ava_b200_bnconv_fwd", l, B, ptr(x), ptr(y), self._p(name + ".weight"),
              self._p(name + ".bias"), self._p("bn%d.weight" % (l + 1)), self._p("bn%d.bias" % (l + 1)),
              st + 8 * 64 * l, self._rm(l), self._rv(l), 1 if train else 0,
@@ -570,7 +585,7 @@ class VAE(nn.Module):
         if not have_tsums:
             call("ava_b200_dz_border_sums", ptr(dz), B, co, ho, ho, mode, ts + 8 * 288 * l, s)
         ws = self._ws(self._scratch_need)
-        _set_conv_precision(self._tc)
+        _set_conv_precision(self._tc_conv)
         call("ava_b200_bnconv_bwd_weight", l, B, ptr(dz), ptr(x), self._p(name + ".weight"), gamma, beta,
              st + 8 * 64 * l, ts + 8 * 288 * l, self._g(name + ".weight"), self._g(name + ".bias"),
              ds + 8 * 64 * l, ptr(ws), s)
@@ -746,21 +761,117 @@ class VAE(nn.Module):
         return self.forward(x, noise=noise)
 
     # ------------------------------------------------------------ data parallel
-    def enable_data_parallel(self, process_group=None):
+    def enable_data_parallel(self, process_group=None, fused=None):
         """Shard batches over the ranks of `process_group` (default: WORLD), one process
         per GPU.  Semantics: the loss is a batch SUM, so rank
         gradients are SUMMED (not averaged) -- the update equals the reference's at the
         global batch; BatchNorm uses each rank's local batch statistics (every rank ==
         the reference run on its shard) and the running buffers are averaged across ranks
         at epoch boundaries (exactly what per-step averaging would give, since the
-        running-average recursion is linear).  Parameters are broadcast from rank 0."""
+        running-average recursion is linear).  Parameters are broadcast from rank 0.
+
+        `fused` (default: on for CUDA ranks of one NCCL node with <= 8 ranks; environment
+        AVA_B200_DP_FUSED=0 turns it off): the optimizer step and its two collectives run as
+        ONE kernel per rank over NVLink peer memory (csrc/dp.cu: each rank sums its 1/world
+        slice of everybody's gradient, applies Adam to that slice, stores the new parameters
+        into every rank's buffer); gradients, parameters and flags then live in symmetric
+        memory.  Otherwise: bucketed NCCL all-reduces overlapped with the backward pass."""
         import torch.distributed as dist
         self._dp_group = process_group if process_group is not None else dist.group.WORLD
         self._dp_world = dist.get_world_size(self._dp_group)
         self._dp_rank = dist.get_rank(self._dp_group)
         for t in (self._flat_p, self._flat_run, self._nbt, self._flat_m, self._flat_v):
             dist.broadcast(t, src=dist.get_global_rank(self._dp_group, 0), group=self._dp_group)
+        self._dp_fused = None
+        want = fused if fused is not None else os.environ.get("AVA_B200_DP_FUSED", "1") != "0"
+        if want and self._dp_world > 1:
+            ok = (self._flat_p.is_cuda and dist.get_backend(self._dp_group) == "nccl"
+                  and self._dp_world <= _DP_MAX_WORLD)
+            if ok:
+                try:
+                    self._enable_fused_dp()
+                except Exception as e:          # no symmetric memory / no peer access on this box
+                    if fused:
+                        raise
+                    warnings.warn("ava_b200: fused NVLink data-parallel step unavailable (%s: %s); "
+                                  "using bucketed NCCL all-reduces" % (type(e).__name__, e))
+                    self._dp_fused = None
+            elif fused:
+                raise RuntimeError("ava_b200: fused data parallelism needs CUDA ranks of one NCCL group "
+                                   "with at most %d ranks" % _DP_MAX_WORLD)
         return self
+
+    def _rebind_flat(self, flat_p, flat_g):
+        """Move the flat parameter / gradient storage into the given buffers (same layout) and
+        re-point every nn.Parameter and gradient view; captured graphs point at the old ones."""
+        flat_p.copy_(self._flat_p)
+        flat_g.zero_()
+        params = dict(self.named_parameters())
+        for k, o in self._off.items():
+            p = params[k]
+            n = p.numel()
+            p.data = flat_p[o:o + n].view(p.shape)
+            self._views_g[k] = flat_g[o:o + n].view(p.shape)
+        self._flat_p, self._flat_g = flat_p, flat_g
+        self._graphs = {}
+
+    def _enable_fused_dp(self):
+        """Gradients | parameters | flags in ONE symmetric-memory allocation, peer-mapped on every
+        rank (torch.distributed._symmetric_memory); the table of peer pointers for csrc/dp.cu."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        n, dev, W = self._n_flat, self._flat_p.device, self._dp_world
+        buf = symm.empty(2 * n + 64, dtype=torch.float32, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, self._dp_group)
+        ptrs = [int(a) for a in hdl.buffer_ptrs]
+        assert len(ptrs) == W and ptrs[self._dp_rank] == buf.data_ptr()
+        self._rebind_flat(buf[n:2 * n], buf[:n])
+        peers = _DpPeers()
+        for r in range(W):
+            peers.grad[r] = ptrs[r]
+            peers.param[r] = ptrs[r] + 4 * n
+            peers.flags[r] = ptrs[r] + 8 * n
+        mc = 0
+        if os.environ.get("AVA_B200_DP_MULTIMEM", "1") != "0":
+            try:
+                mc = int(hdl.multicast_ptr) if hdl.has_multicast_support else 0
+            except Exception:
+                mc = 0
+        peers.grad_mc = mc if mc else None
+        peers.param_mc = (mc + 4 * n) if mc else None
+        local = torch.zeros(4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self._dp_group)       # every rank's flags are zero before anyone signals
+        self._dp_fused = {"buf": buf, "hdl": hdl, "peers": peers, "local": local, "multimem": bool(mc)}
+
+    def _adam_dp_native(self):
+        """The fused data-parallel optimizer step (csrc/dp.cu)."""
+        f = self._dp_fused
+        call("ava_b200_adam_step_dp", ctypes.byref(f["peers"]), self._dp_rank, self._dp_world,
+             ptr(self._flat_m), ptr(self._flat_v), self._n_flat, ptr(self._step_dev), ptr(self._hyper_dev),
+             1.0, ptr(f["local"]), _stream())
+        self._step_host += 1
+
+    def dp_check_status(self):
+        """Raise if a peer ever failed to arrive at a fused data-parallel step (one device read)."""
+        f = getattr(self, "_dp_fused", None)
+        if f is not None and int(f["local"][2].item()) != 0:
+            raise RuntimeError("ava_b200: a data-parallel peer did not arrive within the kernel's timeout; "
+                               "the replicas are out of step")
+
+    def _gather_moment_shards(self):
+        """Fused data parallelism shards the Adam moments (rank r keeps slice r current): bring every
+        slice to every rank (checkpoints are written by rank 0 and must hold them all)."""
+        if getattr(self, "_dp_fused", None) is None:
+            return
+        import torch.distributed as dist
+        n4, W = self._n_flat // 4, self._dp_world
+        for r in range(W):
+            lo, hi = 4 * (n4 * r // W), 4 * (n4 * (r + 1) // W)
+            src = dist.get_global_rank(self._dp_group, r)
+            dist.broadcast(self._flat_m[lo:hi], src=src, group=self._dp_group)
+            dist.broadcast(self._flat_v[lo:hi], src=src, group=self._dp_group)
 
     def _grad_buckets(self):
         """(early, mid, late) slices of the flat gradient buffer, in the order the backward pass
@@ -830,7 +941,7 @@ class VAE(nn.Module):
                 return self._train_step_eager(st["x"], (st["ew"], st["ed"]))
             try:
                 host_step = self._step_host
-                if self._dp_world > 1:
+                if self._dp_world > 1 and self._dp_fused is None:
                     st["graph"] = self._capture_dp_segments(st)
                 else:
                     g = torch.cuda.CUDAGraph()
@@ -909,15 +1020,23 @@ class VAE(nn.Module):
         if self._dp_world <= 1:
             raise ValueError("train_step: empty batch")
         self._flat_g.zero_()
-        early, mid, late = self._grad_buckets()
-        for w in self._allreduce(early + mid + late, async_op=True):
-            w.wait()
-        self._adam_native()
+        if self._dp_fused is not None:
+            self._adam_dp_native()
+        else:
+            early, mid, late = self._grad_buckets()
+            for w in self._allreduce(early + mid + late, async_op=True):
+                w.wait()
+            self._adam_native()
         self._loss_sum += self.loss_constant()
         return torch.full((), self.loss_constant(), dtype=torch.float32, device=self._flat_p.device)
 
     def _train_step_eager(self, x, noise):
         bufs = self._forward_native(x, noise, True, want_grad_seed=True)
+        if self._dp_world > 1 and self._dp_fused is not None:
+            # gradients stay local: the optimizer kernel does the reduction over NVLink itself
+            self._backward_native(bufs)
+            self._adam_dp_native()
+            return bufs.loss[0]
         if self._dp_world > 1:
             early, mid, late = self._grad_buckets()
             works = []
@@ -1039,6 +1158,7 @@ class VAE(nn.Module):
     def save_state(self, filename):
         """Save all the model parameters to the given file (vae.py:433-446); the file
         is readable by the reference's load_state and vice versa."""
+        self._gather_moment_shards()     # (fused data parallelism: a collective -- every rank calls save_state)
         if self._step_host > 0:
             self._ensure_optimizer_state()
             self._publish_optimizer_steps()

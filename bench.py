@@ -225,6 +225,36 @@ def cpu_train_samples_per_sec(batch, steps, warmup, seed=0, threads=None):
     return batch * len(times) / total, 1e3 * total / len(times), torch.get_num_threads()
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: pin this rank's host threads (and so, by first touch, its pinned staging
+    buffers) to the NUMA node its GPU hangs off -- 8 ranks x 64 MiB per step of host->device
+    traffic otherwise cross the socket interconnect (round 1: e2e scaled 6.88x where the
+    device-resident loop scaled 7.36x).  Returns a short description, or None if unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "rank threads bound to NUMA node %d (%d cpus) of GPU %s" % (node, len(cpus), bus)
+    except Exception:      # noqa: BLE001  (no NVML / sysfs entry: leave the affinity alone)
+        return None
+
+
 def make_config(B, world, precision, graphs=None):
     return {"workload": "syllable VAE (z_dim=32) full train step (fwd+ELBO+bwd+Adam) on "
                         "128x128 synthetic specs, batch %d per GPU" % B,
@@ -332,6 +362,34 @@ def dp_check(model, vae_mod, dist, world, rank):
                    "shards summed" % (Bc, world))
     model._flat_run.copy_(keep_run)
     model._nbt.copy_(keep_nbt)
+    if getattr(model, "_dp_fused", None) is not None:
+        # (c) the fused NVLink optimizer kernel (csrc/dp.cu) against bucketed NCCL all-reduce + Adam:
+        # identical initial state, 3 steps on distinct shards, compare the parameters
+        ends = []
+        for fused in (True, False):
+            torch.manual_seed(4321)
+            mm = vae_mod.VAE(save_dir='', device_name='cuda', precision=model.precision, cuda_graphs=False)
+            mm.enable_data_parallel(fused=fused)
+            mm.train()
+            for step in range(3):
+                x, ew, ed = draw(2000 + 10 * step + rank)
+                mm.train_step(x, noise=(ew, ed))
+            mm.dp_check_status()
+            torch.cuda.synchronize()
+            ends.append(mm._flat_p.clone())
+            del mm
+        d = (ends[0] - ends[1]).abs()
+        same = ends[0].clone()
+        dist.broadcast(same, src=0)
+        res["fused_vs_nccl_param_mean_abs"] = float(d.mean())
+        res["fused_vs_nccl_param_max_abs"] = float(d.max())
+        res["fused_replicas_identical"] = bool(torch.equal(same, ends[0]))
+        # Adam's first steps are sign-like (|update| = lr = 1e-3 whatever the gradient's size): an
+        # element whose gradient sum is ~0 can flip with the summation order, so the max is bounded
+        # by steps x lr and the mean says how rare that is
+        res["ok"] = bool(res["ok"] and res["fused_replicas_identical"] and
+                         res["fused_vs_nccl_param_mean_abs"] < 2e-6 and res["fused_vs_nccl_param_max_abs"] < 7e-3)
+        res["what"] += "; (c) 3 steps of the fused NVLink reduce+Adam+broadcast kernel vs NCCL all-reduce + Adam"
     return res
 
 
@@ -460,7 +518,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32x3b", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--all-kernels", action="store_true", help="list every native call, not the top 12")
@@ -482,6 +540,7 @@ def main():
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -499,6 +558,13 @@ def main():
         model.enable_data_parallel()
         model.train()
         dp = dp_check(model, vae_mod, dist, world, rank)
+        f = model._dp_fused
+        dp_mode = ("bucketed NCCL all-reduce (3 buckets overlapped with the backward) + Adam on every rank"
+                   if f is None else
+                   "one fused kernel per rank over NVLink peer memory: reduce-scatter of the gradient (%s) + "
+                   "Adam on the rank's 1/%d slice + parameter broadcast (%s); no NCCL on the step"
+                   % (("multimem.ld_reduce in the NVSwitch", world, "multimem.st") if f["multimem"]
+                      else ("peer loads", world, "peer stores")))
     model.train()
     # two resident synthetic batches (alternated) + pinned host copies for the e2e leg
     xs = [torch.rand(B, 128, 128, device="cuda") for _ in range(2)]
@@ -510,19 +576,23 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-resident
+    # (the clock sampler starts before the warm-up: its NVML initialisation stays out of the timed region)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         model.train_step(xs[i % 2])
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     ev0.record()
     for i in range(args.steps):
         model.train_step(xs[i % 2])
+        marks[i].record()        # per-step marks (diagnostic: `step_ms`); the value is ev0 -> ev1
     ev1.record()
     barrier()
+    per_step = [(ev0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(args.steps)]
     launches = lib.launch_count() - launches0
     # the same K steps again with a CUDA-event pair around every native call (roofline /
     # kernel_families / kernels); the event records cost ~5 %, so `value` is taken from the
@@ -589,6 +659,38 @@ def main():
     sampler.join(timeout=2)
     # ---------------------------------------------------------------- the other BASELINE configs
     extra = {}
+    if world > 1:
+        # where the multi-GPU step time goes: every rank runs the SAME step unsynchronised
+        # (no data parallelism, all ranks at once) -- the slowest rank's free-running time is the
+        # floor of the lock-stepped data-parallel step; the rest is the optimizer/collective kernel
+        solo = vae_mod.VAE(save_dir='', device_name='cuda', precision=args.precision)
+        solo.train()
+        for i in range(4):
+            solo.train_step(xs[i % 2])
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            solo.train_step(xs[i % 2])
+        s1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s0.elapsed_time(s1) / args.steps], device="cuda")
+        ts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(ts, t)
+        extra["dp_diag"] = {"free_running_ms_per_step_by_rank": [round(float(v), 4) for v in ts],
+                            "what": "the same step without data parallelism, all ranks running at once"}
+        del solo
+        if model._dp_fused is not None:
+            # the fused optimizer/collective kernel on its own: 20 back-to-back calls, ranks in step
+            model._flat_g.zero_()
+            barrier()
+            s0.record()
+            for i in range(20):
+                model._adam_dp_native()
+            s1.record()
+            torch.cuda.synchronize()
+            extra["dp_diag"]["adam_step_dp_us_back_to_back"] = round(1e3 * s0.elapsed_time(s1) / 20, 1)
+            model.dp_check_status()
     if not args.no_extra:
         # (secondary workloads never take the headline line down with them: a failure is reported)
         peak_x, _ = measured_peaks()
@@ -632,7 +734,7 @@ def main():
                 for kk in ("ms", "n", "bytes", "flops"):
                     f[kk] += d[kk]
             ftop = sorted(fam.items(), key=lambda kv: -kv[1]["ms"])
-            tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
             tmap = {}
             if os.path.exists(tpath) and B == 1024:
                 with open(tpath) as f:
@@ -674,7 +776,10 @@ def main():
                           ">= 8 channels (mma.sync) are error-compensated 3xTF32 = fp32-level accuracy "
                           "(whole-model gradient parity equal to the fp32 FMA path); 'tf32' is the "
                           "opt-in reduced-precision mode (the reference's own GPU default)",
-            "config": make_config(B, world, args.precision, bool(model._graph_wanted(B))),
+            "config": dict(make_config(B, world, args.precision, bool(model._graph_wanted(B))),
+                           **({"dp_step": dp_mode, "host_numa": numa} if world > 1 else {})),
+            "step_ms": {"median": round(sorted(per_step)[len(per_step) // 2], 4), "min": round(min(per_step), 4),
+                        "max": round(max(per_step), 4), "what": "rank 0's per-step device times inside the timed region"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 128 * 128 * 4,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),

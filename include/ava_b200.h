@@ -78,6 +78,10 @@ int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float*
  *   1  TF32 tensor cores (mma.sync m16n8k8), operands rounded to TF32: rtol ~2e-3
  *   2  error-compensated 3xTF32 on the tensor cores (x = x_hi + x_lo; a_lo*b_hi + a_hi*b_lo +
  *      a_hi*b_hi, fp32 accumulate): fp32-level accuracy (rtol 1e-4 parity holds)
+ *   3  as 2, but where a kernel has the variant (the weight-gradient kernels) the two correction
+ *      terms a_lo*b + a*b_lo run as BF16 mma.m16n8k16 -- two k-chunks per instruction, 4 instead
+ *      of 6 tensor-core instructions per pair of chunks; per-product error <= 2^-18, unbiased:
+ *      rtol 1e-4 parity holds (tests/test_gpu_kernels.py, tests/test_gpu_model.py mode tf32x3b)
  * Layers whose channel counts are not multiples of 8 always use fp32 FMA. */
 int ava_b200_set_conv_precision(int mode);
 int ava_b200_get_conv_precision(void);

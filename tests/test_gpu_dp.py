@@ -40,23 +40,49 @@ def _worker(rank, world, port):
     # (1) summed rank gradients == the gradients of the shards pushed through one model
     res = bench.dp_check(model, vae_mod, dist, world, rank)
     assert res["ok"], res
-    # (2) the captured-graph step (NCCL all-reduces inside the graph) follows the eager step
-    losses = {}
-    for graphs in (True, False):
+    # (2) the captured-graph step follows the eager step, for the fused NVLink optimizer kernel
+    # (csrc/dp.cu; peer loads/stores and, where the box has NVLS, the multimem variant) and for
+    # the bucketed NCCL all-reduce path; and all of them end at the same parameters
+    def run(graphs, fused, multimem=True):
+        os.environ["AVA_B200_DP_MULTIMEM"] = "1" if multimem else "0"
         m = vae_mod.VAE(save_dir='', device_name='cuda', cuda_graphs=graphs)
         m.load_flat_state(vae_oracle.make_params(3))
-        m.enable_data_parallel()
+        m.enable_data_parallel(fused=fused)
         m.train()
+        assert (m._dp_fused is not None) == fused
         out = []
         for step in range(6):
             x = vae_oracle.make_input(100 * rank + step, 16).cuda()
             noise = tuple(t.cuda() for t in vae_oracle.make_noise(100 * rank + step, 16))
             out.append(float(m.train_step(x, noise=noise)))
-        losses[graphs] = out
         if graphs:
             assert m._graphs[16]["graph"] is not None, "the data-parallel step was not captured"
-    for a, b in zip(losses[True], losses[False]):
-        assert abs(a - b) <= 2e-4 * abs(b), (losses[True], losses[False])
+        m.dp_check_status()
+        torch.cuda.synchronize()
+        # replicas stay identical
+        mine = m._flat_p.clone()
+        other = mine.clone()
+        dist.broadcast(other, src=0)
+        assert torch.equal(mine, other), "rank %d's parameters differ from rank 0's" % rank
+        return out, mine, m
+    runs = {}
+    for key in (("nccl", False), ("nccl", True), ("fused", False), ("fused", True), ("fused_p2p", True)):
+        runs[key] = run(graphs=key[1], fused=key[0] != "nccl", multimem=key[0] != "fused_p2p")
+    ref_loss, ref_p, _ = runs[("nccl", False)]
+    for key, (loss, p, m) in runs.items():
+        for a, b in zip(loss, ref_loss):
+            assert abs(a - b) <= 2e-4 * abs(b), (key, loss, ref_loss)
+        # Adam's early steps are sign-like: a near-zero gradient summed in another order can flip an
+        # lr-sized update; everything else agrees to rounding
+        assert (p - ref_p).abs().max().item() <= 6 * 2.5e-3, key
+        assert (p - ref_p).abs().mean().item() <= 2e-6, (key, (p - ref_p).abs().mean().item())
+    # the sharded Adam moments gather into a complete optimizer state (what save_state writes)
+    _, _, mf = runs[("fused", False)]
+    _, _, mn = runs[("nccl", False)]
+    mf._gather_moment_shards()
+    assert (mf._flat_m - mn._flat_m).abs().max().item() <= 1e-3 * mn._flat_m.abs().max().item()
+    assert (mf._flat_v - mn._flat_v).abs().max().item() <= 1e-3 * mn._flat_v.abs().max().item()
+    print("rank %d: fused data-parallel step verified (multimem available: %s)" % (rank, mf._dp_fused["multimem"]))
     # (3) a rank with an empty shard still takes the step (zero gradients into the all-reduce)
     m = vae_mod.VAE(save_dir='', device_name='cuda')
     m.load_flat_state(vae_oracle.make_params(3))
