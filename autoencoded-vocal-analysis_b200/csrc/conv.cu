@@ -312,7 +312,6 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if ((int)blockIdx.x < ngroups) issue(blockIdx.x, 0, 0);
 
   // ---- per-thread transform work list (identical for every sub-tile and stage)
   int q_raw[C::QITERS], q_fin[C::QITERS], q_meta[C::QITERS];   // meta: row | ci<<8, -1 = none
@@ -440,6 +439,11 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       s_w[idx] = P.w[(size_t)co * P.w_so + (size_t)ci * P.w_si + kk];
     }
   }
+  // everything above reads parameters only and may overlap the previous kernel's tail (programmatic
+  // dependent launch, common.cuh); activations and statistics are touched from here on
+  pdl_wait();
+  pdl_launch_dependents();
+  if ((int)blockIdx.x < ngroups) issue(blockIdx.x, 0, 0);
   if (INMODE == IN_AFFINE && tid < CI) {
     BnCoef k = bn_coef(P.stats, tid, P.in_count, P.gamma, P.beta, P.rmean, P.rvar, P.train != 0);
     s_c0[tid] = k.scale;
@@ -1495,7 +1499,7 @@ static int launch_gconv(const GconvParams& P, cudaStream_t stream) {
   if (make_act_map(&map_in, P.in, (long long)P.B * CI, P.H_in, P.W_in, C::BOX_W, G::IN_ROWS, C::CIC)) return 1;
   const long long ngroups = (ntiles + C::NSUB - 1) / C::NSUB;
   int grid = (int)(ngroups < max_ctas ? ngroups : max_ctas);
-  kern<<<grid, C::NT, smem, stream>>>(map_in, P);
+  launch_pdl(kern, dim3(grid), dim3(C::NT), smem, stream, map_in, P);
   return check_launch("gconv");
 }
 
@@ -1611,6 +1615,8 @@ __global__ void __launch_bounds__(256, 2)
     cv_tma_load_3d(sg, &map_g, tx * TWG, ty * T::THG, n * CG, &s_bar[st]);
     cv_tma_load_3d(sg + G_PAD, &map_i, S * tx * TWG - 4, S * ty * T::THG - 1, n * CI, &s_bar[st]);
   };
+  pdl_wait();                 // (programmatic dependent launch, common.cuh)
+  pdl_launch_dependents();
   // coefficients
   if (tid < 32) {
     const int c = tid;
@@ -1858,6 +1864,8 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
     cv_tma_load_3d(sg, &map_g, tx * TWG, ty * T::THG, n * CG, &s_bar[st]);
     cv_tma_load_3d(sg + G_PAD, &map_i, S * tx * TWG - 4, S * ty * T::THG - 1, n * CI, &s_bar[st]);
   };
+  pdl_wait();                 // (programmatic dependent launch, common.cuh)
+  pdl_launch_dependents();
   if (tid < 32) {
     constexpr int CA = CONVT ? CG : CI;
     if (tid < CA) {
@@ -2155,58 +2163,81 @@ struct FinalizeParams {
   double* dstats;         // out: sum g | sum g*(x-mean), accumulated (zeroed by the caller)
 };
 
-// Second stage of the weight gradient: one warp per weight element sums the per-CTA partials in
-// fp64 (lanes stride over the partials, fixed-order shuffle tree: deterministic), finishes dW, and
-// adds the element's contribution to this layer's BatchNorm-backward reductions.
+// Second stage of the weight gradient: a CTA finishes 32 consecutive weight elements.  Lane = element
+// (every load is one coalesced 128-byte row of a per-CTA partial), the 8 warps split the partials
+// (4 loads in flight each), fp64 sums combined through shared memory in a fixed order
+// (deterministic); then dW and the element's contribution to this layer's BatchNorm-backward
+// reductions.  (A first version had one warp per element with the lanes striding over the
+// partials: 32 scattered 4-byte loads per request, 12 us per layer at 296 partials.)
 __global__ void __launch_bounds__(256) bnconv_finalize_kernel(const FinalizeParams P) {
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  __shared__ double s_part[8][33];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   const int NW = P.Cx * P.Cz * 9;
+  double r = 0.0;
+  if (j < NW) {
+    const float* src = P.partial + j;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    int p = warp;
+    for (; p + 24 < P.nparts; p += 32) {
+      const float a0 = src[(size_t)p * P.stride], a1 = src[(size_t)(p + 8) * P.stride];
+      const float a2 = src[(size_t)(p + 16) * P.stride], a3 = src[(size_t)(p + 24) * P.stride];
+      r0 += (double)a0;
+      r1 += (double)a1;
+      r2 += (double)a2;
+      r3 += (double)a3;
+    }
+    for (; p < P.nparts; p += 8) r0 += (double)src[(size_t)p * P.stride];
+    r = (r0 + r1) + (r2 + r3);
+  }
+  s_part[warp][lane] = r;
+  __syncthreads();
+  if (warp != 0) return;
   if (j >= NW + P.Cz) return;
   if (j >= NW) {
     // bias gradient = sum of dz over all pixels
-    if (lane == 0) {
-      const int cz = j - NW;
-      double v;
-      if (P.convt && P.s2)
-        v = P.tsums[cz] + P.tsums[32 + cz] + P.tsums[64 + cz] + P.tsums[96 + cz];
-      else
-        v = P.tsums[cz];
-      P.db[cz] = (float)v;
-    }
+    const int cz = j - NW;
+    double v;
+    if (P.convt && P.s2)
+      v = P.tsums[cz] + P.tsums[32 + cz] + P.tsums[64 + cz] + P.tsums[96 + cz];
+    else
+      v = P.tsums[cz];
+    P.db[cz] = (float)v;
     return;
   }
-  double r = 0.0;
-  for (int p = lane; p < P.nparts; p += 32) r += (double)P.partial[(size_t)p * P.stride + j];
-  r = warp_sum(r);
-  if (lane == 0) {
-    const int k = j % 9;
-    int cx, cz;
-    if (!P.convt) {
-      cx = (j / 9) % P.Cx;
-      cz = j / (9 * P.Cx);
-    } else {
-      cz = (j / 9) % P.Cz;
-      cx = j / (9 * P.Cz);
-    }
-    const double T = trimmed_dz_sum(P.tsums, cz, k / 3, k % 3, P.convt, P.s2);
-    const double mean = P.stats[cx] / P.count;
-    double var = P.stats[32 + cx] / P.count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const double invstd = rsqrt(var + (double)kBnEps);
-    // the kernels centred with the fp32-rounded mean: sum dz*(x-mean) = sum dz*(x-mean32) + (mean32-mean)*T
-    const double rc = r + ((double)(float)mean - mean) * T;
-    const double wv = (double)P.w[j];
-    P.dw[j] = (float)((double)P.gamma[cx] * invstd * rc + (double)P.beta[cx] * T);
-    atomicAdd(&P.dstats[cx], wv * T);
-    atomicAdd(&P.dstats[32 + cx], wv * rc);
+  r = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) r += s_part[w][lane];
+  const int k = j % 9;
+  int cx, cz;
+  if (!P.convt) {
+    cx = (j / 9) % P.Cx;
+    cz = j / (9 * P.Cx);
+  } else {
+    cz = (j / 9) % P.Cz;
+    cx = j / (9 * P.Cz);
   }
+  const double T = trimmed_dz_sum(P.tsums, cz, k / 3, k % 3, P.convt, P.s2);
+  const double mean = P.stats[cx] / P.count;
+  double var = P.stats[32 + cx] / P.count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double invstd = rsqrt(var + (double)kBnEps);
+  // the kernels centred with the fp32-rounded mean: sum dz*(x-mean) = sum dz*(x-mean32) + (mean32-mean)*T
+  const double rc = r + ((double)(float)mean - mean) * T;
+  const double wv = (double)P.w[j];
+  P.dw[j] = (float)((double)P.gamma[cx] * invstd * rc + (double)P.beta[cx] * T);
+  atomicAdd(&P.dstats[cx], wv * T);
+  atomicAdd(&P.dstats[32 + cx], wv * rc);
 }
 
 // The nine per-channel sums of a dz tensor [B, C, H, W] that trimmed_dz_sum consumes.
 __global__ void __launch_bounds__(256)
 dz_border_sums_kernel(const float* __restrict__ dz, int B, int C, int H, int W, int mode, double* tsums) {
   __shared__ double s_red[8][9];
+  pdl_wait();
+  pdl_launch_dependents();
   const int c = blockIdx.y;
   const int w4 = W >> 2, hw4 = (H * W) >> 2;
   const long long total4 = (long long)B * hw4;
@@ -2276,7 +2307,7 @@ static int launch_finalize(const WgradParams& P, FinalizeParams F, int nparts, c
   F.stats = P.stats;
   F.count = P.bn_count;
   const int n = CG * CI * 9 + F.Cz;
-  bnconv_finalize_kernel<<<(n + 7) / 8, 256, 0, stream>>>(F);
+  launch_pdl(bnconv_finalize_kernel, dim3((n + 31) / 32), dim3(256), 0, stream, F);
   return check_launch("bnconv_finalize");
 }
 
@@ -2310,7 +2341,7 @@ static int launch_wgrad(WgradParams P, const FinalizeParams& F, void* ws, cudaSt
   if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, GW, GROWS, CG)) return 1;
   if (make_act_map(&map_i, P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS, CI)) return 1;
   P.partial = reinterpret_cast<float*>(ws);
-  kern<<<grid, 256, smem, stream>>>(map_g, map_i, P);
+  launch_pdl(kern, dim3(grid), dim3(256), smem, stream, map_g, map_i, P);
   if (check_launch("wgrad")) return 1;
   return launch_finalize<S, CG, CI, CONVT>(P, F, grid, stream);
 }
@@ -2346,7 +2377,7 @@ static int launch_wgrad_mma(WgradParams P, const FinalizeParams& F, void* ws, cu
   if (make_act_map(&map_g, P.g_a, (long long)P.B * CG, P.Hg, P.Wg, T::G_W, T::G_ROWS_BOX, CG)) return 1;
   if (make_act_map(&map_i, P.i_a, (long long)P.B * CI, S * P.Hg, S * P.Wg, T::I_PITCH, T::I_ROWS_BOX, CI)) return 1;
   P.partial = reinterpret_cast<float*>(ws);
-  kern<<<grid, NTHR, smem, stream>>>(map_g, map_i, P);
+  launch_pdl(kern, dim3(grid), dim3(NTHR), smem, stream, map_g, map_i, P);
   if (check_launch("wgrad_mma")) return 1;
   return launch_finalize<S, CG, CI, CONVT>(P, F, grid, stream);
 }
@@ -2582,6 +2613,6 @@ extern "C" int ava_b200_dz_border_sums(const float* dz, int B, int C, int H, int
   int gx = (int)(want < 1 ? 1 : want);
   const int cap = (8 * kNumSMs + C - 1) / C;
   if (gx > cap) gx = cap;
-  dz_border_sums_kernel<<<dim3(gx, C), 256, 0, (cudaStream_t)stream>>>(dz, B, C, H, W, mode, tsums);
+  launch_pdl(dz_border_sums_kernel, dim3(gx, C), dim3(256), 0, (cudaStream_t)stream, dz, B, C, H, W, mode, tsums);
   return check_launch("dz_border_sums");
 }

@@ -779,7 +779,8 @@ def main():
             "config": dict(make_config(B, world, args.precision, bool(model._graph_wanted(B))),
                            **({"dp_step": dp_mode, "host_numa": numa} if world > 1 else {})),
             "step_ms": {"median": round(sorted(per_step)[len(per_step) // 2], 4), "min": round(min(per_step), 4),
-                        "max": round(max(per_step), 4), "what": "rank 0's per-step device times inside the timed region"},
+                        "max": round(max(per_step), 4), "argmax": per_step.index(max(per_step)),
+                        "first": round(per_step[0], 4), "what": "rank 0's per-step device times inside the timed region"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 128 * 128 * 4,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
