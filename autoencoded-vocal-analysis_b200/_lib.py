@@ -26,14 +26,14 @@ SIGNATURES = {
     "ava_b200_set_conv_precision": (I,),
     "ava_b200_get_conv_precision": (),
     "ava_b200_bn_param_grads": (P, P, P, P, P, P, P, P),
-    "ava_b200_bn_relu_bwd_apply": (P, P, P, P, P, I, I, I, I, P, P),
+    "ava_b200_bn_relu_bwd_apply": (P, P, P, P, P, I, I, I, I, P, P, I, P),
     "ava_b200_linear_fwd": (P, I, P, P, P, I, I, I, I, I, I, LL, LL, LL, LL, I, P, LL, P),
     "ava_b200_linear_bwd_data": (P, I, P, P, P, I, I, I, I, I, LL, LL, LL, I, I, P, LL, P),
     "ava_b200_linear_bwd_weight": (P, I, P, P, I, P, P, I, I, I, I, LL, LL, LL, LL, I, P, LL, P),
     "ava_b200_linear_ws_bytes": (I, I, I),
     "ava_b200_latent_fwd": (P, P, P, I, I, P, P, P, P),
     "ava_b200_latent_bwd": (P, P, P, P, P, I, I, P, P),
-    "ava_b200_recon": (P, P, LL, F, P, P, P),
+    "ava_b200_recon": (P, P, LL, F, P, P, P, I, I, P),
     "ava_b200_elbo_finalize": (P, I, I, F, P, P, P),
     "ava_b200_adam_step": (P, P, P, P, LL, P, D, D, D, D, F, P),
     "ava_b200_adam_step_dev": (P, P, P, P, LL, P, P, F, P),

@@ -83,27 +83,83 @@ __global__ void bn_param_grads_kernel(const double* stats, const double* dstats,
   grads[T.off_b[l] + c] = (float)ds[c];                  // dbeta
 }
 
+// The nine per-channel border sums of a dz tensor (mode 0 of ava_b200_dz_border_sums: total, first /
+// last row, first / last column, the four corners), accumulated by the kernel that WRITES the dz
+// so that no separate pass reads it again.  fp32 per thread (a few hundred values), fp64 from
+// the warp reduction on.
+struct BorderAcc {
+  float a[9];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = 0.f;
+  }
+  // v = 4 consecutive values of row y starting at column x0 of an H x W plane
+  __device__ __forceinline__ void add(const float4& v, int y, int x0, int H, int W) {
+    const float s = (v.x + v.y) + (v.z + v.w);
+    a[0] += s;
+    const bool fr = (y == 0), lr = (y == H - 1);
+    if (fr) a[1] += s;
+    if (lr) a[2] += s;
+    if (x0 == 0) {
+      a[3] += v.x;
+      if (fr) a[5] += v.x;
+      if (lr) a[7] += v.x;
+    }
+    if (x0 + 4 == W) {
+      a[4] += v.w;
+      if (fr) a[6] += v.w;
+      if (lr) a[8] += v.w;
+    }
+  }
+  // block-wide (256 threads) reduction, one fp64 atomic per slot and CTA into tsums[slot*32 + c]
+  __device__ __forceinline__ void flush(double (*s_red)[9], int c, double* tsums) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double s = warp_sum((double)a[i]);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+      atomicAdd(&tsums[threadIdx.x * 32 + c], s);
+    }
+  }
+};
+
+// grid (chunks, C): a CTA stays within one channel (its coefficients are scalars, and the optional
+// border sums of the written dz are per channel)
 __global__ void __launch_bounds__(256)
 bn_relu_bwd_apply_kernel(const float* g, const float* __restrict__ a, const float* gamma,
-                         const double* stats, const double* dstats, int C, int HW, double count, long long n4,
-                         int relu, float* out) {
+                         const double* stats, const double* dstats, int B, int C, int HW, int W, double count,
+                         int relu, float* out, double* tsums) {
   // HW is a multiple of 4, so a float4 never straddles a channel
-  __shared__ DzCoef s_k[32];
-  if (threadIdx.x < C) s_k[threadIdx.x] = dz_coef(gamma, stats, dstats, threadIdx.x, count);
-  __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+  __shared__ double s_red[8][9];
+  const int c = blockIdx.y;
+  const DzCoef k = dz_coef(gamma, stats, dstats, c, count);
+  const int hw4 = HW >> 2, w4 = W >> 2, H = HW / W;
+  const long long total4 = (long long)B * hw4;
+  BorderAcc acc;
+  acc.clear();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(((i * 4) / HW) % C);
-    const DzCoef k = s_k[c];
-    float4 gv = reinterpret_cast<const float4*>(g)[i];
-    float4 av = __ldg(reinterpret_cast<const float4*>(a) + i);
+    const long long n = i / hw4;
+    const int q = (int)(i - n * hw4);
+    const size_t idx = ((size_t)n * C + c) * hw4 + q;
+    float4 gv = reinterpret_cast<const float4*>(g)[idx];
+    float4 av = __ldg(reinterpret_cast<const float4*>(a) + idx);
     float4 o;
     o.x = (relu && !(av.x > 0.f)) ? 0.f : dz_apply(k, gv.x, av.x);
     o.y = (relu && !(av.y > 0.f)) ? 0.f : dz_apply(k, gv.y, av.y);
     o.z = (relu && !(av.z > 0.f)) ? 0.f : dz_apply(k, gv.z, av.z);
     o.w = (relu && !(av.w > 0.f)) ? 0.f : dz_apply(k, gv.w, av.w);
-    reinterpret_cast<float4*>(out)[i] = o;
+    reinterpret_cast<float4*>(out)[idx] = o;
+    if (tsums) {
+      const int y = q / w4;
+      acc.add(o, y, (q - y * w4) * 4, H, W);
+    }
   }
+  if (tsums) acc.flush(s_red, c, tsums);
 }
 
 // ----------------------------------------------------------------------------- latent
@@ -183,11 +239,16 @@ latent_bwd_kernel(const float* __restrict__ heads, const float* __restrict__ eps
 }
 
 // ------------------------------------------------------------------------------ recon
+// tsums (optional): the border sums of the written gradient g viewed as [*, 1, H, W] planes
 __global__ void __launch_bounds__(256)
 recon_kernel(const float* __restrict__ x, const float* __restrict__ xr, long long n4, float prec,
-             float* __restrict__ g, double* acc) {
+             float* __restrict__ g, double* acc, double* tsums, int H, int W) {
   __shared__ float s_p[8];
+  __shared__ double s_red[8][9];
   float sse = 0.f;
+  const int w4 = W >> 2, hw4 = (H * W) >> 2;
+  BorderAcc bacc;
+  bacc.clear();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
@@ -197,7 +258,15 @@ recon_kernel(const float* __restrict__ x, const float* __restrict__ xr, long lon
     sse = fmaf(d.y, d.y, sse);
     sse = fmaf(d.z, d.z, sse);
     sse = fmaf(d.w, d.w, sse);
-    if (g) reinterpret_cast<float4*>(g)[i] = make_float4(prec * d.x, prec * d.y, prec * d.z, prec * d.w);
+    if (g) {
+      const float4 gv = make_float4(prec * d.x, prec * d.y, prec * d.z, prec * d.w);
+      reinterpret_cast<float4*>(g)[i] = gv;
+      if (tsums) {
+        const int q = (int)(i % hw4);
+        const int y = q / w4;
+        bacc.add(gv, y, (q - y * w4) * 4, H, W);
+      }
+    }
   }
   sse = warp_sum(sse);
   if ((threadIdx.x & 31) == 0) s_p[threadIdx.x >> 5] = sse;
@@ -207,6 +276,7 @@ recon_kernel(const float* __restrict__ x, const float* __restrict__ xr, long lon
     for (int w = 0; w < 8; ++w) t += s_p[w];
     atomicAdd(&acc[1], t);
   }
+  if (g && tsums) bacc.flush(s_red, 0, tsums);
 }
 
 __global__ void elbo_finalize_kernel(const double* acc, int Z, int xdim, float prec, float* loss,
@@ -264,14 +334,20 @@ extern "C" int ava_b200_bn_param_grads(const double* stats, const double* dstats
 
 extern "C" int ava_b200_bn_relu_bwd_apply(const float* g, const float* a, const float* gamma, const double* stats,
                                           const double* dstats, int B, int C, int HW, int relu, float* out,
-                                          void* stream) {
+                                          double* tsums, int W, void* stream) {
   AVA_REQUIRE(HW % 4 == 0, "bn_relu_bwd_apply: HW=%d must be a multiple of 4", HW);
+  AVA_REQUIRE(C >= 1 && C <= 32, "bn_relu_bwd_apply: C=%d", C);
+  AVA_REQUIRE(tsums == nullptr || (W >= 4 && W % 4 == 0 && HW % W == 0 && HW / W >= 2),
+              "bn_relu_bwd_apply: border sums need a row width W (multiple of 4) dividing HW, got %d", W);
   if (B <= 0) return 0;
-  long long n4 = (long long)B * C * HW / 4;
-  int grid = (int)((n4 + 255) / 256);
-  if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
-  bn_relu_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, a, gamma, stats, dstats, C, HW,
-                                                                   (double)B * HW, n4, relu, out);
+  if (tsums == nullptr) W = 4;
+  long long total4 = (long long)B * HW / 4;
+  long long want = (total4 + 255) / 256;
+  int gx = (int)(want < 1 ? 1 : want);
+  const int cap = (8 * kNumSMs + C - 1) / C;
+  if (gx > cap) gx = cap;
+  bn_relu_bwd_apply_kernel<<<dim3(gx, C), 256, 0, (cudaStream_t)stream>>>(g, a, gamma, stats, dstats, B, C, HW, W,
+                                                                         (double)B * HW, relu, out, tsums);
   return check_launch("bn_relu_bwd_apply");
 }
 
@@ -290,13 +366,16 @@ extern "C" int ava_b200_latent_bwd(const float* heads, const float* eps_w, const
 }
 
 extern "C" int ava_b200_recon(const float* x, const float* x_rec, long long n, float precision, float* g,
-                              double* acc, void* stream) {
+                              double* acc, double* tsums, int H, int W, void* stream) {
   AVA_REQUIRE(n % 4 == 0, "recon: n must be a multiple of 4");
+  AVA_REQUIRE(tsums == nullptr || (H >= 2 && W >= 4 && W % 4 == 0 && n % ((long long)H * W) == 0),
+              "recon: border sums need the plane shape (H=%d, W=%d) dividing n", H, W);
   if (n <= 0) return 0;
+  if (tsums == nullptr) H = W = 4;
   long long n4 = n / 4;
   int grid = (int)((n4 + 255) / 256);
   if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
-  recon_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_rec, n4, precision, g, acc);
+  recon_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_rec, n4, precision, g, acc, tsums, H, W);
   return check_launch("recon");
 }
 

@@ -46,6 +46,7 @@ _LAYERS = _CONV + _CONVT           # layer id 0..13 of the C ABI
 _BN_MOMENTUM = 0.1
 # what precision='auto' means for the conv layers (2: 3xTF32; 3: TF32 + BF16 corrections)
 _AUTO_CONV_MODE = int(os.environ.get("AVA_B200_AUTO_CONV_MODE", "3"))
+_DP_MULTIMEM_MIN_WORLD = 4
 _DP_MAX_WORLD = 8          # AVA_DP_MAX_WORLD, include/ava_b200.h
 
 
@@ -549,8 +550,10 @@ class VAE(nn.Module):
         if want_grad_seed:
             bufs.alloc_backward(self.z_dim)
             g = bufs.g[0]
+        # (the gradient written here is convt7's dz: its nine border sums are accumulated on the way)
+        ts13 = (bufs.tsums.data_ptr() + 8 * 288 * 13) if (g is not None and _FUSED_TSUMS) else None
         call("ava_b200_recon", ptr(x), ptr(bufs.act[13]), B * X_DIM, float(self.model_precision),
-             ptr(g), bufs.acc.data_ptr(), s)
+             ptr(g), bufs.acc.data_ptr(), ts13, X_SHAPE[0], X_SHAPE[1], s)
         call("ava_b200_elbo_finalize", bufs.acc.data_ptr(), self.z_dim, X_DIM,
              float(self.model_precision), ptr(bufs.loss), ptr(self._loss_sum), s)
         if train:
@@ -606,7 +609,7 @@ class VAE(nn.Module):
         g_cur, g_nxt = bufs.g[0], bufs.g[1]      # g[0] holds dL/dx_rec = convt7's dz (recon kernel)
         # layer 7 writes the gradient w.r.t. fc8's pre-activation output (bn8 backward + fc8's
         # ReLU) straight into dt8
-        have = False
+        have = _FUSED_TSUMS      # (accumulated by the recon kernel)
         for l in range(13, 6, -1):
             xin = bufs.act[l - 1] if l > 7 else bufs.t8
             out = g_nxt if l > 7 else bufs.dt8
@@ -642,11 +645,12 @@ class VAE(nn.Module):
         parameter gradients of all 14 layers."""
         B, s = bufs.B, _stream()
         # conv7's ReLU on the gradient arriving from fc1 (no BatchNorm at this seam)
+        ts6 = (bufs.tsums.data_ptr() + 8 * 288 * 6) if _FUSED_TSUMS else None
         call("ava_b200_bn_relu_bwd_apply", ptr(bufs.da6), ptr(bufs.act[6]), None, None, None, B, 32, 256,
-             1, ptr(bufs.da6), s)
+             1, ptr(bufs.da6), ts6, 16, s)
         g_cur = bufs.da6
         free = [bufs.g[0], bufs.g[1]]
-        have = False
+        have = _FUSED_TSUMS
         for l in range(6, -1, -1):          # (layer 0 needs no data gradient)
             xin = bufs.act[l - 1] if l > 0 else bufs.x
             out = free[0] if l > 0 else None
@@ -827,23 +831,33 @@ class VAE(nn.Module):
         ptrs = [int(a) for a in hdl.buffer_ptrs]
         assert len(ptrs) == W and ptrs[self._dp_rank] == buf.data_ptr()
         self._rebind_flat(buf[n:2 * n], buf[:n])
-        peers = _DpPeers()
-        for r in range(W):
-            peers.grad[r] = ptrs[r]
-            peers.param[r] = ptrs[r] + 4 * n
-            peers.flags[r] = ptrs[r] + 8 * n
+        def table(mc):
+            peers = _DpPeers()
+            for r in range(W):
+                peers.grad[r] = ptrs[r]
+                peers.param[r] = ptrs[r] + 4 * n
+                peers.flags[r] = ptrs[r] + 8 * n
+            peers.grad_mc = mc if mc else None
+            peers.param_mc = (mc + 4 * n) if mc else None
+            return peers
         mc = 0
-        if os.environ.get("AVA_B200_DP_MULTIMEM", "1") != "0":
-            try:
-                mc = int(hdl.multicast_ptr) if hdl.has_multicast_support else 0
-            except Exception:
-                mc = 0
-        peers.grad_mc = mc if mc else None
-        peers.param_mc = (mc + 4 * n) if mc else None
+        try:
+            mc = int(hdl.multicast_ptr) if hdl.has_multicast_support else 0
+        except Exception:
+            mc = 0
+        peers_p2p, peers_mc = table(0), (table(mc) if mc else None)
+        # Which variant: AVA_B200_DP_MULTIMEM=1/0 forces it; default by measurement (bench.py
+        # dp_diag, profiles/r02_summary.md): plain peer loads/stores win on 2 GPUs (every byte
+        # crosses one link either way and the switch reduction adds latency), the in-switch
+        # reduction wins from 4 GPUs on (a rank reads its slice once instead of world times)
+        env = os.environ.get("AVA_B200_DP_MULTIMEM")
+        use_mc = bool(mc) and (env == "1" if env in ("0", "1") else W >= _DP_MULTIMEM_MIN_WORLD)
+        peers = peers_mc if use_mc else peers_p2p
         local = torch.zeros(4, dtype=torch.int32, device=dev)
         torch.cuda.synchronize(dev)
         dist.barrier(group=self._dp_group)       # every rank's flags are zero before anyone signals
-        self._dp_fused = {"buf": buf, "hdl": hdl, "peers": peers, "local": local, "multimem": bool(mc)}
+        self._dp_fused = {"buf": buf, "hdl": hdl, "peers": peers, "peers_p2p": peers_p2p, "peers_mc": peers_mc,
+                          "local": local, "multimem": use_mc, "multimem_available": bool(mc)}
 
     def _adam_dp_native(self):
         """The fused data-parallel optimizer step (csrc/dp.cu)."""

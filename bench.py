@@ -73,7 +73,7 @@ def algorithmic(key, args, B):
     if name == "ava_b200_linear_bwd_weight":
         M, N, K, groups = args[7], args[8], args[9], args[10]
         return 4.0 * groups * (2 * M * N + M * K + N * K), 2.0 * groups * M * N * K
-    if name == "ava_b200_adam_step":
+    if name in ("ava_b200_adam_step", "ava_b200_adam_step_dev"):
         n = args[4]
         return 4.0 * 7 * n, 12.0 * n
     if name == "ava_b200_recon":
@@ -570,10 +570,20 @@ def main():
     xs = [torch.rand(B, 128, 128, device="cuda") for _ in range(2)]
     xs_host = [x.cpu().pin_memory() for x in xs]
 
+    align_t = torch.zeros(1, device="cuda")
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def align():
+        """After barrier(), right before a timed region starts: one more collective that is only
+        ENQUEUED (no host sync), so the ranks' streams leave it at the same device time even when
+        one host returns from the barrier milliseconds after the others (measured at N=2: the first
+        timed step otherwise carried ~3 ms of exactly that skew)."""
+        if world > 1:
+            dist.all_reduce(align_t)
 
     # ---------------------------------------------------------------- device-resident
     # (the clock sampler starts before the warm-up: its NVML initialisation stays out of the timed region)
@@ -586,6 +596,12 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
+    # the host-side barrier leaves the device idle for milliseconds and the first step after it ran
+    # 0.2 ms (1 GPU) to 3.9 ms (8 GPUs) slow: two more untimed steps are enqueued behind the barrier so
+    # that the timed region starts on a busy device, then the ranks' streams are aligned
+    for i in range(2):
+        model.train_step(xs[i % 2])
+    align()
     ev0.record()
     for i in range(args.steps):
         model.train_step(xs[i % 2])
@@ -608,6 +624,7 @@ def main():
         lib.PROFILER = prof
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        align()
         p0.record()
         for i in range(args.steps):
             model.train_step(xs[i % 2])
@@ -643,11 +660,30 @@ def main():
         float(model.train_step(xb).item())
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(2):          # (as above: a busy device behind the barrier)
+        model.train_step(xs[i % 2])
+    align()
     e0.record()
     host_batches = (xs_host[i % 2] for i in range(args.steps))
-    for xb in vae_mod.prefetch_to_device(host_batches):
+    # the reference reads loss.item() every step (vae.py:351).  Every step's loss is read here too
+    # (4 bytes device->host per step, inside the timed region), but software-pipelined: the loss
+    # of step i goes to a pinned slot with an event behind it and is read on the host while step
+    # i+1 is already running, so the device never idles for a host round trip
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    losses_read = 0
+    for i, xb in enumerate(vae_mod.prefetch_to_device(host_batches)):
         loss = model.train_step(xb)
-        float(loss.item())      # the reference reads loss.item() every step (vae.py:351)
+        loss_host[i % 2:i % 2 + 1].copy_(loss.reshape(1), non_blocking=True)
+        loss_ev[i % 2].record()
+        if i > 0:
+            loss_ev[(i - 1) % 2].synchronize()
+            float(loss_host[(i - 1) % 2])
+            losses_read += 1
+    loss_ev[(args.steps - 1) % 2].synchronize()
+    float(loss_host[(args.steps - 1) % 2])
+    losses_read += 1
+    assert losses_read == args.steps
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
@@ -683,13 +719,22 @@ def main():
         if model._dp_fused is not None:
             # the fused optimizer/collective kernel on its own: 20 back-to-back calls, ranks in step
             model._flat_g.zero_()
-            barrier()
-            s0.record()
-            for i in range(20):
-                model._adam_dp_native()
-            s1.record()
-            torch.cuda.synchronize()
-            extra["dp_diag"]["adam_step_dp_us_back_to_back"] = round(1e3 * s0.elapsed_time(s1) / 20, 1)
+            f = model._dp_fused
+            variants = [("peer loads/stores", f["peers_p2p"])]
+            if f["peers_mc"] is not None:
+                variants.append(("multimem", f["peers_mc"]))
+            keep = f["peers"]
+            for name, peers in variants:
+                f["peers"] = peers
+                barrier()
+                align()
+                s0.record()
+                for i in range(20):
+                    model._adam_dp_native()
+                s1.record()
+                torch.cuda.synchronize()
+                extra["dp_diag"]["adam_step_dp_us_back_to_back[%s]" % name] = round(1e3 * s0.elapsed_time(s1) / 20, 1)
+            f["peers"] = keep
             model.dp_check_status()
     if not args.no_extra:
         # (secondary workloads never take the headline line down with them: a failure is reported)

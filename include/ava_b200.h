@@ -135,9 +135,11 @@ int ava_b200_bn_param_grads(const double* stats, const double* dstats, const int
  * backward of the layer that produced `a`, as one elementwise pass; out may alias g.
  * gamma == NULL: no BatchNorm, only the ReLU mask.  relu == 0: no mask.  The conv layers apply
  * this inside ava_b200_bnconv_bwd_data; the stand-alone pass serves the fc1 -> conv7 seam (ReLU
- * mask of conv7's output on the gradient arriving from fc1). */
+ * mask of conv7's output on the gradient arriving from fc1).  tsums != NULL: the nine border sums
+ * of `out` (rows of width W; mode 0 of ava_b200_dz_border_sums) are accumulated on the way. */
 int ava_b200_bn_relu_bwd_apply(const float* g, const float* a, const float* gamma, const double* stats,
-                               const double* dstats, int B, int C, int HW, int relu, float* out, void* stream);
+                               const double* dstats, int B, int C, int HW, int relu, float* out,
+                               double* tsums, int W, void* stream);
 
 /* ------------------------------------------------------------- dense (Linear) layers
  * Y[M,N] = act(X[M,K] . W[N,K]^T + b): torch.nn.Linear (+F.relu / torch.exp),
@@ -175,9 +177,12 @@ int ava_b200_latent_fwd(const float* heads, const float* eps_w, const float* eps
 int ava_b200_latent_bwd(const float* heads, const float* eps_w, const float* eps_d, const float* z,
                         const float* gz, int B, int Z, float* g_heads, void* stream);
 /* Reconstruction term (ava/models/vae.py:319-320): acc[1] += sum (x - x_rec)^2 and,
- * if g != NULL, g = precision * (x_rec - x) = dL/dx_rec. */
+ * if g != NULL, g = precision * (x_rec - x) = dL/dx_rec.  tsums != NULL (with g): also the nine
+ * border sums of g viewed as [n/(H*W)] single-channel H x W planes (mode 0 of
+ * ava_b200_dz_border_sums, channel 0), accumulated while g is written -- g is the decoder's last
+ * layer's dz, whose weight-gradient finalisation needs them. */
 int ava_b200_recon(const float* x, const float* x_rec, long long n, float precision, float* g, double* acc,
-                   void* stream);
+                   double* tsums, int H, int W, void* stream);
 /* loss = 1/2(acc0 + Z ln 2pi) + 1/2 XDIM ln(2pi/prec) + 1/2 prec acc1 - acc2, written as
  * fp32 to loss[0] and accumulated (fp64) into loss_sum[0] if non-NULL (device-side epoch
  * accumulator replacing loss.item() per step, ava/models/vae.py:351). */

@@ -68,6 +68,7 @@ def _worker(rank, world, port):
     runs = {}
     for key in (("nccl", False), ("nccl", True), ("fused", False), ("fused", True), ("fused_p2p", True)):
         runs[key] = run(graphs=key[1], fused=key[0] != "nccl", multimem=key[0] != "fused_p2p")
+    os.environ.pop("AVA_B200_DP_MULTIMEM", None)
     ref_loss, ref_p, _ = runs[("nccl", False)]
     for key, (loss, p, m) in runs.items():
         for a, b in zip(loss, ref_loss):
@@ -82,7 +83,7 @@ def _worker(rank, world, port):
     mf._gather_moment_shards()
     assert (mf._flat_m - mn._flat_m).abs().max().item() <= 1e-3 * mn._flat_m.abs().max().item()
     assert (mf._flat_v - mn._flat_v).abs().max().item() <= 1e-3 * mn._flat_v.abs().max().item()
-    print("rank %d: fused data-parallel step verified (multimem available: %s)" % (rank, mf._dp_fused["multimem"]))
+    print("rank %d: fused data-parallel step verified (multimem available: %s)" % (rank, mf._dp_fused["multimem_available"]))
     # (3) a rank with an empty shard still takes the step (zero gradients into the all-reduce)
     m = vae_mod.VAE(save_dir='', device_name='cuda')
     m.load_flat_state(vae_oracle.make_params(3))

@@ -302,8 +302,16 @@ def test_latent_and_recon(L, B, Z):
     xr = (x + torch.randn(n, generator=gen, dtype=torch.float64)).float().double()
     g = torch.empty(n, device="cuda")
     dx_, dxr_ = dev(x), dev(xr)
+    ts = torch.zeros(9 * 32, dtype=torch.float64, device="cuda")
     L.call("ava_b200_recon", dx_.data_ptr(), dxr_.data_ptr(), n, 10.0, g.data_ptr(),
-           acc.data_ptr(), stream())
+           acc.data_ptr(), ts.data_ptr(), 128, 128, stream())
+    # the border sums accumulated while g was written == a separate pass over g
+    ts_ref = torch.zeros(9 * 32, dtype=torch.float64, device="cuda")
+    L.call("ava_b200_dz_border_sums", g.data_ptr(), B, 1, 128, 128, 0, ts_ref.data_ptr(), stream())
+    torch.cuda.synchronize()
+    scale = float(g.abs().sum())
+    assert float((ts - ts_ref).abs().max()) <= 1e-6 * scale
+    assert float(ts_ref.abs().max()) > 0
     loss = torch.zeros(1, device="cuda")
     lsum = torch.full((1,), 5.0, dtype=torch.float64, device="cuda")
     L.call("ava_b200_elbo_finalize", acc.data_ptr(), Z, 16384, 10.0, loss.data_ptr(), lsum.data_ptr(),
