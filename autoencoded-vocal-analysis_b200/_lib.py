@@ -31,6 +31,8 @@ SIGNATURES = {
     "ava_b200_linear_bwd_data": (P, I, P, P, P, I, I, I, I, I, LL, LL, LL, I, I, P, LL, P),
     "ava_b200_linear_bwd_weight": (P, I, P, P, I, P, P, I, I, I, I, LL, LL, LL, LL, I, P, LL, P),
     "ava_b200_linear_ws_bytes": (I, I, I),
+    "ava_b200_bias_grads": (P, I, P, LL, P),
+    "ava_b200_bias_grads_ws_bytes": (P, I),
     "ava_b200_latent_fwd": (P, P, P, I, I, P, P, P, P),
     "ava_b200_latent_bwd": (P, P, P, P, P, I, I, P, P),
     "ava_b200_recon": (P, P, LL, F, P, P, P, I, I, P),
@@ -55,6 +57,7 @@ _RESTYPES = {
     "ava_b200_launch_count": LL,
     "ava_b200_bnconv_bwd_weight_ws": LL,
     "ava_b200_linear_ws_bytes": LL,
+    "ava_b200_bias_grads_ws_bytes": LL,
     "ava_b200_pca_ws_bytes": LL,
 }
 # entry points whose int return value is a status code

@@ -14,30 +14,17 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     b2_d = hyper[2];
     eps_d = hyper[3];
   }
-  // Scalars exactly as torch.optim.Adam forms them (Python doubles, rounded to fp32 once):
-  // step number of THIS update (torch increments `step` before using it)
-  const double t = (double)step_count[0] + 1.0;
-  const double bc1 = 1.0 - pow(b1_d, t);
-  const double bc2 = 1.0 - pow(b2_d, t);
-  const float step_size = (float)(lr_d / bc1);
-  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-  const float b1 = (float)b1_d, b2 = (float)b2_d, eps = (float)eps_d;
-  const float omb1 = (float)(1.0 - b1_d), omb2 = (float)(1.0 - b2_d);
+  const AdamCoef k = adam_coef(lr_d, b1_d, b2_d, eps_d, (double)step_count[0] + 1.0);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
     float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
-#define AVA_ADAM1(c)                                         \
-  {                                                          \
-    float gg = gv.c * gscale;                                \
-    mv.c = b1 * mv.c + omb1 * gg;                            \
-    vv.c = b2 * vv.c + omb2 * gg * gg;                       \
-    float denom = sqrtf(vv.c) * inv_sqrt_bc2 + eps;          \
-    pv.c = pv.c - step_size * (mv.c / denom);                \
-  }
-    AVA_ADAM1(x) AVA_ADAM1(y) AVA_ADAM1(z) AVA_ADAM1(w)
+    adam_update(k, __fmul_rn(gv.x, gscale), pv.x, mv.x, vv.x);
+    adam_update(k, __fmul_rn(gv.y, gscale), pv.y, mv.y, vv.y);
+    adam_update(k, __fmul_rn(gv.z, gscale), pv.z, mv.z, vv.z);
+    adam_update(k, __fmul_rn(gv.w, gscale), pv.w, mv.w, vv.w);
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(m)[i] = mv;
     reinterpret_cast<float4*>(v)[i] = vv;
@@ -45,12 +32,11 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   // scalar tail
   if (blockIdx.x == 0) {
     for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
-      float gg = g[i] * gscale;
-      float mm = b1 * m[i] + omb1 * gg;
-      float vv = b2 * v[i] + omb2 * gg * gg;
+      float pp = p[i], mm = m[i], vv = v[i];
+      adam_update(k, __fmul_rn(g[i], gscale), pp, mm, vv);
+      p[i] = pp;
       m[i] = mm;
       v[i] = vv;
-      p[i] = p[i] - step_size * (mm / (sqrtf(vv) * inv_sqrt_bc2 + eps));
     }
   }
 }

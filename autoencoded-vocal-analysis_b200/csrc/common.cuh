@@ -81,6 +81,36 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// The Adam update, shared by adam_kernel (adam.cu) and the fused data-parallel kernel (dp.cu) with
+// every rounding spelled out, so that the two produce the same bits from the same summed gradient
+// whatever the compiler contracts around them: a 1-ulp difference in the first steps is amplified
+// by ReLU kinks and Adam's scale invariance into lr-sized differences of ~1 % of the parameters
+// within a few steps (seen when the two kernels were written independently).
+struct AdamCoef {
+  float b1, b2, omb1, omb2, eps, step_size, inv_sqrt_bc2;
+};
+// Scalars exactly as torch.optim.Adam forms them (Python doubles, rounded to fp32 once); t = the
+// step number of THIS update (torch increments `step` before using it)
+__device__ __forceinline__ AdamCoef adam_coef(double lr_d, double b1_d, double b2_d, double eps_d, double t) {
+  const double bc1 = 1.0 - pow(b1_d, t);
+  const double bc2 = 1.0 - pow(b2_d, t);
+  AdamCoef k;
+  k.step_size = (float)(lr_d / bc1);
+  k.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  k.b1 = (float)b1_d;
+  k.b2 = (float)b2_d;
+  k.eps = (float)eps_d;
+  k.omb1 = (float)(1.0 - b1_d);
+  k.omb2 = (float)(1.0 - b2_d);
+  return k;
+}
+__device__ __forceinline__ void adam_update(const AdamCoef& k, float gg, float& p, float& m, float& v) {
+  m = __fmaf_rn(k.b1, m, __fmul_rn(k.omb1, gg));
+  v = __fmaf_rn(k.b2, v, __fmul_rn(__fmul_rn(k.omb2, gg), gg));
+  const float denom = __fmaf_rn(__fsqrt_rn(v), k.inv_sqrt_bc2, k.eps);
+  p = __fmaf_rn(-k.step_size, __fdiv_rn(m, denom), p);
+}
+
 // BatchNorm coefficients for one channel from accumulated sums (train) or running
 // buffers (eval):  bn(x) = x*scale + shift.
 struct BnCoef {

@@ -110,14 +110,7 @@ adam_dp_kernel(const DpPeers P, const int rank, const int world, float* __restri
   if (tid < world) dp_wait(my_flags + tid, seq, local + 2);
   __syncthreads();
 
-  const double lr_d = hyper[0], b1_d = hyper[1], b2_d = hyper[2], eps_d = hyper[3];
-  const double t = (double)step_count[0] + 1.0;
-  const double bc1 = 1.0 - pow(b1_d, t);
-  const double bc2 = 1.0 - pow(b2_d, t);
-  const float step_size = (float)(lr_d / bc1);
-  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-  const float b1 = (float)b1_d, b2 = (float)b2_d, eps = (float)eps_d;
-  const float omb1 = (float)(1.0 - b1_d), omb2 = (float)(1.0 - b2_d);
+  const AdamCoef k = adam_coef(hyper[0], hyper[1], hyper[2], hyper[3], (double)step_count[0] + 1.0);
 
   // ---- phase 1: this rank's slice (float4 units), U float4 per thread and trip with every
   // gradient load of the trip issued before the first is used (an NVLink / NVSwitch round trip is
@@ -173,15 +166,10 @@ adam_dp_kernel(const DpPeers P, const int rank, const int world, float* __restri
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
       if (i >= hi) continue;
-#define AVA_ADAM_DP1(c)                                            \
-  {                                                                \
-    float gg = gv[u].c * gscale;                                   \
-    mv[u].c = b1 * mv[u].c + omb1 * gg;                            \
-    vv[u].c = b2 * vv[u].c + omb2 * gg * gg;                       \
-    float denom = sqrtf(vv[u].c) * inv_sqrt_bc2 + eps;             \
-    pv[u].c = pv[u].c - step_size * (mv[u].c / denom);             \
-  }
-      AVA_ADAM_DP1(x) AVA_ADAM_DP1(y) AVA_ADAM_DP1(z) AVA_ADAM_DP1(w)
+      adam_update(k, __fmul_rn(gv[u].x, gscale), pv[u].x, mv[u].x, vv[u].x);
+      adam_update(k, __fmul_rn(gv[u].y, gscale), pv[u].y, mv[u].y, vv[u].y);
+      adam_update(k, __fmul_rn(gv[u].z, gscale), pv[u].z, mv[u].z, vv[u].z);
+      adam_update(k, __fmul_rn(gv[u].w, gscale), pv[u].w, mv[u].w, vv[u].w);
       reinterpret_cast<float4*>(m)[i] = mv[u];
       reinterpret_cast<float4*>(v)[i] = vv[u];
       if (MC) {

@@ -376,6 +376,62 @@ static int launch_colsum(const float* dy, const float* mask, int ld, int M, int 
   return 0;
 }
 
+// Bias gradients of several Linear layers in two launches (instead of two per layer): job j is
+// db_j[n] = sum_m (mask_j > 0 ? dy_j : 0)[m, n].  The grid is the concatenation of the jobs' (column
+// block, row split) tiles; per-split sums go to the workspace, the finish kernel adds them in a
+// fixed order (deterministic).
+struct BiasJobs {
+  const float* dy[AVA_MAX_BIAS_JOBS];
+  const float* mask[AVA_MAX_BIAS_JOBS];
+  float* db[AVA_MAX_BIAS_JOBS];
+  int ld[AVA_MAX_BIAS_JOBS], M[AVA_MAX_BIAS_JOBS], N[AVA_MAX_BIAS_JOBS];
+  int splits[AVA_MAX_BIAS_JOBS], rows[AVA_MAX_BIAS_JOBS];
+  int blk0[AVA_MAX_BIAS_JOBS + 1];    // first CTA of job j (kernel 1)
+  int col0[AVA_MAX_BIAS_JOBS + 1];    // first column of job j in the concatenated partial rows
+  int n;
+};
+
+__global__ void __launch_bounds__(256) bias_partial_kernel(const BiasJobs J, float* __restrict__ part) {
+  __shared__ float s[8][33];
+  int j = 0;
+  while (j + 1 < J.n && (int)blockIdx.x >= J.blk0[j + 1]) ++j;
+  const int local = blockIdx.x - J.blk0[j];
+  const int col_blocks = (J.N[j] + 31) / 32;
+  const int cb = local % col_blocks, sp = local / col_blocks;
+  const int n = cb * 32 + (threadIdx.x & 31);
+  const int r = threadIdx.x >> 5;
+  const int m0 = sp * J.rows[j];
+  const int m1 = min(J.M[j], m0 + J.rows[j]);
+  const float* dy = J.dy[j];
+  const float* mask = J.mask[j];
+  const int ld = J.ld[j];
+  float acc = 0.f;
+  if (n < J.N[j]) {
+    for (int m = m0 + r; m < m1; m += 8) {
+      float v = dy[(size_t)m * ld + n];
+      if (mask && !(mask[(size_t)m * ld + n] > 0.f)) v = 0.f;
+      acc += v;
+    }
+  }
+  s[r][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (r == 0 && n < J.N[j]) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x];
+    // partial layout: job j owns columns [col0[j], col0[j+1]) of up to 64 rows (splits)
+    part[(size_t)sp * J.col0[J.n] + J.col0[j] + n] = t;
+  }
+}
+__global__ void __launch_bounds__(256) bias_finish_kernel(const BiasJobs J, const float* __restrict__ part) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= J.col0[J.n]) return;
+  int j = 0;
+  while (j + 1 < J.n && c >= J.col0[j + 1]) ++j;
+  float t = 0.f;
+  for (int sp = 0; sp < J.splits[j]; ++sp) t += part[(size_t)sp * J.col0[J.n] + c];
+  J.db[j][c - J.col0[j]] = t;
+}
+
 void launch_splitk_reduce(const float* part, int splits, int M, int N, const float* bias, float* C, int ldc, int act,
                           cudaStream_t stream) {
   long long total = (long long)M * N;
@@ -551,4 +607,45 @@ extern "C" int ava_b200_linear_bwd_weight(const float* dy, int lddy, const float
     }
   }
   return 0;
+}
+
+extern "C" long long ava_b200_bias_grads_ws_bytes(const ava_b200_bias_job* h_jobs, int njobs) {
+  long long cols = 0;
+  for (int j = 0; j < njobs; ++j) cols += h_jobs[j].N;
+  return 64 * cols * (long long)sizeof(float);
+}
+
+extern "C" int ava_b200_bias_grads(const ava_b200_bias_job* h_jobs, int njobs, void* ws, long long ws_bytes,
+                                   void* stream_) {
+  AVA_REQUIRE(h_jobs != nullptr && njobs >= 1 && njobs <= AVA_MAX_BIAS_JOBS, "bias_grads: 1..%d jobs", AVA_MAX_BIAS_JOBS);
+  AVA_REQUIRE(ws != nullptr && ws_bytes >= ava_b200_bias_grads_ws_bytes(h_jobs, njobs), "bias_grads: workspace too small");
+  BiasJobs J = {};
+  J.n = njobs;
+  int blk = 0, col = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const ava_b200_bias_job& h = h_jobs[j];
+    AVA_REQUIRE(h.dy && h.db && h.M > 0 && h.N > 0 && h.ld >= h.N, "bias_grads: bad job %d", j);
+    J.dy[j] = h.dy;
+    J.mask[j] = h.mask;
+    J.db[j] = h.db;
+    J.ld[j] = h.ld;
+    J.M[j] = h.M;
+    J.N[j] = h.N;
+    const int col_blocks = (h.N + 31) / 32;
+    int splits = 1;
+    while (col_blocks * splits < kNumSMs && h.M / (splits * 2) >= 32 && splits < 64) splits *= 2;
+    J.splits[j] = splits;
+    J.rows[j] = (h.M + splits - 1) / splits;
+    J.blk0[j] = blk;
+    J.col0[j] = col;
+    blk += col_blocks * splits;
+    col += h.N;
+  }
+  J.blk0[njobs] = blk;
+  J.col0[njobs] = col;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  bias_partial_kernel<<<blk, 256, 0, stream>>>(J, reinterpret_cast<float*>(ws));
+  if (check_launch("bias_partial")) return 1;
+  bias_finish_kernel<<<(col + 255) / 256, 256, 0, stream>>>(J, reinterpret_cast<const float*>(ws));
+  return check_launch("bias_finish");
 }

@@ -50,6 +50,12 @@ _DP_MULTIMEM_MIN_WORLD = 4
 _DP_MAX_WORLD = 8          # AVA_DP_MAX_WORLD, include/ava_b200.h
 
 
+class _BiasJob(ctypes.Structure):
+    """ava_b200_bias_job (include/ava_b200.h)."""
+    _fields_ = [("dy", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("db", ctypes.c_void_p),
+                ("ld", ctypes.c_int), ("M", ctypes.c_int), ("N", ctypes.c_int)]
+
+
 class _DpPeers(ctypes.Structure):
     """ava_b200_dp_peers (include/ava_b200.h): per-rank device pointers into symmetric memory."""
     _fields_ = [("grad", ctypes.c_void_p * _DP_MAX_WORLD), ("param", ctypes.c_void_p * _DP_MAX_WORLD),
@@ -447,6 +453,7 @@ class VAE(nn.Module):
         for (n, k) in [(1024, 8192), (256, 1024), (192, 256), (self.z_dim, 64), (64, self.z_dim),
                        (256, 64), (1024, 256), (8192, 1024)]:
             need = max(need, L.ava_b200_linear_ws_bytes(B, n, k))
+        need = max(need, 64 * 4 * (8192 + 1024 + 256 + 64))      # ava_b200_bias_grads, decoder segment
         return int(need)
 
     # ------------------------------------------------------------- native passes
@@ -457,15 +464,31 @@ class VAE(nn.Module):
              K, act, groups, x_gs, w_gs, b_gs, y_gs, tc, ptr(ws), ws.numel(), _stream())
 
     def _linear_bwd(self, dy, lddy, ymask, x, ldx, wkey, bkey, dx, lddx, M, N, K, groups=1,
-                    dy_gs=0, x_gs=0, w_gs=0, b_gs=0, dx_gs=0, tc=0):
-        """dW, db into the flat gradient buffer; dx (if not None) = (dy*mask) W."""
+                    dy_gs=0, x_gs=0, w_gs=0, b_gs=0, dx_gs=0, tc=0, bias_jobs=None):
+        """dW, db into the flat gradient buffer; dx (if not None) = (dy*mask) W.  With `bias_jobs`
+        the bias gradient is not computed here but queued for one batched ava_b200_bias_grads call
+        per backward segment (_flush_bias; the groups of a grouped layer are adjacent column blocks
+        of dy and adjacent biases, i.e. one job)."""
         ws = self._ws(self._scratch_need)
         s = _stream()
+        gb = self._g(bkey)
+        if bias_jobs is not None:
+            assert groups == 1 or (dy_gs == N and b_gs == N)
+            bias_jobs.append((ptr(dy), ptr(ymask), gb, lddy, M, N * groups))
+            gb = None
         call("ava_b200_linear_bwd_weight", ptr(dy), lddy, ptr(ymask), ptr(x), ldx, self._g(wkey),
-             self._g(bkey), M, N, K, groups, dy_gs, x_gs, w_gs, b_gs, tc, ptr(ws), ws.numel(), s)
+             gb, M, N, K, groups, dy_gs, x_gs, w_gs, b_gs, tc, ptr(ws), ws.numel(), s)
         if dx is not None:
             call("ava_b200_linear_bwd_data", ptr(dy), lddy, ptr(ymask), self._p(wkey), ptr(dx), lddx,
                  M, N, K, groups, dy_gs, w_gs, dx_gs, 0, tc, ptr(ws), ws.numel(), s)
+
+    def _flush_bias(self, jobs):
+        """All queued bias gradients of a backward segment in two launches."""
+        arr = (_BiasJob * len(jobs))()
+        for a, (dy, mask, db, ld, M, N) in zip(arr, jobs):
+            a.dy, a.mask, a.db, a.ld, a.M, a.N = dy, mask, db, ld, M, N
+        ws = self._ws(self._scratch_need)
+        call("ava_b200_bias_grads", arr, len(jobs), ptr(ws), ws.numel(), _stream())
 
     def _conv_fwd(self, l, B, x, y, bufs, train, want_stats_out):
         name = _LAYERS[l][0]
@@ -615,14 +638,16 @@ class VAE(nn.Module):
             out = g_nxt if l > 7 else bufs.dt8
             have = self._conv_bwd(l, bufs, g_cur, xin, out, have)
             g_cur, g_nxt = g_nxt, g_cur
+        jobs = []
         self._linear_bwd(bufs.dt8, 8192, None, bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.dt7, 1024,
-                         B, 8192, 1024, tc=self._tc)
+                         B, 8192, 1024, tc=self._tc, bias_jobs=jobs)
         self._linear_bwd(bufs.dt7, 1024, bufs.t7, bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.dt6, 256,
-                         B, 1024, 256, tc=self._tc)
+                         B, 1024, 256, tc=self._tc, bias_jobs=jobs)
         self._linear_bwd(bufs.dt6, 256, bufs.t6, bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.dt5, 64,
-                         B, 256, 64)
+                         B, 256, 64, bias_jobs=jobs)
         self._linear_bwd(bufs.dt5, 64, bufs.t5, bufs.z, Z, "fc5.weight", "fc5.bias", bufs.gz, Z,
-                         B, 64, Z)
+                         B, 64, Z, bias_jobs=jobs)
+        self._flush_bias(jobs)
 
     def _bwd_dense_encoder(self, bufs):
         """Backward segment 2: latent (analytic gradients of sample + prior + entropy) and the
@@ -631,14 +656,17 @@ class VAE(nn.Module):
         B, Z, s = bufs.B, self.z_dim, _stream()
         call("ava_b200_latent_bwd", ptr(bufs.heads), ptr(bufs.eps_w), ptr(bufs.eps_d), ptr(bufs.z),
              ptr(bufs.gz), B, Z, ptr(bufs.gheads), s)
+        jobs = []
         self._linear_bwd(bufs.gheads, 3 * Z, None, bufs.h3, 192, "fc41.weight", "fc41.bias", bufs.dh3,
-                         192, B, Z, 64, groups=3, dy_gs=Z, x_gs=64, w_gs=Z * 64, b_gs=Z, dx_gs=64)
+                         192, B, Z, 64, groups=3, dy_gs=Z, x_gs=64, w_gs=Z * 64, b_gs=Z, dx_gs=64,
+                         bias_jobs=jobs)
         self._linear_bwd(bufs.dh3, 192, bufs.h3, bufs.h2, 256, "fc31.weight", "fc31.bias", bufs.dh2,
-                         256, B, 192, 256)
+                         256, B, 192, 256, bias_jobs=jobs)
         self._linear_bwd(bufs.dh2, 256, bufs.h2, bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.dh1,
-                         1024, B, 256, 1024, tc=self._tc)
+                         1024, B, 256, 1024, tc=self._tc, bias_jobs=jobs)
         self._linear_bwd(bufs.dh1, 1024, bufs.h1, bufs.act[6], 8192, "fc1.weight", "fc1.bias",
-                         bufs.da6, 8192, B, 1024, 8192, tc=self._tc)
+                         bufs.da6, 8192, B, 1024, 8192, tc=self._tc, bias_jobs=jobs)
+        self._flush_bias(jobs)
 
     def _bwd_conv_encoder(self, bufs):
         """Backward segment 3: encoder conv stack (layers 6..0) and the BatchNorm affine

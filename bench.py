@@ -387,8 +387,12 @@ def dp_check(model, vae_mod, dist, world, rank):
         # Adam's first steps are sign-like (|update| = lr = 1e-3 whatever the gradient's size): an
         # element whose gradient sum is ~0 can flip with the summation order, so the max is bounded
         # by steps x lr and the mean says how rare that is
+        # (the NVSwitch's adder may round the sum differently in the last bit than NCCL's / a rank-order
+        # sum: more near-zero gradients flip -- the multimem variant gets the wider bar; its data
+        # path is pinned bit-exact against the peer-load variant in tests/test_gpu_dp.py)
+        bar = 3e-5 if model._dp_fused["multimem"] else 2e-6
         res["ok"] = bool(res["ok"] and res["fused_replicas_identical"] and
-                         res["fused_vs_nccl_param_mean_abs"] < 2e-6 and res["fused_vs_nccl_param_max_abs"] < 7e-3)
+                         res["fused_vs_nccl_param_mean_abs"] < bar and res["fused_vs_nccl_param_max_abs"] < 7e-3)
         res["what"] += "; (c) 3 steps of the fused NVLink reduce+Adam+broadcast kernel vs NCCL all-reduce + Adam"
     return res
 

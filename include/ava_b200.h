@@ -162,6 +162,22 @@ int ava_b200_linear_bwd_weight(const float* dy, int lddy, const float* ymask, co
                                float* db, int M, int N, int K, int groups, long long dy_gs, long long x_gs,
                                long long dw_gs, long long db_gs, int precision, void* ws, long long ws_bytes,
                                void* stream);
+
+/* Bias gradients of up to AVA_MAX_BIAS_JOBS Linear layers in two launches: job j computes
+ * db[n] = sum_m (mask > 0 ? dy : 0)[m, n] over dy [M, N] (row stride ld; mask may be NULL) --
+ * what ava_b200_linear_bwd_weight does per layer when given db; the step passes db = NULL there
+ * and collects the layers of a backward segment into one call.  h_jobs is a HOST array.
+ * Workspace: ava_b200_bias_grads_ws_bytes.  Replaces the bias half of autograd's Linear backward
+ * (ava/models/vae.py:226-232,258-260). */
+#define AVA_MAX_BIAS_JOBS 8
+typedef struct {
+  const float* dy;
+  const float* mask;
+  float* db;
+  int ld, M, N;
+} ava_b200_bias_job;
+long long ava_b200_bias_grads_ws_bytes(const ava_b200_bias_job* h_jobs, int njobs);
+int ava_b200_bias_grads(const ava_b200_bias_job* h_jobs, int njobs, void* ws, long long ws_bytes, void* stream);
 long long ava_b200_linear_ws_bytes(int M, int N, int K);
 
 /* ----------------------------------------------------------------------- ELBO

@@ -76,13 +76,92 @@ def _worker(rank, world, port):
         # Adam's early steps are sign-like: a near-zero gradient summed in another order can flip an
         # lr-sized update; everything else agrees to rounding
         assert (p - ref_p).abs().max().item() <= 6 * 2.5e-3, key
-        assert (p - ref_p).abs().mean().item() <= 2e-6, (key, (p - ref_p).abs().mean().item())
+        # NCCL and the peer-load kernel form the 2-rank sum a+b exactly alike; the NVSwitch's adder
+        # (multimem.ld_reduce) may round differently in the last bit, and a 1-ulp change of a
+        # near-zero gradient flips more of those lr-sized updates: its bar is wider (still 100x
+        # below the per-step parameter change a wrong gradient would cause); the bit-exactness of
+        # the multimem data path itself is pinned below with integer-valued gradients
+        bar = 3e-5 if (key[0] == "fused" and m._dp_fused["multimem"]) else 2e-6
+        mean = (p - ref_p).abs().mean().item()
+        if mean > bar and rank == 0:       # say where before failing
+            for name, off in sorted(m._off.items(), key=lambda kv: kv[1]):
+                n = dict(m.named_parameters())[name].numel()
+                d = (p[off:off + n] - ref_p[off:off + n]).abs()
+                if d.mean().item() > bar:
+                    print("  %s %-14s mean %.3e max %.3e frac>1e-4 %.4f" % (key, name, d.mean().item(), d.max().item(),
+                                                                         (d > 1e-4).float().mean().item()))
+        assert mean <= bar, (key, mean)
     # the sharded Adam moments gather into a complete optimizer state (what save_state writes)
     _, _, mf = runs[("fused", False)]
     _, _, mn = runs[("nccl", False)]
     mf._gather_moment_shards()
     assert (mf._flat_m - mn._flat_m).abs().max().item() <= 1e-3 * mn._flat_m.abs().max().item()
     assert (mf._flat_v - mn._flat_v).abs().max().item() <= 1e-3 * mn._flat_v.abs().max().item()
+    # ONE fused optimizer step against its definition, isolated from training dynamics: local
+    # gradients from a real backward pass; expected = Adam (the single-GPU kernel) on the NCCL sum
+    # of the ranks' gradients, from the same parameters / moments / step count
+    lib = importlib.import_module(PKG + "._lib")
+    for variant in ("peers_p2p", "peers_mc"):
+        if mf._dp_fused[variant] is None:
+            continue
+        mf._dp_fused["peers"] = mf._dp_fused[variant]
+        x = vae_oracle.make_input(900 + rank, 16).cuda()
+        noise = tuple(t.cuda() for t in vae_oracle.make_noise(900 + rank, 16))
+        mf._ensure_optimizer_state()
+        mf._sync_hyper()
+        bufs = mf._forward_native(x, noise, True, want_grad_seed=True)
+        mf._backward_native(bufs)
+        torch.cuda.synchronize()
+        g_sum = mf._flat_g.clone()
+        dist.all_reduce(g_sum)
+        p0, m0, v0, s0 = mf._flat_p.clone(), mf._flat_m.clone(), mf._flat_v.clone(), mf._step_dev.clone()
+        lib.call("ava_b200_adam_step_dev", p0.data_ptr(), g_sum.data_ptr(), m0.data_ptr(), v0.data_ptr(),
+                 mf._n_flat, s0.data_ptr(), mf._hyper_dev.data_ptr(), 1.0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        mf._adam_dp_native()
+        torch.cuda.synchronize()
+        dist.barrier()
+        d = (mf._flat_p - p0).abs()
+        n4, W = mf._n_flat // 4, world
+        lo, hi = 4 * (n4 * rank // W), 4 * (n4 * (rank + 1) // W)
+        dm = ((mf._flat_m[lo:hi] - m0[lo:hi]).abs() / (m0[lo:hi].abs() + 1e-30)).max().item()
+        dv = ((mf._flat_v[lo:hi] - v0[lo:hi]).abs() / (v0[lo:hi].abs() + 1e-30)).max().item()
+        print("rank %d %s: one-step |p - expected| max %.3e mean %.3e; own-slice moments rel. max %.1e / %.1e"
+              % (rank, variant, d.max().item(), d.mean().item(), dm, dv))
+        # p moves by <= lr = 1e-3 per step: agreement to a few ulps of the UPDATE; the 2-rank sum is
+        # a + b on every path, so peer loads must reproduce the single-GPU kernel bit for bit
+        assert d.max().item() <= 2e-6, (variant, d.max().item())
+        assert dm <= 1e-5 and dv <= 1e-5, (variant, dm, dv)
+        if variant == "peers_p2p" and world == 2:
+            assert torch.equal(mf._flat_p, p0), d.max().item()
+        mf._gather_moment_shards()
+    mf.dp_check_status()
+    # the two variants of the fused kernel move the same data: with integer-valued gradients every
+    # sum is exact whatever the adder's rounding, so peer loads and multimem must agree bit for bit
+    f = mf._dp_fused
+    if f["peers_mc"] is not None:
+        ends = []
+        gen = torch.Generator(device="cuda").manual_seed(11 + rank)
+        gint = torch.randint(-64, 65, (mf._n_flat,), device="cuda", generator=gen).float()
+        keep_p, keep_m, keep_v = mf._flat_p.clone(), mf._flat_m.clone(), mf._flat_v.clone()
+        keep_step = mf._step_dev.clone()
+        for peers in (f["peers_p2p"], f["peers_mc"]):
+            mf._flat_p.copy_(keep_p)
+            mf._flat_m.copy_(keep_m)
+            mf._flat_v.copy_(keep_v)
+            mf._step_dev.copy_(keep_step)        # (same bias correction for both variants)
+            mf._flat_g.copy_(gint)
+            f["peers"] = peers
+            torch.cuda.synchronize()
+            dist.barrier()
+            mf._adam_dp_native()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ends.append(mf._flat_p.clone())
+        mf.dp_check_status()
+        assert torch.equal(ends[0], ends[1]), (ends[0] - ends[1]).abs().max().item()
+        assert not torch.equal(ends[0], keep_p)
     print("rank %d: fused data-parallel step verified (multimem available: %s)" % (rank, mf._dp_fused["multimem_available"]))
     # (3) a rank with an empty shard still takes the step (zero gradients into the all-reduce)
     m = vae_mod.VAE(save_dir='', device_name='cuda')

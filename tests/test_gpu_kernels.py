@@ -332,6 +332,46 @@ def test_latent_and_recon(L, B, Z):
     assert abs(lsum.item() - 5.0 - want) <= 1e-6 * abs(want)
 
 
+@pytest.mark.parametrize("M", [7, 64, 1024])
+def test_bias_grads_batched(L, M):
+    """ava_b200_bias_grads: the bias gradients of several Linear layers (column sums of the masked
+    upstream gradient, incl. a grouped layer's adjacent column blocks as one job) in two launches,
+    against float64 sums; bit-identical run to run (fixed-order reduction)."""
+    import ctypes
+
+    class Job(ctypes.Structure):
+        _fields_ = [("dy", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("db", ctypes.c_void_p),
+                    ("ld", ctypes.c_int), ("M", ctypes.c_int), ("N", ctypes.c_int)]
+    gen = torch.Generator().manual_seed(M)
+    shapes = [(8192, True, 8192), (1024, True, 1024), (96, False, 96), (64, True, 80), (256, False, 256)]
+    jobs = (Job * len(shapes))()
+    keep, want, outs = [], [], []
+    for a, (N, masked, ld) in zip(jobs, shapes):
+        dy = torch.randn(M, ld, generator=gen, dtype=torch.float64).float()
+        mk = torch.randn(M, ld, generator=gen, dtype=torch.float64).float() if masked else None
+        ref = dy.double()[:, :N]
+        if masked:
+            ref = torch.where(mk.double()[:, :N] > 0, ref, torch.zeros_like(ref))
+        want.append(ref.sum(0))
+        ddy, dmk = dev(dy), (dev(mk) if masked else None)
+        db = torch.full((N,), 3.0, device="cuda")
+        keep += [ddy, dmk, db]
+        outs.append(db)
+        a.dy, a.mask, a.db = ddy.data_ptr(), (dmk.data_ptr() if masked else None), db.data_ptr()
+        a.ld, a.M, a.N = ld, M, N
+    need = L.lib().ava_b200_bias_grads_ws_bytes(jobs, len(shapes))
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    L.call("ava_b200_bias_grads", jobs, len(shapes), ws.data_ptr(), need, stream())
+    torch.cuda.synchronize()
+    first = [o.clone() for o in outs]
+    for o, w in zip(outs, want):
+        assert rel_err(o.cpu().numpy(), w.numpy()) <= 1e-5
+    L.call("ava_b200_bias_grads", jobs, len(shapes), ws.data_ptr(), need, stream())
+    torch.cuda.synchronize()
+    for o, f in zip(outs, first):
+        assert torch.equal(o, f)
+
+
 def test_adam_matches_torch(L):
     from oracle import vae_oracle
     n = 100003
