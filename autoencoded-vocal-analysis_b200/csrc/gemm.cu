@@ -80,7 +80,7 @@ __device__ __forceinline__ void gm_mma(float (&c)[4], const uint32_t (&a)[4], ui
 //   warp w owns rows 16*(w&3).. and columns 32*(w>>2).. of the 64x64 tile (4 n8 tiles); the
 //   row pitch of the staged tiles is 72 floats (8 mod 32) so fragment loads are conflict-free.
 template <bool A_KCONTIG, bool B_NCONTIG, bool MASK, int TERMS>
-__global__ void __launch_bounds__(256, TERMS == 3 ? 3 : 4) sgemm_kernel(const GemmParams P) {
+__device__ __forceinline__ void sgemm_body(const GemmParams& P, const int bx, const int by, const int bz) {
   constexpr int PAD = TERMS ? 8 : 4;
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
@@ -90,10 +90,10 @@ __global__ void __launch_bounds__(256, TERMS == 3 ? 3 : 4) sgemm_kernel(const Ge
   const int lane = tid & 31, warp = tid >> 5;
   const int fg = lane >> 2, ft = lane & 3;
   const int wm0 = (warp & 3) * 16, wn0 = (warp >> 2) * 32;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int grp = blockIdx.z / P.splits, split = blockIdx.z % P.splits;
+  const int m0 = by * BM, n0 = bx * BN;
+  const int grp = bz / P.splits, split = bz % P.splits;
   const float* A = P.A + (size_t)grp * P.a_gs;
-  const float* Am = MASK ? P.Amask + (size_t)grp * P.a_gs : nullptr;
+  const float* Am = (MASK && P.Amask != nullptr) ? P.Amask + (size_t)grp * P.a_gs : nullptr;
   const float* B = P.B + (size_t)grp * P.b_gs;
   // split-K by INTERLEAVED 16-deep chunks: split s takes chunks s, s+splits, s+2*splits, ...  The
   // CTAs that share an output tile run concurrently and march through K together, so at any
@@ -120,13 +120,13 @@ __global__ void __launch_bounds__(256, TERMS == 3 ? 3 : 4) sgemm_kernel(const Ge
       int valid = (m < P.M) ? (k_end - k) : 0;
       const float* p = A + (size_t)m * P.sam + k;
       ra = load4(p, valid);
-      if (MASK) ra = mask4(ra, load4(Am + (size_t)m * P.sam + k, valid));
+      if (MASK && Am != nullptr) ra = mask4(ra, load4(Am + (size_t)m * P.sam + k, valid));
     } else {
       int k = k0 + (tid >> 4), m = m0 + (tid & 15) * 4;
       int valid = (k < k_end) ? (P.M - m) : 0;
       const float* p = A + (size_t)k * P.sak + m;
       ra = load4(p, valid);
-      if (MASK) ra = mask4(ra, load4(Am + (size_t)k * P.sak + m, valid));
+      if (MASK && Am != nullptr) ra = mask4(ra, load4(Am + (size_t)k * P.sak + m, valid));
     }
     if (B_NCONTIG) {
       int k = k0 + (tid >> 4), n = n0 + (tid & 15) * 4;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256, TERMS == 3 ? 3 : 4) sgemm_kernel(const Ge
       }
     }
   } else {
-    float* part = P.part + (size_t)blockIdx.z * P.M * P.N;
+    float* part = P.part + (size_t)bz * P.M * P.N;
     if constexpr (TERMS == 0) {
       const int n = n0 + tx * 4;
       const bool vec = (n + 3 < P.N) && ((P.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(part) & 15) == 0);
@@ -305,6 +305,28 @@ __global__ void __launch_bounds__(256, TERMS == 3 ? 3 : 4) sgemm_kernel(const Ge
       }
     }
   }
+}
+
+template <bool A_KCONTIG, bool B_NCONTIG, bool MASK, int TERMS>
+__global__ void __launch_bounds__(256, TERMS == 3 ? 3 : 4) sgemm_kernel(const GemmParams P) {
+  sgemm_body<A_KCONTIG, B_NCONTIG, MASK, TERMS>(P, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Several weight-gradient GEMMs (dW = (dY (.) mask)^T X of the small dense layers) as ONE launch: the
+// grid is the concatenation of the jobs' 64x64 output tiles, every tile reduces over the whole batch
+// (no split-K: the six small layers of the VAE happen to make 148 tiles -- one wave).
+struct GemmJobs {
+  GemmParams p[AVA_MAX_WGRAD_JOBS];
+  int blk0[AVA_MAX_WGRAD_JOBS + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256, 4) sgemm_jobs_kernel(const GemmJobs J) {
+  int j = 0;
+  while (j + 1 < J.n && (int)blockIdx.x >= J.blk0[j + 1]) ++j;
+  const GemmParams& P = J.p[j];
+  const int local = blockIdx.x - J.blk0[j];
+  const int tx = (P.N + BN - 1) / BN, ty = (P.M + BM - 1) / BM;
+  sgemm_body<false, true, true, 0>(P, local % tx, (local / tx) % ty, local / (tx * ty));
 }
 
 __global__ void __launch_bounds__(256)
@@ -407,11 +429,31 @@ __global__ void __launch_bounds__(256) bias_partial_kernel(const BiasJobs J, flo
   const int ld = J.ld[j];
   float acc = 0.f;
   if (n < J.N[j]) {
-    for (int m = m0 + r; m < m1; m += 8) {
+    // 4 rows in flight per thread (the loop is otherwise one dependent load after another)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int m = m0 + r;
+    for (; m + 24 < m1; m += 32) {
+      float v0 = dy[(size_t)m * ld + n], v1 = dy[(size_t)(m + 8) * ld + n];
+      float v2 = dy[(size_t)(m + 16) * ld + n], v3 = dy[(size_t)(m + 24) * ld + n];
+      if (mask) {
+        const float k0 = mask[(size_t)m * ld + n], k1 = mask[(size_t)(m + 8) * ld + n];
+        const float k2 = mask[(size_t)(m + 16) * ld + n], k3 = mask[(size_t)(m + 24) * ld + n];
+        if (!(k0 > 0.f)) v0 = 0.f;
+        if (!(k1 > 0.f)) v1 = 0.f;
+        if (!(k2 > 0.f)) v2 = 0.f;
+        if (!(k3 > 0.f)) v3 = 0.f;
+      }
+      a0 += v0;
+      a1 += v1;
+      a2 += v2;
+      a3 += v3;
+    }
+    for (; m < m1; m += 8) {
       float v = dy[(size_t)m * ld + n];
       if (mask && !(mask[(size_t)m * ld + n] > 0.f)) v = 0.f;
-      acc += v;
+      a0 += v;
     }
+    acc = (a0 + a1) + (a2 + a3);
   }
   s[r][threadIdx.x & 31] = acc;
   __syncthreads();
@@ -633,7 +675,7 @@ extern "C" int ava_b200_bias_grads(const ava_b200_bias_job* h_jobs, int njobs, v
     J.N[j] = h.N;
     const int col_blocks = (h.N + 31) / 32;
     int splits = 1;
-    while (col_blocks * splits < kNumSMs && h.M / (splits * 2) >= 32 && splits < 64) splits *= 2;
+    while (col_blocks * splits < 8 * kNumSMs && h.M / (splits * 2) >= 32 && splits < 64) splits *= 2;
     J.splits[j] = splits;
     J.rows[j] = (h.M + splits - 1) / splits;
     J.blk0[j] = blk;
@@ -648,4 +690,29 @@ extern "C" int ava_b200_bias_grads(const ava_b200_bias_job* h_jobs, int njobs, v
   if (check_launch("bias_partial")) return 1;
   bias_finish_kernel<<<(col + 255) / 256, 256, 0, stream>>>(J, reinterpret_cast<const float*>(ws));
   return check_launch("bias_finish");
+}
+
+extern "C" int ava_b200_linear_bwd_weight_multi(const ava_b200_wgrad_job* h_jobs, int njobs, void* stream_) {
+  AVA_REQUIRE(h_jobs != nullptr && njobs >= 1 && njobs <= AVA_MAX_WGRAD_JOBS, "linear_bwd_weight_multi: 1..%d jobs",
+              AVA_MAX_WGRAD_JOBS);
+  GemmJobs J = {};
+  J.n = njobs;
+  int blk = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const ava_b200_wgrad_job& h = h_jobs[j];
+    AVA_REQUIRE(h.dy && h.x && h.dw && h.M > 0 && h.N > 0 && h.K > 0 && h.groups >= 1, "linear_bwd_weight_multi: bad job %d", j);
+    // dW[N,K] = dY^T[N,M] . X[M,K] -> gemm (N, K, M); A'(n,m) = dY[m*lddy + n]
+    GemmParams& P = J.p[j];
+    P.A = h.dy; P.Amask = h.ymask; P.sam = 1; P.sak = h.lddy;
+    P.B = h.x; P.sbk = h.ldx; P.sbn = 1;
+    P.C = h.dw; P.ldc = h.K;
+    P.M = h.N; P.N = h.K; P.K = h.M; P.act = 0;
+    P.splits = 1; P.kchunk = (h.M + BK - 1) / BK * BK;
+    P.groups = h.groups; P.a_gs = h.dy_gs; P.b_gs = h.x_gs; P.c_gs = h.dw_gs;
+    J.blk0[j] = blk;
+    blk += ((P.M + BM - 1) / BM) * ((P.N + BN - 1) / BN) * h.groups;
+  }
+  J.blk0[njobs] = blk;
+  sgemm_jobs_kernel<<<blk, 256, 0, (cudaStream_t)stream_>>>(J);
+  return check_launch("sgemm_jobs");
 }

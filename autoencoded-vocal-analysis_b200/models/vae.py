@@ -50,6 +50,29 @@ _DP_MULTIMEM_MIN_WORLD = 4
 _DP_MAX_WORLD = 8          # AVA_DP_MAX_WORLD, include/ava_b200.h
 
 
+# The row-wise fused kernels of csrc/mlp.cu are parity-green but measured SLOWER than the per-layer
+# GEMM launches under graph replay (batch 1024: 7.32 vs 7.04 ms/step, batch 64: 1.43 vs 1.30 ms;
+# gpurun_out s16/s17): each CTA re-streams the 2.6 MB of weights for its R <= 8 rows.  Off unless asked for.
+_FUSED_MLP = os.environ.get("AVA_B200_FUSED_MLP", "0") == "1"
+
+
+class _MlpParams(ctypes.Structure):
+    """ava_b200_mlp_params (include/ava_b200.h)."""
+    _fields_ = [("B", ctypes.c_int), ("Z", ctypes.c_int), ("stages", ctypes.c_int)] + \
+        [(n, ctypes.c_void_p) for n in
+         ("w2", "b2", "w3", "b3", "w4", "b4", "w5", "b5", "w6", "b6", "w7", "b7", "eps_w", "eps_d",
+          "h1", "h2", "h3", "heads", "z", "d", "t5", "t6", "t7",
+          "dt7", "dt6", "dt5", "gz", "gheads", "dh3", "dh2", "dh1", "acc")]
+
+
+class _WgradJob(ctypes.Structure):
+    """ava_b200_wgrad_job (include/ava_b200.h)."""
+    _fields_ = [("dy", ctypes.c_void_p), ("ymask", ctypes.c_void_p), ("x", ctypes.c_void_p),
+                ("dw", ctypes.c_void_p), ("lddy", ctypes.c_int), ("ldx", ctypes.c_int), ("M", ctypes.c_int),
+                ("N", ctypes.c_int), ("K", ctypes.c_int), ("groups", ctypes.c_int),
+                ("dy_gs", ctypes.c_longlong), ("x_gs", ctypes.c_longlong), ("dw_gs", ctypes.c_longlong)]
+
+
 class _BiasJob(ctypes.Structure):
     """ava_b200_bias_job (include/ava_b200.h)."""
     _fields_ = [("dy", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("db", ctypes.c_void_p),
@@ -464,7 +487,7 @@ class VAE(nn.Module):
              K, act, groups, x_gs, w_gs, b_gs, y_gs, tc, ptr(ws), ws.numel(), _stream())
 
     def _linear_bwd(self, dy, lddy, ymask, x, ldx, wkey, bkey, dx, lddx, M, N, K, groups=1,
-                    dy_gs=0, x_gs=0, w_gs=0, b_gs=0, dx_gs=0, tc=0, bias_jobs=None):
+                    dy_gs=0, x_gs=0, w_gs=0, b_gs=0, dx_gs=0, tc=0, bias_jobs=None, wgrad_jobs=None):
         """dW, db into the flat gradient buffer; dx (if not None) = (dy*mask) W.  With `bias_jobs`
         the bias gradient is not computed here but queued for one batched ava_b200_bias_grads call
         per backward segment (_flush_bias; the groups of a grouped layer are adjacent column blocks
@@ -476,11 +499,53 @@ class VAE(nn.Module):
             assert groups == 1 or (dy_gs == N and b_gs == N)
             bias_jobs.append((ptr(dy), ptr(ymask), gb, lddy, M, N * groups))
             gb = None
+        if wgrad_jobs is not None:
+            # (small layer: its weight gradient joins one multi-job launch, _flush_wgrad)
+            assert gb is None and dx is None
+            wgrad_jobs.append((ptr(dy), ptr(ymask), ptr(x), self._g(wkey), lddy, ldx, M, N, K, groups,
+                               dy_gs, x_gs, w_gs))
+            return
         call("ava_b200_linear_bwd_weight", ptr(dy), lddy, ptr(ymask), ptr(x), ldx, self._g(wkey),
              gb, M, N, K, groups, dy_gs, x_gs, w_gs, b_gs, tc, ptr(ws), ws.numel(), s)
         if dx is not None:
             call("ava_b200_linear_bwd_data", ptr(dy), lddy, ptr(ymask), self._p(wkey), ptr(dx), lddx,
                  M, N, K, groups, dy_gs, w_gs, dx_gs, 0, tc, ptr(ws), ws.numel(), s)
+
+    def _mlp_ok(self):
+        """The fused row-wise kernels of csrc/mlp.cu serve z_dim % 4 == 0, z_dim <= 64."""
+        return _FUSED_MLP and self.z_dim % 4 == 0 and 4 <= self.z_dim <= 64
+
+    def _mlp_params(self, bufs, stages, z=None, backward=False):
+        P = _MlpParams()
+        P.B, P.Z, P.stages = bufs.B, self.z_dim, stages
+        for f, key in (("w2", "fc2.weight"), ("b2", "fc2.bias"), ("w3", "fc31.weight"), ("b3", "fc31.bias"),
+                       ("w4", "fc41.weight"), ("b4", "fc41.bias"), ("w5", "fc5.weight"), ("b5", "fc5.bias"),
+                       ("w6", "fc6.weight"), ("b6", "fc6.bias"), ("w7", "fc7.weight"), ("b7", "fc7.bias")):
+            setattr(P, f, self._p(key))
+        for f in ("h1", "h2", "h3", "heads", "d", "t5", "t6", "t7"):
+            setattr(P, f, ptr(getattr(bufs, f)))
+        P.z = ptr(z if z is not None else bufs.z)
+        P.acc = bufs.acc.data_ptr()
+        if stages & 2 or backward:
+            P.eps_w, P.eps_d = ptr(bufs.eps_w), ptr(bufs.eps_d)
+        if backward:
+            for f in ("dt7", "dt6", "dt5", "gz", "gheads", "dh3", "dh2", "dh1"):
+                setattr(P, f, ptr(getattr(bufs, f)))
+        return P
+
+    def _mlp_fwd(self, bufs, stages, z=None):
+        """fc2 .. heads (1) | reparameterised sample + latent loss terms (2) | fc5 .. fc7 (4) as one
+        launch (csrc/mlp.cu)."""
+        call("ava_b200_mlp_fwd", ctypes.byref(self._mlp_params(bufs, stages, z)), _stream())
+
+    def _flush_wgrad(self, jobs):
+        """The queued small-layer weight gradients in one launch."""
+        if not jobs:
+            return
+        arr = (_WgradJob * len(jobs))()
+        for a, j in zip(arr, jobs):
+            (a.dy, a.ymask, a.x, a.dw, a.lddy, a.ldx, a.M, a.N, a.K, a.groups, a.dy_gs, a.x_gs, a.dw_gs) = j
+        call("ava_b200_linear_bwd_weight_multi", arr, len(jobs), _stream())
 
     def _flush_bias(self, jobs):
         """All queued bias gradients of a backward segment in two launches."""
@@ -499,8 +564,9 @@ class VAE(nn.Module):
              st + 8 * 64 * l, self._rm(l), self._rv(l), 1 if train else 0,
              (st + 8 * 64 * (l + 1)) if want_stats_out else None, _stream())
 
-    def _encode_native(self, x, bufs, train):
-        """x [B,128,128] -> bufs.heads (mu | u | log d).  ava/models/vae.py:216-232."""
+    def _encode_native(self, x, bufs, train, tail=True):
+        """x [B,128,128] -> bufs.heads (mu | u | log d).  ava/models/vae.py:216-232.
+        tail=False stops after fc1 (the caller runs the small layers fused with what follows)."""
         B, Z, s = bufs.B, self.z_dim, _stream()
         if train:
             call("ava_b200_channel_stats", ptr(x), B, 1, X_DIM, bufs.stats.data_ptr(), s)
@@ -510,6 +576,11 @@ class VAE(nn.Module):
             h = bufs.act[l]
         tc = self._tc
         self._linear(h, 8192, "fc1.weight", "fc1.bias", bufs.h1, 1024, B, 1024, 8192, 1, tc=tc)
+        if not tail:
+            return
+        if self._mlp_ok():
+            self._mlp_fwd(bufs, 1)
+            return
         self._linear(bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.h2, 256, B, 256, 1024, 1, tc=tc)
         # fc31|fc32|fc33 share their input: one [192,256] layer
         self._linear(bufs.h2, 256, "fc31.weight", "fc31.bias", bufs.h3, 192, B, 192, 256, 1)
@@ -517,13 +588,17 @@ class VAE(nn.Module):
         self._linear(bufs.h3, 192, "fc41.weight", "fc41.bias", bufs.heads, 3 * Z, B, Z, 64, 0,
                      groups=3, x_gs=64, w_gs=Z * 64, b_gs=Z, y_gs=Z)
 
-    def _decode_native(self, z, bufs, train):
-        """z [B,Z] -> bufs.act[13] = x_rec [B,1,128,128].  ava/models/vae.py:258-270."""
+    def _decode_native(self, z, bufs, train, head=True):
+        """z [B,Z] -> bufs.act[13] = x_rec [B,1,128,128].  ava/models/vae.py:258-270.
+        head=False: fc5..fc7 have already run (fused with the encoder tail)."""
         B, Z, s = bufs.B, self.z_dim, _stream()
         tc = self._tc
-        self._linear(z, Z, "fc5.weight", "fc5.bias", bufs.t5, 64, B, 64, Z, 1)
-        self._linear(bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.t6, 256, B, 256, 64, 1)
-        self._linear(bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.t7, 1024, B, 1024, 256, 1, tc=tc)
+        if head and self._mlp_ok():
+            self._mlp_fwd(bufs, 4, z=z)
+        elif head:
+            self._linear(z, Z, "fc5.weight", "fc5.bias", bufs.t5, 64, B, 64, Z, 1)
+            self._linear(bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.t6, 256, B, 256, 64, 1)
+            self._linear(bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.t7, 1024, B, 1024, 256, 1, tc=tc)
         self._linear(bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.t8, 8192, B, 8192, 1024, 1, tc=tc)
         if train:
             call("ava_b200_channel_stats", ptr(bufs.t8), B, 32, 256,
@@ -561,14 +636,19 @@ class VAE(nn.Module):
         self._scratch_need = self._scratch_need_for(B)
         s = _stream()
         bufs.accum.zero_()
-        self._encode_native(x, bufs, train)
+        fused = self._mlp_ok()
+        self._encode_native(x, bufs, train, tail=not fused)
         ew, ed = noise if noise is not None else self._draw_noise(B)
         ew = ew.to(torch.float32).contiguous()
         ed = ed.to(torch.float32).contiguous()
         bufs.eps_w, bufs.eps_d = ew, ed
-        call("ava_b200_latent_fwd", ptr(bufs.heads), ptr(ew), ptr(ed), B, self.z_dim, ptr(bufs.z),
-             ptr(bufs.d), bufs.acc.data_ptr(), s)
-        self._decode_native(bufs.z, bufs, train)
+        if fused:
+            # fc2 .. heads, the reparameterised sample and fc5 .. fc7: one launch
+            self._mlp_fwd(bufs, 7)
+        else:
+            call("ava_b200_latent_fwd", ptr(bufs.heads), ptr(ew), ptr(ed), B, self.z_dim, ptr(bufs.z),
+                 ptr(bufs.d), bufs.acc.data_ptr(), s)
+        self._decode_native(bufs.z, bufs, train, head=not fused)
         g = None
         if want_grad_seed:
             bufs.alloc_backward(self.z_dim)
@@ -641,12 +721,20 @@ class VAE(nn.Module):
         jobs = []
         self._linear_bwd(bufs.dt8, 8192, None, bufs.t7, 1024, "fc8.weight", "fc8.bias", bufs.dt7, 1024,
                          B, 8192, 1024, tc=self._tc, bias_jobs=jobs)
-        self._linear_bwd(bufs.dt7, 1024, bufs.t7, bufs.t6, 256, "fc7.weight", "fc7.bias", bufs.dt6, 256,
-                         B, 1024, 256, tc=self._tc, bias_jobs=jobs)
-        self._linear_bwd(bufs.dt6, 256, bufs.t6, bufs.t5, 64, "fc6.weight", "fc6.bias", bufs.dt5, 64,
-                         B, 256, 64, bias_jobs=jobs)
-        self._linear_bwd(bufs.dt5, 64, bufs.t5, bufs.z, Z, "fc5.weight", "fc5.bias", bufs.gz, Z,
-                         B, 64, Z, bias_jobs=jobs)
+        fused = self._mlp_ok()
+        if fused:
+            # every data gradient between fc8 and fc1 (dt6, dt5, gz, the latent gradient gheads,
+            # dh3, dh2, dh1) in one launch; the per-layer calls below only form weight gradients
+            call("ava_b200_mlp_bwd", ctypes.byref(self._mlp_params(bufs, 7, backward=True)), _stream())
+        wj = [] if fused else None
+        self._linear_bwd(bufs.dt7, 1024, bufs.t7, bufs.t6, 256, "fc7.weight", "fc7.bias",
+                         None if fused else bufs.dt6, 256, B, 1024, 256, tc=self._tc, bias_jobs=jobs,
+                         wgrad_jobs=wj)
+        self._linear_bwd(bufs.dt6, 256, bufs.t6, bufs.t5, 64, "fc6.weight", "fc6.bias",
+                         None if fused else bufs.dt5, 64, B, 256, 64, bias_jobs=jobs, wgrad_jobs=wj)
+        self._linear_bwd(bufs.dt5, 64, bufs.t5, bufs.z, Z, "fc5.weight", "fc5.bias",
+                         None if fused else bufs.gz, Z, B, 64, Z, bias_jobs=jobs, wgrad_jobs=wj)
+        self._flush_wgrad(wj)
         self._flush_bias(jobs)
 
     def _bwd_dense_encoder(self, bufs):
@@ -654,16 +742,21 @@ class VAE(nn.Module):
         encoder's dense layers.  Afterwards the gradients of fc1..fc43 are final (fc1.weight is
         half of all parameters)."""
         B, Z, s = bufs.B, self.z_dim, _stream()
-        call("ava_b200_latent_bwd", ptr(bufs.heads), ptr(bufs.eps_w), ptr(bufs.eps_d), ptr(bufs.z),
-             ptr(bufs.gz), B, Z, ptr(bufs.gheads), s)
+        fused = self._mlp_ok()       # (then gheads, dh3, dh2, dh1 came from ava_b200_mlp_bwd)
+        if not fused:
+            call("ava_b200_latent_bwd", ptr(bufs.heads), ptr(bufs.eps_w), ptr(bufs.eps_d), ptr(bufs.z),
+                 ptr(bufs.gz), B, Z, ptr(bufs.gheads), s)
         jobs = []
-        self._linear_bwd(bufs.gheads, 3 * Z, None, bufs.h3, 192, "fc41.weight", "fc41.bias", bufs.dh3,
-                         192, B, Z, 64, groups=3, dy_gs=Z, x_gs=64, w_gs=Z * 64, b_gs=Z, dx_gs=64,
-                         bias_jobs=jobs)
-        self._linear_bwd(bufs.dh3, 192, bufs.h3, bufs.h2, 256, "fc31.weight", "fc31.bias", bufs.dh2,
-                         256, B, 192, 256, bias_jobs=jobs)
-        self._linear_bwd(bufs.dh2, 256, bufs.h2, bufs.h1, 1024, "fc2.weight", "fc2.bias", bufs.dh1,
-                         1024, B, 256, 1024, tc=self._tc, bias_jobs=jobs)
+        wj = [] if fused else None
+        self._linear_bwd(bufs.gheads, 3 * Z, None, bufs.h3, 192, "fc41.weight", "fc41.bias",
+                         None if fused else bufs.dh3, 192, B, Z, 64, groups=3, dy_gs=Z, x_gs=64,
+                         w_gs=Z * 64, b_gs=Z, dx_gs=64, bias_jobs=jobs, wgrad_jobs=wj)
+        self._linear_bwd(bufs.dh3, 192, bufs.h3, bufs.h2, 256, "fc31.weight", "fc31.bias",
+                         None if fused else bufs.dh2, 256, B, 192, 256, bias_jobs=jobs, wgrad_jobs=wj)
+        self._linear_bwd(bufs.dh2, 256, bufs.h2, bufs.h1, 1024, "fc2.weight", "fc2.bias",
+                         None if fused else bufs.dh1, 1024, B, 256, 1024, tc=self._tc, bias_jobs=jobs,
+                         wgrad_jobs=wj)
+        self._flush_wgrad(wj)
         self._linear_bwd(bufs.dh1, 1024, bufs.h1, bufs.act[6], 8192, "fc1.weight", "fc1.bias",
                          bufs.da6, 8192, B, 1024, 8192, tc=self._tc, bias_jobs=jobs)
         self._flush_bias(jobs)

@@ -332,6 +332,87 @@ def test_latent_and_recon(L, B, Z):
     assert abs(lsum.item() - 5.0 - want) <= 1e-6 * abs(want)
 
 
+@pytest.mark.parametrize("B,Z", [(5, 32), (64, 32), (300, 32), (1024, 32), (1029, 8), (64, 64)])
+def test_fused_mlp_chain(L, B, Z):
+    """csrc/mlp.cu: fc2 .. heads, the reparameterised sample and fc5 .. fc7 in one launch, and the
+    whole backward-data chain (incl. the analytic latent gradient) in one launch, against a float64
+    autograd reference of the same chain (ava/models/vae.py:226-232, 298-316, 258-260); every row-tile
+    width (R = 1, 2, 4, 8) and ragged last tiles."""
+    import ctypes
+    from oracle import vae_oracle
+    vae_mod = importlib.import_module(PKG + ".models.vae")
+    gen = torch.Generator().manual_seed(B * 3 + Z)
+
+    def rnd(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=gen, dtype=torch.float64) * scale).float().double()
+    W = {"w2": rnd(256, 1024, scale=1 / 32), "b2": rnd(256, scale=0.1), "w3": rnd(192, 256, scale=1 / 16),
+         "b3": rnd(192, scale=0.1), "w4": rnd(3 * Z, 64, scale=1 / 8), "b4": rnd(3 * Z, scale=0.1),
+         "w5": rnd(64, Z, scale=Z ** -0.5), "b5": rnd(64, scale=0.1), "w6": rnd(256, 64, scale=1 / 8),
+         "b6": rnd(256, scale=0.1), "w7": rnd(1024, 256, scale=1 / 16), "b7": rnd(1024, scale=0.1)}
+    h1 = torch.relu(rnd(B, 1024)).requires_grad_(True)
+    ew, ed = rnd(B, 1), rnd(B, Z)
+    dt7 = rnd(B, 1024)
+    # float64 reference
+    h2 = torch.relu(F.linear(h1, W["w2"], W["b2"])); h2.retain_grad()
+    h3 = torch.relu(F.linear(h2, W["w3"], W["b3"])); h3.retain_grad()
+    heads = torch.cat([F.linear(h3[:, 64 * g:64 * g + 64], W["w4"][Z * g:Z * g + Z], W["b4"][Z * g:Z * g + Z])
+                       for g in range(3)], dim=1)
+    heads.retain_grad()
+    mu, u, logd = heads[:, :Z], heads[:, Z:2 * Z], heads[:, 2 * Z:]
+    d = torch.exp(logd)
+    z = vae_oracle.rsample(mu, u.unsqueeze(-1), d, ew, ed); z.retain_grad()
+    ent = vae_oracle.entropy(u.unsqueeze(-1), d).sum()
+    t5 = torch.relu(F.linear(z, W["w5"], W["b5"])); t5.retain_grad()
+    t6 = torch.relu(F.linear(t5, W["w6"], W["b6"])); t6.retain_grad()
+    t7 = torch.relu(F.linear(t6, W["w7"], W["b7"]))
+    ((t7 * dt7).sum() + 0.5 * (z * z).sum() - ent).backward()
+    # device
+    P = vae_mod._MlpParams()
+    keep = {}
+
+    def put(name, t):
+        keep[name] = dev(t)
+        setattr(P, name, keep[name].data_ptr())
+
+    def out(name, *shape):
+        keep[name] = torch.full(shape, 7.0, device="cuda")
+        setattr(P, name, keep[name].data_ptr())
+    for k, v in W.items():
+        put(k, v)
+    put("h1", h1.detach()); put("eps_w", ew); put("eps_d", ed); put("dt7", dt7)
+    for name, n in (("h2", 256), ("h3", 192), ("heads", 3 * Z), ("z", Z), ("d", Z), ("t5", 64), ("t6", 256),
+                    ("t7", 1024), ("dt6", 256), ("dt5", 64), ("gz", Z), ("gheads", 3 * Z), ("dh3", 192),
+                    ("dh2", 256), ("dh1", 1024)):
+        out(name, B, n)
+    acc = torch.zeros(4, dtype=torch.float64, device="cuda")
+    P.acc = acc.data_ptr()
+    P.B, P.Z, P.stages = B, Z, 7
+    L.call("ava_b200_mlp_fwd", ctypes.byref(P), stream())
+    L.call("ava_b200_mlp_bwd", ctypes.byref(P), stream())
+    torch.cuda.synchronize()
+    ref = {"h2": h2, "h3": h3, "heads": heads, "z": z, "d": d, "t5": t5, "t6": t6, "t7": t7}
+    for name, r in ref.items():
+        assert rel_err(keep[name].cpu().numpy(), r.detach().numpy()) <= TOL, name
+    a = acc.cpu().numpy()
+    assert abs(a[0] - (z * z).sum().item()) <= 1e-5 * (z * z).sum().item()
+    assert abs(a[2] - ent.item()) <= 1e-5 * abs(ent.item())
+    # z.grad holds the decoder-path gradient PLUS the prior term z; gz is the decoder path alone
+    gref = {"dt6": t6.grad, "dt5": t5.grad, "gz": z.grad - z.detach(), "gheads": heads.grad, "dh3": h3.grad,
+            "dh2": h2.grad, "dh1": h1.grad}
+    for name, r in gref.items():
+        assert rel_err(keep[name].cpu().numpy(), r.numpy()) <= TOL, name
+    # the staged forms used by encode() / decode(): stage 1 alone, stage 4 alone from a given z
+    for name in ("h2", "h3", "heads", "t5", "t6", "t7"):
+        keep[name].fill_(7.0)
+    P.stages = 1
+    L.call("ava_b200_mlp_fwd", ctypes.byref(P), stream())
+    P.stages = 4
+    L.call("ava_b200_mlp_fwd", ctypes.byref(P), stream())
+    torch.cuda.synchronize()
+    for name in ("h2", "h3", "heads", "t5", "t6", "t7"):
+        assert rel_err(keep[name].cpu().numpy(), ref[name].detach().numpy()) <= TOL, name
+
+
 @pytest.mark.parametrize("M", [7, 64, 1024])
 def test_bias_grads_batched(L, M):
     """ava_b200_bias_grads: the bias gradients of several Linear layers (column sums of the masked

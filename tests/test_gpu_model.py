@@ -120,6 +120,15 @@ def test_forward_backward_matches_reference_golden(vae_mod, name, precision):
             assert rel_err(sd[kk].cpu().numpy(), g[k]) <= FWD_TOL, kk
 
 
+@pytest.mark.parametrize("name", ["vae_train_b7", "vae_train_b64"])
+def test_fused_mlp_path_matches_reference_golden(vae_mod, name, monkeypatch):
+    """The opt-in fused small-layer path (AVA_B200_FUSED_MLP=1: csrc/mlp.cu forward / backward chains
+    + ava_b200_linear_bwd_weight_multi) through the same golden / float64-oracle bars as the
+    default per-layer path."""
+    monkeypatch.setattr(vae_mod, "_FUSED_MLP", True)
+    test_forward_backward_matches_reference_golden(vae_mod, name, "tf32x3b")
+
+
 def test_reduced_precision_mode_tf32(vae_mod):
     """'tf32' is the opt-in reduced-precision mode (what torch/cuDNN do by default for the
     reference's convs on a GPU) with its own stated tolerance: forward 1e-2,
