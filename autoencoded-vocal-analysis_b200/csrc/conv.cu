@@ -104,7 +104,10 @@ struct TileGeom {
 
 // TERMS == 0: fp32 SIMT FMA loop.  TERMS == 1 / 3: the inner product runs on the tensor cores as
 // mma.sync m16n8k8 TF32 (1 term: operands rounded to TF32; 3 terms: error-compensated
-// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with x = x_hi + x_lo, fp32-level accuracy); every warp then
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with x = x_hi + x_lo, fp32-level accuracy).  TERMS == 2: the
+// same compensated product with BOTH correction terms of a tap in ONE BF16 m16n8k16 instruction
+// (cv_mma_bf16 below: k16 = {a_lo | a} x {b | b_lo}), 2 tensor-core instructions per tap instead
+// of 3.  Every warp then
 // owns 4 output rows x 16 pixels x all output channels, one 8-input-channel chunk per stage;
 // a CTA is 4 warps on one 256-pixel sub-tile, 4 (3 for the widest layers) CTAs per SM, so that
 // the load / transform / MMA / epilogue phases of independent CTAs overlap.
@@ -152,7 +155,7 @@ struct GconvCfg {
   // staged weights: SIMT [CI][9][CO]; MMA: B fragments in register order
   // [CI/8][9][NTL][32 lanes]: {b0,b1} TF32-rounded (TERMS 1); {b0_hi,b1_hi,b0_lo,b1_lo}
   // (TERMS 3, PRESPLIT) or, for the widest layers, {b0,b1} in full fp32 split where used
-  static constexpr bool PRESPLIT = (TERMS == 3) && (CI * CO <= 384);
+  static constexpr bool PRESPLIT = (TERMS >= 2) && (CI * CO <= 384);
   static constexpr int WF = PRESPLIT ? 4 : 2;   // floats per lane per fragment
   // A-resident loop order when the fragments of 6 input rows fit next to the accumulators
   static constexpr bool ARES = (TERMS == 1) ? (NTL <= 3) : (NTL <= 2);
@@ -204,6 +207,11 @@ __device__ __forceinline__ uint32_t cv_pack_bf16(float lo_half, float hi_half) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
   return r;
+}
+__device__ __forceinline__ void cv_mma_bf16_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
 }
 __device__ __forceinline__ void cv_mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm(
@@ -422,8 +430,13 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       const float w1 = P.w[(size_t)co * P.w_so + (size_t)(ci0 + 4) * P.w_si + kk];
       if (C::PRESPLIT) {
         const float h0 = __uint_as_float(cv_tf32(w0)), h1 = __uint_as_float(cv_tf32(w1));
-        *reinterpret_cast<float4*>(s_w + 4 * idx) = make_float4(h0, h1, w0 - h0, w1 - h1);
-      } else if (TERMS == 3) {
+        if (TERMS == 2)   // {b_hi | k16 B fragment: (b, paired with a_lo), (b_lo, paired with a)}
+          *reinterpret_cast<float4*>(s_w + 4 * idx) =
+              make_float4(h0, h1, __uint_as_float(cv_pack_bf16(w0, w1)),
+                          __uint_as_float(cv_pack_bf16(w0 - h0, w1 - h1)));
+        else
+          *reinterpret_cast<float4*>(s_w + 4 * idx) = make_float4(h0, h1, w0 - h0, w1 - h1);
+      } else if (TERMS >= 2) {
         *reinterpret_cast<float2*>(s_w + 2 * idx) = make_float2(w0, w1);
       } else {
         *reinterpret_cast<float2*>(s_w + 2 * idx) =
@@ -558,8 +571,16 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
             const float av[4] = {p[0], p[8], p[4 * G::PLANE], p[4 * G::PLANE + 8]};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              ah[j] = (TERMS == 3) ? cv_tf32_hi(av[j]) : __float_as_uint(av[j]);
+              ah[j] = (TERMS >= 2) ? cv_tf32_hi(av[j]) : __float_as_uint(av[j]);
               al[j] = (TERMS == 3) ? __float_as_uint(av[j] - __uint_as_float(ah[j])) : 0u;
+            }
+            if (TERMS == 2) {
+              // k16 A fragment of the correction instruction: k = {2t, 2t+1} <- a_lo of channels
+              // (t, t+4), k = {2t+8, 2t+9} <- a itself; rows g (regs 0, 2) and g+8 (regs 1, 3)
+              al[0] = cv_pack_bf16(av[0] - __uint_as_float(ah[0]), av[2] - __uint_as_float(ah[2]));
+              al[1] = cv_pack_bf16(av[1] - __uint_as_float(ah[1]), av[3] - __uint_as_float(ah[3]));
+              al[2] = cv_pack_bf16(av[0], av[2]);
+              al[3] = cv_pack_bf16(av[1], av[3]);
             }
           };
           auto load_b = [&](int k, int i, uint32_t (&bh)[2], uint32_t (&bl)[2]) {
@@ -572,10 +593,14 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
               bl[1] = __float_as_uint(b.w);
             } else {
               const float2 b = *reinterpret_cast<const float2*>(wp);
-              bh[0] = (TERMS == 3) ? cv_tf32_hi(b.x) : __float_as_uint(b.x);
-              bh[1] = (TERMS == 3) ? cv_tf32_hi(b.y) : __float_as_uint(b.y);
+              bh[0] = (TERMS >= 2) ? cv_tf32_hi(b.x) : __float_as_uint(b.x);
+              bh[1] = (TERMS >= 2) ? cv_tf32_hi(b.y) : __float_as_uint(b.y);
               bl[0] = (TERMS == 3) ? __float_as_uint(b.x - __uint_as_float(bh[0])) : 0u;
               bl[1] = (TERMS == 3) ? __float_as_uint(b.y - __uint_as_float(bh[1])) : 0u;
+              if (TERMS == 2) {
+                bl[0] = cv_pack_bf16(b.x, b.y);
+                bl[1] = cv_pack_bf16(b.x - __uint_as_float(bh[0]), b.y - __uint_as_float(bh[1]));
+              }
             }
           };
           if constexpr (KIND == K_UP) {
@@ -598,7 +623,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 #pragma unroll
                 for (int q = 0; q < NTAP; ++q)
                   if (taps[pass][q] >= 0) load_b(taps[pass][q], i, bh[q], bl[q]);
-                if (TERMS == 3) {
+                if (TERMS >= 2) {
                   // one short chain per tap (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi on a fresh accumulator:
                   // a single truncating add at full magnitude), the taps of the pass interleaved
                   float tq[NTAP][4];
@@ -609,7 +634,10 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
                       const int k = taps[pass][q];
                       if (k < 0) continue;
                       const int dy = (k / 3 == 0) ? 1 : 0, dx = (k % 3 == 0) ? 1 : 0;
-                      if (term == 0) cv_mma_tf32_zero(tq[q], al[dy][dx], bh[q][0], bh[q][1]);
+                      if (TERMS == 2) {
+                        if (term == 0) cv_mma_bf16_zero(tq[q], al[dy][dx], bl[q][0], bl[q][1]);
+                        else if (term == 2) cv_mma_tf32(tq[q], ah[dy][dx], bh[q][0], bh[q][1]);
+                      } else if (term == 0) cv_mma_tf32_zero(tq[q], al[dy][dx], bh[q][0], bh[q][1]);
                       else if (term == 1) cv_mma_tf32(tq[q], ah[dy][dx], bl[q][0], bl[q][1]);
                       else cv_mma_tf32(tq[q], ah[dy][dx], bh[q][0], bh[q][1]);
                     }
@@ -650,7 +678,23 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
                 uint32_t bh[3][2], bl[3][2];
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) load_b(ky * 3 + kx, i, bh[ky], bl[ky]);
-                if (TERMS == 3) {
+                if (TERMS == 2) {
+                  float tq[2][4];
+#pragma unroll
+                  for (int o = 0; o < 2; ++o) cv_mma_bf16_zero(tq[o], al[2 * o], bl[0][0], bl[0][1]);
+#pragma unroll
+                  for (int ky = 1; ky < 3; ++ky)
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) cv_mma_bf16(tq[o], al[2 * o + ky], bl[ky][0], bl[ky][1]);
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) cv_mma_tf32(tq[o], ah[2 * o + ky], bh[ky][0], bh[ky][1]);
+#pragma unroll
+                  for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[o][i][q] += tq[o][q];
+                } else if (TERMS == 3) {
                   float tq[2][4];
 #pragma unroll
                   for (int o = 0; o < 2; ++o) cv_mma_tf32_zero(tq[o], al[2 * o], bh[0][0], bh[0][1]);
@@ -688,7 +732,30 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
               uint32_t ah[6][4], al[6][4];
 #pragma unroll
               for (int r = 0; r < 6; ++r) load_a(tin + r * G::PITCH + kx, ah[r], al[r]);
-              if constexpr (TERMS == 3) {
+              if constexpr (TERMS == 2) {
+                // as below with one BF16 k16 instruction per tap for both correction terms
+#pragma unroll
+                for (int i = 0; i < NTL; ++i) {
+                  uint32_t bh[3][2], bl[3][2];
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky) load_b(ky * 3 + kx, i, bh[ky], bl[ky]);
+                  float tq[4][4];
+#pragma unroll
+                  for (int o = 0; o < 4; ++o) cv_mma_bf16_zero(tq[o], al[o], bl[0][0], bl[0][1]);
+#pragma unroll
+                  for (int ky = 1; ky < 3; ++ky)
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) cv_mma_bf16(tq[o], al[o + ky], bl[ky][0], bl[ky][1]);
+#pragma unroll
+                  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) cv_mma_tf32(tq[o], ah[o + ky], bh[ky][0], bh[ky][1]);
+#pragma unroll
+                  for (int o = 0; o < 4; ++o)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[o][i][q] += tq[o][q];
+                }
+              } else if constexpr (TERMS == 3) {
                 // chain over the 3 taps of this kernel column on a fresh accumulator (6 small-term
                 // MMAs, then the 3 main terms), then one round-to-nearest add into the running sum
 #pragma unroll
@@ -744,7 +811,21 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 #pragma unroll
                   for (int ky = 0; ky < 3; ++ky)
                     if (r - ky >= 0 && r - ky <= 3) load_b(ky * 3 + kx, i, bh[ky], bl[ky]);
-                  if (TERMS == 3) {
+                  if (TERMS == 2) {
+                    float tq[3][4];
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                      if (r - ky >= 0 && r - ky <= 3) cv_mma_bf16_zero(tq[ky], al, bl[ky][0], bl[ky][1]);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                      if (r - ky >= 0 && r - ky <= 3) cv_mma_tf32(tq[ky], ah, bh[ky][0], bh[ky][1]);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                      if (r - ky >= 0 && r - ky <= 3) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[r - ky][i][q] += tq[ky][q];
+                      }
+                  } else if (TERMS == 3) {
                     float tq[3][4];
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
@@ -1462,8 +1543,10 @@ static int make_act_map(CUtensorMap* map, const float* base, long long nc, int H
 
 // 0: fp32 SIMT; 1: TF32 tensor cores; 3: error-compensated 3xTF32 (layers the tensor-core path covers)
 static int g_conv_terms = 0;
-// 3-term layers: correction terms as half-rate BF16 k16 instructions (cv_pack_bf16) where a kernel
-// has that variant (mode 3 of ava_b200_set_conv_precision); mode 2 keeps all three terms in TF32
+// 3-term layers: correction terms as half-rate BF16 k16 instructions (cv_pack_bf16), a bit mask:
+// 1 = the weight-gradient kernels, 2 = the backward-data kernels, 4 = the forward kernels
+// (ava_b200_set_conv_precision: mode 3 = 1, mode 5 = 1|2, mode 4 = 1|2|4; mode 2 keeps all three
+// terms in TF32)
 static int g_conv_bf16corr = 0;
 
 template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN, int TERMS = 0>
@@ -2414,7 +2497,9 @@ using namespace ava;
 
 // layers with channel counts that are multiples of 8 on both sides can run on the tensor cores
 #define GCONV_TC(KIND, CI, CO, TW, INMODE, EPI, HIN)                                               \
-  (g_conv_terms == 3   ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 3>(P, stream)            \
+  (g_conv_terms == 3   ? ((g_conv_bf16corr & (EPI == EPI_FWD ? 4 : 2))                                 \
+                              ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 2>(P, stream)         \
+                              : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 3>(P, stream))        \
    : g_conv_terms == 1 ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 1>(P, stream)            \
                        : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 0>(P, stream))
 
@@ -2423,15 +2508,20 @@ using namespace ava;
 #define GCONV_TC1(KIND, CI, CO, TW, INMODE, EPI, HIN)                                              \
   (g_conv_terms == 1 ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 1>(P, stream)              \
                      : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 0>(P, stream))
+// (measured again with the 2-instruction-per-tap variant, TERMS == 2: 304.8 vs 307.7 us -- that
+// layer is bound by its epilogue's reads of x, not by the inner product)
 
 extern "C" int ava_b200_set_conv_precision(int mode) {
-  AVA_REQUIRE(mode >= 0 && mode <= 3, "set_conv_precision: mode %d (0 fp32, 1 tf32, 2 tf32x3, 3 tf32 + bf16 corrections)",
-              mode);
+  AVA_REQUIRE(mode >= 0 && mode <= 5,
+              "set_conv_precision: mode %d (0 fp32, 1 tf32, 2 tf32x3, 3 / 4 / 5 tf32 + bf16 corrections)", mode);
   g_conv_terms = (mode >= 2) ? 3 : mode;
-  g_conv_bf16corr = (mode == 3) ? 1 : 0;
+  g_conv_bf16corr = (mode == 3) ? 1 : (mode == 4) ? 7 : (mode == 5) ? 3 : 0;
   return 0;
 }
-extern "C" int ava_b200_get_conv_precision(void) { return g_conv_terms == 3 ? (g_conv_bf16corr ? 3 : 2) : g_conv_terms; }
+extern "C" int ava_b200_get_conv_precision(void) {
+  if (g_conv_terms != 3) return g_conv_terms;
+  return g_conv_bf16corr == 1 ? 3 : g_conv_bf16corr == 7 ? 4 : g_conv_bf16corr == 3 ? 5 : 2;
+}
 
 extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float* w, const float* b,
                                    const float* gamma, const float* beta, const double* stats_in,

@@ -44,8 +44,13 @@ _CONVT = [("convt1", 32, 24, 1, 16), ("convt2", 24, 24, 2, 16), ("convt3", 24, 1
           ("convt7", 8, 1, 1, 128)]
 _LAYERS = _CONV + _CONVT           # layer id 0..13 of the C ABI
 _BN_MOMENTUM = 0.1
-# what precision='auto' means for the conv layers (2: 3xTF32; 3: TF32 + BF16 corrections)
-_AUTO_CONV_MODE = int(os.environ.get("AVA_B200_AUTO_CONV_MODE", "3"))
+# what precision='auto' means for the conv layers (ava_b200_set_conv_precision): 2 = 3xTF32;
+# 3 / 5 / 4 = BF16 correction terms in the weight-gradient / + backward-data / + forward kernels.
+# Measured at batch 1024 (gpurun_out s18-s21 -> profiles/r02_summary.md): 7.00 / 6.83 / 6.69 ms per
+# step; worst gradient error vs float64 4.2e-5 / 4.4e-5 / 7.2e-5 and 191 / 191 / 403 ReLU units on
+# the other side of zero.  5 is free in accuracy; 4 ('tf32x3c') holds the 1e-4 bar with less margin
+# and stays opt-in.
+_AUTO_CONV_MODE = int(os.environ.get("AVA_B200_AUTO_CONV_MODE", "5"))
 _DP_MULTIMEM_MIN_WORLD = 4
 _DP_MAX_WORLD = 8          # AVA_DP_MAX_WORLD, include/ava_b200.h
 
@@ -234,13 +239,18 @@ class VAE(nn.Module):
     ----------
     save_dir, lr, z_dim, model_precision, device, optimizer, epoch, loss :
         as in the reference (ava/models/vae.py:43-122).
-    precision : {'auto', 'fp32', 'tf32x3', 'tf32'}
-        How the two 8192x1024 dense layers (fc1, fc8) are computed; everything else is
-        always fp32 SIMT.  'fp32': fp32 SIMT GEMM.  'tf32x3': tcgen05 tensor cores with
-        error-compensated 3xTF32 products and fp32 accumulation in TMEM (measured
-        parity 2e-5 vs float64, i.e. fp32-level; needs batch % 128 == 0, else falls
-        back to 'fp32').  'tf32': single-pass TF32 tensor cores (stated tolerance
-        3e-3).  'auto' (default) = 'tf32x3'.
+    precision : {'auto', 'fp32', 'tf32x3', 'tf32x3b', 'tf32x3d', 'tf32x3c', 'tf32'}
+        Arithmetic of the inner products (storage and accumulation are fp32 in every mode).
+        'fp32': fp32 FMA everywhere.  'tf32x3': error-compensated 3xTF32 on the tensor cores
+        (tcgen05 for fc1/fc8 at batch % 128 == 0, mma.sync for the conv layers with >= 8
+        channels on both sides): fp32-level parity (rtol 1e-4 vs float64).  'tf32x3b' /
+        'tf32x3d' / 'tf32x3c': as 'tf32x3' with the two correction terms of the conv products
+        as half-rate BF16 instructions in the weight-gradient kernels / also the backward-data
+        kernels / all three conv kernel families (include/ava_b200.h,
+        ava_b200_set_conv_precision modes 3 / 5 / 4; all hold rtol 1e-4, with decreasing
+        margin).  'tf32': single-pass TF32, the opt-in reduced-precision mode (stated
+        tolerance 1e-2 forward).  'auto' (default): 'tf32x3' dense layers with the conv mode
+        named by _AUTO_CONV_MODE.
     """
 
     def __init__(self, save_dir='', lr=1e-3, z_dim=32, model_precision=10.0,
@@ -256,12 +266,13 @@ class VAE(nn.Module):
         self.device = torch.device(device_name)
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        assert precision in ('auto', 'fp32', 'tf32x3', 'tf32x3b', 'tf32')
+        assert precision in ('auto', 'fp32', 'tf32x3', 'tf32x3b', 'tf32x3c', 'tf32x3d', 'tf32')
         self.precision = precision
-        # dense layers: 0 fp32 FMA, 1 TF32, 2 3xTF32; conv layers additionally 3 = 3-term product
+        # dense layers: 0 fp32 FMA, 1 TF32, 2 3xTF32; conv layers additionally 3 / 4 = 3-term product
         # with the two correction terms as half-rate BF16 instructions (csrc/conv.cu, cv_pack_bf16)
-        self._tc = {'auto': 2, 'fp32': 0, 'tf32x3': 2, 'tf32x3b': 2, 'tf32': 1}[precision]
-        self._tc_conv = {'auto': _AUTO_CONV_MODE, 'tf32x3b': 3}.get(precision, self._tc)
+        # in the weight-gradient kernels / in all three kernel families
+        self._tc = {'auto': 2, 'fp32': 0, 'tf32x3': 2, 'tf32x3b': 2, 'tf32x3c': 2, 'tf32x3d': 2, 'tf32': 1}[precision]
+        self._tc_conv = {'auto': _AUTO_CONV_MODE, 'tf32x3b': 3, 'tf32x3c': 4, 'tf32x3d': 5}.get(precision, self._tc)
         # CUDA graphs for the train step: 'auto' = when the step is host-bound (batch <= 256)
         assert cuda_graphs in ('auto', True, False)
         self.cuda_graphs = cuda_graphs

@@ -522,7 +522,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32x3b", "tf32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32x3b", "tf32x3c", "tf32x3d", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--all-kernels", action="store_true", help="list every native call, not the top 12")

@@ -82,6 +82,13 @@ int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float*
  *      terms a_lo*b + a*b_lo run as BF16 mma.m16n8k16 -- two k-chunks per instruction, 4 instead
  *      of 6 tensor-core instructions per pair of chunks; per-product error <= 2^-18, unbiased:
  *      rtol 1e-4 parity holds (tests/test_gpu_kernels.py, tests/test_gpu_model.py mode tf32x3b)
+ *   4  as 3, and the forward / backward-data kernels form both correction terms of a tap in ONE
+ *      BF16 mma.m16n8k16 (k16 = {a_lo | a} x {b | b_lo}): 2 instead of 3 tensor-core instructions
+ *      per tap; per-product error <= 2^-19 (3xTF32: 2^-22): rtol 1e-4 parity holds (same tests,
+ *      mode tf32x3c) with less margin -- batch-1024 gradients within 7.2e-5 of float64 (mode 3:
+ *      4.2e-5), twice as many ReLU units on the other side of zero
+ *   5  as 4 for the weight-gradient and backward-data kernels only; the forward kernels (whose
+ *      rounding decides ReLU states and feeds every later layer) keep three TF32 terms
  * Layers whose channel counts are not multiples of 8 always use fp32 FMA. */
 int ava_b200_set_conv_precision(int mode);
 int ava_b200_get_conv_precision(void);

@@ -107,6 +107,64 @@ def test_vae_container_matches_reference_layout(tmp_path):
         model._as_input(torch.zeros(2, 64, 64))
 
 
+def test_checkpoints_interchange_with_the_real_reference(tmp_path):
+    """A checkpoint written by the UNMODIFIED reference VAE (ava/models/vae.py:432-472, imported from
+    /root/reference; one torch-Adam step taken so the optimizer state is populated) loads into this
+    package's VAE, and a checkpoint written here loads into the reference -- parameters, BatchNorm
+    buffers, Adam moments / step, epoch and loss history identical.  Runs where the reference is
+    mounted (the CPU container); skipped on the GPU box."""
+    from oracle import _ref_import
+    if not _ref_import.reference_available():
+        pytest.skip("/root/reference not present")
+    ref_vae = _ref_import.import_reference()[0]
+    vae = importlib.import_module(PKG + ".models.vae")
+    rdir, odir = str(tmp_path / "ref"), str(tmp_path / "ours")
+    torch.manual_seed(11)
+    ref = ref_vae.VAE(save_dir=rdir, device_name='cpu')
+    x = torch.rand(3, 128, 128)
+    ref.train()
+    ref.optimizer.zero_grad()
+    ref.forward(x).backward()
+    ref.optimizer.step()
+    ref.epoch = 4
+    ref.loss['train'][3] = 12.5
+    ref.loss['test'][3] = 13.5
+    ref.save_state(os.path.join(rdir, "checkpoint_004.tar"))
+    # reference -> ours
+    ours = vae.VAE(save_dir=odir, device_name='cpu')
+    ours.load_state(os.path.join(rdir, "checkpoint_004.tar"))
+    assert ours.epoch == 4 and ours.loss['train'][3] == 12.5 and ours.loss['test'][3] == 13.5
+    rsd = ref.state_dict()
+    osd = ours.state_dict()
+    assert list(rsd.keys()) == list(osd.keys())
+    for k in rsd:
+        assert torch.equal(rsd[k], osd[k]), k
+    assert ours._step_host == 1
+    rparams = dict(ref.named_parameters())
+    for k in ("conv1.weight", "fc1.weight", "fc43.bias", "bn14.weight", "convt7.bias"):
+        st = ref.optimizer.state[rparams[k]]
+        assert torch.equal(ours._views_m[k], st['exp_avg']), k
+        assert torch.equal(ours._views_v[k], st['exp_avg_sq']), k
+    # ours -> reference (written from the flat native state: moments, step and all)
+    ours.save_state(os.path.join(odir, "checkpoint_004.tar"))
+    ref2 = ref_vae.VAE(save_dir=rdir, device_name='cpu')
+    ref2.load_state(os.path.join(odir, "checkpoint_004.tar"))
+    assert ref2.epoch == 4 and ref2.loss['train'][3] == 12.5
+    for k, v in ref2.state_dict().items():
+        assert torch.equal(v, rsd[k]), k
+    r2params = dict(ref2.named_parameters())
+    for k in ("conv1.weight", "fc1.weight", "fc43.bias", "bn14.weight"):
+        a, b = ref2.optimizer.state[r2params[k]], ref.optimizer.state[rparams[k]]
+        assert torch.equal(a['exp_avg'], b['exp_avg']) and torch.equal(a['exp_avg_sq'], b['exp_avg_sq']), k
+        assert float(a['step']) == float(b['step']) == 1.0
+    # and the reference keeps training from it (its own Adam accepts the restored state)
+    ref2.train()
+    ref2.optimizer.zero_grad()
+    ref2.forward(x).backward()
+    ref2.optimizer.step()
+    assert float(ref2.optimizer.state[r2params["fc1.weight"]]['step']) == 2.0
+
+
 def test_time_bracketing_matches_oracle_coordinates():
     pre = importlib.import_module(PKG + ".preprocessing.utils")
     rng = np.random.default_rng(0)
