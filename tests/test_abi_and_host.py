@@ -107,7 +107,7 @@ def test_vae_container_matches_reference_layout(tmp_path):
         model._as_input(torch.zeros(2, 64, 64))
 
 
-def test_checkpoints_interchange_with_the_real_reference(tmp_path):
+def test_checkpoints_interchange_with_the_real_reference(tmp_path, monkeypatch):
     """A checkpoint written by the UNMODIFIED reference VAE (ava/models/vae.py:432-472, imported from
     /root/reference; one torch-Adam step taken so the optimizer state is populated) loads into this
     package's VAE, and a checkpoint written here loads into the reference -- parameters, BatchNorm
@@ -116,6 +116,13 @@ def test_checkpoints_interchange_with_the_real_reference(tmp_path):
     from oracle import _ref_import
     if not _ref_import.reference_available():
         pytest.skip("/root/reference not present")
+    # (the stand-in h5py / affinewarp / matplotlib modules the reference import needs must not
+    # leak into the tests that follow)
+    import sys
+    for name in ("h5py", "affinewarp", "affinewarp.crossval", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, None)
+            monkeypatch.delitem(sys.modules, name)
     ref_vae = _ref_import.import_reference()[0]
     vae = importlib.import_module(PKG + ".models.vae")
     rdir, odir = str(tmp_path / "ref"), str(tmp_path / "ours")
