@@ -243,6 +243,15 @@ __device__ __forceinline__ void cv_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // 3-D box [channels][rows][cols] of a [B*C, H, W] activation tensor; out-of-range rows/columns
 // (image border, negative coordinates) are zero-filled by the TMA unit
+// (gconv_kernel's issue(): also requesting the stage AFTER the one being fetched into L2.  Measured:
+// forward family 1970 -> 2009 us per step at batch 1024, backward-data +35 us -- the extra TMA
+// requests compete with the loads that are needed now.  Off.)
+constexpr bool kPrefetchAhead = false;
+// request a box into L2 only (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void cv_tma_prefetch_3d(const CUtensorMap* map, int x, int y, int z) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z)
+               : "memory");
+}
 __device__ __forceinline__ void cv_tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z,
                                                uint64_t* bar) {
   asm volatile(
@@ -296,6 +305,22 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
   const int ntiles = P.B * tiles_per_img;
   const int ngroups = (ntiles + NSUB - 1) / NSUB;
 
+  // ---- EPI_BWD: the epilogue reads this layer's forward input x_self for the tile it has just
+  // computed (BatchNorm backward + ReLU mask); straight from DRAM those loads are the largest stall of
+  // the backward-data kernels (long scoreboard 20-41% of the samples, profiles/r02_ncu_top_kernels.txt).
+  // The tile's lines are requested into L2 when the tile STARTS, so that they arrive while the
+  // inner product runs (no registers or shared memory held).
+  auto prefetch_x = [&](int n, int ty, int tx, int me, int nthr) {
+    constexpr int OTH = (KIND == K_UP) ? 2 * G::TH : G::TH;
+    constexpr int OTW = (KIND == K_UP) ? 2 * TW : TW;
+    constexpr int LPR = (OTW * 4 + 127) / 128;   // 128-byte lines per row segment
+    const float* base = P.x_self + ((size_t)n * CO * H_out + (size_t)ty * OTH) * W_out + tx * OTW;
+    for (int i = me; i < CO * OTH * LPR; i += nthr) {
+      const int l = i % LPR, r = (i / LPR) % OTH, c = i / (LPR * OTH);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((size_t)c * H_out + r) * W_out + l * 32));
+    }
+  };
+
   // ---- TMA: boxes of stage (grp, ch) into ring slot `buf`, issued by thread 0
   auto issue = [&](int grp, int ch, int buf) {
     if (tid != 0) return;
@@ -312,6 +337,26 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       const int iy0 = (KIND == K_S1) ? lty * G::TH - 1 : (KIND == K_S2 ? 2 * lty * G::TH - 1 : lty * G::TH);
       const int X0 = (KIND == K_S2) ? 2 * ltx * TW : ltx * TW;
       cv_tma_load_3d(dst + sb * SUBF, &map_in, X0 - G::RAW_X_SHIFT, iy0, ln * CI + ch * CIC, s_bar);
+    }
+    // ... and the stage AFTER this one is requested into L2 (one stage of look-ahead hides the TMA
+    // round trip only when the inner product of a stage outlasts a DRAM access)
+    int g2 = grp, c2 = ch + 1;
+    if (c2 == NCHUNK) {
+      g2 = grp + gridDim.x;
+      c2 = 0;
+    }
+    if (kPrefetchAhead && g2 < ngroups) {
+      int nsub2 = ntiles - g2 * NSUB;
+      if (nsub2 > NSUB) nsub2 = NSUB;
+      for (int sb = 0; sb < nsub2; ++sb) {
+        const int ltile = g2 * NSUB + sb;
+        const int ln = ltile / tiles_per_img;
+        const int lrem = ltile - ln * tiles_per_img;
+        const int lty = lrem / tiles_x, ltx = lrem - lty * tiles_x;
+        const int iy0 = (KIND == K_S1) ? lty * G::TH - 1 : (KIND == K_S2 ? 2 * lty * G::TH - 1 : lty * G::TH);
+        const int X0 = (KIND == K_S2) ? 2 * ltx * TW : ltx * TW;
+        cv_tma_prefetch_3d(&map_in, X0 - G::RAW_X_SHIFT, iy0, ln * CI + c2 * CIC);
+      }
     }
   };
 
@@ -416,6 +461,10 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
 
   // ---- one-time per CTA: weights, coefficients
   if constexpr (C::MMA) {
+    // (Measured and dropped: copying the contiguous weight tensor into shared memory with coalesced
+    // loads first and gathering from there.  ncu -- which flushes the caches -- shows this gather as
+    // 7-10% of a mid-layer kernel's samples, but in a real step the 27 KB are L2-hot and the two extra
+    // barriers cost more than the gather: +2 us per launch.)
     // B fragments of mma.m16n8k8 (col): lane (g = lane>>2, t = lane&3) holds b0 = W[k=t][n=g],
     // b1 = W[k=t+4][n=g], k = input channel within the 8-channel chunk, n = output channel
     for (int idx = tid; idx < (CI / 8) * 9 * C::NTL * 32; idx += NT) {
@@ -538,6 +587,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
       const int n = tile / tiles_per_img;
       const int trem = tile - n * tiles_per_img;
       const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+      if (EPI == EPI_BWD && tvalid) prefetch_x(n, ty, tx, tid, NT);
 
       float acc[R][NTL][4];
 #pragma unroll
@@ -1196,6 +1246,7 @@ __global__ void __launch_bounds__(GconvCfg<KIND, CI, CO, TW, INMODE, TERMS>::NT,
     const int n = tile / tiles_per_img;
     const int trem = tile - n * tiles_per_img;
     const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    if (EPI == EPI_BWD && tvalid) prefetch_x(n, ty, tx, t2, 64 * NCOG);
 
     float acc[NOUT][COT];
 #pragma unroll
@@ -1886,6 +1937,7 @@ __global__ void __launch_bounds__(256, 2)
 // accumulators persist over the CTA's whole persistent loop.  Fragments are read straight from
 // the channel-planar TMA tiles; the planes are 4 (mod 8) floats apart (spare box rows / columns)
 // so that the fragment loads (8 channels x 4 pixels per warp) are bank-conflict free.
+constexpr int kWgradMmaDbBytes = 47 * 1024;   // stage size up to which the tensor-core kernel double-buffers
 template <int S, int TWG>
 struct WTileM : WTile<S, TWG> {
   using B = WTile<S, TWG>;
@@ -1915,7 +1967,8 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
   constexpr int IITERS = (NQI + NTHR - 1) / NTHR;
   constexpr int KSTEPS = T::THG * TWG / 8;
 
-  constexpr bool DB = (G_PAD + I_PAD) * 4 <= 40 * 1024;   // see wgrad_kernel
+  // (two stages while two CTAs still fit an SM: 2 x 2 x 47 KB + reductions < 228 KB)
+  constexpr bool DB = (G_PAD + I_PAD) * 4 <= kWgradMmaDbBytes;
   constexpr int NSTG = DB ? 2 : 1;
   extern __shared__ __align__(128) float smem[];
   float* s_aff = smem + NSTG * (G_PAD + I_PAD);
@@ -1946,6 +1999,13 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
     cv_mbar_expect_tx(&s_bar[st], BYTES);
     cv_tma_load_3d(sg, &map_g, tx * TWG, ty * T::THG, n * CG, &s_bar[st]);
     cv_tma_load_3d(sg + G_PAD, &map_i, S * tx * TWG - 4, S * ty * T::THG - 1, n * CI, &s_bar[st]);
+  };
+  auto prefetch = [&](int tile) {
+    const int n = tile / tiles_per_img;
+    const int trem = tile - n * tiles_per_img;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    cv_tma_prefetch_3d(&map_g, tx * TWG, ty * T::THG, n * CG);
+    cv_tma_prefetch_3d(&map_i, S * tx * TWG - 4, S * ty * T::THG - 1, n * CI);
   };
   pdl_wait();                 // (programmatic dependent launch, common.cuh)
   pdl_launch_dependents();
@@ -1983,8 +2043,12 @@ __global__ void __launch_bounds__((((CG + 15) / 16) * (CI / 8) == 6) ? 192 : 256
     float* s_i = s_g + G_PAD;
     __syncthreads();   // previous tile's MMA loop is done with the buffers
     if (tid == 0) {
-      if (!DB) issue(tile, 0);
-      else if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, st ^ 1);
+      if (!DB) {
+        issue(tile, 0);
+        // single stage (two would cost the second CTA of the SM): at least bring the NEXT tile's
+        // boxes into L2 while this one is consumed (ncu: 12% of the samples sat on the barrier)
+        if (tile + (int)gridDim.x < ntiles) prefetch(tile + gridDim.x);
+      } else if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, st ^ 1);
     }
     cv_mbar_wait(&s_bar[st], DB ? ((it >> 1) & 1) : (it & 1));
     if (CONVT) {
@@ -2436,7 +2500,7 @@ static int launch_wgrad_mma(WgradParams P, const FinalizeParams& F, void* ws, cu
   constexpr int NTHR = (NPAIR == 6) ? 192 : 256;
   constexpr int G_PAD = (CG * T::G_PLANE + 31) / 32 * 32;
   constexpr int I_PAD = (CI * T::I_PLANE + 31) / 32 * 32;
-  constexpr int NSTG = ((G_PAD + I_PAD) * 4 <= 40 * 1024) ? 2 : 1;   // as in the kernel
+  constexpr int NSTG = ((G_PAD + I_PAD) * 4 <= kWgradMmaDbBytes) ? 2 : 1;   // as in the kernel
   size_t smem_f = (size_t)NSTG * (G_PAD + I_PAD) + 64 + 8;
   if (smem_f < (size_t)CG * CI * 9 + 32) smem_f = (size_t)CG * CI * 9 + 32;
   const size_t smem = smem_f * sizeof(float) + 128;

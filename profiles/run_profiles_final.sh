@@ -15,6 +15,7 @@ rm -f $OUT/r02_step.ncu-rep
 i=0
 for RX in 'wgrad_mma_kernel<\(int\)1, \(int\)24, \(int\)16, \(int\)32, \(int\)0, \(int\)2' \
           'gconv_kernel<\(int\)0, \(int\)16, \(int\)24, \(int\)32, \(int\)0, \(int\)0' \
+          'gconv_kernel<\(int\)0, \(int\)24, \(int\)16, \(int\)32, \(int\)1, \(int\)1' \
           'gconv_kernel<\(int\)2, \(int\)8, \(int\)8, \(int\)32, \(int\)1, \(int\)1' \
           'tc_gemm_kernel<\(int\)3'; do
   i=$((i+1))
