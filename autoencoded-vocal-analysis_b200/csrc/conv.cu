@@ -26,6 +26,7 @@
 // shared-memory reads), each thread owns 4 output rows x COT(<=8) output channels in
 // registers; output-channel groups of 8 are warp-uniform so weight reads are broadcasts.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -2561,7 +2562,8 @@ using namespace ava;
 
 // layers with channel counts that are multiples of 8 on both sides can run on the tensor cores
 #define GCONV_TC(KIND, CI, CO, TW, INMODE, EPI, HIN)                                               \
-  (g_conv_terms == 3   ? ((g_conv_bf16corr & (EPI == EPI_FWD ? 4 : 2))                                 \
+  (g_conv_terms == 3   ? ((EPI == EPI_FWD ? ((g_conv_bf16corr & 4) || ((fwd_bf16_layers() >> layer) & 1))  \
+                                              : (g_conv_bf16corr & 2))                                  \
                               ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 2>(P, stream)         \
                               : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 3>(P, stream))        \
    : g_conv_terms == 1 ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 1>(P, stream)            \
@@ -2574,6 +2576,17 @@ using namespace ava;
                      : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 0>(P, stream))
 // (measured again with the 2-instruction-per-tap variant, TERMS == 2: 304.8 vs 307.7 us -- that
 // layer is bound by its epilogue's reads of x, not by the inner product)
+
+// (experiment switch: forward layers that take the BF16-correction form although the mode says no;
+// bit l = layer l, hexadecimal)
+static unsigned fwd_bf16_layers() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AVA_B200_FWD_BF16_LAYERS");
+    v = e ? (int)strtoul(e, nullptr, 16) : 0;
+  }
+  return (unsigned)v;
+}
 
 extern "C" int ava_b200_set_conv_precision(int mode) {
   AVA_REQUIRE(mode >= 0 && mode <= 5,

@@ -92,6 +92,12 @@ class _DpPeers(ctypes.Structure):
 # the backward-data kernels accumulate the border sums of the dz they write in their epilogue
 # (AVA_B200_FUSED_TSUMS=0: a separate ava_b200_dz_border_sums pass per layer instead)
 _FUSED_TSUMS = os.environ.get("AVA_B200_FUSED_TSUMS", "1") != "0"
+# The dense layers' weight and bias gradients are off the backward pass's critical path (only the
+# data gradients feed the next layer): they are issued on a second stream that forks where their
+# inputs are complete and joins before a gradient bucket is declared final / before the optimizer
+# step, with a scratch buffer of its own.  Captured like everything else (a fork / join inside the
+# CUDA graph).  AVA_B200_SIDE_STREAM=0: everything on one stream.
+_SIDE_STREAM = os.environ.get("AVA_B200_SIDE_STREAM", "1") != "0"
 
 
 def _out_hw(layer):
@@ -470,6 +476,30 @@ class VAE(nn.Module):
         self._bufs[B] = b          # most recently used last
         return b
 
+    def _side_fork(self):
+        """The second stream, waiting for everything issued so far on the current one."""
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(device=self._flat_p.device)
+        side.wait_stream(torch.cuda.current_stream())
+        self._side_dirty = True
+        return side
+
+    def _side_join(self):
+        """The current stream waits for the work issued on the second one."""
+        if getattr(self, "_side_dirty", False):
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            self._side_dirty = False
+
+    def _ws_side(self, nbytes):
+        ws = getattr(self, "_scratch_side", None)
+        if ws is None or ws.numel() < nbytes:
+            if ws is not None:
+                self._graphs = {}
+            ws = self._scratch_side = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8,
+                                                  device=self._flat_p.device)
+        return ws
+
     def _ws(self, nbytes):
         if self._scratch is None or self._scratch.numel() < nbytes:
             if self._scratch is not None:
@@ -516,8 +546,15 @@ class VAE(nn.Module):
             wgrad_jobs.append((ptr(dy), ptr(ymask), ptr(x), self._g(wkey), lddy, ldx, M, N, K, groups,
                                dy_gs, x_gs, w_gs))
             return
-        call("ava_b200_linear_bwd_weight", ptr(dy), lddy, ptr(ymask), ptr(x), ldx, self._g(wkey),
-             gb, M, N, K, groups, dy_gs, x_gs, w_gs, b_gs, tc, ptr(ws), ws.numel(), s)
+        if _SIDE_STREAM and gb is None:
+            side = self._side_fork()
+            ws2 = self._ws_side(self._scratch_need)
+            with torch.cuda.stream(side):
+                call("ava_b200_linear_bwd_weight", ptr(dy), lddy, ptr(ymask), ptr(x), ldx, self._g(wkey),
+                     None, M, N, K, groups, dy_gs, x_gs, w_gs, b_gs, tc, ptr(ws2), ws2.numel(), _stream())
+        else:
+            call("ava_b200_linear_bwd_weight", ptr(dy), lddy, ptr(ymask), ptr(x), ldx, self._g(wkey),
+                 gb, M, N, K, groups, dy_gs, x_gs, w_gs, b_gs, tc, ptr(ws), ws.numel(), s)
         if dx is not None:
             call("ava_b200_linear_bwd_data", ptr(dy), lddy, ptr(ymask), self._p(wkey), ptr(dx), lddx,
                  M, N, K, groups, dy_gs, w_gs, dx_gs, 0, tc, ptr(ws), ws.numel(), s)
@@ -563,6 +600,12 @@ class VAE(nn.Module):
         arr = (_BiasJob * len(jobs))()
         for a, (dy, mask, db, ld, M, N) in zip(arr, jobs):
             a.dy, a.mask, a.db, a.ld, a.M, a.N = dy, mask, db, ld, M, N
+        if _SIDE_STREAM:
+            side = self._side_fork()
+            ws2 = self._ws_side(self._scratch_need)
+            with torch.cuda.stream(side):
+                call("ava_b200_bias_grads", arr, len(jobs), ptr(ws2), ws2.numel(), _stream())
+            return
         ws = self._ws(self._scratch_need)
         call("ava_b200_bias_grads", arr, len(jobs), ptr(ws), ws.numel(), _stream())
 
@@ -800,11 +843,14 @@ class VAE(nn.Module):
         ava/models/vae.py:352.  The two callbacks fire where a gradient bucket becomes final."""
         self._bwd_decoder(bufs)
         if after_decoder is not None:
+            self._side_join()
             after_decoder()
         self._bwd_dense_encoder(bufs)
         if after_dense is not None:
+            self._side_join()
             after_dense()
         self._bwd_conv_encoder(bufs)
+        self._side_join()
 
     def _sync_hyper(self):
         """lr / betas / eps as torch.optim.Adam holds them (optimizer.param_groups[0]: what
@@ -1096,7 +1142,7 @@ class VAE(nn.Module):
                     st["graph"] = [g]
                 self._step_host = host_step      # capture records, it does not execute
                 # the graph owns references to everything it points into
-                st["bufs"], st["scratch"] = self._bufs[B], self._scratch
+                st["bufs"], st["scratch"] = self._bufs[B], (self._scratch, getattr(self, "_scratch_side", None))
             except Exception:
                 self.cuda_graphs = False
                 st["graph"] = None
@@ -1134,10 +1180,13 @@ class VAE(nn.Module):
         with torch.cuda.graph(graphs[0], pool=pool):
             bufs = self._forward_native(x, noise, True, want_grad_seed=True)
             self._bwd_decoder(bufs)
+            self._side_join()        # (a capture ends with every forked stream joined)
         with torch.cuda.graph(graphs[1], pool=pool):
             self._bwd_dense_encoder(bufs)
+            self._side_join()
         with torch.cuda.graph(graphs[2], pool=pool):
             self._bwd_conv_encoder(bufs)
+            self._side_join()
         with torch.cuda.graph(graphs[3], pool=pool):
             self._adam_native()
         st["loss"] = bufs.loss[0]
