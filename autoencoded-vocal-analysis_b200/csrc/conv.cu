@@ -26,7 +26,6 @@
 // shared-memory reads), each thread owns 4 output rows x COT(<=8) output channels in
 // registers; output-channel groups of 8 are warp-uniform so weight reads are broadcasts.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -1596,9 +1595,10 @@ static int make_act_map(CUtensorMap* map, const float* base, long long nc, int H
 // 0: fp32 SIMT; 1: TF32 tensor cores; 3: error-compensated 3xTF32 (layers the tensor-core path covers)
 static int g_conv_terms = 0;
 // 3-term layers: correction terms as half-rate BF16 k16 instructions (cv_pack_bf16), a bit mask:
-// 1 = the weight-gradient kernels, 2 = the backward-data kernels, 4 = the forward kernels
-// (ava_b200_set_conv_precision: mode 3 = 1, mode 5 = 1|2, mode 4 = 1|2|4; mode 2 keeps all three
-// terms in TF32)
+// 1 = the weight-gradient kernels, 2 = the backward-data kernels, 4 = the forward kernels, 8 = the
+// forward kernels of the decoder (layers 7..13) only
+// (ava_b200_set_conv_precision: mode 3 = 1, mode 5 = 1|2, mode 6 = 1|2|8, mode 4 = 1|2|4; mode 2 keeps
+// all three terms in TF32)
 static int g_conv_bf16corr = 0;
 
 template <int KIND, int CI, int CO, int TW, int INMODE, int EPI, int HIN, int TERMS = 0>
@@ -2312,13 +2312,15 @@ struct FinalizeParams {
 };
 
 // Second stage of the weight gradient: a CTA finishes 32 consecutive weight elements.  Lane = element
-// (every load is one coalesced 128-byte row of a per-CTA partial), the 8 warps split the partials
-// (4 loads in flight each), fp64 sums combined through shared memory in a fixed order
-// (deterministic); then dW and the element's contribution to this layer's BatchNorm-backward
-// reductions.  (A first version had one warp per element with the lanes striding over the
-// partials: 32 scattered 4-byte loads per request, 12 us per layer at 296 partials.)
-__global__ void __launch_bounds__(256) bnconv_finalize_kernel(const FinalizeParams P) {
-  __shared__ double s_part[8][33];
+// (every load is one coalesced 128-byte row of a per-CTA partial), the 32 warps split the partials
+// (4 loads in flight each: 296 partials are 3 rounds of latency; with 8 warps it was 10 rounds, 11 us
+// per layer ON THE CRITICAL PATH between a layer's weight-gradient and backward-data kernels at any
+// batch size), fp64 sums combined through shared memory in a fixed order (deterministic); then dW and
+// the element's contribution to this layer's BatchNorm-backward reductions.  (A first version had one
+// warp per element with the lanes striding over the partials: 32 scattered 4-byte loads per request.)
+constexpr int kFinWarps = 32;
+__global__ void __launch_bounds__(kFinWarps * 32) bnconv_finalize_kernel(const FinalizeParams P) {
+  __shared__ double s_part[kFinWarps][33];
   pdl_wait();
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -2329,15 +2331,15 @@ __global__ void __launch_bounds__(256) bnconv_finalize_kernel(const FinalizePara
     const float* src = P.partial + j;
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
     int p = warp;
-    for (; p + 24 < P.nparts; p += 32) {
-      const float a0 = src[(size_t)p * P.stride], a1 = src[(size_t)(p + 8) * P.stride];
-      const float a2 = src[(size_t)(p + 16) * P.stride], a3 = src[(size_t)(p + 24) * P.stride];
+    for (; p + 3 * kFinWarps < P.nparts; p += 4 * kFinWarps) {
+      const float a0 = src[(size_t)p * P.stride], a1 = src[(size_t)(p + kFinWarps) * P.stride];
+      const float a2 = src[(size_t)(p + 2 * kFinWarps) * P.stride], a3 = src[(size_t)(p + 3 * kFinWarps) * P.stride];
       r0 += (double)a0;
       r1 += (double)a1;
       r2 += (double)a2;
       r3 += (double)a3;
     }
-    for (; p < P.nparts; p += 8) r0 += (double)src[(size_t)p * P.stride];
+    for (; p < P.nparts; p += kFinWarps) r0 += (double)src[(size_t)p * P.stride];
     r = (r0 + r1) + (r2 + r3);
   }
   s_part[warp][lane] = r;
@@ -2357,7 +2359,7 @@ __global__ void __launch_bounds__(256) bnconv_finalize_kernel(const FinalizePara
   }
   r = 0.0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) r += s_part[w][lane];
+  for (int w = 0; w < kFinWarps; ++w) r += s_part[w][lane];
   const int k = j % 9;
   int cx, cz;
   if (!P.convt) {
@@ -2455,7 +2457,7 @@ static int launch_finalize(const WgradParams& P, FinalizeParams F, int nparts, c
   F.stats = P.stats;
   F.count = P.bn_count;
   const int n = CG * CI * 9 + F.Cz;
-  launch_pdl(bnconv_finalize_kernel, dim3((n + 31) / 32), dim3(256), 0, stream, F);
+  launch_pdl(bnconv_finalize_kernel, dim3((n + 31) / 32), dim3(kFinWarps * 32), 0, stream, F);
   return check_launch("bnconv_finalize");
 }
 
@@ -2562,7 +2564,7 @@ using namespace ava;
 
 // layers with channel counts that are multiples of 8 on both sides can run on the tensor cores
 #define GCONV_TC(KIND, CI, CO, TW, INMODE, EPI, HIN)                                               \
-  (g_conv_terms == 3   ? ((EPI == EPI_FWD ? ((g_conv_bf16corr & 4) || ((fwd_bf16_layers() >> layer) & 1))  \
+  (g_conv_terms == 3   ? ((EPI == EPI_FWD ? (g_conv_bf16corr & (layer >= 7 ? 12 : 4))                  \
                                               : (g_conv_bf16corr & 2))                                  \
                               ? launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 2>(P, stream)         \
                               : launch_gconv<KIND, CI, CO, TW, INMODE, EPI, HIN, 3>(P, stream))        \
@@ -2577,27 +2579,16 @@ using namespace ava;
 // (measured again with the 2-instruction-per-tap variant, TERMS == 2: 304.8 vs 307.7 us -- that
 // layer is bound by its epilogue's reads of x, not by the inner product)
 
-// (experiment switch: forward layers that take the BF16-correction form although the mode says no;
-// bit l = layer l, hexadecimal)
-static unsigned fwd_bf16_layers() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("AVA_B200_FWD_BF16_LAYERS");
-    v = e ? (int)strtoul(e, nullptr, 16) : 0;
-  }
-  return (unsigned)v;
-}
-
 extern "C" int ava_b200_set_conv_precision(int mode) {
-  AVA_REQUIRE(mode >= 0 && mode <= 5,
-              "set_conv_precision: mode %d (0 fp32, 1 tf32, 2 tf32x3, 3 / 4 / 5 tf32 + bf16 corrections)", mode);
+  AVA_REQUIRE(mode >= 0 && mode <= 6,
+              "set_conv_precision: mode %d (0 fp32, 1 tf32, 2 tf32x3, 3 .. 6 tf32 + bf16 corrections)", mode);
   g_conv_terms = (mode >= 2) ? 3 : mode;
-  g_conv_bf16corr = (mode == 3) ? 1 : (mode == 4) ? 7 : (mode == 5) ? 3 : 0;
+  g_conv_bf16corr = (mode == 3) ? 1 : (mode == 4) ? 7 : (mode == 5) ? 3 : (mode == 6) ? 11 : 0;
   return 0;
 }
 extern "C" int ava_b200_get_conv_precision(void) {
   if (g_conv_terms != 3) return g_conv_terms;
-  return g_conv_bf16corr == 1 ? 3 : g_conv_bf16corr == 7 ? 4 : g_conv_bf16corr == 3 ? 5 : 2;
+  return g_conv_bf16corr == 1 ? 3 : g_conv_bf16corr == 7 ? 4 : g_conv_bf16corr == 3 ? 5 : g_conv_bf16corr == 11 ? 6 : 2;
 }
 
 extern "C" int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float* w, const float* b,

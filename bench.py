@@ -522,7 +522,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32x3b", "tf32x3c", "tf32x3d", "tf32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32x3b", "tf32x3c", "tf32x3d", "tf32x3e", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--all-kernels", action="store_true", help="list every native call, not the top 12")
@@ -622,6 +622,11 @@ def main():
     if prof is not None:
         graphs_default = model.cuda_graphs
         model.cuda_graphs = False
+        # per-call times are taken with every kernel alone on the device: the forked stream that
+        # carries the dense weight / bias gradients beside the conv backward in the `value` and `e2e`
+        # loops would lengthen whatever it overlaps (same kernels, same launch count)
+        side_default = vae_mod._SIDE_STREAM
+        vae_mod._SIDE_STREAM = False
         for i in range(2):
             model.train_step(xs[i % 2])
         launches_eager0 = lib.launch_count()
@@ -636,6 +641,7 @@ def main():
         barrier()
         lib.PROFILER = None
         model.cuda_graphs = graphs_default
+        vae_mod._SIDE_STREAM = side_default
         ms_prof = p0.elapsed_time(p1) / args.steps
         if launches == 0:
             # the `value` loop replayed CUDA graphs (no host-side launch calls to count): the

@@ -89,6 +89,9 @@ int ava_b200_bnconv_fwd(int layer, int B, const float* x, float* y, const float*
  *      4.2e-5), twice as many ReLU units on the other side of zero
  *   5  as 4 for the weight-gradient and backward-data kernels only; the forward kernels (whose
  *      rounding decides ReLU states and feeds every later layer) keep three TF32 terms
+ *   6  as 5, plus the forward kernels of the DECODER (layers 7..13): their roundings reach only the
+ *      reconstruction, not the latent path -- batch-1024 gradients 4.0e-5 (as mode 5), 260 ReLU units
+ *      on the other side of zero (mode 5: 191, mode 4: 403, the float32 reference itself: 129)
  * Layers whose channel counts are not multiples of 8 always use fp32 FMA. */
 int ava_b200_set_conv_precision(int mode);
 int ava_b200_get_conv_precision(void);

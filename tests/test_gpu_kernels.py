@@ -22,10 +22,10 @@ TOL = 1e-4   # fp32 kernels vs float64 reference (north_star rtol 1e-4)
 # conv inner-product arithmetic (ava_b200_set_conv_precision): fp32 FMA and error-compensated
 # 3xTF32 on the tensor cores hold the fp32 bar; plain TF32 has its own stated tolerance
 # (mode 3: the 3-term product with its two correction terms as half-rate BF16 instructions)
-CONV_MODES = [(0, TOL), (2, TOL), (3, TOL), (4, TOL), (5, TOL), (1, 5e-3)]
+CONV_MODES = [(0, TOL), (2, TOL), (3, TOL), (4, TOL), (5, TOL), (6, TOL), (1, 5e-3)]
 
 
-@pytest.fixture(params=CONV_MODES, ids=["fp32", "tf32x3", "tf32x3b", "tf32x3c", "tf32x3d", "tf32"])
+@pytest.fixture(params=CONV_MODES, ids=["fp32", "tf32x3", "tf32x3b", "tf32x3c", "tf32x3d", "tf32x3e", "tf32"])
 def conv_mode(request, L):
     mode, tol = request.param
     L.call("ava_b200_set_conv_precision", mode)

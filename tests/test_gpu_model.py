@@ -73,7 +73,7 @@ def build(vae_mod, seed, prec=10.0, **kw):
     return model
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32x3b", "tf32x3c", "tf32x3d"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32x3b", "tf32x3c", "tf32x3d", "tf32x3e"])
 @pytest.mark.parametrize("name", ["vae_train_b7", "vae_eval_b7", "vae_train_b1",
                                   "vae_train_b64"])
 def test_forward_backward_matches_reference_golden(vae_mod, name, precision):
