@@ -436,6 +436,8 @@ class VAE(nn.Module):
                 self.device = self._flat_p.device
             except AttributeError:
                 pass
+            # the forked stream and its scratch belong to the device the model was on
+            self._side_stream, self._scratch_side, self._side_dirty = None, None, False
         return out
 
     def _p(self, key):

@@ -129,6 +129,36 @@ def test_fused_mlp_path_matches_reference_golden(vae_mod, name, monkeypatch):
     test_forward_backward_matches_reference_golden(vae_mod, name, "tf32x3b")
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_forked_stream_changes_scheduling_only(vae_mod, monkeypatch, graphs):
+    """The dense layers' weight / bias gradients run on a second stream beside the conv backward
+    (VAE._side_fork / _side_join).  Same kernels, same inputs: five train steps with and without the fork
+    must end on the same parameters and losses -- a missing dependency (a gradient read before it is
+    written, a scratch buffer shared across the streams, a join that comes after the optimizer step)
+    shows up as a difference far above the 1e-6 that the order of the fp64 statistics atomics allows."""
+    seed, B = 5, 24
+    x = vae_oracle.make_input(seed, B).cuda()
+    ends = []
+    for side in (True, False):
+        monkeypatch.setattr(vae_mod, "_SIDE_STREAM", side)
+        model = build(vae_mod, seed, cuda_graphs=graphs)
+        model.train()
+        gen = torch.Generator(device="cuda").manual_seed(77)
+        losses = []
+        for step in range(5):
+            ew = torch.randn(B, 1, device="cuda", generator=gen)
+            ed = torch.randn(B, 32, device="cuda", generator=gen)
+            losses.append(model.train_step(x, noise=(ew, ed)).clone())
+        torch.cuda.synchronize()
+        ends.append((model._flat_p.clone(), torch.stack(losses), model._flat_m.clone()))
+    (p1, l1, m1), (p0, l0, m0) = ends
+    assert float((l1 - l0).abs().max() / l0.abs().max()) <= 1e-6
+    assert float((m1 - m0).abs().max() / m0.abs().max()) <= 1e-5
+    # Adam's first steps are sign-like (|update| = lr whatever the gradient's size), so a parameter
+    # whose gradient is ~0 may move differently: bound the mean, not the max
+    assert float((p1 - p0).abs().mean()) <= 1e-7
+
+
 def test_reduced_precision_mode_tf32(vae_mod):
     """'tf32' is the opt-in reduced-precision mode (what torch/cuDNN do by default for the
     reference's convs on a GPU) with its own stated tolerance: forward 1e-2,
