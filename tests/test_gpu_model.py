@@ -153,10 +153,11 @@ def test_forked_stream_changes_scheduling_only(vae_mod, monkeypatch, graphs):
         ends.append((model._flat_p.clone(), torch.stack(losses), model._flat_m.clone()))
     (p1, l1, m1), (p0, l0, m0) = ends
     assert float((l1 - l0).abs().max() / l0.abs().max()) <= 1e-6
-    assert float((m1 - m0).abs().max() / m0.abs().max()) <= 1e-5
+    assert float((m1 - m0).abs().max() / m0.abs().max()) <= 1e-4
     # Adam's first steps are sign-like (|update| = lr whatever the gradient's size), so a parameter
-    # whose gradient is ~0 may move differently: bound the mean, not the max
-    assert float((p1 - p0).abs().mean()) <= 1e-7
+    # whose gradient is ~0 may move differently: bound the mean, not the max.  (A dependency bug on
+    # fc1.weight or fc8.weight -- half of all parameters each -- would move the mean by ~lr/2 = 5e-4.)
+    assert float((p1 - p0).abs().mean()) <= 1e-6
 
 
 def test_reduced_precision_mode_tf32(vae_mod):
